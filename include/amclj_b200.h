@@ -1,0 +1,252 @@
+/*
+ * amclj_b200.h — C ABI of libamclj_b200.so: the B200-native implementation of the
+ * per-update particle-filter hot path of jvia/amclj.
+ *
+ * The reference has no FFI/plugin interface of its own: the hot path is plain Clojure
+ * called from mcl* (reference src/amclj/pf.clj:229-233).  The entry points below are the
+ * smallest seam that keeps those call signatures, so a Clojure/JNA shim
+ * can keep `apply-motion-model`, `apply-sensor-model`, `roulette-selection` and the
+ * per-particle model functions unchanged.  Each entry point cites the reference function
+ * it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every function returns int32 status: AMCLJ_OK (0) or a negative AMCLJ_ERR_* code;
+ *     amclj_last_error(ctx) gives a human-readable message owned by the ctx (valid until
+ *     the next call on that ctx).  No exception crosses the boundary.
+ *   - the caller owns every host buffer; the library owns all device memory behind the
+ *     opaque amclj_ctx.  One ctx drives ONE GPU (one rank of a sharded filter).
+ *   - a ctx is not thread-safe; distinct ctxs are independent (the reference has exactly
+ *     one caller thread: the single `go` block at pf.clj:297).
+ *   - calls are synchronous on return unless the name ends in `_async`; `_async` calls
+ *     only enqueue work on the ctx stream (amclj_set_stream).
+ *   - there is NO CPU fallback: without a usable CUDA device amclj_create fails with
+ *     AMCLJ_ERR_NODEVICE.
+ */
+#ifndef AMCLJ_B200_H
+#define AMCLJ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMCLJ_ABI_VERSION 1
+
+#define AMCLJ_OK 0
+#define AMCLJ_ERR_INVALID (-1)  /* bad argument */
+#define AMCLJ_ERR_CUDA (-2)     /* CUDA runtime error, see amclj_last_error */
+#define AMCLJ_ERR_STATE (-3)    /* call order: no map / particles / scan yet */
+#define AMCLJ_ERR_NOMEM (-4)
+#define AMCLJ_ERR_NODEVICE (-5) /* no usable CUDA device: there is no CPU fallback */
+
+#define AMCLJ_PRESET_REF 0 /* the reference as written, bug for bug */
+#define AMCLJ_PRESET_NS 1  /* north-star semantics (Probabilistic Robotics) */
+
+#define AMCLJ_RESAMPLE_ROULETTE 0   /* pf.clj:156-167 */
+#define AMCLJ_RESAMPLE_SYSTEMATIC 1 /* PR table 4.4, integer CDF */
+#define AMCLJ_RESAMPLE_TOURNAMENT 2 /* pf.clj:182-195 */
+
+/*
+ * Model constants and the ten semantic switches.  POD, passed by
+ * pointer.  Defaults = the Clojure `def` constants: sensor.clj:11-21, motion.clj:12-16.
+ */
+typedef struct amclj_params {
+  /* S1 sensor.clj:131,133 — 0: ray direction = obs-bearing only (REF); 1: theta+bearing */
+  int32_t s1_use_heading;
+  /* S2 sensor.clj:12,133,121 — 0: ray length and miss value = global max_range (-1.0);
+   * 1: the scan's rangeMax */
+  int32_t s2_use_scan_range_max;
+  /* S3 sensor.clj:137-138 — 0: non-steep rays get end = start (diagonal walk); 1: proper */
+  int32_t s3_proper_endpoint;
+  /* S4 sensor.clj:121 — 0: `(> x max-x)` tested after the cell test; 1: stop after
+   * testing the endpoint cell */
+  int32_t s4_endpoint_termination;
+  /* S5 sensor.clj:151-153 — 0: z_hit doubles as sigma; 1: sigma_hit */
+  int32_t s5_use_sigma_hit;
+  /* S6 sensor.clj:13,144-145 — beams = range(0, n, int((n-1)/(max_beams-1)));
+   * <= 0 means every beam */
+  int32_t s6_max_beams;
+  /* S7 sensor.clj:162,173 — 0: weight = sum (p)^3; 1: log-weight = sum log p */
+  int32_t s7_log_weights;
+  /* S8 pf.clj:156-167 — resampler used by amclj_filter_update (AMCLJ_RESAMPLE_*) */
+  int32_t s8_resampler;
+  /* S9 motion.clj:35 — 0: rot1 variance a1*rot1^2 + a2*rot2^2 (REF); 1: a2*trans^2 (PR) */
+  int32_t s9_pr_rot1_variance;
+  /* S10 sensor.clj:78-81,142 — 0: base->laser offset ignored (REF and NS default) */
+  int32_t s10_apply_laser_offset;
+  int32_t collect_stats; /* count cells visited / probes (small cost) */
+  int32_t reserved0;
+  float max_range;    /* sensor.clj:12  (-1.0) */
+  float z_hit;        /* sensor.clj:14 */
+  float z_short;      /* sensor.clj:15 */
+  float z_max;        /* sensor.clj:16 */
+  float z_rand;       /* sensor.clj:17 */
+  float sigma_hit;    /* sensor.clj:18 */
+  float lambda_short; /* sensor.clj:19 */
+  float laser_x;      /* sensor.clj:80 (0.135), used only when s10 != 0 */
+  float laser_y;
+  float alpha1; /* motion.clj:12 */
+  float alpha2; /* motion.clj:13 */
+  float alpha3; /* motion.clj:14 */
+  float alpha4; /* motion.clj:15 */
+  float reserved1[3];
+} amclj_params;
+
+typedef struct amclj_stats {
+  double ms_motion;   /* last update, device time from CUDA events on the ctx stream */
+  double ms_sensor;
+  double ms_resample;
+  double ms_total;
+  uint64_t rays;          /* rays cast in the last sensor pass */
+  uint64_t cells_visited; /* Bresenham cells the reference would have tested */
+  uint64_t probes;        /* distance-field probes actually issued */
+  uint64_t hits;
+  int64_t n_particles;
+  int32_t beams_used;
+  int32_t map_in_smem; /* 1 when the nibble-packed distance field fits shared memory */
+} amclj_stats;
+
+typedef struct amclj_ctx amclj_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------- */
+int32_t amclj_abi_version(void);
+/* Fill *p with a preset (AMCLJ_PRESET_REF / AMCLJ_PRESET_NS). */
+int32_t amclj_params_default(amclj_params *p, int32_t preset);
+/* One ctx per GPU.  `device` is a CUDA ordinal. */
+int32_t amclj_create(int32_t device, amclj_ctx **out);
+int32_t amclj_destroy(amclj_ctx *ctx);
+const char *amclj_last_error(const amclj_ctx *ctx);
+/* Run on a caller-owned cudaStream_t (e.g. the host framework's current stream).
+ * NULL restores the ctx's own stream. */
+int32_t amclj_set_stream(amclj_ctx *ctx, void *cuda_stream);
+int32_t amclj_synchronize(amclj_ctx *ctx);
+int32_t amclj_set_params(amclj_ctx *ctx, const amclj_params *p);
+int32_t amclj_get_params(const amclj_ctx *ctx, amclj_params *p);
+/* Shard identity for a particle set split over `world` GPUs: this ctx holds
+ * global particles [global_offset, global_offset + n_local) of n_global. */
+int32_t amclj_set_shard(amclj_ctx *ctx, int32_t rank, int32_t world, int64_t global_offset,
+                        int64_t n_global);
+
+/* ---- map: nav_msgs/OccupancyGrid as amclj sees it (nav_msgs.clj:27-38, map.clj:19-57) */
+/* cells: int8 [height][width] row-major, -1 unknown / 0 free / 100 occupied. */
+int32_t amclj_set_map(amclj_ctx *ctx, const int8_t *cells, int32_t width, int32_t height,
+                      float resolution);
+
+/* ---- particles: PoseArray <-> SoA (geometry_msgs.clj:54-72,224-242) ----------------- */
+/* theta = quat/to-heading of the orientation (quaternions.clj:82-97), done by the shim. */
+int32_t amclj_set_particles(amclj_ctx *ctx, const float *x, const float *y,
+                            const float *theta, const float *w, int64_t n);
+int32_t amclj_get_particles(amclj_ctx *ctx, float *x, float *y, float *theta, float *w);
+int64_t amclj_num_particles(const amclj_ctx *ctx);
+/* map.clj:71-84 uniform-initialization / map.clj:108-111 gaussian-initialization, on device
+ * (in-kernel Philox).  heading_mode 0: N(0,1) rad (REF, map.clj:67-68); 1: U(-pi,pi). */
+int32_t amclj_init_uniform(amclj_ctx *ctx, int64_t n, int32_t heading_mode, uint64_t seed);
+int32_t amclj_init_gaussian(amclj_ctx *ctx, int64_t n, double x, double y, double theta,
+                            double sd_xy, double sd_theta, uint64_t seed);
+
+/* ---- motion: apply-motion-model pf.clj:139-145 -> motion.clj:24-45,68-79 ----------- */
+/* curr/prev = (x, y, yaw) of the odom->base transforms.  normals: host float [n][3]
+ * standard normals (rot1, trans, rot2 draw per particle, motion.clj:35-38) or NULL to
+ * draw them in-kernel from Philox4x32-10 keyed by (seed, global particle id). */
+int32_t amclj_motion_update(amclj_ctx *ctx, const double curr[3], const double prev[3],
+                            const float *normals, uint64_t seed);
+
+/* ---- sensor: apply-sensor-model pf.clj:148-154 -> sensor.clj:141-173 ---------------- */
+/* LaserScan fields angleMin, angleIncrement, rangeMax, ranges (sensor_msgs.clj:8-12). */
+int32_t amclj_sensor_update(amclj_ctx *ctx, const float *ranges, int32_t n, float angle_min,
+                            float angle_increment, float range_max);
+/* Raw per-particle weight of the last sensor pass: sum p^3 or sum log p (S7). */
+int32_t amclj_get_raw_weights(amclj_ctx *ctx, float *raw);
+/* Parity probe for map-range / extract-line (sensor.clj:112-139): ray-casts particles
+ * [first, first+count) for every used beam; outputs are [count][beams_used] (any may be
+ * NULL).  steps = major-axis steps taken to the hit (or last tested step on a miss). */
+int32_t amclj_raycast_debug(amclj_ctx *ctx, int32_t n, float angle_min, float angle_increment,
+                            float range_max, int64_t first, int64_t count, int32_t *hit_x,
+                            int32_t *hit_y, int32_t *steps, uint8_t *hit, float *range_m);
+/* Number of beams selected by S6 for an n-beam scan. */
+int32_t amclj_beams_used(const amclj_ctx *ctx, int32_t n);
+
+/* ---- normalise + resample: roulette-selection pf.clj:156-167 ----------------------- */
+/* Linear weights (w = raw, or exp(raw - max raw) under S7) -> fixed point
+ * q_i = floor(w_i / w_max * 2^32), inclusive integer CDF.  total_out = sum q_i. */
+int32_t amclj_normalize(amclj_ctx *ctx, int32_t from_raw, uint64_t *total_out,
+                        float *wmax_out);
+/* mode AMCLJ_RESAMPLE_*.  u0 in [0,1): the single systematic draw.  stream_idx/stream_u:
+ * injected roulette/tournament attempt stream of stream_len entries (idx in [0,n),
+ * u = numerator of u/2^32) or NULL for the Philox stream keyed by `seed`.
+ * idx_out (host int32 [n]) receives the selected source indices, or NULL. */
+int32_t amclj_resample(amclj_ctx *ctx, int32_t mode, double u0, const int32_t *stream_idx,
+                       const uint32_t *stream_u, int64_t stream_len, uint64_t seed,
+                       int32_t *idx_out);
+
+/* ---- fused update: one mcl* iteration's hot path (pf.clj:229-233) ------------------- */
+/* motion -> sensor -> normalise -> resample, device-resident in and out.  The scan is
+ * copied to the device inside the call. */
+int32_t amclj_filter_update(amclj_ctx *ctx, const double curr[3], const double prev[3],
+                            const float *normals, uint64_t seed, const float *ranges,
+                            int32_t n, float angle_min, float angle_increment,
+                            float range_max, double u0);
+/* Enqueue-only variant: scan must have been staged with amclj_stage_scan. */
+int32_t amclj_stage_scan(amclj_ctx *ctx, const float *ranges, int32_t n, float angle_min,
+                         float angle_increment, float range_max);
+int32_t amclj_filter_update_async(amclj_ctx *ctx, const double curr[3], const double prev[3],
+                                  uint64_t seed, double u0);
+/* The same step for a host-resident PoseArray: uploads x,y,theta, runs the fused update,
+ * downloads the resampled particles and weights (in place). */
+int32_t amclj_filter_update_host(amclj_ctx *ctx, float *x, float *y, float *theta, float *w,
+                                 int64_t n, const double curr[3], const double prev[3],
+                                 const float *normals, uint64_t seed, const float *ranges,
+                                 int32_t n_ranges, float angle_min, float angle_increment,
+                                 float range_max, double u0);
+
+/* ---- pose-estimate pf.clj:67-84: unweighted mean of x, y, and of (qz, qw) ----------- */
+/* out = {mean x, mean y, mean qz, mean qw}. */
+int32_t amclj_pose_estimate(amclj_ctx *ctx, double out[4]);
+
+int32_t amclj_get_stats(amclj_ctx *ctx, amclj_stats *out);
+
+/* ---- sharded (multi-GPU) building blocks, SURVEY 8e --------------------------------- */
+/* Stage 1: motion + sensor, enqueue only; the local max raw weight lands in a device
+ * float (amclj_device_ptr(AMCLJ_BUF_RAW_MAX)) for the all-reduce(max). */
+int32_t amclj_shard_motion_sensor_async(amclj_ctx *ctx, const double curr[3],
+                                        const double prev[3], uint64_t seed);
+/* Stage 2: fixed-point CDF of the local weights against the GLOBAL max (read from
+ * AMCLJ_BUF_RAW_MAX after the all-reduce); local total lands in AMCLJ_BUF_TOTAL (u64). */
+int32_t amclj_shard_cdf_async(amclj_ctx *ctx);
+/* Stage 3: systematic offspring for global slots [m_lo, m_lo+count) whose thresholds fall
+ * in this rank's CDF interval [cdf_offset, cdf_offset + local total).  Output: float4
+ * (x, y, theta, w) rows in AMCLJ_BUF_STAGE_OUT, global source index in idx (optional
+ * host int32/int64 readback through amclj_shard_get_stage_idx). */
+int32_t amclj_shard_generate_async(amclj_ctx *ctx, uint64_t total_global, uint64_t cdf_offset,
+                                   uint64_t r, int64_t m_lo, int64_t count);
+/* Stage 4: adopt `count` float4 rows from AMCLJ_BUF_STAGE_IN as the new local particles. */
+int32_t amclj_shard_adopt_async(amclj_ctx *ctx, int64_t count);
+/* Host-only planning (no GPU needed): for per-rank totals T_g, systematic offset
+ * r = floor(u0 * T), and slots split evenly (n_global / world per rank, remainder to the
+ * low ranks) computes m_lo[g], m_cnt[g] and the world x world send matrix (row = source). */
+int32_t amclj_plan_systematic(const uint64_t *totals, int32_t world, int64_t n_global,
+                              double u0, uint64_t *r_out, uint64_t *cdf_offsets,
+                              int64_t *m_lo, int64_t *m_cnt, int64_t *send_matrix);
+
+#define AMCLJ_BUF_X 0
+#define AMCLJ_BUF_Y 1
+#define AMCLJ_BUF_THETA 2
+#define AMCLJ_BUF_W 3
+#define AMCLJ_BUF_RAW 4
+#define AMCLJ_BUF_RAW_MAX 5   /* float[1] */
+#define AMCLJ_BUF_TOTAL 6     /* uint64[1] */
+#define AMCLJ_BUF_STAGE_OUT 7 /* float4[capacity] */
+#define AMCLJ_BUF_STAGE_IN 8  /* float4[capacity] */
+#define AMCLJ_BUF_CDF 9       /* uint64[n] */
+/* Raw device pointer + size in bytes of a library-owned buffer, for zero-copy interop
+ * with the host framework's collectives (the pointer stays valid until the particle count
+ * changes or the ctx is destroyed). */
+int32_t amclj_device_ptr(amclj_ctx *ctx, int32_t which, void **ptr, int64_t *bytes);
+/* Make sure the staging buffers hold at least `rows` float4 rows. */
+int32_t amclj_reserve_stage(amclj_ctx *ctx, int64_t rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMCLJ_B200_H */
