@@ -1,0 +1,1135 @@
+// api.cu — the C ABI of libamclj_b200.so (include/amclj_b200.h): context, staging of the
+// launch-uniform tables, and the stream choreography of one filter update.
+//
+// Boundary replaced (jvia/amclj): the three calls of one mcl* iteration, pf.clj:229-233 —
+// apply-motion-model (pf.clj:139-145), apply-sensor-model (:148-154) and
+// roulette-selection (:156-167) — plus pose-estimate (:67-84, :234).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "internal.h"
+
+using namespace amclj;
+
+namespace {
+
+int fail(amclj_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? AMCLJ_ERR_NOMEM : AMCLJ_ERR_CUDA, \
+                  "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);  \
+  } while (0)
+
+#define NEED(cond, code, ...)                          \
+  do {                                                 \
+    if (!(cond)) return fail(ctx, code, __VA_ARGS__);  \
+  } while (0)
+
+#define ENTER()                                                             \
+  do {                                                                      \
+    if (!ctx) return AMCLJ_ERR_INVALID;                                     \
+    cudaError_t e0_ = cudaSetDevice(ctx->device);                           \
+    if (e0_ != cudaSuccess)                                                 \
+      return fail(ctx, AMCLJ_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e0_)); \
+  } while (0)
+
+template <class T>
+cudaError_t dalloc(T **p, size_t count) {
+  return cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T));
+}
+template <class T>
+void dfree(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+void preset(amclj_params *p, int which) {
+  memset(p, 0, sizeof(*p));
+  p->max_range = -1.0f; /* sensor.clj:12 */
+  p->z_hit = 0.95f;     /* sensor.clj:14-19 */
+  p->z_short = 0.1f;
+  p->z_max = 0.05f;
+  p->z_rand = 0.05f;
+  p->sigma_hit = 0.2f;
+  p->lambda_short = 0.1f;
+  p->laser_x = 0.135f; /* sensor.clj:80 */
+  p->laser_y = 0.0f;
+  p->alpha1 = 0.002f; /* motion.clj:12-15 */
+  p->alpha2 = 0.002f;
+  p->alpha3 = 0.02f;
+  p->alpha4 = 0.02f;
+  if (which == AMCLJ_PRESET_REF) {
+    p->s6_max_beams = 30; /* sensor.clj:13 */
+    p->s8_resampler = AMCLJ_RESAMPLE_ROULETTE;
+  } else {
+    p->s1_use_heading = 1;
+    p->s2_use_scan_range_max = 1;
+    p->s3_proper_endpoint = 1;
+    p->s4_endpoint_termination = 1;
+    p->s5_use_sigma_hit = 1;
+    p->s6_max_beams = 0;
+    p->s7_log_weights = 1;
+    p->s8_resampler = AMCLJ_RESAMPLE_SYSTEMATIC;
+  }
+}
+
+/* sensor.clj:144-145: step = int((n-1)/(max-beams-1)); range(0, n, step) */
+int beam_step(int n, int max_beams) {
+  if (max_beams <= 1) return 1;
+  int step = (n - 1) / (max_beams - 1);
+  return step < 1 ? 1 : step;
+}
+int beams_used(int n, int max_beams) {
+  if (n <= 0) return 0;
+  int step = beam_step(n, max_beams);
+  return (n + step - 1) / step;
+}
+
+int ensure_particles(amclj_ctx *ctx, int64_t n) {
+  if (n <= ctx->cap) return AMCLJ_OK;
+  int64_t cap = (n + 1023) / 1024 * 1024;
+  float **bufs[] = {&ctx->x, &ctx->y, &ctx->th, &ctx->w, &ctx->raw, &ctx->x2, &ctx->y2, &ctx->th2, &ctx->w2};
+  /* growing keeps the live particles */
+  for (float **b : bufs) {
+    float *nb = nullptr;
+    CK(dalloc(&nb, (size_t)cap));
+    if (*b && ctx->n > 0)
+      CK(cudaMemcpyAsync(nb, *b, sizeof(float) * (size_t)ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    dfree(*b);
+    *b = nb;
+  }
+  dfree(ctx->cdf);
+  CK(dalloc(&ctx->cdf, (size_t)cap));
+  dfree(ctx->idx);
+  CK(dalloc(&ctx->idx, (size_t)cap));
+  dfree(ctx->normals);
+  CK(dalloc(&ctx->normals, (size_t)cap * 3));
+  int64_t tiles = scan_tiles(cap) + 1;
+  if (tiles < (1 << 16)) tiles = 1 << 16; /* also serves the roulette compaction */
+  dfree(ctx->scan_state);
+  CK(dalloc(&ctx->scan_state, (size_t)tiles));
+  ctx->scan_state_cap = tiles;
+  ctx->cap = cap;
+  ctx->have_cdf = false;
+  return AMCLJ_OK;
+}
+
+int ensure_stage(amclj_ctx *ctx, int64_t rows) {
+  if (rows <= ctx->stage_cap) return AMCLJ_OK;
+  int64_t cap = (rows + 1023) / 1024 * 1024;
+  dfree(ctx->stage_out);
+  dfree(ctx->stage_in);
+  dfree(ctx->stage_idx);
+  CK(dalloc(&ctx->stage_out, (size_t)cap));
+  CK(dalloc(&ctx->stage_in, (size_t)cap));
+  CK(dalloc(&ctx->stage_idx, (size_t)cap));
+  ctx->stage_cap = cap;
+  return AMCLJ_OK;
+}
+
+/* motion.clj:68-79 + :24-34: the control is launch-uniform; doubles as on the JVM. */
+void make_control(const amclj_params &p, const double curr[3], const double prev[3],
+                  MotionLaunch &m) {
+  double xn = curr[0], yn = curr[1], tn = curr[2], x = prev[0], y = prev[1], t = prev[2];
+  m.is_static = ((x - xn) == 0.0 && (y - yn) == 0.0 && (t - tn) == 0.0); /* motion.clj:26 */
+  m.trans_zero = 0;
+  m.rot1 = m.trans = m.rot2 = m.sd1 = m.sdt = m.sd2 = 0.f;
+  if (m.is_static) return;
+  double rot1 = atan2(yn - y, xn - x) - t;
+  double trans = hypot(x - xn, y - yn);
+  double rot2 = tn - t - rot1;
+  double a1 = p.alpha1, a2 = p.alpha2, a3 = p.alpha3, a4 = p.alpha4;
+  double v1 = p.s9_pr_rot1_variance ? a1 * rot1 * rot1 + a2 * trans * trans
+                                    : a1 * rot1 * rot1 + a2 * rot2 * rot2; /* motion.clj:35 */
+  m.trans_zero = trans == 0.0; /* motion.clj:36 */
+  m.rot1 = (float)rot1;
+  m.trans = (float)trans;
+  m.rot2 = (float)rot2;
+  m.sd1 = (float)sqrt(v1);
+  m.sdt = (float)sqrt(a3 * trans * trans + a4 * rot1 * rot1 + a4 * rot2 * rot2);
+  m.sd2 = (float)sqrt(a1 * rot2 * rot2 + a2 * trans * trans);
+}
+
+int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min, float angle_inc,
+                    float range_max) {
+  NEED(n > 0 && n <= (1 << 20), AMCLJ_ERR_INVALID, "scan: n = %d out of range", n);
+  NEED(ctx->map.df4, AMCLJ_ERR_STATE, "scan: no map set");
+  const amclj_params &p = ctx->p;
+  float R = p.s2_use_scan_range_max ? range_max : p.max_range; /* S2 */
+  NEED(isfinite(R) && isfinite(range_max) && isfinite(angle_min) && isfinite(angle_inc),
+       AMCLJ_ERR_INVALID, "scan: non-finite geometry");
+  double rcells = fabs((double)R) / (double)ctx->map.res;
+  NEED(rcells < 4.0e6, AMCLJ_ERR_INVALID, "scan: ray of %.0f cells is too long", rcells);
+  int step = beam_step(n, p.s6_max_beams);
+  int nb = beams_used(n, p.s6_max_beams);
+  std::vector<float> h((size_t)nb * 5);
+  float *cb = h.data(), *sb = cb + nb, *obs = sb + nb, *e2 = obs + nb, *p34 = e2 + nb;
+  float zshort = p.z_short, lam = p.lambda_short;
+  int j = 0;
+  for (int i = 0; i < n; i += step, j++) {
+    /* sensor.clj:93-97 bearing: float32 message fields, double arithmetic */
+    double a = (double)angle_min + (double)i * (double)angle_inc;
+    cb[j] = (float)cos(a);
+    sb[j] = (float)sin(a);
+    float o = ranges ? ranges[i] : 0.0f;
+    obs[j] = o;
+    e2[j] = zshort * lam * expf(-lam * o);                     /* sensor.clj:154-157 */
+    float pz3 = o == range_max ? p.z_max : 0.0f;               /* sensor.clj:158-159 */
+    float pz4 = o < range_max ? p.z_rand / range_max : 0.0f;   /* sensor.clj:160-161 */
+    p34[j] = pz3 + pz4;
+  }
+  BeamTable &b = ctx->beams;
+  if (nb > b.cap) {
+    dfree(b.dev);
+    CK(dalloc(&b.dev, (size_t)nb * 5));
+    b.cap = nb;
+  }
+  CK(cudaMemcpyAsync(b.dev, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+  b.nb = nb;
+  b.n_scan = n;
+  b.angle_min = angle_min;
+  b.angle_inc = angle_inc;
+  b.range_max = range_max;
+  /* magic reciprocals for j(k): M = ceil(2^(31+L) / D), D = 2*dx, L = floor(log2 D) */
+  int ndiv = (int)ceil(rcells) + 8;
+  DivTable &d = ctx->divs;
+  if (ndiv > d.n) {
+    std::vector<uint2> t((size_t)ndiv);
+    t[0] = make_uint2(0u, 0u);
+    for (int dx = 1; dx < ndiv; dx++) {
+      uint64_t D = 2ull * (uint64_t)dx;
+      int L = 63 - __builtin_clzll(D);
+      uint64_t M = ((1ull << (31 + L)) + D - 1) / D;
+      t[dx] = make_uint2((uint32_t)M, (uint32_t)(L - 1));
+    }
+    if (ndiv > d.cap) {
+      dfree(d.dev);
+      CK(dalloc(&d.dev, (size_t)ndiv));
+      d.cap = ndiv;
+    }
+    CK(cudaMemcpyAsync(d.dev, t.data(), sizeof(uint2) * t.size(), cudaMemcpyHostToDevice, ctx->stream));
+    d.n = ndiv;
+  }
+  CK(cudaStreamSynchronize(ctx->stream)); /* the host vectors go out of scope */
+  b.staged = true;
+  return AMCLJ_OK;
+}
+
+int df_mode_of(const amclj_ctx *ctx) {
+  switch (ctx->p.df_mode) {
+    case 1: return ctx->map.fits_smem ? DF_SMEM4 : -1;
+    case 2: return ctx->map.df8 ? DF_GLOBAL8 : -1;
+    case 3: return DF_GLOBAL4;
+    default: return ctx->map.fits_smem ? DF_SMEM4 : (ctx->map.df8 ? DF_GLOBAL8 : DF_GLOBAL4);
+  }
+}
+
+void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode) {
+  const amclj_params &p = ctx->p;
+  const DeviceMap &m = ctx->map;
+  memset(&a, 0, sizeof(a));
+  a.W = m.W;
+  a.H = m.H;
+  a.res = m.res;
+  if (mode == DF_GLOBAL8) {
+    a.df = m.df8;
+    a.row_nib = m.pitch8;
+    a.df_bytes = m.bytes8;
+  } else {
+    a.df = m.df4;
+    a.row_nib = m.row_bytes4 * 2;
+    a.df_bytes = m.bytes4;
+  }
+  a.beam = ctx->beams.dev;
+  a.nb = ctx->beams.nb;
+  a.divtab = ctx->divs.dev;
+  a.ndiv = ctx->divs.n;
+  a.R = p.s2_use_scan_range_max ? ctx->beams.range_max : p.max_range;
+  a.miss_value = a.R; /* sensor.clj:121 returns max-range on a miss */
+  a.s1 = p.s1_use_heading;
+  a.s3 = p.s3_proper_endpoint;
+  a.s4 = p.s4_endpoint_termination;
+  a.s7 = p.s7_log_weights;
+  a.s10 = p.s10_apply_laser_offset;
+  a.z_hit = p.z_hit;
+  float sig = p.s5_use_sigma_hit ? p.sigma_hit : p.z_hit; /* S5, sensor.clj:151-153 */
+  a.inv2s2 = 1.0f / (2.0f * sig * sig);
+  a.laser_x = p.laser_x;
+  a.laser_y = p.laser_y;
+}
+
+/* enqueue motion + sensor on the ctx stream */
+int enqueue_motion(amclj_ctx *ctx, const double curr[3], const double prev[3], bool injected,
+                   uint64_t seed) {
+  MotionLaunch m;
+  memset(&m, 0, sizeof(m));
+  make_control(ctx->p, curr, prev, m);
+  m.x = ctx->x;
+  m.y = ctx->y;
+  m.th = ctx->th;
+  m.n = ctx->n;
+  m.gid0 = ctx->global_offset;
+  m.normals = injected ? ctx->normals : nullptr;
+  m.seed = seed;
+  CK(launch_motion(m, ctx->stream));
+  return AMCLJ_OK;
+}
+
+int enqueue_sensor(amclj_ctx *ctx) {
+  NEED(ctx->beams.staged, AMCLJ_ERR_STATE, "sensor: no scan staged");
+  NEED(ctx->n > 0, AMCLJ_ERR_STATE, "sensor: no particles");
+  int mode = df_mode_of(ctx);
+  NEED(mode >= 0, AMCLJ_ERR_INVALID, "sensor: df_mode %d unavailable for this map", ctx->p.df_mode);
+  SensorLaunch a;
+  fill_sensor_args(ctx, a, mode);
+  a.x = ctx->x;
+  a.y = ctx->y;
+  a.th = ctx->th;
+  a.raw = ctx->raw;
+  a.n = ctx->n;
+  a.rawmax_ord = ctx->rawmax_ord;
+  bool diag = ctx->p.collect_stats != 0;
+  a.stats = diag ? ctx->stats : nullptr;
+  CK(cudaMemsetAsync(ctx->rawmax_ord, 0, sizeof(uint32_t), ctx->stream));
+  if (diag) CK(cudaMemsetAsync(ctx->stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  CK(launch_sensor(ctx, a, mode, diag, ctx->stream));
+  CK(launch_decode_max(ctx->rawmax_ord, ctx->rawmax, ctx->stream));
+  ctx->have_raw = true;
+  ctx->have_cdf = false;
+  ctx->st.map_in_smem = mode == DF_SMEM4;
+  ctx->st.beams_used = ctx->beams.nb;
+  ctx->st.n_particles = ctx->n;
+  return AMCLJ_OK;
+}
+
+/* raw (or w) -> max -> fixed point -> CDF, all on the stream */
+int enqueue_cdf(amclj_ctx *ctx, bool from_raw, bool max_known) {
+  const float *v = from_raw ? ctx->raw : ctx->w;
+  int is_log = from_raw && ctx->p.s7_log_weights;
+  if (!max_known) CK(launch_max(v, ctx->n, ctx->rawmax_ord, ctx->rawmax, ctx->sm_count, ctx->stream));
+  CK(launch_scan(v, ctx->rawmax, is_log, ctx->n, ctx->cdf, ctx->scan_state, ctx->scan_counter,
+                 ctx->total, ctx->stream));
+  ctx->have_cdf = true;
+  ctx->cdf_from_raw = from_raw;
+  return AMCLJ_OK;
+}
+
+void swap_particles(amclj_ctx *ctx) {
+  std::swap(ctx->x, ctx->x2);
+  std::swap(ctx->y, ctx->y2);
+  std::swap(ctx->th, ctx->th2);
+  std::swap(ctx->w, ctx->w2);
+}
+
+int enqueue_systematic(amclj_ctx *ctx, double u0) {
+  uint64_t bits = (uint64_t)ldexp(u0, 64); /* u0 in [0,1) as a 0.64 fraction */
+  CK(launch_plan(ctx->total, bits, ctx->n, ctx->plan, ctx->stream));
+  GatherArgs g;
+  memset(&g, 0, sizeof(g));
+  g.cdf = ctx->cdf;
+  g.n_local = ctx->n;
+  g.cdf_offset = 0;
+  g.plan = ctx->plan;
+  g.m_lo = 0;
+  g.count = ctx->n;
+  g.x = ctx->x;
+  g.y = ctx->y;
+  g.th = ctx->th;
+  g.ox = ctx->x2;
+  g.oy = ctx->y2;
+  g.oth = ctx->th2;
+  g.ow = ctx->w2;
+  g.oidx = ctx->idx;
+  g.wout = 1.0f / (float)ctx->n;
+  CK(launch_systematic(g, ctx->stream));
+  swap_particles(ctx);
+  ctx->have_raw = false;
+  ctx->have_cdf = false;
+  return AMCLJ_OK;
+}
+
+int read_scalars(amclj_ctx *ctx, uint64_t *total, float *wmax) {
+  uint64_t *pt = reinterpret_cast<uint64_t *>(ctx->pinned);
+  float *pm = reinterpret_cast<float *>(pt + 1);
+  CK(cudaMemcpyAsync(pt, ctx->total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(pm, ctx->rawmax, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->last_total = *pt;
+  ctx->last_wmax = *pm;
+  if (total) *total = *pt;
+  if (wmax) *wmax = *pm;
+  return AMCLJ_OK;
+}
+
+int run_roulette(amclj_ctx *ctx, const int32_t *h_sidx, const uint32_t *h_su, int64_t stream_len,
+                 uint64_t seed) {
+  int rc = read_scalars(ctx, nullptr, nullptr);
+  if (rc) return rc;
+  uint64_t T = ctx->last_total;
+  NEED(T > 0, AMCLJ_ERR_STATE, "roulette: all weights are zero");
+  int64_t n = ctx->n;
+  int32_t *d_sidx = nullptr;
+  uint32_t *d_su = nullptr;
+  if (h_sidx) {
+    NEED(h_su && stream_len > 0, AMCLJ_ERR_INVALID, "roulette: incomplete injected stream");
+    CK(dalloc(&d_sidx, (size_t)stream_len));
+    CK(dalloc(&d_su, (size_t)stream_len));
+    CK(cudaMemcpyAsync(d_sidx, h_sidx, sizeof(int32_t) * (size_t)stream_len, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_su, h_su, sizeof(uint32_t) * (size_t)stream_len, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  unsigned long long *cnt = ctx->stats + 4; /* accepted, last attempt */
+  CK(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  int64_t got = 0, t0 = 0;
+  int status = AMCLJ_OK;
+  unsigned long long *h = reinterpret_cast<unsigned long long *>(ctx->pinned);
+  while (got < n) {
+    /* expected attempts per acceptance = n (pf.clj:161-166): size the super-chunk for what is
+     * still missing, within [2^16, 2^30] */
+    double want = (double)(n - got) * (double)n * 1.25 + 65536.0;
+    int64_t len = want > 1073741824.0 ? 1073741824ll : (int64_t)want;
+    if (h_sidx) {
+      len = stream_len - t0;
+      if (len <= 0) { status = fail(ctx, AMCLJ_ERR_INVALID, "roulette: injected stream exhausted after %lld of %lld", (long long)got, (long long)n); break; }
+    }
+    int per_thread = len >= (1 << 24) ? 64 : (len >= (1 << 18) ? 16 : 4);
+    int64_t tiles = (len + 256ll * per_thread - 1) / (256ll * per_thread);
+    if (tiles > ctx->scan_state_cap) { /* cap the chunk to the descriptor array */
+      tiles = ctx->scan_state_cap;
+      len = tiles * 256ll * per_thread;
+    }
+    RouletteArgs a;
+    memset(&a, 0, sizeof(a));
+    a.cdf = ctx->cdf;
+    a.n = n;
+    a.total = T;
+    a.seed = seed;
+    a.sidx = d_sidx;
+    a.su = d_su;
+    a.t0 = t0;
+    a.t_end = t0 + len;
+    a.per_thread = per_thread;
+    a.got_before = got;
+    a.idx_out = ctx->idx;
+    a.tile_state = ctx->scan_state;
+    a.tile_counter = ctx->scan_counter;
+    a.accepted_out = cnt;
+    a.last_attempt = cnt + 1;
+    cudaError_t e = launch_roulette(a, tiles, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { status = fail(ctx, AMCLJ_ERR_CUDA, "roulette: %s", cudaGetErrorString(e)); break; }
+    got += (int64_t)h[0];
+    t0 += len;
+  }
+  dfree(d_sidx);
+  dfree(d_su);
+  if (status) return status;
+  /* carried weight = the normalised weight (pf.clj:160) */
+  CK(launch_gather_idx(ctx->idx, n, ctx->x, ctx->y, ctx->th, 1, ctx->cdf, T, nullptr, 0.f, ctx->x2,
+                       ctx->y2, ctx->th2, ctx->w2, ctx->stream));
+  swap_particles(ctx);
+  ctx->have_raw = false;
+  ctx->have_cdf = false;
+  return AMCLJ_OK;
+}
+
+int run_tournament(amclj_ctx *ctx, const int32_t *h_sidx, int64_t stream_len, uint64_t seed) {
+  int64_t n = ctx->n;
+  const float *wv = ctx->have_raw ? ctx->raw : ctx->w;
+  int32_t *d_sidx = nullptr;
+  if (h_sidx) {
+    NEED(stream_len >= 2 * n, AMCLJ_ERR_INVALID, "tournament: stream needs 2n entries");
+    CK(dalloc(&d_sidx, (size_t)(2 * n)));
+    CK(cudaMemcpyAsync(d_sidx, h_sidx, sizeof(int32_t) * (size_t)(2 * n), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  cudaError_t e = launch_tournament(wv, n, d_sidx, seed, ctx->idx, ctx->stream);
+  if (e == cudaSuccess)
+    e = launch_gather_idx(ctx->idx, n, ctx->x, ctx->y, ctx->th, 2, nullptr, 0, wv, 0.f, ctx->x2, ctx->y2,
+                          ctx->th2, ctx->w2, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  dfree(d_sidx);
+  CK(e);
+  swap_particles(ctx);
+  ctx->have_raw = false;
+  ctx->have_cdf = false;
+  return AMCLJ_OK;
+}
+
+int upload_normals(amclj_ctx *ctx, const float *normals) {
+  if (!normals) return AMCLJ_OK;
+  CK(cudaMemcpyAsync(ctx->normals, normals, sizeof(float) * 3 * (size_t)ctx->n, cudaMemcpyHostToDevice,
+                     ctx->stream));
+  return AMCLJ_OK;
+}
+
+void stamp(amclj_ctx *ctx, int k) { cudaEventRecord(ctx->ev[k], ctx->stream); }
+
+void collect_times(amclj_ctx *ctx) {
+  float a = 0, b = 0, c = 0, t = 0;
+  cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]);
+  cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[3]);
+  ctx->st.ms_motion = a;
+  ctx->st.ms_sensor = b;
+  ctx->st.ms_resample = c;
+  ctx->st.ms_total = t;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t amclj_abi_version(void) { return AMCLJ_ABI_VERSION; }
+
+int32_t amclj_params_default(amclj_params *p, int32_t which) {
+  if (!p || (which != AMCLJ_PRESET_REF && which != AMCLJ_PRESET_NS)) return AMCLJ_ERR_INVALID;
+  preset(p, which);
+  return AMCLJ_OK;
+}
+
+int32_t amclj_create(int32_t device, amclj_ctx **out) {
+  if (!out) return AMCLJ_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) return AMCLJ_ERR_NODEVICE; /* no CPU fallback */
+  if (device < 0 || device >= count) return AMCLJ_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return AMCLJ_ERR_NODEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return AMCLJ_ERR_NODEVICE;
+  amclj_ctx *ctx = new amclj_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  preset(&ctx->p, AMCLJ_PRESET_REF);
+  memset(&ctx->st, 0, sizeof(ctx->st));
+  bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ctx->stream = ctx->own_stream;
+  for (int i = 0; ok && i < 5; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+  ok = ok && dalloc(&ctx->rawmax_ord, 1) == cudaSuccess && dalloc(&ctx->rawmax, 1) == cudaSuccess &&
+       dalloc(&ctx->total, 1) == cudaSuccess && dalloc(&ctx->stats, 8) == cudaSuccess &&
+       dalloc(&ctx->scan_counter, 1) == cudaSuccess && dalloc(&ctx->plan, 1) == cudaSuccess &&
+       dalloc(&ctx->pose_part, (size_t)pose_blocks() * 4) == cudaSuccess &&
+       cudaMallocHost(&ctx->pinned, 4096) == cudaSuccess;
+  if (ok) ok = cudaMemset(ctx->stats, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;
+  if (!ok) {
+    amclj_destroy(ctx);
+    return AMCLJ_ERR_CUDA;
+  }
+  for (int i = 0; i < 4; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
+  *out = ctx;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_destroy(amclj_ctx *ctx) {
+  if (!ctx) return AMCLJ_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  dfree(ctx->map.cells); dfree(ctx->map.df4); dfree(ctx->map.df8);
+  dfree(ctx->beams.dev); dfree(ctx->divs.dev);
+  dfree(ctx->x); dfree(ctx->y); dfree(ctx->th); dfree(ctx->w); dfree(ctx->raw);
+  dfree(ctx->x2); dfree(ctx->y2); dfree(ctx->th2); dfree(ctx->w2);
+  dfree(ctx->cdf); dfree(ctx->idx); dfree(ctx->normals);
+  dfree(ctx->rawmax_ord); dfree(ctx->rawmax); dfree(ctx->total); dfree(ctx->stats);
+  dfree(ctx->scan_state); dfree(ctx->scan_counter); dfree(ctx->pose_part); dfree(ctx->plan);
+  dfree(ctx->stage_out); dfree(ctx->stage_in); dfree(ctx->stage_idx);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (int i = 0; i < 5; i++)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return AMCLJ_OK;
+}
+
+const char *amclj_last_error(const amclj_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int32_t amclj_set_stream(amclj_ctx *ctx, void *cuda_stream) {
+  ENTER();
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_synchronize(amclj_ctx *ctx) {
+  ENTER();
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AMCLJ_OK;
+}
+
+int32_t amclj_set_params(amclj_ctx *ctx, const amclj_params *p) {
+  ENTER();
+  NEED(p, AMCLJ_ERR_INVALID, "set_params: null");
+  NEED(p->df_mode >= 0 && p->df_mode <= 3, AMCLJ_ERR_INVALID, "set_params: df_mode %d", p->df_mode);
+  NEED(p->s8_resampler >= 0 && p->s8_resampler <= 2, AMCLJ_ERR_INVALID, "set_params: resampler %d", p->s8_resampler);
+  ctx->p = *p;
+  ctx->beams.staged = false; /* the beam table bakes S2/S5/S6 and the mixture constants */
+  ctx->have_cdf = false;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_get_params(const amclj_ctx *ctx, amclj_params *p) {
+  if (!ctx || !p) return AMCLJ_ERR_INVALID;
+  *p = ctx->p;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_set_shard(amclj_ctx *ctx, int32_t rank, int32_t world, int64_t global_offset,
+                        int64_t n_global) {
+  ENTER();
+  NEED(world >= 1 && rank >= 0 && rank < world && global_offset >= 0 && n_global >= 0,
+       AMCLJ_ERR_INVALID, "set_shard: bad shard (%d of %d)", rank, world);
+  ctx->rank = rank;
+  ctx->world = world;
+  ctx->global_offset = global_offset;
+  ctx->n_global = n_global;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_set_map(amclj_ctx *ctx, const int8_t *cells, int32_t width, int32_t height,
+                      float resolution) {
+  ENTER();
+  NEED(cells && width > 0 && height > 0 && width <= 32768 && height <= 32768, AMCLJ_ERR_INVALID,
+       "set_map: bad dimensions %d x %d", width, height);
+  NEED(isfinite(resolution) && resolution > 0.f, AMCLJ_ERR_INVALID, "set_map: bad resolution");
+  CK(cudaStreamSynchronize(ctx->stream));
+  DeviceMap &m = ctx->map;
+  dfree(m.cells); dfree(m.df4); dfree(m.df8);
+  m.W = width;
+  m.H = height;
+  m.res = resolution;
+  size_t ncell = (size_t)width * height;
+  CK(dalloc(&m.cells, ncell));
+  CK(cudaMemcpyAsync(m.cells, cells, ncell, cudaMemcpyHostToDevice, ctx->stream));
+  m.row_bytes4 = ((width + 2 + 1) / 2 + 15) / 16 * 16;
+  m.bytes4 = (size_t)m.row_bytes4 * (height + 2);
+  m.fits_smem = m.bytes4 + 2048 <= (size_t)ctx->max_smem_optin;
+  CK(dalloc(&m.df4, m.bytes4));
+  bool want8 = !m.fits_smem || ctx->p.df_mode == 2;
+  m.pitch8 = (width + 2 + 3) / 4 * 4;
+  m.bytes8 = (size_t)m.pitch8 * (height + 2);
+  if (want8) CK(dalloc(&m.df8, m.bytes8));
+  CK(build_distance_fields(ctx, want8, ctx->stream));
+  ctx->beams.staged = false;
+  ctx->divs.n = 0;
+  ctx->st.map_in_smem = m.fits_smem;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_set_particles(amclj_ctx *ctx, const float *x, const float *y, const float *theta,
+                            const float *w, int64_t n) {
+  ENTER();
+  NEED(x && y && theta && n > 0 && n <= (1ll << 31) - 1, AMCLJ_ERR_INVALID, "set_particles: bad arguments");
+  int64_t keep = ctx->n;
+  ctx->n = 0; /* nothing to preserve when the set is replaced */
+  int rc = ensure_particles(ctx, n);
+  if (rc) { ctx->n = keep; return rc; }
+  size_t b = sizeof(float) * (size_t)n;
+  CK(cudaMemcpyAsync(ctx->x, x, b, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->y, y, b, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->th, theta, b, cudaMemcpyHostToDevice, ctx->stream));
+  if (w) CK(cudaMemcpyAsync(ctx->w, w, b, cudaMemcpyHostToDevice, ctx->stream));
+  else CK(launch_fill(ctx->w, n, 1.0f / (float)n, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->n = n;
+  if (ctx->world == 1) { ctx->n_global = n; ctx->global_offset = 0; }
+  ctx->have_raw = false;
+  ctx->have_cdf = false;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_get_particles(amclj_ctx *ctx, float *x, float *y, float *theta, float *w) {
+  ENTER();
+  NEED(ctx->n > 0, AMCLJ_ERR_STATE, "get_particles: no particles");
+  size_t b = sizeof(float) * (size_t)ctx->n;
+  if (x) CK(cudaMemcpyAsync(x, ctx->x, b, cudaMemcpyDeviceToHost, ctx->stream));
+  if (y) CK(cudaMemcpyAsync(y, ctx->y, b, cudaMemcpyDeviceToHost, ctx->stream));
+  if (theta) CK(cudaMemcpyAsync(theta, ctx->th, b, cudaMemcpyDeviceToHost, ctx->stream));
+  if (w) CK(cudaMemcpyAsync(w, ctx->w, b, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AMCLJ_OK;
+}
+
+int64_t amclj_num_particles(const amclj_ctx *ctx) { return ctx ? ctx->n : 0; }
+
+int32_t amclj_init_uniform(amclj_ctx *ctx, int64_t n, int32_t heading_mode, uint64_t seed) {
+  ENTER();
+  NEED(ctx->map.cells, AMCLJ_ERR_STATE, "init_uniform: no map set");
+  NEED(n > 0 && n <= (1ll << 31) - 1, AMCLJ_ERR_INVALID, "init_uniform: bad n");
+  ctx->n = 0;
+  int rc = ensure_particles(ctx, n);
+  if (rc) return rc;
+  if (ctx->world == 1) { ctx->n_global = n; ctx->global_offset = 0; }
+  float w0 = 1.0f / (float)(ctx->n_global > 0 ? ctx->n_global : n);
+  CK(launch_init_uniform(ctx->map.cells, ctx->map.W, ctx->map.H, ctx->map.res, ctx->global_offset, n,
+                         heading_mode, seed, ctx->x, ctx->y, ctx->th, ctx->w, w0, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->n = n;
+  ctx->have_raw = ctx->have_cdf = false;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_init_gaussian(amclj_ctx *ctx, int64_t n, double x, double y, double theta,
+                            double sd_xy, double sd_theta, uint64_t seed) {
+  ENTER();
+  NEED(n > 0 && n <= (1ll << 31) - 1, AMCLJ_ERR_INVALID, "init_gaussian: bad n");
+  ctx->n = 0;
+  int rc = ensure_particles(ctx, n);
+  if (rc) return rc;
+  if (ctx->world == 1) { ctx->n_global = n; ctx->global_offset = 0; }
+  float w0 = 1.0f / (float)(ctx->n_global > 0 ? ctx->n_global : n);
+  CK(launch_init_gaussian((float)x, (float)y, (float)theta, (float)sd_xy, (float)sd_theta,
+                          ctx->global_offset, n, seed, ctx->x, ctx->y, ctx->th, ctx->w, w0, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->n = n;
+  ctx->have_raw = ctx->have_cdf = false;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_motion_update(amclj_ctx *ctx, const double curr[3], const double prev[3],
+                            const float *normals, uint64_t seed) {
+  ENTER();
+  NEED(curr && prev, AMCLJ_ERR_INVALID, "motion: null control");
+  NEED(ctx->n > 0, AMCLJ_ERR_STATE, "motion: no particles");
+  int rc = upload_normals(ctx, normals);
+  if (rc) return rc;
+  stamp(ctx, 0);
+  rc = enqueue_motion(ctx, curr, prev, normals != nullptr, seed);
+  if (rc) return rc;
+  stamp(ctx, 1);
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+  ctx->st.ms_motion = ms;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_stage_scan(amclj_ctx *ctx, const float *ranges, int32_t n, float angle_min,
+                         float angle_increment, float range_max) {
+  ENTER();
+  NEED(ranges, AMCLJ_ERR_INVALID, "scan: null ranges");
+  return stage_scan_impl(ctx, ranges, n, angle_min, angle_increment, range_max);
+}
+
+int32_t amclj_sensor_update(amclj_ctx *ctx, const float *ranges, int32_t n, float angle_min,
+                            float angle_increment, float range_max) {
+  ENTER();
+  NEED(ranges, AMCLJ_ERR_INVALID, "scan: null ranges");
+  int rc = stage_scan_impl(ctx, ranges, n, angle_min, angle_increment, range_max);
+  if (rc) return rc;
+  stamp(ctx, 1);
+  rc = enqueue_sensor(ctx);
+  if (rc) return rc;
+  stamp(ctx, 2);
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+  ctx->st.ms_sensor = ms;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_get_raw_weights(amclj_ctx *ctx, float *raw) {
+  ENTER();
+  NEED(raw, AMCLJ_ERR_INVALID, "get_raw_weights: null");
+  NEED(ctx->have_raw, AMCLJ_ERR_STATE, "get_raw_weights: no sensor pass since the last resample");
+  CK(cudaMemcpyAsync(raw, ctx->raw, sizeof(float) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AMCLJ_OK;
+}
+
+int32_t amclj_beams_used(const amclj_ctx *ctx, int32_t n) {
+  if (!ctx) return AMCLJ_ERR_INVALID;
+  return beams_used(n, ctx->p.s6_max_beams);
+}
+
+int32_t amclj_raycast_debug(amclj_ctx *ctx, int32_t n, float angle_min, float angle_increment,
+                            float range_max, int64_t first, int64_t count, int32_t *hit_x,
+                            int32_t *hit_y, int32_t *steps, uint8_t *hit, float *range_m) {
+  ENTER();
+  NEED(ctx->n > 0, AMCLJ_ERR_STATE, "raycast_debug: no particles");
+  NEED(first >= 0 && count > 0 && first + count <= ctx->n, AMCLJ_ERR_INVALID, "raycast_debug: bad range");
+  int rc = stage_scan_impl(ctx, nullptr, n, angle_min, angle_increment, range_max);
+  if (rc) return rc;
+  ctx->beams.staged = false; /* the staged table carries no ranges */
+  int mode = df_mode_of(ctx);
+  NEED(mode >= 0, AMCLJ_ERR_INVALID, "raycast_debug: df_mode unavailable");
+  size_t rays = (size_t)count * ctx->beams.nb;
+  int32_t *d_hx = nullptr, *d_hy = nullptr, *d_st = nullptr;
+  uint8_t *d_hit = nullptr;
+  float *d_rng = nullptr;
+  int status = AMCLJ_OK;
+  cudaError_t e = cudaSuccess;
+  if (hit_x) e = dalloc(&d_hx, rays);
+  if (e == cudaSuccess && hit_y) e = dalloc(&d_hy, rays);
+  if (e == cudaSuccess && steps) e = dalloc(&d_st, rays);
+  if (e == cudaSuccess && hit) e = dalloc(&d_hit, rays);
+  if (e == cudaSuccess && range_m) e = dalloc(&d_rng, rays);
+  if (e == cudaSuccess) {
+    SensorLaunch a;
+    fill_sensor_args(ctx, a, mode);
+    a.x = ctx->x + first;
+    a.y = ctx->y + first;
+    a.th = ctx->th + first;
+    a.n = count;
+    a.dbg_first = 0;
+    a.dbg_count = count;
+    a.dbg_hit_x = d_hx;
+    a.dbg_hit_y = d_hy;
+    a.dbg_steps = d_st;
+    a.dbg_hit = d_hit;
+    a.dbg_range = d_rng;
+    a.stats = ctx->stats;
+    cudaMemsetAsync(ctx->stats, 0, 4 * sizeof(unsigned long long), ctx->stream);
+    e = launch_sensor(ctx, a, mode, true, ctx->stream);
+  }
+  auto back = [&](void *dst, const void *src, size_t bytes) {
+    if (e == cudaSuccess && dst) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  };
+  back(hit_x, d_hx, rays * 4);
+  back(hit_y, d_hy, rays * 4);
+  back(steps, d_st, rays * 4);
+  back(hit, d_hit, rays);
+  back(range_m, d_rng, rays * 4);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) status = fail(ctx, AMCLJ_ERR_CUDA, "raycast_debug: %s", cudaGetErrorString(e));
+  dfree(d_hx); dfree(d_hy); dfree(d_st); dfree(d_hit); dfree(d_rng);
+  return status;
+}
+
+int32_t amclj_normalize(amclj_ctx *ctx, int32_t from_raw, uint64_t *total_out, float *wmax_out) {
+  ENTER();
+  NEED(ctx->n > 0, AMCLJ_ERR_STATE, "normalize: no particles");
+  NEED(!from_raw || ctx->have_raw, AMCLJ_ERR_STATE, "normalize: no sensor pass to normalise");
+  int rc = enqueue_cdf(ctx, from_raw != 0, false);
+  if (rc) return rc;
+  return read_scalars(ctx, total_out, wmax_out);
+}
+
+int32_t amclj_resample(amclj_ctx *ctx, int32_t mode, double u0, const int32_t *stream_idx,
+                       const uint32_t *stream_u, int64_t stream_len, uint64_t seed,
+                       int32_t *idx_out) {
+  ENTER();
+  NEED(ctx->n > 0, AMCLJ_ERR_STATE, "resample: no particles");
+  NEED(mode >= 0 && mode <= 2, AMCLJ_ERR_INVALID, "resample: mode %d", mode);
+  int rc = AMCLJ_OK;
+  stamp(ctx, 2);
+  if (mode != AMCLJ_RESAMPLE_TOURNAMENT && !ctx->have_cdf) {
+    rc = enqueue_cdf(ctx, ctx->have_raw, false);
+    if (rc) return rc;
+  }
+  if (mode == AMCLJ_RESAMPLE_SYSTEMATIC) {
+    NEED(u0 >= 0.0 && u0 < 1.0, AMCLJ_ERR_INVALID, "resample: u0 must be in [0,1)");
+    rc = read_scalars(ctx, nullptr, nullptr);
+    if (rc) return rc;
+    NEED(ctx->last_total > 0, AMCLJ_ERR_STATE, "resample: all weights are zero");
+    rc = enqueue_systematic(ctx, u0);
+  } else if (mode == AMCLJ_RESAMPLE_ROULETTE) {
+    rc = run_roulette(ctx, stream_idx, stream_u, stream_len, seed);
+  } else {
+    rc = run_tournament(ctx, stream_idx, stream_len, seed);
+  }
+  if (rc) return rc;
+  stamp(ctx, 3);
+  if (idx_out)
+    CK(cudaMemcpyAsync(idx_out, ctx->idx, sizeof(int32_t) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+  ctx->st.ms_resample = ms;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_get_resample_indices(amclj_ctx *ctx, int32_t *idx_out) {
+  ENTER();
+  NEED(idx_out && ctx->n > 0, AMCLJ_ERR_INVALID, "get_resample_indices: bad arguments");
+  CK(cudaMemcpyAsync(idx_out, ctx->idx, sizeof(int32_t) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AMCLJ_OK;
+}
+
+int32_t amclj_filter_update_async(amclj_ctx *ctx, const double curr[3], const double prev[3],
+                                  uint64_t seed, double u0) {
+  ENTER();
+  NEED(curr && prev, AMCLJ_ERR_INVALID, "filter_update: null control");
+  NEED(ctx->n > 0, AMCLJ_ERR_STATE, "filter_update: no particles");
+  NEED(ctx->beams.staged, AMCLJ_ERR_STATE, "filter_update: no scan staged");
+  NEED(ctx->p.s8_resampler == AMCLJ_RESAMPLE_SYSTEMATIC, AMCLJ_ERR_INVALID,
+       "filter_update_async: only the systematic resampler runs without a host round trip");
+  NEED(u0 >= 0.0 && u0 < 1.0, AMCLJ_ERR_INVALID, "filter_update: u0 must be in [0,1)");
+  stamp(ctx, 0);
+  int rc = enqueue_motion(ctx, curr, prev, ctx->normals_staged, seed);
+  ctx->normals_staged = false;
+  if (rc) return rc;
+  stamp(ctx, 1);
+  rc = enqueue_sensor(ctx);
+  if (rc) return rc;
+  stamp(ctx, 2);
+  rc = enqueue_cdf(ctx, true, true);
+  if (rc) return rc;
+  rc = enqueue_systematic(ctx, u0);
+  if (rc) return rc;
+  stamp(ctx, 3);
+  return AMCLJ_OK;
+}
+
+int32_t amclj_filter_update(amclj_ctx *ctx, const double curr[3], const double prev[3],
+                            const float *normals, uint64_t seed, const float *ranges, int32_t n,
+                            float angle_min, float angle_increment, float range_max, double u0) {
+  ENTER();
+  NEED(curr && prev && ranges, AMCLJ_ERR_INVALID, "filter_update: null argument");
+  NEED(ctx->n > 0, AMCLJ_ERR_STATE, "filter_update: no particles");
+  int rc = stage_scan_impl(ctx, ranges, n, angle_min, angle_increment, range_max);
+  if (rc) return rc;
+  rc = upload_normals(ctx, normals);
+  if (rc) return rc;
+  if (ctx->p.s8_resampler == AMCLJ_RESAMPLE_SYSTEMATIC) {
+    ctx->normals_staged = normals != nullptr;
+    rc = amclj_filter_update_async(ctx, curr, prev, seed, u0);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    collect_times(ctx);
+    return AMCLJ_OK;
+  }
+  /* roulette / tournament need the host in the loop (pf.clj:156-167 has an unbounded
+   * attempt count) */
+  stamp(ctx, 0);
+  rc = enqueue_motion(ctx, curr, prev, normals != nullptr, seed);
+  if (rc) return rc;
+  stamp(ctx, 1);
+  rc = enqueue_sensor(ctx);
+  if (rc) return rc;
+  stamp(ctx, 2);
+  if (ctx->p.s8_resampler == AMCLJ_RESAMPLE_ROULETTE) {
+    rc = enqueue_cdf(ctx, true, true);
+    if (rc) return rc;
+    rc = run_roulette(ctx, nullptr, nullptr, 0, seed ^ 0x9E3779B97F4A7C15ull);
+  } else {
+    rc = run_tournament(ctx, nullptr, 0, seed ^ 0x9E3779B97F4A7C15ull);
+  }
+  if (rc) return rc;
+  stamp(ctx, 3);
+  CK(cudaStreamSynchronize(ctx->stream));
+  collect_times(ctx);
+  return AMCLJ_OK;
+}
+
+int32_t amclj_filter_update_host(amclj_ctx *ctx, float *x, float *y, float *theta, float *w,
+                                 int64_t n, const double curr[3], const double prev[3],
+                                 const float *normals, uint64_t seed, const float *ranges,
+                                 int32_t n_ranges, float angle_min, float angle_increment,
+                                 float range_max, double u0) {
+  int rc = amclj_set_particles(ctx, x, y, theta, nullptr, n);
+  if (rc) return rc;
+  rc = amclj_filter_update(ctx, curr, prev, normals, seed, ranges, n_ranges, angle_min,
+                           angle_increment, range_max, u0);
+  if (rc) return rc;
+  return amclj_get_particles(ctx, x, y, theta, w);
+}
+
+int32_t amclj_pose_estimate(amclj_ctx *ctx, double out[4]) {
+  ENTER();
+  NEED(out, AMCLJ_ERR_INVALID, "pose_estimate: null");
+  NEED(ctx->n > 0, AMCLJ_ERR_STATE, "pose_estimate: no particles");
+  int nb = pose_blocks();
+  CK(launch_pose(ctx->x, ctx->y, ctx->th, ctx->n, ctx->pose_part, ctx->stream));
+  std::vector<double> h((size_t)nb * 4);
+  CK(cudaMemcpyAsync(h.data(), ctx->pose_part, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  double s[4] = {0, 0, 0, 0};
+  for (int b = 0; b < nb; b++)
+    for (int k = 0; k < 4; k++) s[k] += h[(size_t)b * 4 + k];
+  /* sums only: a sharded caller adds the ranks' sums before dividing (out[k] / n_global) */
+  double inv = 1.0 / (double)(ctx->world > 1 ? 1 : ctx->n);
+  for (int k = 0; k < 4; k++) out[k] = s[k] * inv;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_get_stats(amclj_ctx *ctx, amclj_stats *out) {
+  ENTER();
+  NEED(out, AMCLJ_ERR_INVALID, "get_stats: null");
+  CK(cudaStreamSynchronize(ctx->stream));
+  unsigned long long h[4] = {0, 0, 0, 0};
+  CK(cudaMemcpy(h, ctx->stats, sizeof(h), cudaMemcpyDeviceToHost));
+  ctx->st.rays = h[0];
+  ctx->st.cells_visited = h[1];
+  ctx->st.probes = h[2];
+  ctx->st.hits = h[3];
+  ctx->st.n_particles = ctx->n;
+  *out = ctx->st;
+  return AMCLJ_OK;
+}
+
+/* ---- sharded building blocks ------------------------------------------- */
+int32_t amclj_shard_motion_sensor_async(amclj_ctx *ctx, const double curr[3], const double prev[3],
+                                        uint64_t seed) {
+  ENTER();
+  NEED(curr && prev, AMCLJ_ERR_INVALID, "shard: null control");
+  NEED(ctx->n > 0, AMCLJ_ERR_STATE, "shard: no particles");
+  stamp(ctx, 0);
+  int rc = enqueue_motion(ctx, curr, prev, false, seed);
+  if (rc) return rc;
+  stamp(ctx, 1);
+  rc = enqueue_sensor(ctx);
+  if (rc) return rc;
+  stamp(ctx, 2);
+  return AMCLJ_OK;
+}
+
+int32_t amclj_shard_cdf_async(amclj_ctx *ctx) {
+  ENTER();
+  NEED(ctx->have_raw, AMCLJ_ERR_STATE, "shard_cdf: no sensor pass");
+  return enqueue_cdf(ctx, true, true); /* AMCLJ_BUF_RAW_MAX already holds the global max */
+}
+
+int32_t amclj_shard_generate_async(amclj_ctx *ctx, uint64_t total_global, uint64_t cdf_offset,
+                                   uint64_t r, int64_t m_lo, int64_t count) {
+  ENTER();
+  NEED(ctx->have_cdf, AMCLJ_ERR_STATE, "shard_generate: no CDF");
+  NEED(count >= 0 && ctx->n_global > 0, AMCLJ_ERR_INVALID, "shard_generate: bad arguments");
+  if (count == 0) return AMCLJ_OK;
+  int rc = ensure_stage(ctx, count);
+  if (rc) return rc;
+  SysPlan p;
+  p.total = total_global;
+  p.n = (uint64_t)ctx->n_global;
+  p.a = total_global / p.n;
+  p.b = total_global % p.n;
+  p.r = r;
+  CK(launch_set_plan(p, ctx->plan, ctx->stream));
+  GatherArgs g;
+  memset(&g, 0, sizeof(g));
+  g.cdf = ctx->cdf;
+  g.n_local = ctx->n;
+  g.cdf_offset = cdf_offset;
+  g.plan = ctx->plan;
+  g.m_lo = m_lo;
+  g.count = count;
+  g.x = ctx->x;
+  g.y = ctx->y;
+  g.th = ctx->th;
+  g.orow = ctx->stage_out;
+  g.oidx64 = ctx->stage_idx;
+  g.gid0 = ctx->global_offset;
+  g.wout = 1.0f / (float)ctx->n_global;
+  CK(launch_systematic(g, ctx->stream));
+  return AMCLJ_OK;
+}
+
+int32_t amclj_shard_get_stage_idx(amclj_ctx *ctx, int64_t *idx_out, int64_t count) {
+  ENTER();
+  NEED(idx_out && count >= 0 && count <= ctx->stage_cap, AMCLJ_ERR_INVALID, "shard_get_stage_idx: bad arguments");
+  if (count == 0) return AMCLJ_OK;
+  CK(cudaMemcpyAsync(idx_out, ctx->stage_idx, sizeof(int64_t) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AMCLJ_OK;
+}
+
+int32_t amclj_shard_adopt_async(amclj_ctx *ctx, int64_t count) {
+  ENTER();
+  NEED(count > 0 && count <= ctx->stage_cap, AMCLJ_ERR_INVALID, "shard_adopt: bad count");
+  ctx->n = 0;
+  int rc = ensure_particles(ctx, count);
+  if (rc) return rc;
+  CK(launch_adopt(ctx->stage_in, count, ctx->x, ctx->y, ctx->th, ctx->w, ctx->stream));
+  ctx->n = count;
+  ctx->have_raw = ctx->have_cdf = false;
+  stamp(ctx, 3);
+  return AMCLJ_OK;
+}
+
+int32_t amclj_plan_systematic(const uint64_t *totals, int32_t world, int64_t n_global, double u0,
+                              uint64_t *r_out, uint64_t *cdf_offsets, int64_t *m_lo,
+                              int64_t *m_cnt, int64_t *send_matrix) {
+  if (!totals || world < 1 || n_global < 0 || !(u0 >= 0.0 && u0 < 1.0)) return AMCLJ_ERR_INVALID;
+  typedef unsigned __int128 u128;
+  uint64_t T = 0;
+  std::vector<uint64_t> off((size_t)world);
+  for (int g = 0; g < world; g++) {
+    off[g] = T;
+    T += totals[g];
+  }
+  uint64_t r = T ? (uint64_t)(((u128)(uint64_t)ldexp(u0, 64) * T) >> 64) : 0;
+  if (r_out) *r_out = r;
+  /* #{m : U_m < C} = ceil((C*N - r) / T), clamped to [0, N] */
+  auto below = [&](uint64_t C) -> int64_t {
+    u128 cn = (u128)C * (uint64_t)n_global;
+    if (cn <= r) return 0;
+    u128 v = (cn - r + T - 1) / T;
+    return v > (u128)n_global ? n_global : (int64_t)v;
+  };
+  std::vector<int64_t> lo((size_t)world), cnt((size_t)world);
+  for (int g = 0; g < world; g++) {
+    if (cdf_offsets) cdf_offsets[g] = off[g];
+    if (T == 0) {
+      lo[g] = 0;
+      cnt[g] = 0;
+    } else {
+      lo[g] = below(off[g]);
+      cnt[g] = below(off[g] + totals[g]) - lo[g];
+    }
+    if (m_lo) m_lo[g] = lo[g];
+    if (m_cnt) m_cnt[g] = cnt[g];
+  }
+  if (send_matrix) {
+    /* slot m belongs to rank d with slots [d*q + min(d, rem), ...): n_global / world each,
+     * the remainder to the low ranks */
+    int64_t q = n_global / world, rem = n_global % world;
+    auto start = [&](int d) { return (int64_t)d * q + (d < rem ? d : rem); };
+    for (int g = 0; g < world; g++)
+      for (int d = 0; d < world; d++) {
+        int64_t a = lo[g] > start(d) ? lo[g] : start(d);
+        int64_t b = lo[g] + cnt[g] < start(d + 1) ? lo[g] + cnt[g] : start(d + 1);
+        send_matrix[(size_t)g * world + d] = b > a ? b - a : 0;
+      }
+  }
+  return AMCLJ_OK;
+}
+
+int32_t amclj_device_ptr(amclj_ctx *ctx, int32_t which, void **ptr, int64_t *bytes) {
+  ENTER();
+  NEED(ptr, AMCLJ_ERR_INVALID, "device_ptr: null");
+  void *p = nullptr;
+  int64_t b = 0;
+  switch (which) {
+    case AMCLJ_BUF_X: p = ctx->x; b = 4 * ctx->cap; break;
+    case AMCLJ_BUF_Y: p = ctx->y; b = 4 * ctx->cap; break;
+    case AMCLJ_BUF_THETA: p = ctx->th; b = 4 * ctx->cap; break;
+    case AMCLJ_BUF_W: p = ctx->w; b = 4 * ctx->cap; break;
+    case AMCLJ_BUF_RAW: p = ctx->raw; b = 4 * ctx->cap; break;
+    case AMCLJ_BUF_RAW_MAX: p = ctx->rawmax; b = 4; break;
+    case AMCLJ_BUF_TOTAL: p = ctx->total; b = 8; break;
+    case AMCLJ_BUF_STAGE_OUT: p = ctx->stage_out; b = 16 * ctx->stage_cap; break;
+    case AMCLJ_BUF_STAGE_IN: p = ctx->stage_in; b = 16 * ctx->stage_cap; break;
+    case AMCLJ_BUF_CDF: p = ctx->cdf; b = 8 * ctx->cap; break;
+    default: return fail(ctx, AMCLJ_ERR_INVALID, "device_ptr: unknown buffer %d", which);
+  }
+  *ptr = p;
+  if (bytes) *bytes = b;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_reserve_stage(amclj_ctx *ctx, int64_t rows) {
+  ENTER();
+  NEED(rows >= 0, AMCLJ_ERR_INVALID, "reserve_stage: bad rows");
+  CK(cudaStreamSynchronize(ctx->stream));
+  return ensure_stage(ctx, rows);
+}
+
+}  // extern "C"

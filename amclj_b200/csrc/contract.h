@@ -1,0 +1,128 @@
+// contract.h — the fp32 / integer arithmetic contract of libamclj_b200, shared by host
+// and device code of the PRODUCT.  Everything here is written with explicit fmaf and is
+// compiled without implicit contraction (nvcc --fmad=false), so every integer that leaves
+// the library (cells, steps, fixed-point weights, resample indices) is reproducible bit
+// for bit by an independent CPU restatement.
+//
+// Reference functions restated with this arithmetic (jvia/amclj, paths from its root):
+//   map.clj:36-46 world->map, sensor.clj:99-103 project-pose, motion.clj:24-45.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define AMCLJ_HD __host__ __device__ __forceinline__
+#else
+#define AMCLJ_HD inline
+#endif
+
+namespace amclj {
+
+// Deterministic sincos: 3-constant Cody-Waite reduction by pi/2 and the Cephes minimax
+// polynomials; only IEEE mul/add/fma/rint, so host and device agree bit for bit.
+AMCLJ_HD void sincos_det(float a, float &sn, float &cs) {
+  float j = rintf(a * 0.636619772f);
+  j = fminf(fmaxf(j, -1.0e9f), 1.0e9f);
+  float r = fmaf(j, -1.5707962513e+00f, a);
+  r = fmaf(j, -7.5497894159e-08f, r);
+  r = fmaf(j, -5.3903029534e-15f, r);
+  int q = ((int)j) & 3;
+  float z = r * r;
+  float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = fmaf(ps, z, -1.6666654611e-1f);
+  float s = fmaf(ps * z, r, r);
+  float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = fmaf(pc, z, 4.166664568298827e-2f);
+  float c = fmaf(pc * z, z, fmaf(-0.5f, z, 1.0f));
+  float so = (q & 1) ? c : s, co = (q & 1) ? s : c;
+  if (q & 2) so = -so;
+  if ((q + 1) & 2) co = -co;
+  sn = so;
+  cs = co;
+}
+
+// Deterministic exp for x <= 0 (used to turn log-weights into linear ones before the
+// fixed-point conversion): Cody-Waite by ln2, Cephes degree-5 polynomial, exact 2^n scale.
+// Anything below -87 (and NaN) flushes to 0.
+AMCLJ_HD float exp_det(float x) {
+  if (!(x > -87.0f)) return 0.0f;
+  if (x > 0.0f) x = 0.0f;
+  float n = rintf(x * 1.44269504088896341f);
+  float r = fmaf(n, -0.693359375f, x);
+  r = fmaf(n, 2.12194440e-4f, r);
+  float p = fmaf(r, 1.9875691500e-4f, 1.3981999507e-3f);
+  p = fmaf(p, r, 8.3334519073e-3f);
+  p = fmaf(p, r, 4.1665795894e-2f);
+  p = fmaf(p, r, 1.6666665459e-1f);
+  p = fmaf(p, r, 5.0000001201e-1f);
+  float y = fmaf(p, r * r, r) + 1.0f;
+  int e = (int)n + 127; /* n >= -126 here */
+  union { uint32_t u; float f; } sc;
+  sc.u = (uint32_t)e << 23;
+  return y * sc.f;
+}
+
+// map.clj:36-46: Math/round(v / resolution) = floor(v/res + 0.5), IEEE divide.
+AMCLJ_HD int32_t round_cell(float v, float res) {
+  float t = floorf(v / res + 0.5f);
+  t = fminf(fmaxf(t, -1.0e9f), 1.0e9f); /* NaN -> -1e9 */
+  return (int32_t)t;
+}
+
+// Fixed-point weight: q = floor(clamp(w / wmax, 0, 1) * 2^32)  (NaN -> 0).
+AMCLJ_HD uint64_t fixed_weight(float w, float wmax) {
+  if (!(wmax > 0.0f)) return 0;
+  float r = w / wmax;
+  r = fminf(fmaxf(r, 0.0f), 1.0f);
+  return (uint64_t)(r * 4294967296.0f); /* exact power-of-two scale, truncation = floor */
+}
+
+// Philox4x32-10 (Salmon et al., SC'11).
+AMCLJ_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                            uint32_t k1, uint32_t out[4]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+constexpr uint32_t TAG_MOTION = 0x4d4f5449u;
+constexpr uint32_t TAG_ROULETTE = 0x524f554cu;
+constexpr uint32_t TAG_TOURNAMENT = 0x544f5552u;
+constexpr uint32_t TAG_INIT = 0x494e4954u;
+constexpr uint32_t TAG_GAUSS = 0x47415553u;
+
+AMCLJ_HD float u24(uint32_t r) { return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+// Systematic-resampling arithmetic on the integer CDF (Probabilistic Robotics table 4.4):
+// pointer m sits at U_m = floor((m*T + r) / N).  With T = a*N + b this is
+// m*a + floor((m*b + r) / N); m*b + r < 2^63 for N <= 2^31, T < 2^62.
+struct SysPlan {
+  uint64_t total, a, b, r, n;
+};
+AMCLJ_HD uint64_t sys_threshold(const SysPlan &s, uint64_t m) {
+  return m * s.a + (m * s.b + s.r) / s.n;
+}
+
+// roulette acceptance (pf.clj:165): wn[idx] > u  <=>  q * 2^32 > u32 * T
+AMCLJ_HD bool roulette_accept(uint64_t q, uint32_t u, uint64_t total) {
+#if defined(__CUDA_ARCH__)
+  uint64_t lo = (uint64_t)u * total; /* may wrap: compute 96-bit product */
+  uint64_t hi = __umul64hi((uint64_t)u, total);
+  /* q*2^32 as (qhi, qlo) */
+  uint64_t qhi = q >> 32, qlo = q << 32;
+  return qhi > hi || (qhi == hi && qlo > lo);
+#else
+  return ((unsigned __int128)q << 32) > (unsigned __int128)u * total;
+#endif
+}
+
+}  // namespace amclj

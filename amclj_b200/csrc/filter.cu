@@ -1,0 +1,657 @@
+// filter.cu — every hot-path kernel except the ray caster: K1 motion sample, map staging
+// (distance transform), K3 weight normalisation -> fixed point -> decoupled-look-back
+// prefix sum, K4 systematic binary-search gather, K5 roulette / tournament selection,
+// K6 pose estimate, and on-device particle initialisation.
+//
+// Reference functions replaced (jvia/amclj): pf.clj:139-145 apply-motion-model ->
+// motion.clj:24-45; pf.clj:156-167 roulette-selection; pf.clj:182-195 tournament-selection;
+// pf.clj:67-84 pose-estimate; map.clj:59-84 uniform-initialization, :87-111
+// gaussian-initialization.
+#include "internal.h"
+
+namespace amclj {
+
+// ======================================================================================
+// K1 motion.clj:24-45 sample-motion-model-odometry*.  rot1/trans/rot2 and the three sigmas
+// are launch-uniform (computed once on the host, motion.clj:68-79 did it per particle);
+// per particle: three normals, one sincos, three FMAs.  24 B/particle of HBM traffic.
+// ======================================================================================
+__device__ __forceinline__ void philox_normals3(uint64_t seed, uint64_t gid, uint32_t tag,
+                                                float &n1, float &n2, float &n3) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), 0u, tag, (uint32_t)seed,
+                (uint32_t)(seed >> 32), r);
+  float ra = sqrtf(-2.0f * logf(u24(r[0]))), rb = sqrtf(-2.0f * logf(u24(r[2])));
+  float a = 6.283185307179586f * u24(r[1]), b = 6.283185307179586f * u24(r[3]);
+  n1 = ra * cosf(a);
+  n2 = ra * sinf(a);
+  n3 = rb * cosf(b);
+}
+
+__global__ void __launch_bounds__(256) motion_kernel(const MotionLaunch a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  float n1, n2, n3;
+  if (a.normals) {
+    n1 = __ldg(a.normals + 3 * i);
+    n2 = __ldg(a.normals + 3 * i + 1);
+    n3 = __ldg(a.normals + 3 * i + 2);
+  } else {
+    philox_normals3(a.seed, (uint64_t)(a.gid0 + i), TAG_MOTION, n1, n2, n3);
+  }
+  float th = a.th[i];
+  float r1 = fmaf(-n1, a.sd1, a.rot1);                          /* motion.clj:35 */
+  float tr = a.trans_zero ? 0.0f : fmaf(-n2, a.sdt, a.trans);   /* motion.clj:36-37 */
+  float r2 = fmaf(-n3, a.sd2, a.rot2);                          /* motion.clj:38 */
+  float sn, cs;
+  sincos_det(th + r1, sn, cs);
+  a.x[i] = fmaf(tr, cs, a.x[i]); /* motion.clj:39-44 */
+  a.y[i] = fmaf(tr, sn, a.y[i]);
+  a.th[i] = th + (r1 + r2);      /* quat/rotate by rot1* + rot2* */
+}
+
+cudaError_t launch_motion(const MotionLaunch &a, cudaStream_t s) {
+  if (a.n <= 0 || a.is_static) return cudaSuccess; /* motion.clj:26-27 */
+  motion_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+// ======================================================================================
+// Map staging: Chebyshev (L-infinity) distance to the nearest blocked cell, separable:
+// d(x,y) = min over rows y' of max(|y'-y|, rowdist(x,y')).  The field is padded by a ring
+// of blocked cells, which also stands for everything beyond it (map.clj:19-24: out of
+// range reads -1, which is uninhabitable).
+// ======================================================================================
+__global__ void rowdist_kernel(const int8_t *__restrict__ cells, int W, int H, int cap,
+                               uint8_t *__restrict__ rd) {
+  int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
+  int PW = W + 2;
+  if (px >= PW) return;
+  auto blocked = [&](int qx) -> bool {
+    if (qx <= 0 || qx >= W + 1 || py == 0 || py == H + 1) return true;
+    return cells[(size_t)(py - 1) * W + (qx - 1)] != 0; /* map.clj:48-57 */
+  };
+  int d = 0;
+  if (!blocked(px)) {
+    for (d = 1; d < cap; d++)
+      if (blocked(px - d) || blocked(px + d)) break;
+  }
+  rd[(size_t)py * PW + px] = (uint8_t)d;
+}
+
+__global__ void coldist_kernel(const uint8_t *__restrict__ rd, int W, int H, int cap,
+                               uint8_t *__restrict__ df4, int row_bytes4,
+                               uint8_t *__restrict__ df8, int pitch8) {
+  /* one thread per PAIR of cells so that a nibble-packed byte has a single writer */
+  int pp = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
+  int PW = W + 2, PH = H + 2;
+  if (2 * pp >= PW) return;
+  int dd[2];
+  for (int h = 0; h < 2; h++) {
+    int px = 2 * pp + h;
+    int best = 0;
+    if (px < PW) {
+      best = rd[(size_t)py * PW + px];
+      for (int dy = 1; dy < best; dy++) {
+        int up = py - dy >= 0 ? rd[(size_t)(py - dy) * PW + px] : 0;
+        int dn = py + dy < PH ? rd[(size_t)(py + dy) * PW + px] : 0;
+        int m = min(up, dn);
+        best = min(best, max(dy, m));
+      }
+    }
+    dd[h] = min(best, cap);
+  }
+  if (df4) df4[(size_t)py * row_bytes4 + pp] = (uint8_t)(min(dd[0], 15) | (min(dd[1], 15) << 4));
+  if (df8) {
+    df8[(size_t)py * pitch8 + 2 * pp] = (uint8_t)min(dd[0], 255);
+    if (2 * pp + 1 < pitch8) df8[(size_t)py * pitch8 + 2 * pp + 1] = (uint8_t)min(dd[1], 255);
+  }
+}
+
+cudaError_t build_distance_fields(amclj_ctx *c, bool want8, cudaStream_t s) {
+  DeviceMap &m = c->map;
+  int PW = m.W + 2, PH = m.H + 2;
+  uint8_t *rd = nullptr;
+  cudaError_t e = cudaMalloc(&rd, (size_t)PW * PH);
+  if (e != cudaSuccess) return e;
+  int cap = want8 ? 255 : 15;
+  dim3 g1((PW + 127) / 128, PH), g2(((PW + 1) / 2 + 127) / 128, PH);
+  rowdist_kernel<<<g1, 128, 0, s>>>(m.cells, m.W, m.H, cap, rd);
+  cudaMemsetAsync(m.df4, 0, m.bytes4, s);
+  if (want8) cudaMemsetAsync(m.df8, 0, m.bytes8, s);
+  coldist_kernel<<<g2, 128, 0, s>>>(rd, m.W, m.H, cap, m.df4, m.row_bytes4, want8 ? m.df8 : nullptr,
+                                    m.pitch8);
+  e = cudaGetLastError();
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  cudaFree(rd);
+  return e != cudaSuccess ? e : e2;
+}
+
+// ======================================================================================
+// K3 normalise -> fixed point -> prefix sum.
+// pf.clj:159-160 divides every weight by a float sum; a float prefix sum depends on the
+// summation order, so the contract here is integer: q_i = floor(w_i / w_max * 2^32)
+// elementwise, then an exact u64 inclusive scan (single pass, decoupled look-back).
+// ======================================================================================
+__device__ __forceinline__ uint32_t ord_of_float(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float float_of_ord(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+__global__ void max_kernel(const float *__restrict__ v, int64_t n, uint32_t *out_ord) {
+  float m = -INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, __ldg(v + i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > -INFINITY) atomicMax(out_ord, ord_of_float(m));
+}
+
+__global__ void decode_max_kernel(const uint32_t *ord, float *out) {
+  uint32_t o = *ord;
+  *out = o == 0 ? -INFINITY : float_of_ord(o);
+}
+
+cudaError_t launch_max(const float *v, int64_t n, uint32_t *ord, float *out, int sm_count,
+                       cudaStream_t s) {
+  cudaMemsetAsync(ord, 0, sizeof(uint32_t), s);
+  if (n > 0) {
+    int64_t blocks = (n + 1023) / 1024;
+    if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
+    max_kernel<<<(unsigned)blocks, 256, 0, s>>>(v, n, ord);
+  }
+  decode_max_kernel<<<1, 1, 0, s>>>(ord, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_decode_max(const uint32_t *ord, float *out, cudaStream_t s) {
+  decode_max_kernel<<<1, 1, 0, s>>>(ord, out);
+  return cudaGetLastError();
+}
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr uint64_t ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint64_t weight_to_fixed(float v, float vmax, int is_log) {
+  /* log-weights: w = exp(v - max) in (0, 1], max maps to exactly 1; linear: w / w_max */
+  if (is_log) return fixed_weight(exp_det(v - vmax), 1.0f);
+  return fixed_weight(v, vmax);
+}
+
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_kernel(const float *__restrict__ v, const float *__restrict__ vmaxp, int is_log, int64_t n,
+            uint64_t *__restrict__ cdf, uint64_t *tile_state, uint32_t *tile_counter,
+            uint64_t *total_out) {
+  __shared__ uint64_t warp_sums[SCAN_THREADS / 32];
+  __shared__ uint64_t s_excl;
+  __shared__ uint32_t s_tile;
+  if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const float vmax = *vmaxp;
+  const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  uint64_t q[SCAN_ITEMS];
+  if (base + SCAN_ITEMS <= n) { /* 128-bit loads: base is a multiple of 8 */
+    const float4 *v4 = reinterpret_cast<const float4 *>(v + base);
+    float4 a = __ldg(v4), b = __ldg(v4 + 1);
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) q[k] = weight_to_fixed(f[k], vmax, is_log);
+  } else {
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++)
+      q[k] = base + k < n ? weight_to_fixed(__ldg(v + base + k), vmax, is_log) : 0;
+  }
+  uint64_t run = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { run += q[k]; q[k] = run; }
+  /* block-wide exclusive scan of the per-thread totals */
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint64_t inc = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  uint64_t woff = 0, tile_total = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_THREADS / 32; k++) {
+    uint64_t ws = warp_sums[k];
+    if (k < wid) woff += ws;
+    tile_total += ws;
+  }
+  uint64_t thread_excl = woff + inc - run;
+  /* decoupled look-back (Merrill & Garland): publish the aggregate, then walk back */
+  if (wid == 0) {
+    uint64_t excl = 0;
+    if (tile == 0) {
+      if (lane == 0) {
+        __threadfence();
+        atomicExch((unsigned long long *)&tile_state[0], ST_PREFIX | tile_total);
+      }
+    } else {
+      if (lane == 0) atomicExch((unsigned long long *)&tile_state[tile], ST_AGG | tile_total);
+      int64_t look = (int64_t)tile - 1;
+      for (;;) {
+        int64_t t = look - lane;
+        uint64_t sv;
+        do { /* spin until every descriptor of the window is published */
+          sv = t >= 0 ? ld_volatile_u64(&tile_state[t]) : ST_PREFIX;
+        } while (__any_sync(0xffffffffu, (sv >> 62) == 0));
+        uint32_t is_prefix = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+        int first = is_prefix ? __ffs(is_prefix) - 1 : 32; /* nearest tile with a prefix */
+        uint64_t contrib = lane <= first ? (sv & ST_MASK) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (is_prefix) break;
+        look -= 32;
+      }
+      if (lane == 0)
+        atomicExch((unsigned long long *)&tile_state[tile], ST_PREFIX | (excl + tile_total));
+    }
+    if (lane == 0) {
+      s_excl = excl;
+      if ((int64_t)(tile + 1) * SCAN_TILE >= n) *total_out = excl + tile_total;
+    }
+  }
+  __syncthreads();
+  const uint64_t off = s_excl + thread_excl;
+  if (base + SCAN_ITEMS <= n) {
+    ulonglong2 *o2 = reinterpret_cast<ulonglong2 *>(cdf + base);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k += 2) o2[k / 2] = make_ulonglong2(off + q[k], off + q[k + 1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++)
+      if (base + k < n) cdf[base + k] = off + q[k];
+  }
+}
+
+int64_t scan_tiles(int64_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+
+cudaError_t launch_scan(const float *v, const float *vmaxp, int is_log, int64_t n, uint64_t *cdf,
+                        uint64_t *tile_state, uint32_t *tile_counter, uint64_t *total_out,
+                        cudaStream_t s) {
+  int64_t tiles = scan_tiles(n);
+  cudaMemsetAsync(total_out, 0, sizeof(uint64_t), s);
+  if (tiles == 0) return cudaGetLastError();
+  cudaMemsetAsync(tile_state, 0, sizeof(uint64_t) * (size_t)tiles, s);
+  cudaMemsetAsync(tile_counter, 0, sizeof(uint32_t), s);
+  scan_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(v, vmaxp, is_log, n, cdf, tile_state,
+                                                        tile_counter, total_out);
+  return cudaGetLastError();
+}
+
+// ======================================================================================
+// K4 low-variance / systematic resampling (Probabilistic Robotics table 4.4) as a gather:
+// output slot m looks up the particle whose CDF interval contains U_m.
+// ======================================================================================
+// r = floor(u0 * T) with u0 given as a 0.64 fixed-point fraction; T = a*N + b.
+__global__ void plan_kernel(const uint64_t *total, uint64_t u0_bits, int64_t n_global, SysPlan *out) {
+  SysPlan p;
+  p.total = *total;
+  p.n = (uint64_t)n_global;
+  p.a = p.total / p.n;
+  p.b = p.total % p.n;
+  p.r = __umul64hi(u0_bits, p.total);
+  *out = p;
+}
+cudaError_t launch_plan(const uint64_t *total, uint64_t u0_bits, int64_t n_global, SysPlan *out,
+                        cudaStream_t s) {
+  plan_kernel<<<1, 1, 0, s>>>(total, u0_bits, n_global, out);
+  return cudaGetLastError();
+}
+__global__ void set_plan_kernel(const SysPlan p, SysPlan *out) { *out = p; }
+cudaError_t launch_set_plan(const SysPlan &p, SysPlan *out, cudaStream_t s) {
+  set_plan_kernel<<<1, 1, 0, s>>>(p, out);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) systematic_gather_kernel(const GatherArgs a) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.count) return;
+  const SysPlan plan = *a.plan;
+  uint64_t U = sys_threshold(plan, (uint64_t)(a.m_lo + k));
+  uint64_t key = U - a.cdf_offset; /* caller guarantees U >= cdf_offset */
+  int64_t lo = 0, hi = a.n_local;
+  while (lo < hi) { /* first i with cdf[i] > key */
+    int64_t mid = (lo + hi) >> 1;
+    if (__ldg(a.cdf + mid) > key) hi = mid; else lo = mid + 1;
+  }
+  int64_t i = lo < a.n_local ? lo : a.n_local - 1;
+  float px = __ldg(a.x + i), py = __ldg(a.y + i), pt = __ldg(a.th + i);
+  if (a.ox) { a.ox[k] = px; a.oy[k] = py; a.oth[k] = pt; a.ow[k] = a.wout; }
+  if (a.orow) a.orow[k] = make_float4(px, py, pt, a.wout);
+  if (a.oidx) a.oidx[k] = (int32_t)i;
+  if (a.oidx64) a.oidx64[k] = a.gid0 + i;
+}
+
+cudaError_t launch_systematic(const GatherArgs &a, cudaStream_t s) {
+  if (a.count <= 0) return cudaSuccess;
+  systematic_gather_kernel<<<(unsigned)((a.count + 255) / 256), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+// ======================================================================================
+// K5 pf.clj:156-167 roulette-selection: attempt t draws idx ~ U{0..N-1}, u ~ U[0,1) and is
+// accepted when wn[idx] > u; the output keeps acceptance order.  Attempts are independent,
+// so a super-chunk of them is tested in parallel and compacted in attempt order (count ->
+// block scan -> look-back over blocks -> regenerate and write).
+// ======================================================================================
+__device__ __forceinline__ void roulette_attempt(uint64_t seed, uint64_t t, int64_t n,
+                                                 int32_t &idx, uint32_t &u) {
+  uint64_t b = t >> 1;
+  uint32_t r[4];
+  philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), 0u, TAG_ROULETTE, (uint32_t)seed,
+                (uint32_t)(seed >> 32), r);
+  int k = (int)(t & 1) * 2;
+  idx = (int32_t)(((uint64_t)r[k] * (uint64_t)n) >> 32);
+  u = r[k + 1];
+}
+
+__device__ __forceinline__ bool roulette_test(const RouletteArgs &a, int64_t t, int32_t &idx) {
+  uint32_t u;
+  if (a.sidx) {
+    idx = __ldg(a.sidx + t);
+    u = __ldg(a.su + t);
+    if (idx < 0 || idx >= a.n) return false;
+  } else {
+    roulette_attempt(a.seed, (uint64_t)t, a.n, idx, u);
+  }
+  uint64_t hiC = __ldg(a.cdf + idx), loC = idx > 0 ? __ldg(a.cdf + idx - 1) : 0;
+  return roulette_accept(hiC - loC, u, a.total);
+}
+
+__global__ void __launch_bounds__(256) roulette_kernel(const RouletteArgs a) {
+  __shared__ uint32_t warp_sums[8];
+  __shared__ uint64_t s_excl;
+  __shared__ uint32_t s_tile;
+  if (threadIdx.x == 0) s_tile = atomicAdd(a.tile_counter, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const int64_t tb = a.t0 + ((int64_t)tile * 256 + threadIdx.x) * a.per_thread;
+  uint32_t cnt = 0;
+  for (int k = 0; k < a.per_thread; k++) {
+    int64_t t = tb + k;
+    int32_t idx;
+    if (t < a.t_end && roulette_test(a, t, idx)) cnt++;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  uint32_t woff = 0, tile_total = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    uint32_t ws = warp_sums[k];
+    if (k < wid) woff += ws;
+    tile_total += ws;
+  }
+  if (wid == 0) {
+    uint64_t excl = 0;
+    if (tile == 0) {
+      if (lane == 0) atomicExch((unsigned long long *)&a.tile_state[0], ST_PREFIX | tile_total);
+    } else {
+      if (lane == 0) atomicExch((unsigned long long *)&a.tile_state[tile], ST_AGG | tile_total);
+      int64_t look = (int64_t)tile - 1;
+      for (;;) {
+        int64_t t = look - lane;
+        uint64_t sv;
+        do {
+          sv = t >= 0 ? ld_volatile_u64(&a.tile_state[t]) : ST_PREFIX;
+        } while (__any_sync(0xffffffffu, (sv >> 62) == 0));
+        uint32_t is_prefix = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+        int first = is_prefix ? __ffs(is_prefix) - 1 : 32;
+        uint64_t contrib = lane <= first ? (sv & ST_MASK) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (is_prefix) break;
+        look -= 32;
+      }
+      if (lane == 0)
+        atomicExch((unsigned long long *)&a.tile_state[tile], ST_PREFIX | (excl + tile_total));
+    }
+    if (lane == 0) {
+      s_excl = excl;
+      if (tile == gridDim.x - 1) *a.accepted_out = excl + tile_total;
+    }
+  }
+  __syncthreads();
+  if (cnt == 0) return;
+  int64_t slot = a.got_before + (int64_t)s_excl + woff + (inc - cnt);
+  for (int k = 0; k < a.per_thread && slot < a.n; k++) {
+    int64_t t = tb + k;
+    int32_t idx;
+    if (t < a.t_end && roulette_test(a, t, idx)) {
+      a.idx_out[slot] = idx;
+      if (slot == a.n - 1) *a.last_attempt = (unsigned long long)(t + 1);
+      slot++;
+    }
+  }
+}
+
+cudaError_t launch_roulette(const RouletteArgs &a, int64_t tiles, cudaStream_t s) {
+  cudaMemsetAsync(a.tile_state, 0, sizeof(uint64_t) * (size_t)tiles, s);
+  cudaMemsetAsync(a.tile_counter, 0, sizeof(uint32_t), s);
+  cudaMemsetAsync(a.accepted_out, 0, sizeof(unsigned long long), s);
+  roulette_kernel<<<(unsigned)tiles, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+// pf.clj:182-195 tournament-selection: N rounds of two uniform draws, keep the heavier
+// (`(> w1 w2)` ? p1 : p2 — ties keep the second).
+__global__ void __launch_bounds__(256)
+tournament_kernel(const float *__restrict__ w, int64_t n, const int32_t *__restrict__ sidx,
+                  uint64_t seed, int32_t *__restrict__ idx_out) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int32_t a, b;
+  if (sidx) {
+    a = __ldg(sidx + 2 * k);
+    b = __ldg(sidx + 2 * k + 1);
+  } else {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)k, (uint32_t)((uint64_t)k >> 32), 0u, TAG_TOURNAMENT, (uint32_t)seed,
+                  (uint32_t)(seed >> 32), r);
+    a = (int32_t)(((uint64_t)r[0] * (uint64_t)n) >> 32);
+    b = (int32_t)(((uint64_t)r[1] * (uint64_t)n) >> 32);
+  }
+  idx_out[k] = (__ldg(w + a) > __ldg(w + b)) ? a : b;
+}
+
+cudaError_t launch_tournament(const float *w, int64_t n, const int32_t *sidx, uint64_t seed,
+                              int32_t *idx_out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  tournament_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, n, sidx, seed, idx_out);
+  return cudaGetLastError();
+}
+
+// gather by an index list; the carried weight is the normalised weight q_i / T
+// (pf.clj:160 `(/ w normalizer)` under the integer contract) or a constant.
+__global__ void __launch_bounds__(256)
+gather_idx_kernel(const int32_t *__restrict__ idx, int64_t n, const float *__restrict__ x,
+                  const float *__restrict__ y, const float *__restrict__ th,
+                  int wmode, const uint64_t *__restrict__ cdf, uint64_t total,
+                  const float *__restrict__ wsrc, float wconst, float *ox, float *oy, float *oth,
+                  float *ow) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int32_t i = __ldg(idx + k);
+  ox[k] = __ldg(x + i);
+  oy[k] = __ldg(y + i);
+  oth[k] = __ldg(th + i);
+  float wv = wconst;
+  if (wmode == 1) {
+    uint64_t q = __ldg(cdf + i) - (i > 0 ? __ldg(cdf + i - 1) : 0);
+    wv = total ? (float)((double)q / (double)total) : 0.0f;
+  } else if (wmode == 2) {
+    wv = __ldg(wsrc + i);
+  }
+  ow[k] = wv;
+}
+
+cudaError_t launch_gather_idx(const int32_t *idx, int64_t n, const float *x, const float *y,
+                              const float *th, int wmode, const uint64_t *cdf, uint64_t total,
+                              const float *wsrc, float wconst, float *ox, float *oy, float *oth,
+                              float *ow, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  gather_idx_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(idx, n, x, y, th, wmode, cdf, total,
+                                                               wsrc, wconst, ox, oy, oth, ow);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+adopt_rows_kernel(const float4 *__restrict__ rows, int64_t n, float *x, float *y, float *th,
+                  float *w) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  float4 r = __ldg(rows + k);
+  x[k] = r.x; y[k] = r.y; th[k] = r.z; w[k] = r.w;
+}
+
+cudaError_t launch_adopt(const float4 *rows, int64_t n, float *x, float *y, float *th, float *w,
+                         cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  adopt_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rows, n, x, y, th, w);
+  return cudaGetLastError();
+}
+
+__global__ void fill_kernel(float *p, int64_t n, float v) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) p[k] = v;
+}
+cudaError_t launch_fill(float *p, int64_t n, float v, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n, v);
+  return cudaGetLastError();
+}
+
+// ======================================================================================
+// K6 pf.clj:67-84 pose-estimate: unweighted mean of x, y and of the planar quaternion
+// components (0, 0, sin(theta/2), cos(theta/2)).
+// ======================================================================================
+constexpr int POSE_BLOCKS = 296;
+__global__ void __launch_bounds__(256)
+pose_kernel(const float *__restrict__ x, const float *__restrict__ y,
+            const float *__restrict__ th, int64_t n, double *__restrict__ part) {
+  double sx = 0, sy = 0, sz = 0, sw = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float s, c;
+    sincosf(0.5f * __ldg(th + i), &s, &c);
+    sx += (double)__ldg(x + i);
+    sy += (double)__ldg(y + i);
+    sz += (double)s;
+    sw += (double)c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    sw += __shfl_xor_sync(0xffffffffu, sw, o);
+  }
+  __shared__ double sm[8][4];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { sm[wid][0] = sx; sm[wid][1] = sy; sm[wid][2] = sz; sm[wid][3] = sw; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0;
+    for (int k = 0; k < 8; k++) t += sm[k][threadIdx.x];
+    part[blockIdx.x * 4 + threadIdx.x] = t;
+  }
+}
+int pose_blocks() { return POSE_BLOCKS; }
+cudaError_t launch_pose(const float *x, const float *y, const float *th, int64_t n, double *part,
+                        cudaStream_t s) {
+  pose_kernel<<<POSE_BLOCKS, 256, 0, s>>>(x, y, th, n, part);
+  return cudaGetLastError();
+}
+
+// ======================================================================================
+// map.clj:59-84 uniform-initialization: proposals (x, y) ~ U[0,W) x U[0,H) in cell units,
+// kept when cell (int x, int y) is inhabitable (map.clj:52-55 truncates), then scaled by
+// the resolution (map.clj:29-34).  Each particle owns a Philox stream, so the result does
+// not depend on how particles are spread over GPUs.
+// ======================================================================================
+__global__ void __launch_bounds__(256)
+init_uniform_kernel(const int8_t *__restrict__ cells, int W, int H, float res, int64_t gid0,
+                    int64_t n, int heading_mode, uint64_t seed, float *x, float *y, float *th,
+                    float *w, float w0) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t gid = (uint64_t)(gid0 + i);
+  for (uint32_t at = 0;; at++) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), at, TAG_INIT, (uint32_t)seed,
+                  (uint32_t)(seed >> 32), r);
+    float px = u24(r[0]) * (float)W, py = u24(r[1]) * (float)H;
+    int cx = (int)px, cy = (int)py;
+    bool bad = cx >= W || cy >= H || cx < 0 || cy < 0 || cells[(size_t)cy * W + cx] != 0;
+    if (at < 100000u && bad) continue;
+    x[i] = px * res;
+    y[i] = py * res;
+    if (heading_mode == 0) /* map.clj:67-68: N(0,1) rad */
+      th[i] = sqrtf(-2.0f * logf(u24(r[2]))) * cosf(6.283185307179586f * u24(r[3]));
+    else
+      th[i] = (u24(r[2]) * 2.0f - 1.0f) * 3.14159265358979f;
+    w[i] = w0;
+    break;
+  }
+}
+
+cudaError_t launch_init_uniform(const int8_t *cells, int W, int H, float res, int64_t gid0,
+                                int64_t n, int heading_mode, uint64_t seed, float *x, float *y,
+                                float *th, float *w, float w0, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  init_uniform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cells, W, H, res, gid0, n,
+                                                                 heading_mode, seed, x, y, th, w, w0);
+  return cudaGetLastError();
+}
+
+// map.clj:87-111 gaussian-initialization: x, y ~ N(pose, sd_xy), heading rotated by
+// N(0, sd_theta) (the reference passes sd = rot-mean = 0, map.clj:106).
+__global__ void __launch_bounds__(256)
+init_gaussian_kernel(float mx, float my, float mth, float sd_xy, float sd_th, int64_t gid0,
+                     int64_t n, uint64_t seed, float *x, float *y, float *th, float *w, float w0) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float n1, n2, n3;
+  philox_normals3(seed, (uint64_t)(gid0 + i), TAG_GAUSS, n1, n2, n3);
+  x[i] = fmaf(sd_xy, n1, mx);
+  y[i] = fmaf(sd_xy, n2, my);
+  th[i] = fmaf(sd_th, n3, mth);
+  w[i] = w0;
+}
+
+cudaError_t launch_init_gaussian(float mx, float my, float mth, float sd_xy, float sd_th,
+                                 int64_t gid0, int64_t n, uint64_t seed, float *x, float *y,
+                                 float *th, float *w, float w0, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  init_gaussian_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mx, my, mth, sd_xy, sd_th, gid0,
+                                                                  n, seed, x, y, th, w, w0);
+  return cudaGetLastError();
+}
+
+}  // namespace amclj

@@ -1,0 +1,195 @@
+// internal.h — context layout and kernel-launcher prototypes of libamclj_b200 (not part of
+// the C ABI; include/amclj_b200.h is).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/amclj_b200.h"
+#include "contract.h"
+
+namespace amclj {
+
+// ---------------------------------------------------------------------------------------
+// occupancy grid on the device: a Chebyshev distance field ("how many Bresenham steps are
+// certainly free from here"), padded by a one-cell ring of zeros (out of range = blocked,
+// map.clj:19-24), nibble-packed when it has to live in shared memory.
+// ---------------------------------------------------------------------------------------
+struct DeviceMap {
+  int32_t W = 0, H = 0;
+  float res = 0.f;
+  int8_t *cells = nullptr;   // [H][W] as uploaded (init kernels, debug)
+  uint8_t *df4 = nullptr;    // nibble-packed, (H+2) rows of row_bytes4, distance capped at 15
+  uint8_t *df8 = nullptr;    // one byte per cell, (H+2) x pitch8, capped at 255
+  int32_t row_bytes4 = 0;    // multiple of 16
+  int32_t pitch8 = 0;
+  size_t bytes4 = 0, bytes8 = 0;
+  bool fits_smem = false;
+};
+
+struct BeamTable {       // one float array of 5*nb: cb | sb | obs | e2 | p34
+  float *dev = nullptr;
+  int32_t nb = 0, cap = 0;
+  int32_t n_scan = 0;
+  float angle_min = 0, angle_inc = 0, range_max = 0;
+  bool staged = false;
+};
+
+struct DivTable {        // magic reciprocals for the Bresenham minor-axis division
+  uint2 *dev = nullptr;
+  int32_t n = 0, cap = 0;
+};
+
+struct SensorLaunch {
+  const float *x, *y, *th;
+  float *raw;
+  int64_t n;
+  const uint8_t *df;
+  int32_t row_nib;   // nibbles (df4) or bytes (df8) per padded row
+  int32_t W, H;
+  size_t df_bytes;
+  float res;
+  const float *beam;
+  int32_t nb;
+  const uint2 *divtab;
+  int32_t ndiv;
+  float R;            // ray length (S2)
+  float miss_value;
+  int32_t s1, s3, s4, s7, s10;
+  float z_hit, inv2s2, laser_x, laser_y;
+  uint32_t *rawmax_ord;          // ordered-uint max of raw (may be null)
+  unsigned long long *stats;     // rays, cells, probes, hits (may be null)
+  // parity probe
+  int64_t dbg_first, dbg_count;
+  int32_t *dbg_hit_x, *dbg_hit_y, *dbg_steps;
+  uint8_t *dbg_hit;
+  float *dbg_range;
+};
+
+struct MotionLaunch {
+  float *x, *y, *th;
+  int64_t n;
+  int64_t gid0;
+  const float *normals;  // [n][3] or null -> Philox
+  uint64_t seed;
+  int32_t is_static, trans_zero;
+  float rot1, trans, rot2, sd1, sdt, sd2;
+};
+
+}  // namespace amclj
+
+struct amclj_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::string err;
+  amclj_params p;
+  amclj::DeviceMap map;
+  amclj::BeamTable beams;
+  amclj::DivTable divs;
+  // particles (SoA), double-buffered for the resampling gather
+  int64_t n = 0, cap = 0;
+  float *x = nullptr, *y = nullptr, *th = nullptr, *w = nullptr, *raw = nullptr;
+  float *x2 = nullptr, *y2 = nullptr, *th2 = nullptr, *w2 = nullptr;
+  uint64_t *cdf = nullptr;
+  int32_t *idx = nullptr;       // last resample's source indices
+  float *normals = nullptr;     // staged injected normals [n][3]
+  // scalars on the device
+  uint32_t *rawmax_ord = nullptr;  // ordered-uint of max raw
+  float *rawmax = nullptr;         // float[1] (AMCLJ_BUF_RAW_MAX)
+  uint64_t *total = nullptr;       // u64[1]  (AMCLJ_BUF_TOTAL)
+  unsigned long long *stats = nullptr;  // rays, cells, probes, hits | roulette: accepted, last attempt
+  uint64_t *scan_state = nullptr;  // decoupled look-back tile descriptors
+  int64_t scan_state_cap = 0;
+  uint32_t *scan_counter = nullptr;
+  double *pose_part = nullptr;     // pose-estimate partials
+  amclj::SysPlan *plan = nullptr;  // device copy of the systematic plan
+  // roulette scratch
+  uint32_t *r_counts = nullptr;
+  int64_t r_counts_cap = 0;
+  // sharding
+  int32_t rank = 0, world = 1;
+  int64_t global_offset = 0, n_global = 0;
+  float4 *stage_out = nullptr, *stage_in = nullptr;
+  int64_t stage_cap = 0;
+  int64_t *stage_idx = nullptr;
+  bool have_raw = false, have_cdf = false, cdf_from_raw = false, normals_staged = false;
+  float last_wmax = 0.f;
+  uint64_t last_total = 0;
+  amclj_stats st;
+  void *pinned = nullptr;  // small pinned scratch for scalar readbacks
+};
+
+namespace amclj {
+// sensor.cu
+cudaError_t launch_sensor(const amclj_ctx *c, const SensorLaunch &a, int mode, bool diag,
+                          cudaStream_t s);
+enum { DF_SMEM4 = 0, DF_GLOBAL8 = 1, DF_GLOBAL4 = 2 };
+
+// filter.cu
+struct GatherArgs {
+  const uint64_t *cdf;
+  int64_t n_local;
+  uint64_t cdf_offset;
+  const SysPlan *plan;  /* device pointer */
+  int64_t m_lo, count;
+  const float *x, *y, *th;
+  float *ox, *oy, *oth, *ow;  /* SoA outputs (single GPU) or null */
+  float4 *orow;               /* row outputs (sharded) or null */
+  int32_t *oidx;
+  int64_t *oidx64;
+  int64_t gid0;
+  float wout;
+};
+struct RouletteArgs {
+  const uint64_t *cdf;
+  int64_t n;
+  uint64_t total;
+  uint64_t seed;
+  const int32_t *sidx;  /* injected stream or null */
+  const uint32_t *su;
+  int64_t t0, t_end;    /* attempts [t0, t_end) */
+  int per_thread;
+  int64_t got_before;
+  int32_t *idx_out;     /* [n] */
+  uint64_t *tile_state;
+  uint32_t *tile_counter;
+  unsigned long long *accepted_out; /* accepted in this launch */
+  unsigned long long *last_attempt; /* attempt index (+1) of the acceptance filling slot n-1 */
+};
+cudaError_t launch_motion(const MotionLaunch &a, cudaStream_t s);
+cudaError_t build_distance_fields(amclj_ctx *c, bool want8, cudaStream_t s);
+cudaError_t launch_max(const float *v, int64_t n, uint32_t *ord, float *out, int sm_count,
+                       cudaStream_t s);
+cudaError_t launch_decode_max(const uint32_t *ord, float *out, cudaStream_t s);
+int64_t scan_tiles(int64_t n);
+cudaError_t launch_scan(const float *v, const float *vmaxp, int is_log, int64_t n, uint64_t *cdf,
+                        uint64_t *tile_state, uint32_t *tile_counter, uint64_t *total_out,
+                        cudaStream_t s);
+cudaError_t launch_plan(const uint64_t *total, uint64_t u0_bits, int64_t n_global, SysPlan *out,
+                        cudaStream_t s);
+cudaError_t launch_set_plan(const SysPlan &p, SysPlan *out, cudaStream_t s);
+cudaError_t launch_systematic(const GatherArgs &a, cudaStream_t s);
+cudaError_t launch_roulette(const RouletteArgs &a, int64_t tiles, cudaStream_t s);
+cudaError_t launch_tournament(const float *w, int64_t n, const int32_t *sidx, uint64_t seed,
+                              int32_t *idx_out, cudaStream_t s);
+/* wmode 0: constant wconst, 1: q_i / total from the cdf, 2: copy wsrc[i] */
+cudaError_t launch_gather_idx(const int32_t *idx, int64_t n, const float *x, const float *y,
+                              const float *th, int wmode, const uint64_t *cdf, uint64_t total,
+                              const float *wsrc, float wconst, float *ox, float *oy, float *oth,
+                              float *ow, cudaStream_t s);
+cudaError_t launch_adopt(const float4 *rows, int64_t n, float *x, float *y, float *th, float *w,
+                         cudaStream_t s);
+cudaError_t launch_fill(float *p, int64_t n, float v, cudaStream_t s);
+int pose_blocks();
+cudaError_t launch_pose(const float *x, const float *y, const float *th, int64_t n, double *part,
+                        cudaStream_t s);
+cudaError_t launch_init_uniform(const int8_t *cells, int W, int H, float res, int64_t gid0,
+                                int64_t n, int heading_mode, uint64_t seed, float *x, float *y,
+                                float *th, float *w, float w0, cudaStream_t s);
+cudaError_t launch_init_gaussian(float mx, float my, float mth, float sd_xy, float sd_th,
+                                 int64_t gid0, int64_t n, uint64_t seed, float *x, float *y,
+                                 float *th, float *w, float w0, cudaStream_t s);
+}  // namespace amclj

@@ -76,7 +76,9 @@ typedef struct amclj_params {
   /* S10 sensor.clj:78-81,142 — 0: base->laser offset ignored (REF and NS default) */
   int32_t s10_apply_laser_offset;
   int32_t collect_stats; /* count cells visited / probes (small cost) */
-  int32_t reserved0;
+  /* distance-field placement: 0 auto (shared memory when the nibble-packed field fits,
+   * else one byte per cell in L2), 1 shared nibbles, 2 global bytes, 3 global nibbles */
+  int32_t df_mode;
   float max_range;    /* sensor.clj:12  (-1.0) */
   float z_hit;        /* sensor.clj:14 */
   float z_short;      /* sensor.clj:15 */
@@ -180,6 +182,9 @@ int32_t amclj_resample(amclj_ctx *ctx, int32_t mode, double u0, const int32_t *s
                        const uint32_t *stream_u, int64_t stream_len, uint64_t seed,
                        int32_t *idx_out);
 
+/* Source indices chosen by the last resample (host int32 [n]). */
+int32_t amclj_get_resample_indices(amclj_ctx *ctx, int32_t *idx_out);
+
 /* ---- fused update: one mcl* iteration's hot path (pf.clj:229-233) ------------------- */
 /* motion -> sensor -> normalise -> resample, device-resident in and out.  The scan is
  * copied to the device inside the call. */
@@ -201,7 +206,8 @@ int32_t amclj_filter_update_host(amclj_ctx *ctx, float *x, float *y, float *thet
                                  float range_max, double u0);
 
 /* ---- pose-estimate pf.clj:67-84: unweighted mean of x, y, and of (qz, qw) ----------- */
-/* out = {mean x, mean y, mean qz, mean qw}. */
+/* out = {mean x, mean y, mean qz, mean qw}.  On a shard (world > 1) out holds the local
+ * SUMS; the caller adds the ranks' sums and divides by n_global. */
 int32_t amclj_pose_estimate(amclj_ctx *ctx, double out[4]);
 
 int32_t amclj_get_stats(amclj_ctx *ctx, amclj_stats *out);
@@ -220,6 +226,8 @@ int32_t amclj_shard_cdf_async(amclj_ctx *ctx);
  * host int32/int64 readback through amclj_shard_get_stage_idx). */
 int32_t amclj_shard_generate_async(amclj_ctx *ctx, uint64_t total_global, uint64_t cdf_offset,
                                    uint64_t r, int64_t m_lo, int64_t count);
+/* Global source index of each generated row (host int64 [count]); parity probe. */
+int32_t amclj_shard_get_stage_idx(amclj_ctx *ctx, int64_t *idx_out, int64_t count);
 /* Stage 4: adopt `count` float4 rows from AMCLJ_BUF_STAGE_IN as the new local particles. */
 int32_t amclj_shard_adopt_async(amclj_ctx *ctx, int64_t count);
 /* Host-only planning (no GPU needed): for per-rank totals T_g, systematic offset

@@ -43,7 +43,7 @@ class Params(C.Structure):
         ("s9_pr_rot1_variance", C.c_int32),
         ("s10_apply_laser_offset", C.c_int32),
         ("collect_stats", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("df_mode", C.c_int32),
         ("max_range", C.c_float),
         ("z_hit", C.c_float),
         ("z_short", C.c_float),
@@ -187,6 +187,13 @@ def lib():
     L.amclj_oracle_uniform_init.argtypes = [i8p, C.c_int32, C.c_int32, C.c_float, C.c_int64,
                                             C.c_int64, C.c_int32, C.c_uint64, f32p, f32p, f32p]
     L.amclj_oracle_threads.restype = C.c_int32
+    L.amclj_oracle_expf_contract.argtypes = [C.c_float]
+    L.amclj_oracle_expf_contract.restype = C.c_float
+    L.amclj_oracle_linear_weights.argtypes = [f32p, C.c_int64, C.c_float, f32p]
+    L.amclj_oracle_max.argtypes = [f32p, C.c_int64]
+    L.amclj_oracle_max.restype = C.c_float
+    L.amclj_oracle_gaussian_init.argtypes = [C.c_float] * 5 + [C.c_int64, C.c_int64, C.c_uint64,
+                                                               f32p, f32p, f32p]
     _lib = L
     return L
 
@@ -382,6 +389,28 @@ def uniform_init(grid, gid_first, n, heading_mode, seed):
     cells, W, H, res = _grid(grid)
     x, y, t = (np.zeros(n, np.float32) for _ in range(3))
     lib().amclj_oracle_uniform_init(cells, W, H, res, gid_first, n, heading_mode, seed, x, y, t)
+    return x, y, t
+
+
+def expf_contract(x):
+    return np.float32(lib().amclj_oracle_expf_contract(float(np.float32(x))))
+
+
+def linear_weights(raw, log_weights):
+    """The normaliser's input: raw itself (sum p^3) or exp(raw - max) under S7.  Returns
+    (w float32, wmax float32)."""
+    raw = np.ascontiguousarray(raw, np.float32)
+    m = np.float32(lib().amclj_oracle_max(raw, len(raw)))
+    if not log_weights:
+        return raw, m
+    w = np.zeros(len(raw), np.float32)
+    lib().amclj_oracle_linear_weights(raw, len(raw), float(m), w)
+    return w, np.float32(1.0)
+
+
+def gaussian_init(mx, my, mth, sd_xy, sd_th, gid_first, n, seed):
+    x, y, t = (np.zeros(n, np.float32) for _ in range(3))
+    lib().amclj_oracle_gaussian_init(mx, my, mth, sd_xy, sd_th, gid_first, n, seed, x, y, t)
     return x, y, t
 
 

@@ -777,6 +777,58 @@ ORACLE_API void amclj_oracle_uniform_init(const int8_t *cells, int32_t W, int32_
   }
 }
 
+/* ------------------------------------------------------------------------------------
+ * Log-weights -> linear weights before the fixed-point conversion (S7 = 1; no reference
+ * counterpart: the reference's weights are linear, sensor.clj:162).  Contract: w_i =
+ * exp(raw_i - max raw) with a specified exp (Cody-Waite by ln2, Cephes degree-5
+ * polynomial, explicit fmaf, flush below -87), so raw -> q_i is bit-reproducible.
+ * ---------------------------------------------------------------------------------- */
+ORACLE_API float amclj_oracle_expf_contract(float x) {
+  if (!(x > -87.0f)) return 0.0f;
+  if (x > 0.0f) x = 0.0f;
+  float n = rintf(x * 1.44269504088896341f);
+  float r = fmaf(n, -0.693359375f, x);
+  r = fmaf(n, 2.12194440e-4f, r);
+  float p = fmaf(r, 1.9875691500e-4f, 1.3981999507e-3f);
+  p = fmaf(p, r, 8.3334519073e-3f);
+  p = fmaf(p, r, 4.1665795894e-2f);
+  p = fmaf(p, r, 1.6666665459e-1f);
+  p = fmaf(p, r, 5.0000001201e-1f);
+  float y = fmaf(p, r * r, r) + 1.0f;
+  return ldexpf(y, (int)n);
+}
+
+ORACLE_API void amclj_oracle_linear_weights(const float *raw, int64_t n, float rawmax,
+                                            float *w) {
+  for (int64_t i = 0; i < n; i++) w[i] = amclj_oracle_expf_contract(raw[i] - rawmax);
+}
+
+ORACLE_API float amclj_oracle_max(const float *v, int64_t n) {
+  float m = -INFINITY;
+  for (int64_t i = 0; i < n; i++) m = fmaxf(m, v[i]);
+  return m;
+}
+
+/* map.clj:87-111 gaussian-initialization / gaussian-noise: x, y ~ N(pose, sd_xy); heading
+ * rotated by N(rot-mean, sd) where the reference passes sd = rot-mean = 0 (map.clj:106).
+ * Device contract: Philox counter (gid lo, gid hi, 0, TAG_GAUSS), Box-Muller as for motion. */
+#define TAG_GAUSS 0x47415553u
+ORACLE_API void amclj_oracle_gaussian_init(float mx, float my, float mth, float sd_xy,
+                                           float sd_th, int64_t gid_first, int64_t np,
+                                           uint64_t seed, float *x, float *y, float *theta) {
+  for (int64_t i = 0; i < np; i++) {
+    uint64_t gid = (uint64_t)(gid_first + i);
+    uint32_t r[4];
+    philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), 0u, TAG_GAUSS, (uint32_t)seed,
+                  (uint32_t)(seed >> 32), r);
+    float ra = sqrtf(-2.0f * logf(u24(r[0]))), rb = sqrtf(-2.0f * logf(u24(r[2])));
+    float a = 6.283185307179586f * u24(r[1]), b = 6.283185307179586f * u24(r[3]);
+    x[i] = fmaf(sd_xy, ra * cosf(a), mx);
+    y[i] = fmaf(sd_xy, ra * sinf(a), my);
+    theta[i] = fmaf(sd_th, rb * cosf(b), mth);
+  }
+}
+
 ORACLE_API int32_t amclj_oracle_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

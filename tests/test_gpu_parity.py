@@ -1,0 +1,365 @@
+"""GPU parity: the CUDA path (through the C ABI, amclj_b200/_lib.py) against the CPU oracle
+on identical seeded inputs.  Bars (BASELINE.json north_star): bit-exact for hit flag, hit
+cell, steps, fixed-point weights and resample index lists; 1e-5 relative (fp32) for poses
+and weights.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from amclj_b200 import _lib, maps, workloads
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north_star: floating-point log-weights and poses within 1e-5 relative (fp32)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def lg():
+    return maps.lgfloor()
+
+
+def _pair(preset, **kw):
+    """Matching parameter blocks for the library and the oracle."""
+    return _lib.params(preset, **kw), oracle.params(preset, **kw)
+
+
+def _ray_parity(ctx, grid, x, y, th, scan, preset, **kw):
+    pl, po = _pair(preset, **kw)
+    ctx.set_params(pl)
+    ctx.set_particles(x, y, th)
+    dbg = ctx.raycast_debug(len(scan.ranges), scan.angle_min, scan.angle_inc, scan.range_max)
+    _, st, ref = oracle.sensor_f32(po, grid, scan.ranges, scan.angle_min, scan.angle_inc,
+                                   scan.range_max, x, y, th, debug=True, want_raw=False)
+    for k in ("hit", "hit_x", "hit_y", "steps"):
+        assert np.array_equal(dbg[k], ref[k]), f"{preset}: {k} differs at {np.argwhere(dbg[k] != ref[k])[:5]}"
+    assert np.array_equal(dbg["range_m"], ref["range_m"]), "range in metres is exact in the fp32 contract"
+    s = ctx.stats()
+    assert (s.rays, s.cells_visited, s.hits) == (st.rays, st.cells, st.hits)
+    return s
+
+
+@pytest.mark.parametrize("preset", ["NS", "REF"])
+def test_raycast_bit_exact_c1(ctx, lg, preset):
+    w = workloads.c1()
+    ctx.set_map(lg)
+    s = _ray_parity(ctx, lg, w.x, w.y, w.theta, w.scan, preset)
+    assert s.probes < s.cells_visited or preset == "REF"
+
+
+@pytest.mark.parametrize("preset", ["NS", "REF"])
+def test_raycast_bit_exact_uniform_and_edges(ctx, lg, preset):
+    """Global-localisation poses plus the edge cases the walk must get right: particles on
+    blocked / unknown cells, outside the map on every side, at the far corner, NaN."""
+    x, y, th = workloads.uniform_particles(lg, 3000, seed=11)
+    res = float(lg.info.resolution)
+    W, H = lg.info.width, lg.info.height
+    ex = np.array([-1.0, (W + 3) * res, 5.0, 5.0, 0.0, (W - 1) * res, (W - 0.6) * res, 16.3,
+                   np.nan, 1e12, -0.024, 0.0251], np.float32)
+    ey = np.array([5.0, 5.0, -2.0, (H + 10) * res, 0.0, (H - 1) * res, (H - 0.6) * res, np.nan,
+                   3.0, -1e12, -0.024, 0.0251], np.float32)
+    et = np.linspace(-4, 4, len(ex)).astype(np.float32)
+    occ = np.argwhere(lg.data == 100)[::97][:40]
+    x = np.concatenate([x, ex, (occ[:, 1] * res).astype(np.float32)])
+    y = np.concatenate([y, ey, (occ[:, 0] * res).astype(np.float32)])
+    th = np.concatenate([th, et, np.zeros(len(occ), np.float32)])
+    ctx.set_map(lg)
+    scan = workloads.make_scan(lg, workloads.TRUE_POSE, 360, -math.pi, 2 * math.pi / 360, 5.6)
+    _ray_parity(ctx, lg, x, y, th, scan, preset)
+
+
+@pytest.mark.parametrize("switches", [
+    dict(s1_use_heading=0), dict(s3_proper_endpoint=0), dict(s4_endpoint_termination=0),
+    dict(s2_use_scan_range_max=0), dict(s10_apply_laser_offset=1),
+    dict(s3_proper_endpoint=0, s4_endpoint_termination=0), dict(s6_max_beams=30),
+])
+def test_raycast_switch_matrix(ctx, lg, switches):
+    """Every semantic switch is a launch-uniform parameter of the same kernel."""
+    x, y, th = workloads.uniform_particles(lg, 1500, seed=12)
+    ctx.set_map(lg)
+    scan = workloads.make_scan(lg, workloads.TRUE_POSE, 180, -math.pi / 2, math.pi / 179, 5.6)
+    _ray_parity(ctx, lg, x, y, th, scan, "NS", **switches)
+
+
+@pytest.mark.parametrize("df_mode", [1, 2, 3])
+def test_raycast_all_field_placements(ctx, lg, df_mode):
+    """Shared-memory nibbles, global bytes and global nibbles give the same answers."""
+    x, y, th = workloads.uniform_particles(lg, 1500, seed=13)
+    ctx.set_params(_lib.params("NS", df_mode=df_mode))
+    ctx.set_map(lg)
+    scan = workloads.make_scan(lg, workloads.TRUE_POSE, 360, -math.pi, 2 * math.pi / 360, 5.6)
+    s = _ray_parity(ctx, lg, x, y, th, scan, "NS", df_mode=df_mode)
+    assert s.map_in_smem == (1 if df_mode == 1 else 0)
+
+
+def test_raycast_tiny_known_answer_map(ctx):
+    """8x8 hand-checkable map (the oracle's known-answer fixture shape): a wall at x = 6."""
+    g = np.zeros((8, 8), np.int8)
+    g[:, 6] = 100
+    g[0, :] = -1
+    grid = maps.OccupancyGrid(maps.MapMetaData(np.float32(1.0), 8, 8), g)
+    ctx.set_map(grid)
+    ctx.set_params(_lib.params("NS"))
+    ctx.set_particles(np.array([2.0], np.float32), np.array([3.0], np.float32), np.array([0.0], np.float32))
+    d = ctx.raycast_debug(4, 0.0, math.pi / 2, 10.0)
+    # beam 0 (+x): wall at x = 6 after 4 steps; beam 1 (+y): leaves the map at y = 8;
+    # beam 2 (-x): leaves at x = -1; beam 3 (-y): unknown row y = 0
+    assert d["hit"].tolist() == [[1, 1, 1, 1]]
+    assert d["hit_x"].tolist() == [[6, 2, -1, 2]]
+    assert d["hit_y"].tolist() == [[3, 8, 3, 0]]
+    assert d["steps"].tolist() == [[4, 5, 3, 3]]
+    np.testing.assert_array_equal(d["range_m"], np.array([[4, 5, 3, 3]], np.float32))
+
+
+@pytest.mark.parametrize("preset", ["NS", "REF"])
+def test_sensor_weights_c1(ctx, lg, preset):
+    w = workloads.c1()
+    pl, po = _pair(preset)
+    ctx.set_map(lg)
+    ctx.set_params(pl)
+    ctx.set_particles(w.x, w.y, w.theta)
+    ctx.sensor_update(w.scan.ranges, w.scan.angle_min, w.scan.angle_inc, w.scan.range_max)
+    raw = ctx.raw_weights()
+    ref, _, _ = oracle.sensor_f32(po, lg, w.scan.ranges, w.scan.angle_min, w.scan.angle_inc,
+                                  w.scan.range_max, w.x, w.y, w.theta)
+    np.testing.assert_allclose(raw, ref, rtol=RTOL)
+    # and against the double restatement of the Clojure (same cells except where fp32
+    # rounding moves a start/end cell): the bulk must agree to 1e-5 as well
+    ref64, _ = oracle.sensor_f64(po, lg, w.scan.ranges, w.scan.angle_min, w.scan.angle_inc,
+                                 w.scan.range_max, w.x, w.y, w.theta)
+    close = np.isclose(raw, ref64, rtol=RTOL)
+    assert close.mean() > 0.97
+
+
+def test_sensor_weights_c2_sample(ctx, lg):
+    """BASELINE config C2 (100k x 360): full GPU pass, oracle on a 2,000-particle sample."""
+    w = workloads.c2()
+    pl, po = _pair("NS")
+    ctx.set_map(lg)
+    ctx.set_params(pl)
+    ctx.set_particles(w.x, w.y, w.theta)
+    ctx.sensor_update(w.scan.ranges, w.scan.angle_min, w.scan.angle_inc, w.scan.range_max)
+    raw = ctx.raw_weights()
+    sel = np.random.Generator(np.random.PCG64(7)).choice(w.n, 2000, replace=False)
+    ref, _, _ = oracle.sensor_f32(po, lg, w.scan.ranges, w.scan.angle_min, w.scan.angle_inc,
+                                  w.scan.range_max, w.x[sel], w.y[sel], w.theta[sel])
+    np.testing.assert_allclose(raw[sel], ref, rtol=RTOL)
+
+
+@pytest.mark.parametrize("curr,prev", [((0.2, 0.0, 0.1), (0.0, 0.0, 0.0)),
+                                       ((1.0, 2.0, 0.3), (1.0, 2.0, -0.2)),  # trans == 0
+                                       ((0.5, -0.25, 1.0), (0.75, 0.5, 2.5)),
+                                       ((3.0, 1.0, 0.5), (3.0, 1.0, 0.5))])   # static
+def test_motion_injected_normals(ctx, lg, curr, prev):
+    w = workloads.c1(5000)
+    nrm = w.normals()
+    pl, po = _pair("REF")
+    ctx.set_params(pl)
+    ctx.set_particles(w.x, w.y, w.theta)
+    ctx.motion_update(curr, prev, nrm)
+    x, y, t, _ = ctx.get_particles()
+    rx, ry, rt = oracle.motion_f32(po, curr, prev, nrm, w.x, w.y, w.theta)
+    # same explicit-fma contract on both sides: identical bits, well inside 1e-5
+    assert np.array_equal(x, rx) and np.array_equal(y, ry) and np.array_equal(t, rt)
+    dx, dy, dt = oracle.motion_f64(po, curr, prev, nrm, w.x, w.y, w.theta)
+    np.testing.assert_allclose(x, dx, rtol=RTOL)
+    np.testing.assert_allclose(y, dy, rtol=RTOL)
+    np.testing.assert_allclose(t, dt, rtol=RTOL, atol=1e-6)
+
+
+def test_motion_philox_normals(ctx):
+    w = workloads.c1(4096)
+    pl, po = _pair("NS")
+    ctx.set_params(pl)
+    ctx.set_particles(w.x, w.y, w.theta)
+    ctx.motion_update(w.curr, w.prev, None, seed=1234)
+    x, y, t, _ = ctx.get_particles()
+    nrm = oracle.motion_normals(1234, 0, w.n)
+    rx, ry, rt = oracle.motion_f32(po, w.curr, w.prev, nrm, w.x, w.y, w.theta)
+    np.testing.assert_allclose(x, rx, rtol=RTOL)
+    np.testing.assert_allclose(y, ry, rtol=RTOL)
+    np.testing.assert_allclose(t, rt, rtol=RTOL, atol=1e-6)
+    assert abs(float(np.mean(nrm))) < 0.05 and abs(float(np.std(nrm)) - 1) < 0.05
+
+
+def _weights(n, seed, spiky=False):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    w = rng.random(n).astype(np.float32) ** (12 if spiky else 3)
+    w[rng.integers(0, n, max(1, n // 50))] = 0.0
+    return w
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 2048, 2049, 100_000, 1_000_003])
+def test_normalize_cdf_bit_exact(ctx, n):
+    w = _weights(n, 40 + n % 7)
+    if n == 1:
+        w[:] = 0.25
+    z = np.zeros(n, np.float32)
+    ctx.set_particles(z, z, z, w)
+    total, wmax = ctx.normalize(from_raw=False)
+    q, rtotal = oracle.fixed_weights(w, oracle.wmax(w))
+    assert wmax == float(oracle.wmax(w))
+    assert total == rtotal
+    assert np.array_equal(ctx.cdf(), np.cumsum(q, dtype=np.uint64))
+
+
+@pytest.mark.parametrize("n,u0", [(1, 0.5), (1000, 0.0), (1000, 0.999999), (100_000, 0.37),
+                                  (1_000_003, 0.8125)])
+def test_systematic_indices_bit_exact(ctx, n, u0):
+    w = _weights(n, 3, spiky=True)
+    if n == 1:
+        w[:] = 1.0
+    x = np.arange(n, dtype=np.float32)
+    ctx.set_particles(x, -x, x * 0.5, w)
+    idx = ctx.resample(_lib.RESAMPLE_SYSTEMATIC, u0)
+    ref = oracle.systematic_resample(w, u0)
+    assert np.array_equal(idx.astype(np.int64), ref)
+    assert (np.diff(idx) >= 0).all()
+    gx, gy, gt, gw = ctx.get_particles()
+    assert np.array_equal(gx, x[idx]) and np.array_equal(gy, -x[idx]) and np.array_equal(gt, (x * 0.5)[idx])
+    np.testing.assert_allclose(gw, 1.0 / n, rtol=1e-7)
+
+
+def test_systematic_from_log_weights(ctx, lg):
+    """raw log-weights -> exp contract -> fixed point -> indices: exact given the raw values."""
+    w = workloads.c1()
+    pl, _ = _pair("NS")
+    ctx.set_map(lg)
+    ctx.set_params(pl)
+    ctx.set_particles(w.x, w.y, w.theta)
+    ctx.sensor_update(w.scan.ranges, w.scan.angle_min, w.scan.angle_inc, w.scan.range_max)
+    raw = ctx.raw_weights()
+    idx = ctx.resample(_lib.RESAMPLE_SYSTEMATIC, w.u0)
+    lin, wmax = oracle.linear_weights(raw, True)
+    q, total = oracle.fixed_weights(lin, wmax)
+    r = oracle.systematic_offset(w.u0, total)
+    ref = oracle.systematic(q, total, 0, r, w.n, 0, w.n)
+    assert np.array_equal(idx.astype(np.int64), ref)
+
+
+def test_roulette_injected_stream(ctx, golden):
+    r = golden["roulette"]
+    w = np.asarray(r["weights"], np.float32)
+    z = np.zeros(len(w), np.float32)
+    ctx.set_particles(z, z, z, w)
+    idx = ctx.resample(_lib.RESAMPLE_ROULETTE, 0.0, stream_idx=r["attempt_idx"], stream_u=r["attempt_u32"])
+    assert idx.tolist() == r["selected"]
+    _, _, _, gw = ctx.get_particles()
+    np.testing.assert_allclose(gw, np.asarray(r["normalized"])[idx], rtol=2e-6)
+
+
+@pytest.mark.parametrize("n", [64, 1000, 20_000])
+def test_roulette_philox_bit_exact(ctx, n):
+    w = _weights(n, 5)
+    z = np.zeros(n, np.float32)
+    ctx.set_particles(z, z, z, w)
+    idx = ctx.resample(_lib.RESAMPLE_ROULETTE, 0.0, seed=6)
+    q, total = oracle.fixed_weights(w, oracle.wmax(w))
+    ref, _ = oracle.roulette_philox(q, total, 6)
+    assert np.array_equal(idx, ref)
+
+
+def test_tournament_bit_exact(ctx):
+    n = 50_000
+    w = _weights(n, 8)
+    z = np.zeros(n, np.float32)
+    ctx.set_particles(z, z, z, w)
+    idx = ctx.resample(_lib.RESAMPLE_TOURNAMENT, 0.0, seed=9)
+    assert np.array_equal(idx, oracle.tournament_philox(w, 9))
+    sidx = np.random.Generator(np.random.PCG64(2)).integers(0, n, 2 * n).astype(np.int32)
+    ctx.set_particles(z, z, z, w)
+    idx = ctx.resample(_lib.RESAMPLE_TOURNAMENT, 0.0, stream_idx=sidx)
+    assert np.array_equal(idx, oracle.tournament_stream(w, sidx))
+
+
+def test_pose_estimate(ctx):
+    w = workloads.c1(10_000)
+    ctx.set_particles(w.x, w.y, w.theta)
+    np.testing.assert_allclose(ctx.pose_estimate(), oracle.pose_estimate(w.x, w.y, w.theta), rtol=1e-6)
+
+
+@pytest.mark.parametrize("heading_mode", [0, 1])
+def test_init_uniform(ctx, lg, heading_mode):
+    ctx.set_map(lg)
+    ctx.init_uniform(20_000, heading_mode, seed=77)
+    x, y, t, w = ctx.get_particles()
+    rx, ry, rt = oracle.uniform_init(lg, 0, 20_000, heading_mode, 77)
+    assert np.array_equal(x, rx) and np.array_equal(y, ry)
+    np.testing.assert_allclose(t, rt, rtol=RTOL, atol=1e-6)
+    res = float(lg.info.resolution)
+    assert (lg.data[(y / res).astype(int), (x / res).astype(int)] == 0).all()
+
+
+def test_init_gaussian(ctx):
+    ctx.init_gaussian(10_000, 16.3, 15.8, 2.0, 0.1, 0.0, seed=5)
+    x, y, t, _ = ctx.get_particles()
+    rx, ry, rt = oracle.gaussian_init(16.3, 15.8, 2.0, 0.1, 0.0, 0, 10_000, 5)
+    np.testing.assert_allclose(x, rx, rtol=RTOL)
+    np.testing.assert_allclose(y, ry, rtol=RTOL)
+    assert np.array_equal(t, rt)
+
+
+@pytest.mark.parametrize("preset", ["NS", "REF"])
+def test_filter_update_stagewise(ctx, lg, preset):
+    """One full mcl* hot-path iteration (pf.clj:229-233) through amclj_filter_update, checked
+    stage by stage against the oracle fed with the same injected streams."""
+    w = workloads.c1()
+    nrm = w.normals()
+    pl, po = _pair(preset)
+    ctx.set_map(lg)
+    ctx.set_params(pl)
+    ctx.set_particles(w.x, w.y, w.theta)
+    s = w.scan
+    ctx.filter_update(w.curr, w.prev, s.ranges, s.angle_min, s.angle_inc, s.range_max, w.u0,
+                      normals=nrm, seed=6)
+    idx = ctx.resample_indices()
+    gx, gy, gt, gw = ctx.get_particles()
+    mx, my, mt = oracle.motion_f32(po, w.curr, w.prev, nrm, w.x, w.y, w.theta)
+    raw, _, _ = oracle.sensor_f32(po, lg, s.ranges, s.angle_min, s.angle_inc, s.range_max, mx, my, mt)
+    # resample the oracle's way from the GPU's own raw weights is covered above; here the
+    # end-to-end list must agree wherever the two raw vectors round to the same fixed point
+    lin, wmax = oracle.linear_weights(raw, bool(po.s7_log_weights))
+    q, total = oracle.fixed_weights(lin, wmax)
+    if preset == "NS":
+        ref = oracle.systematic(q, total, 0, oracle.systematic_offset(w.u0, total), w.n, 0, w.n)
+        assert (idx == ref).mean() > 0.98  # raw weights agree to 1e-5, not bit for bit
+        np.testing.assert_allclose(gw, 1.0 / w.n, rtol=1e-7)
+    assert np.array_equal(gx, mx[idx]) and np.array_equal(gy, my[idx]) and np.array_equal(gt, mt[idx])
+    st = ctx.stats()
+    assert st.ms_total > 0 and st.n_particles == w.n
+
+
+def test_filter_update_host_roundtrip(ctx, lg):
+    w = workloads.c1()
+    ctx.set_map(lg)
+    ctx.set_params(_lib.params("NS"))
+    x, y, t = w.x.copy(), w.y.copy(), w.theta.copy()
+    wt = np.zeros(w.n, np.float32)
+    s = w.scan
+    ctx.filter_update_host(x, y, t, wt, w.curr, w.prev, s.ranges, s.angle_min, s.angle_inc,
+                           s.range_max, w.u0, seed=3)
+    gx, gy, gt, gw = ctx.get_particles()
+    assert np.array_equal(x, gx) and np.array_equal(y, gy) and np.array_equal(t, gt) and np.array_equal(wt, gw)
+    # resampled cloud concentrates near the true pose
+    assert np.hypot(x.mean() - (workloads.TRUE_POSE[0] + 0.2 * math.cos(workloads.TRUE_POSE[2])),
+                    y.mean() - (workloads.TRUE_POSE[1] + 0.2 * math.sin(workloads.TRUE_POSE[2]))) < 0.5
+
+
+def test_errors_are_loud(ctx):
+    with pytest.raises(_lib.AmcljError):
+        ctx.resample(_lib.RESAMPLE_SYSTEMATIC, 1.5)
+    z = np.zeros(4, np.float32)
+    ctx.set_particles(z, z, z, z)  # all weights zero
+    with pytest.raises(_lib.AmcljError):
+        ctx.resample(_lib.RESAMPLE_SYSTEMATIC, 0.5)
+    with pytest.raises(_lib.AmcljError):
+        _lib.Context(99)
