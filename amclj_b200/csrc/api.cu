@@ -483,10 +483,11 @@ void stamp(amclj_ctx *ctx, int k) { cudaEventRecord(ctx->ev[k], ctx->stream); }
 
 void collect_times(amclj_ctx *ctx) {
   float a = 0, b = 0, c = 0, t = 0;
-  cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
-  cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
-  cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]);
-  cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[3]);
+  if (cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]) != cudaSuccess || a < 0) a = 0;
+  if (cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]) != cudaSuccess || b < 0) b = 0;
+  if (cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]) != cudaSuccess || c < 0) c = 0;
+  if (cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[3]) != cudaSuccess || t < 0) t = 0;
+  (void)cudaGetLastError();
   ctx->st.ms_motion = a;
   ctx->st.ms_sensor = b;
   ctx->st.ms_resample = c;
@@ -796,6 +797,8 @@ int32_t amclj_raycast_debug(amclj_ctx *ctx, int32_t n, float angle_min, float an
     a.dbg_hit = d_hit;
     a.dbg_range = d_rng;
     a.stats = ctx->stats;
+    ctx->st.map_in_smem = mode == DF_SMEM4;
+    ctx->st.beams_used = ctx->beams.nb;
     cudaMemsetAsync(ctx->stats, 0, 4 * sizeof(unsigned long long), ctx->stream);
     e = launch_sensor(ctx, a, mode, true, ctx->stream);
   }
@@ -965,6 +968,7 @@ int32_t amclj_get_stats(amclj_ctx *ctx, amclj_stats *out) {
   ENTER();
   NEED(out, AMCLJ_ERR_INVALID, "get_stats: null");
   CK(cudaStreamSynchronize(ctx->stream));
+  collect_times(ctx);
   unsigned long long h[4] = {0, 0, 0, 0};
   CK(cudaMemcpy(h, ctx->stats, sizeof(h), cudaMemcpyDeviceToHost));
   ctx->st.rays = h[0];
