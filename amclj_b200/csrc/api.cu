@@ -167,6 +167,15 @@ void make_control(const amclj_params &p, const double curr[3], const double prev
   m.sd2 = (float)sqrt(a1 * rot2 * rot2 + a2 * trans * trans);
 }
 
+int df_mode_of(const amclj_ctx *ctx) {
+  switch (ctx->p.df_mode) {
+    case 1: return ctx->map.fits_smem ? DF_SMEM4 : -1;
+    case 2: return ctx->map.df8 ? DF_GLOBAL8 : -1;
+    case 3: return DF_GLOBAL4;
+    default: return ctx->map.fits_smem ? DF_SMEM4 : (ctx->map.df8 ? DF_GLOBAL8 : DF_GLOBAL4);
+  }
+}
+
 int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min, float angle_inc,
                     float range_max) {
   NEED(n > 0 && n <= (1 << 20), AMCLJ_ERR_INVALID, "scan: n = %d out of range", n);
@@ -207,17 +216,24 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
   b.angle_min = angle_min;
   b.angle_inc = angle_inc;
   b.range_max = range_max;
-  /* magic reciprocals for j(k): M = ceil(2^(31+L) / D), D = 2*dx, L = floor(log2 D) */
+  /* magic reciprocals for the minor-axis step count jd = floor(t / D), D = 2*dx, t < (dcap+1)*D
+   * (dcap = largest jump the field can return).  Shift-free form M = ceil(2^32 / D) is exact
+   * while (dcap+1) * D^2 <= 2^32; longer rays use M = ceil(2^(31+L) / D) >> (L-1), L = floor(log2 D). */
   int ndiv = (int)ceil(rcells) + 8;
+  int mode = df_mode_of(ctx);
+  NEED(mode >= 0, AMCLJ_ERR_INVALID, "scan: df_mode %d unavailable for this map", ctx->p.df_mode);
+  int dcap = mode == DF_GLOBAL8 ? 255 : 15;
+  uint64_t Dmax = 2ull * (uint64_t)(ndiv - 1);
+  int wide = (uint64_t)(dcap + 1) * Dmax * Dmax > (1ull << 32);
   DivTable &d = ctx->divs;
-  if (ndiv > d.n) {
+  if (ndiv > d.n || wide != d.wide || dcap != d.dcap) {
     std::vector<uint2> t((size_t)ndiv);
     t[0] = make_uint2(0u, 0u);
     for (int dx = 1; dx < ndiv; dx++) {
       uint64_t D = 2ull * (uint64_t)dx;
       int L = 63 - __builtin_clzll(D);
-      uint64_t M = ((1ull << (31 + L)) + D - 1) / D;
-      t[dx] = make_uint2((uint32_t)M, (uint32_t)(L - 1));
+      if (wide) t[dx] = make_uint2((uint32_t)(((1ull << (31 + L)) + D - 1) / D), (uint32_t)(L - 1));
+      else t[dx] = make_uint2((uint32_t)(((1ull << 32) + D - 1) / D), 0u);
     }
     if (ndiv > d.cap) {
       dfree(d.dev);
@@ -225,20 +241,14 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
       d.cap = ndiv;
     }
     CK(cudaMemcpyAsync(d.dev, t.data(), sizeof(uint2) * t.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     d.n = ndiv;
+    d.wide = wide;
+    d.dcap = dcap;
   }
   CK(cudaStreamSynchronize(ctx->stream)); /* the host vectors go out of scope */
   b.staged = true;
   return AMCLJ_OK;
-}
-
-int df_mode_of(const amclj_ctx *ctx) {
-  switch (ctx->p.df_mode) {
-    case 1: return ctx->map.fits_smem ? DF_SMEM4 : -1;
-    case 2: return ctx->map.df8 ? DF_GLOBAL8 : -1;
-    case 3: return DF_GLOBAL4;
-    default: return ctx->map.fits_smem ? DF_SMEM4 : (ctx->map.df8 ? DF_GLOBAL8 : DF_GLOBAL4);
-  }
 }
 
 void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode) {
@@ -261,6 +271,8 @@ void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode) {
   a.nb = ctx->beams.nb;
   a.divtab = ctx->divs.dev;
   a.ndiv = ctx->divs.n;
+  a.div_wide = ctx->divs.wide;
+  a.refill = ctx->refill;
   a.R = p.s2_use_scan_range_max ? ctx->beams.range_max : p.max_range;
   a.miss_value = a.R; /* sensor.clj:121 returns max-range on a miss */
   a.s1 = p.s1_use_heading;
@@ -521,6 +533,10 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   preset(&ctx->p, AMCLJ_PRESET_REF);
+  if (const char *e = getenv("AMCLJ_REFILL")) { /* tuning knob, 1..32 */
+    int v = atoi(e);
+    if (v >= 1 && v <= 32) ctx->refill = v;
+  }
   memset(&ctx->st, 0, sizeof(ctx->st));
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ctx->stream = ctx->own_stream;

@@ -38,6 +38,7 @@ struct BeamTable {       // one float array of 5*nb: cb | sb | obs | e2 | p34
 struct DivTable {        // magic reciprocals for the Bresenham minor-axis division
   uint2 *dev = nullptr;
   int32_t n = 0, cap = 0;
+  int32_t wide = 0, dcap = 0;
 };
 
 struct SensorLaunch {
@@ -53,6 +54,8 @@ struct SensorLaunch {
   int32_t nb;
   const uint2 *divtab;
   int32_t ndiv;
+  int32_t div_wide;  // 1: j-step = umulhi(t, M) >> sh; 0: shift-free (short rays)
+  int32_t refill;    // pull new beams when fewer lanes than this are still walking
   float R;            // ray length (S2)
   float miss_value;
   int32_t s1, s3, s4, s7, s10;
@@ -119,6 +122,7 @@ struct amclj_ctx {
   float last_wmax = 0.f;
   uint64_t last_total = 0;
   amclj_stats st;
+  int32_t refill = 20;
   void *pinned = nullptr;  // small pinned scratch for scalar readbacks
 };
 

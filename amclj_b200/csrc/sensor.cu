@@ -1,4 +1,4 @@
-// sensor.cu — K2: laser measurement model.  One warp per particle, one lane per beam:
+// sensor.cu — K2: laser measurement model.  One warp per particle, lanes pull beams:
 // ray-cast through the occupancy grid and score with the beam mixture.
 //
 // Replaces (jvia/amclj): pf.clj:148-154 apply-sensor-model ->
@@ -12,8 +12,14 @@
 // next d-1 cells of the line are certainly free and the walk can jump d steps at once; the
 // minor-axis position after any number of steps has the closed form
 //   j(k) = floor((2*k*dy + dx) / (2*dx))
-// (the reference's error accumulator, sensor.clj:123-127, unrolled).  First blocked cell,
-// step count and range are therefore bit-identical to the cell-by-cell walk.
+// (the reference's error accumulator, sensor.clj:123-127, unrolled), evaluated incrementally
+// with a per-ray magic reciprocal.  First blocked cell, step count and range are therefore
+// bit-identical to the cell-by-cell walk.
+//
+// Divergence: rays of one particle need 1..70 probes.  Lanes do not march in lock step over
+// rounds of 32 beams; a lane whose ray has ended parks its result, and when fewer than
+// `refill` lanes are still walking, the parked lanes score their ray and pull the next
+// beams (while-while persistent lanes).
 #include "internal.h"
 
 namespace amclj {
@@ -27,109 +33,44 @@ __device__ __forceinline__ uint32_t ord_of_float(float f) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-struct RayOut {
-  int k, j, hit;
-  int probes;
+// One ray in flight.  idx4 = 4 * (nibble index) for the packed fields (so the nibble shift
+// is idx4 & 4 and the byte address idx4 >> 3), or the byte index for the byte field.
+struct Ray {
+  int idx, k, j, err;
+  int dy, ndx, kmax, stepA, stepB; /* ndx = -dx */
+  uint32_t M, sh, d;
+  int beam;
+};
+
+// The field is addressed either through a 32-bit shared-window address (MODE DF_SMEM4, so the
+// probe is one LDS with a register base) or through a global pointer.
+struct Field {
+  const uint8_t *g;
+  uint32_t s;
 };
 
 template <int MODE>
-__device__ __forceinline__ uint32_t df_probe(const uint8_t *__restrict__ df, int idx) {
-  if (MODE == DF_GLOBAL8) return __ldg(df + idx);
-  uint32_t byte = (MODE == DF_SMEM4) ? df[idx >> 1] : __ldg(df + (idx >> 1));
-  return (byte >> ((idx & 1) << 2)) & 15u;
-}
-
-// sensor.clj:130-139 map-range + :112-128 extract-line for one beam.
-template <int MODE, bool DIAG>
-__device__ __forceinline__ float cast_ray(const SensorLaunch &a, const uint8_t *__restrict__ df,
-                                          float ox, float oy, float ct, float st, int x0, int y0,
-                                          bool start_in, float cb, float sb, RayOut &out,
-                                          int &hx, int &hy, int &steps) {
-  float c = cb, s = sb;
-  if (a.s1) { /* S1: theta + obs-bearing by the angle-addition identity */
-    c = fmaf(ct, cb, -(st * sb));
-    s = fmaf(st, cb, ct * sb);
-  }
-  /* sensor.clj:99-103 project-pose, map.clj:36-46 world->map */
-  int x1 = round_cell(fmaf(a.R, c, ox), a.res);
-  int y1 = round_cell(fmaf(a.R, s, oy), a.res);
-  int adx = abs(x1 - x0), ady = abs(y1 - y0);
-  bool steep = ady > adx; /* sensor.clj:87-91 */
-  int a0 = steep ? y0 : x0, b0 = steep ? x0 : y0;
-  int a1, b1;
-  if (steep) {
-    a1 = y1; b1 = x1;
-  } else if (a.s3) {
-    a1 = x1; b1 = y1;
-  } else { /* sensor.clj:138 `(if steep [y1 x1] [x0 y0])`: end = start */
-    a1 = a0; b1 = b0;
-  }
-  int xs = a0 < a1 ? 1 : -1, ys = b0 < b1 ? 1 : -1; /* sensor.clj:108-110, ties -> -1 */
-  int dx = abs(a0 - a1), dy = abs(b0 - b1);
-  /* the miss test runs AFTER the cell test at step k: S4=1 `x == max-x`;
-   * S4=0 (sensor.clj:121) `x > max-x` */
-  int kmax;
-  if (a.s4) kmax = dx;
-  else if (xs > 0) kmax = dx + 1;
-  else if (dx > 0) kmax = 0;
-  else { /* dx = dy = 0: `2*err >= 0` always holds -> diagonal walk until a blocked cell */
-    kmax = 0x3fffffff; dx = 1; dy = 1;
-  }
-  uint32_t M; int sh;
-  if (dx < a.ndiv) {
-    uint2 e = __ldg(a.divtab + dx);
-    M = e.x; sh = (int)e.y;
-  } else if (dx > 0) { /* never taken for validated ranges; kept exact */
-    uint32_t D = 2u * (uint32_t)dx;
-    int L = 31 - __clz(D);
-    M = (uint32_t)(((1ull << (31 + L)) + D - 1) / D);
-    sh = L - 1;
-  } else { M = 0; sh = 0; }
-  int stepA = xs * (steep ? a.row_nib : 1), stepB = ys * (steep ? 1 : a.row_nib);
-  /* padded field: cell (x, y) lives at (y+1)*row + (x+1); entry 0 is a ring cell (d = 0),
-   * which makes an out-of-range start an immediate hit (the start cell is tested first) */
-  int idx = start_in ? (y0 + 1) * a.row_nib + (x0 + 1) : 0;
-  int k = 0, j = 0, err = 0, hit, probes = 0;
-  for (;;) {
-    uint32_t d = df_probe<MODE>(df, idx);
-    if (DIAG) probes++;
-    if (d == 0) { hit = 1; break; }
-    k += (int)d;
-    if (k > kmax) { hit = 0; break; }
-    err += (int)d * dy;
-    uint32_t t = (uint32_t)(2 * err + dx);
-    int jd = (int)(__umulhi(t, M) >> sh);
-    err -= jd * dx;
-    j += jd;
-    idx += (int)d * stepA + jd * stepB;
-  }
-  float rng;
-  if (hit) {
-    uint32_t d2 = (uint32_t)k * (uint32_t)k + (uint32_t)j * (uint32_t)j;
-    rng = __fmul_rn(__fsqrt_rn(__uint2float_rn(d2)), a.res);
+__device__ __forceinline__ uint32_t df_probe(const Field &f, int idx) {
+  if (MODE == DF_GLOBAL8) return __ldg(f.g + idx);
+  uint32_t byte;
+  if (MODE == DF_SMEM4) {
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(byte) : "r"(f.s + (uint32_t)(idx >> 3)));
   } else {
-    rng = a.miss_value;
-    k = kmax;
+    byte = __ldg(f.g + (idx >> 3));
   }
-  out.k = k; out.hit = hit; out.probes = probes;
-  if (DIAG) {
-    if (!hit) j = dx > 0 ? (int)((2ll * k * dy + dx) / (2ll * dx)) : 0;
-    int ca = a0 + xs * k, cbb = b0 + ys * j;
-    hx = steep ? cbb : ca;
-    hy = steep ? ca : cbb;
-    steps = k;
-  }
-  out.j = j;
-  return rng;
+  return (byte >> (idx & 4)) & 15u;
 }
 
 constexpr int kMaxThreads = 1024;
+constexpr uint32_t FULL = 0xffffffffu;
 
-template <int MODE, bool DIAG>
+template <int MODE, bool DIAG, bool WIDE>
 __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaunch a) {
   extern __shared__ uint4 smem_dyn[];
   __shared__ uint64_t bar;
-  const uint8_t *df = a.df;
+  Field df;
+  df.g = a.df;
+  df.s = 0;
   if (MODE == DF_SMEM4) {
     /* stage the whole nibble-packed field with the bulk-copy engine (TMA, UBLKCP) */
     uint8_t *sdf = reinterpret_cast<uint8_t *>(smem_dyn);
@@ -162,15 +103,20 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
           : "r"(smem_u32(&bar))
           : "memory");
     }
-    df = sdf;
+    df.s = smem_u32(sdf);
   }
   const int lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   const int wpb = blockDim.x >> 5;
   const int64_t nwarps = (int64_t)gridDim.x * wpb;
-  const float *cbp = a.beam, *sbp = a.beam + a.nb, *obsp = a.beam + 2 * a.nb,
-              *e2p = a.beam + 3 * a.nb, *p34p = a.beam + 4 * a.nb;
+  const int nb = a.nb;
+  const float *cbp = a.beam, *sbp = a.beam + nb, *obsp = a.beam + 2 * nb, *e2p = a.beam + 3 * nb,
+              *p34p = a.beam + 4 * nb;
+  const int idx_scale = MODE == DF_GLOBAL8 ? 1 : 4;
+  const int row = a.row_nib * idx_scale;
   float wmax = -INFINITY;
   unsigned long long n_cells = 0, n_probes = 0, n_hits = 0, n_rays = 0;
+
   for (int64_t p = (int64_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x; p < a.n; p += nwarps) {
     float ox = __ldg(a.x + p), oy = __ldg(a.y + p), th = __ldg(a.th + p);
     float st, ct;
@@ -180,38 +126,137 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
       float ny = oy + fmaf(a.laser_x, st, a.laser_y * ct);
       ox = nx; oy = ny;
     }
-    int x0 = round_cell(ox, a.res), y0 = round_cell(oy, a.res);
-    bool start_in = (uint32_t)x0 < (uint32_t)a.W && (uint32_t)y0 < (uint32_t)a.H;
-    bool dbg = DIAG && a.dbg_count > 0 && p >= a.dbg_first && p < a.dbg_first + a.dbg_count;
-    float acc = 0.0f;
-    for (int jb = lane; jb < a.nb; jb += 32) {
-      float cb = __ldg(cbp + jb), sb = __ldg(sbp + jb), obs = __ldg(obsp + jb);
-      RayOut ro;
-      int hx = 0, hy = 0, steps = 0;
-      float rng = cast_ray<MODE, DIAG>(a, df, ox, oy, ct, st, x0, y0, start_in, cb, sb, ro, hx,
-                                       hy, steps);
-      /* sensor.clj:149-162 beam mixture; pz2's exponential and pz3/pz4 depend on the beam
-       * only and come precomputed (e2, p34) */
-      float z = obs - rng;
-      float pz1 = a.z_hit * expf(-(z * z) * a.inv2s2);
-      float pz2 = z < 0.0f ? __ldg(e2p + jb) : 0.0f;
-      float sum = (pz1 + pz2) + __ldg(p34p + jb);
-      acc += a.s7 ? logf(sum) : (sum * sum) * sum;
-      if (DIAG) {
-        n_rays++; n_cells += (unsigned)ro.k + 1u; n_probes += (unsigned)ro.probes;
-        n_hits += (unsigned)ro.hit;
-        if (dbg) {
-          int64_t o = (p - a.dbg_first) * a.nb + jb;
-          if (a.dbg_hit_x) a.dbg_hit_x[o] = hx;
-          if (a.dbg_hit_y) a.dbg_hit_y[o] = hy;
-          if (a.dbg_steps) a.dbg_steps[o] = steps;
-          if (a.dbg_hit) a.dbg_hit[o] = (uint8_t)ro.hit;
-          if (a.dbg_range) a.dbg_range[o] = rng;
+    const int x0 = round_cell(ox, a.res), y0 = round_cell(oy, a.res);
+    const bool start_in = (uint32_t)x0 < (uint32_t)a.W && (uint32_t)y0 < (uint32_t)a.H;
+    /* padded field: cell (x, y) lives at (y+1)*row + (x+1); entry 0 is a ring cell (d = 0),
+     * which makes an out-of-range start an immediate hit (the start cell is tested first) */
+    const int idx0 = start_in ? (y0 + 1) * row + (x0 + 1) * idx_scale : 0;
+    const bool dbg = DIAG && a.dbg_count > 0 && p >= a.dbg_first && p < a.dbg_first + a.dbg_count;
+
+    Ray r;
+    r.idx = 0; r.k = 0; r.j = 0; r.err = 0; r.dy = 0; r.ndx = 0; r.kmax = 0; r.stepA = 0; r.stepB = 0;
+    r.M = 0; r.sh = 0; r.d = 0; r.beam = 0;
+    int dg_a0 = 0, dg_b0 = 0, dg_xs = 0, dg_ys = 0, dg_steep = 0, dg_probes = 0; /* DIAG only */
+    bool active = false, pending = false;
+    float acc = 0.0f, prod = 1.0f;
+    int nextb = 0;
+
+    for (;;) {
+      /* ---- (1) lanes whose ray has ended score it: sensor.clj:149-162 beam mixture ---- */
+      if (pending) {
+        const bool hit = r.d == 0;
+        float rng;
+        if (hit) { /* sensor.clj:118-120: hypot(x - x0, y - y0) * resolution */
+          uint32_t d2 = (uint32_t)r.k * (uint32_t)r.k + (uint32_t)r.j * (uint32_t)r.j;
+          rng = __fmul_rn(__fsqrt_rn(__uint2float_rn(d2)), a.res);
+        } else { /* sensor.clj:121: max-range */
+          rng = a.miss_value;
         }
+        const int jb = r.beam;
+        float z = __ldg(obsp + jb) - rng;
+        float pz1 = a.z_hit * expf(-(z * z) * a.inv2s2);
+        float pz2 = z < 0.0f ? __ldg(e2p + jb) : 0.0f; /* pz2's exponential, pz3 + pz4 depend */
+        float sum = (pz1 + pz2) + __ldg(p34p + jb);    /* on the beam only: precomputed      */
+        if (a.s7) { /* sum of logs as the log of a running product, flushed before underflow */
+          prod *= sum;
+          if (!(prod >= 1.0e-25f)) { acc += logf(prod); prod = 1.0f; }
+        } else {
+          acc += (sum * sum) * sum; /* sensor.clj:162 (pow . 3) */
+        }
+        if (DIAG) {
+          int kk = hit ? r.k : r.kmax, jj = r.j;
+          n_rays++; n_cells += (unsigned)kk + 1u; n_probes += (unsigned)dg_probes; n_hits += hit ? 1u : 0u;
+          if (dbg) {
+            if (!hit) jj = r.ndx < 0 ? (int)((2ll * kk * r.dy - r.ndx) / (-2ll * r.ndx)) : 0;
+            int ca = dg_a0 + dg_xs * kk, cb2 = dg_b0 + dg_ys * jj;
+            int64_t o = (p - a.dbg_first) * nb + jb;
+            if (a.dbg_hit_x) a.dbg_hit_x[o] = dg_steep ? cb2 : ca;
+            if (a.dbg_hit_y) a.dbg_hit_y[o] = dg_steep ? ca : cb2;
+            if (a.dbg_steps) a.dbg_steps[o] = kk;
+            if (a.dbg_hit) a.dbg_hit[o] = (uint8_t)hit;
+            if (a.dbg_range) a.dbg_range[o] = rng;
+          }
+        }
+        pending = false;
       }
-    }
+      /* ---- (2) idle lanes pull the next beams: sensor.clj:130-139 map-range ------------- */
+      if (nextb < nb) {
+        const uint32_t idle = __ballot_sync(FULL, !active);
+        const int jb = nextb + __popc(idle & lt_mask);
+        if (!active && jb < nb) {
+          float cb = __ldg(cbp + jb), sb = __ldg(sbp + jb);
+          float c = cb, s = sb;
+          if (a.s1) { /* S1: theta + obs-bearing by the angle-addition identity */
+            c = fmaf(ct, cb, -(st * sb));
+            s = fmaf(st, cb, ct * sb);
+          }
+          /* sensor.clj:99-103 project-pose, map.clj:36-46 world->map */
+          int x1 = round_cell(fmaf(a.R, c, ox), a.res);
+          int y1 = round_cell(fmaf(a.R, s, oy), a.res);
+          int adx = abs(x1 - x0), ady = abs(y1 - y0);
+          bool steep = ady > adx; /* sensor.clj:87-91 */
+          int a0 = steep ? y0 : x0, b0 = steep ? x0 : y0;
+          int a1, b1;
+          if (steep) {
+            a1 = y1; b1 = x1;
+          } else if (a.s3) {
+            a1 = x1; b1 = y1;
+          } else { /* sensor.clj:138 `(if steep [y1 x1] [x0 y0])`: end = start */
+            a1 = a0; b1 = b0;
+          }
+          int xs = a0 < a1 ? 1 : -1, ys = b0 < b1 ? 1 : -1; /* sensor.clj:108-110, ties -> -1 */
+          int dx = abs(a0 - a1), dy = abs(b0 - b1);
+          /* the miss test runs AFTER the cell test at step k: S4=1 `x == max-x`;
+           * S4=0 (sensor.clj:121) `x > max-x` */
+          int kmax;
+          if (a.s4) kmax = dx;
+          else if (xs > 0) kmax = dx + 1;
+          else if (dx > 0) kmax = 0;
+          else { /* dx = dy = 0: `2*err >= 0` always holds -> diagonal walk to a blocked cell */
+            kmax = 0x3fffffff; dx = 1; dy = 1;
+          }
+          uint2 e = __ldg(a.divtab + min(dx, a.ndiv - 1)); /* dx < ndiv unless the start is out of range */
+          r.M = e.x; r.sh = e.y;
+          r.stepA = xs * (steep ? row : idx_scale);
+          r.stepB = ys * (steep ? idx_scale : row);
+          r.idx = idx0; r.k = 0; r.j = 0; r.err = 0;
+          r.ndx = -dx; r.dy = dy; r.kmax = kmax; r.beam = jb; r.d = 1;
+          if (DIAG) { dg_a0 = a0; dg_b0 = b0; dg_xs = xs; dg_ys = ys; dg_steep = steep; dg_probes = 0; }
+          active = true;
+        }
+        nextb += __popc(idle);
+      }
+      uint32_t act = __ballot_sync(FULL, active);
+      if (act == 0) break;
+      /* ---- (3) walk: sensor.clj:112-128 extract-line, d cells per probe ------------------ */
+      const int thresh = nextb < nb ? a.refill : 1;
+      do {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        for (int u = 0; u < 2; u++) {
+          /* branch-free: every lane probes (a parked lane re-reads its last cell), the
+           * advance is committed only where the ray is still walking */
+          const uint32_t d = df_probe<MODE>(df, r.idx);
+          if (DIAG) dg_probes += active ? 1 : 0;
+          const int k2 = r.k + (int)d;
+          const bool fin = d == 0 || k2 > r.kmax; /* blocked cell, or all cells to the end free */
+          const int e2 = r.err + (int)d * r.dy;
+          const uint32_t t = (uint32_t)(2 * e2 - r.ndx);
+          const uint32_t jd = WIDE ? (__umulhi(t, r.M) >> r.sh) : __umulhi(t, r.M);
+          const bool adv = active && !fin;
+          if (active) r.d = d;
+          pending = pending || (active && fin);
+          r.k = adv ? k2 : r.k;
+          r.err = adv ? e2 + (int)jd * r.ndx : r.err;
+          r.j = adv ? r.j + (int)jd : r.j;
+          r.idx = adv ? r.idx + (int)d * r.stepA + (int)jd * r.stepB : r.idx;
+          active = adv;
+        }
+        act = __ballot_sync(FULL, active);
+      } while (__popc(act) >= thresh);
+    }
+    if (a.s7) acc += logf(prod);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
     if (lane == 0 && a.raw) a.raw[p] = acc;
     wmax = fmaxf(wmax, acc);
   }
@@ -219,10 +264,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
   if (DIAG && a.stats) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      n_rays += __shfl_xor_sync(0xffffffffu, n_rays, o);
-      n_cells += __shfl_xor_sync(0xffffffffu, n_cells, o);
-      n_probes += __shfl_xor_sync(0xffffffffu, n_probes, o);
-      n_hits += __shfl_xor_sync(0xffffffffu, n_hits, o);
+      n_rays += __shfl_xor_sync(FULL, n_rays, o);
+      n_cells += __shfl_xor_sync(FULL, n_cells, o);
+      n_probes += __shfl_xor_sync(FULL, n_probes, o);
+      n_hits += __shfl_xor_sync(FULL, n_hits, o);
     }
     if (lane == 0) {
       atomicAdd(a.stats + 0, n_rays);
@@ -233,9 +278,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
   }
 }
 
-template <int MODE, bool DIAG>
+template <int MODE, bool DIAG, bool WIDE>
 static cudaError_t launch_t(const amclj_ctx *c, const SensorLaunch &a, cudaStream_t s) {
-  auto kern = sensor_kernel<MODE, DIAG>;
+  auto kern = sensor_kernel<MODE, DIAG, WIDE>;
   size_t smem = MODE == DF_SMEM4 ? a.df_bytes : 0;
   if (smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -252,13 +297,21 @@ static cudaError_t launch_t(const amclj_ctx *c, const SensorLaunch &a, cudaStrea
   return cudaGetLastError();
 }
 
+template <int MODE>
+static cudaError_t launch_m(const amclj_ctx *c, const SensorLaunch &a, bool diag, bool wide,
+                            cudaStream_t s) {
+  if (diag) return wide ? launch_t<MODE, true, true>(c, a, s) : launch_t<MODE, true, false>(c, a, s);
+  return wide ? launch_t<MODE, false, true>(c, a, s) : launch_t<MODE, false, false>(c, a, s);
+}
+
 cudaError_t launch_sensor(const amclj_ctx *c, const SensorLaunch &a, int mode, bool diag,
                           cudaStream_t s) {
   if (a.n <= 0 || a.nb <= 0) return cudaSuccess;
+  bool wide = a.div_wide != 0;
   switch (mode) {
-    case DF_SMEM4: return diag ? launch_t<DF_SMEM4, true>(c, a, s) : launch_t<DF_SMEM4, false>(c, a, s);
-    case DF_GLOBAL8: return diag ? launch_t<DF_GLOBAL8, true>(c, a, s) : launch_t<DF_GLOBAL8, false>(c, a, s);
-    default: return diag ? launch_t<DF_GLOBAL4, true>(c, a, s) : launch_t<DF_GLOBAL4, false>(c, a, s);
+    case DF_SMEM4: return launch_m<DF_SMEM4>(c, a, diag, wide, s);
+    case DF_GLOBAL8: return launch_m<DF_GLOBAL8>(c, a, diag, wide, s);
+    default: return launch_m<DF_GLOBAL4>(c, a, diag, wide, s);
   }
 }
 
