@@ -273,6 +273,7 @@ void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode) {
   a.ndiv = ctx->divs.n;
   a.div_wide = ctx->divs.wide;
   a.refill = ctx->refill;
+  a.chunks = 1;
   a.R = p.s2_use_scan_range_max ? ctx->beams.range_max : p.max_range;
   a.miss_value = a.R; /* sensor.clj:121 returns max-range on a miss */
   a.s1 = p.s1_use_heading;
@@ -317,6 +318,18 @@ int enqueue_sensor(amclj_ctx *ctx) {
   a.raw = ctx->raw;
   a.n = ctx->n;
   a.rawmax_ord = ctx->rawmax_ord;
+  a.chunks = ctx->force_chunks > 0 ? ctx->force_chunks : sensor_chunks(ctx, ctx->n, a.nb);
+  if (a.chunks > a.nb) a.chunks = a.nb;
+  if (a.chunks > 1) {
+    int64_t need = (int64_t)a.chunks * ctx->n;
+    if (need > ctx->partials_cap) {
+      CK(cudaStreamSynchronize(ctx->stream));
+      dfree(ctx->partials);
+      CK(dalloc(&ctx->partials, (size_t)need));
+      ctx->partials_cap = need;
+    }
+    a.partials = ctx->partials;
+  }
   bool diag = ctx->p.collect_stats != 0;
   a.stats = diag ? ctx->stats : nullptr;
   CK(cudaMemsetAsync(ctx->rawmax_ord, 0, sizeof(uint32_t), ctx->stream));
@@ -537,6 +550,7 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
     int v = atoi(e);
     if (v >= 1 && v <= 32) ctx->refill = v;
   }
+  if (const char *e = getenv("AMCLJ_CHUNKS")) ctx->force_chunks = atoi(e);
   memset(&ctx->st, 0, sizeof(ctx->st));
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ctx->stream = ctx->own_stream;
@@ -564,7 +578,7 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
   dfree(ctx->beams.dev); dfree(ctx->divs.dev);
   dfree(ctx->x); dfree(ctx->y); dfree(ctx->th); dfree(ctx->w); dfree(ctx->raw);
   dfree(ctx->x2); dfree(ctx->y2); dfree(ctx->th2); dfree(ctx->w2);
-  dfree(ctx->cdf); dfree(ctx->idx); dfree(ctx->normals);
+  dfree(ctx->cdf); dfree(ctx->idx); dfree(ctx->normals); dfree(ctx->partials);
   dfree(ctx->rawmax_ord); dfree(ctx->rawmax); dfree(ctx->total); dfree(ctx->stats);
   dfree(ctx->scan_state); dfree(ctx->scan_counter); dfree(ctx->pose_part); dfree(ctx->plan);
   dfree(ctx->stage_out); dfree(ctx->stage_in); dfree(ctx->stage_idx);

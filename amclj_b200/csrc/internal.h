@@ -55,7 +55,9 @@ struct SensorLaunch {
   const uint2 *divtab;
   int32_t ndiv;
   int32_t div_wide;  // 1: j-step = umulhi(t, M) >> sh; 0: shift-free (short rays)
-  int32_t refill;    // pull new beams when fewer lanes than this are still walking
+  int32_t refill;    // set up new beams when fewer lanes than this (of 32) are still walking
+  int32_t chunks;    // beam chunks per particle group (warp tasks = groups x chunks)
+  float *partials;   // [chunks][n] partial weights when chunks > 1
   float R;            // ray length (S2)
   float miss_value;
   int32_t s1, s3, s4, s7, s10;
@@ -99,6 +101,8 @@ struct amclj_ctx {
   uint64_t *cdf = nullptr;
   int32_t *idx = nullptr;       // last resample's source indices
   float *normals = nullptr;     // staged injected normals [n][3]
+  float *partials = nullptr;    // sensor chunk partials
+  int64_t partials_cap = 0;
   // scalars on the device
   uint32_t *rawmax_ord = nullptr;  // ordered-uint of max raw
   float *rawmax = nullptr;         // float[1] (AMCLJ_BUF_RAW_MAX)
@@ -122,7 +126,8 @@ struct amclj_ctx {
   float last_wmax = 0.f;
   uint64_t last_total = 0;
   amclj_stats st;
-  int32_t refill = 20;
+  int32_t refill = 10;
+  int32_t force_chunks = 0;
   void *pinned = nullptr;  // small pinned scratch for scalar readbacks
 };
 
@@ -131,6 +136,7 @@ namespace amclj {
 cudaError_t launch_sensor(const amclj_ctx *c, const SensorLaunch &a, int mode, bool diag,
                           cudaStream_t s);
 enum { DF_SMEM4 = 0, DF_GLOBAL8 = 1, DF_GLOBAL4 = 2 };
+int sensor_chunks(const amclj_ctx *c, int64_t n, int nb);
 
 // filter.cu
 struct GatherArgs {

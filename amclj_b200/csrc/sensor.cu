@@ -1,5 +1,5 @@
-// sensor.cu — K2: laser measurement model.  One warp per particle, lanes pull beams:
-// ray-cast through the occupancy grid and score with the beam mixture.
+// sensor.cu — K2: laser measurement model.  One lane per particle, walking that particle's
+// beams one after the other: ray-cast through the occupancy grid, score with the beam mixture.
 //
 // Replaces (jvia/amclj): pf.clj:148-154 apply-sensor-model ->
 //   sensor.clj:165-173 likelihood-field-range-finder-model -> :141-162 (beam loop, mixture)
@@ -16,10 +16,12 @@
 // with a per-ray magic reciprocal.  First blocked cell, step count and range are therefore
 // bit-identical to the cell-by-cell walk.
 //
-// Divergence: rays of one particle need 1..70 probes.  Lanes do not march in lock step over
-// rounds of 32 beams; a lane whose ray has ended parks its result, and when fewer than
-// `refill` lanes are still walking, the parked lanes score their ray and pull the next
-// beams (while-while persistent lanes).
+// Divergence: rays need 1..70 probes.  A warp task is 32 particles x a chunk of beams; every
+// lane owns one particle and walks its beams in order, so particles that sit close together
+// (pose tracking, resampled duplicates) run in lock step by themselves.  A lane whose ray has
+// ended parks; when fewer than `refill` lanes are still walking, the parked lanes score their
+// ray and set up their next beam together (while-while persistent lanes).  Each particle's
+// weight is accumulated by one lane in beam order: deterministic, no cross-lane reduction.
 #include "internal.h"
 
 namespace amclj {
@@ -33,36 +35,31 @@ __device__ __forceinline__ uint32_t ord_of_float(float f) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// One ray in flight.  idx4 = 4 * (nibble index) for the packed fields (so the nibble shift
-// is idx4 & 4 and the byte address idx4 >> 3), or the byte index for the byte field.
-struct Ray {
-  int idx, k, j, err;
-  int dy, ndx, kmax, stepA, stepB; /* ndx = -dx */
-  uint32_t M, sh, d;
-  int beam;
-};
-
 // The field is addressed either through a 32-bit shared-window address (MODE DF_SMEM4, so the
-// probe is one LDS with a register base) or through a global pointer.
+// probe is one LDS with a register base) or through a global pointer.  Index units: 4 per
+// nibble for the packed fields (nibble shift = idx & 4, byte address = idx >> 3), 1 per byte.
 struct Field {
   const uint8_t *g;
   uint32_t s;
 };
 
 template <int MODE>
-__device__ __forceinline__ uint32_t df_probe(const Field &f, int idx) {
-  if (MODE == DF_GLOBAL8) return __ldg(f.g + idx);
+__device__ __forceinline__ uint32_t df_probe(const Field &f, int idx, uint32_t mask) {
+  if (MODE == DF_GLOBAL8) return (uint32_t)__ldg(f.g + idx) & mask;
   uint32_t byte;
   if (MODE == DF_SMEM4) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(byte) : "r"(f.s + (uint32_t)(idx >> 3)));
   } else {
     byte = __ldg(f.g + (idx >> 3));
   }
-  return (byte >> (idx & 4)) & 15u;
+  return (byte >> (idx & 4)) & mask;
 }
 
 constexpr int kMaxThreads = 1024;
 constexpr uint32_t FULL = 0xffffffffu;
+#ifndef PROBES_PER_VOTE
+#define PROBES_PER_VOTE 3
+#endif
 
 template <int MODE, bool DIAG, bool WIDE>
 __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaunch a) {
@@ -106,19 +103,28 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
     df.s = smem_u32(sdf);
   }
   const int lane = threadIdx.x & 31;
-  const uint32_t lt_mask = (1u << lane) - 1u;
   const int wpb = blockDim.x >> 5;
   const int64_t nwarps = (int64_t)gridDim.x * wpb;
   const int nb = a.nb;
   const float *cbp = a.beam, *sbp = a.beam + nb, *obsp = a.beam + 2 * nb, *e2p = a.beam + 3 * nb,
               *p34p = a.beam + 4 * nb;
   const int idx_scale = MODE == DF_GLOBAL8 ? 1 : 4;
+  const uint32_t DMASK = MODE == DF_GLOBAL8 ? 255u : 15u;
   const int row = a.row_nib * idx_scale;
+  const int64_t ngroups = (a.n + 31) >> 5;
+  const int64_t ntasks = ngroups * a.chunks;
   float wmax = -INFINITY;
   unsigned long long n_cells = 0, n_probes = 0, n_hits = 0, n_rays = 0;
 
-  for (int64_t p = (int64_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x; p < a.n; p += nwarps) {
-    float ox = __ldg(a.x + p), oy = __ldg(a.y + p), th = __ldg(a.th + p);
+  /* task = 32 consecutive particles x one chunk of beams; chunk-major so that the warps of a
+   * CTA work on neighbouring particles */
+  for (int64_t task = (int64_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x; task < ntasks; task += nwarps) {
+    const int chunk = (int)(task / ngroups);
+    const int64_t p = (task - (int64_t)chunk * ngroups) * 32 + lane;
+    const bool valid = p < a.n;
+    const int b_lo = (int)((int64_t)nb * chunk / a.chunks), b_hi = (int)((int64_t)nb * (chunk + 1) / a.chunks);
+    float ox = 0.f, oy = 0.f, th = 0.f;
+    if (valid) { ox = __ldg(a.x + p); oy = __ldg(a.y + p); th = __ldg(a.th + p); }
     float st, ct;
     sincos_det(th, st, ct);
     if (a.s10) { /* S10: base->laser offset (sensor.clj:78-81), off by default */
@@ -131,59 +137,57 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
     /* padded field: cell (x, y) lives at (y+1)*row + (x+1); entry 0 is a ring cell (d = 0),
      * which makes an out-of-range start an immediate hit (the start cell is tested first) */
     const int idx0 = start_in ? (y0 + 1) * row + (x0 + 1) * idx_scale : 0;
-    const bool dbg = DIAG && a.dbg_count > 0 && p >= a.dbg_first && p < a.dbg_first + a.dbg_count;
+    const bool dbg = DIAG && a.dbg_count > 0 && valid && p >= a.dbg_first && p < a.dbg_first + a.dbg_count;
 
-    Ray r;
-    r.idx = 0; r.k = 0; r.j = 0; r.err = 0; r.dy = 0; r.ndx = 0; r.kmax = 0; r.stepA = 0; r.stepB = 0;
-    r.M = 0; r.sh = 0; r.d = 0; r.beam = 0;
+    /* the ray in flight; a parked lane (am == 0) turns every update below into a no-op */
+    int idx = 0, k = 0, j = 0, err = 0, dy = 0, ndx = 0, kmax = 0, stepA = 0, stepB = 0;
+    uint32_t M = 0, sh = 0, am = 0;
     int dg_a0 = 0, dg_b0 = 0, dg_xs = 0, dg_ys = 0, dg_steep = 0, dg_probes = 0; /* DIAG only */
-    bool active = false, pending = false;
+    bool have_ray = false;
     float acc = 0.0f, prod = 1.0f;
-    int nextb = 0;
+    int jb = valid ? b_lo : b_hi; /* this lane's current beam */
 
     for (;;) {
-      /* ---- (1) lanes whose ray has ended score it: sensor.clj:149-162 beam mixture ---- */
-      if (pending) {
-        const bool hit = r.d == 0;
-        float rng;
-        if (hit) { /* sensor.clj:118-120: hypot(x - x0, y - y0) * resolution */
-          uint32_t d2 = (uint32_t)r.k * (uint32_t)r.k + (uint32_t)r.j * (uint32_t)r.j;
-          rng = __fmul_rn(__fsqrt_rn(__uint2float_rn(d2)), a.res);
-        } else { /* sensor.clj:121: max-range */
-          rng = a.miss_value;
-        }
-        const int jb = r.beam;
-        float z = __ldg(obsp + jb) - rng;
-        float pz1 = a.z_hit * expf(-(z * z) * a.inv2s2);
-        float pz2 = z < 0.0f ? __ldg(e2p + jb) : 0.0f; /* pz2's exponential, pz3 + pz4 depend */
-        float sum = (pz1 + pz2) + __ldg(p34p + jb);    /* on the beam only: precomputed      */
-        if (a.s7) { /* sum of logs as the log of a running product, flushed before underflow */
-          prod *= sum;
-          if (!(prod >= 1.0e-25f)) { acc += logf(prod); prod = 1.0f; }
-        } else {
-          acc += (sum * sum) * sum; /* sensor.clj:162 (pow . 3) */
-        }
-        if (DIAG) {
-          int kk = hit ? r.k : r.kmax, jj = r.j;
-          n_rays++; n_cells += (unsigned)kk + 1u; n_probes += (unsigned)dg_probes; n_hits += hit ? 1u : 0u;
-          if (dbg) {
-            if (!hit) jj = r.ndx < 0 ? (int)((2ll * kk * r.dy - r.ndx) / (-2ll * r.ndx)) : 0;
-            int ca = dg_a0 + dg_xs * kk, cb2 = dg_b0 + dg_ys * jj;
-            int64_t o = (p - a.dbg_first) * nb + jb;
-            if (a.dbg_hit_x) a.dbg_hit_x[o] = dg_steep ? cb2 : ca;
-            if (a.dbg_hit_y) a.dbg_hit_y[o] = dg_steep ? ca : cb2;
-            if (a.dbg_steps) a.dbg_steps[o] = kk;
-            if (a.dbg_hit) a.dbg_hit[o] = (uint8_t)hit;
-            if (a.dbg_range) a.dbg_range[o] = rng;
+      if (am == 0) {
+        /* ---- (1) score the ray that has ended: sensor.clj:149-162 beam mixture ---------- */
+        if (have_ray) {
+          const bool hit = k <= kmax; /* a miss leaves k beyond the last cell to test */
+          float rng;
+          if (hit) { /* sensor.clj:118-120: hypot(x - x0, y - y0) * resolution */
+            uint32_t d2 = (uint32_t)k * (uint32_t)k + (uint32_t)j * (uint32_t)j;
+            rng = __fmul_rn(__fsqrt_rn(__uint2float_rn(d2)), a.res);
+          } else { /* sensor.clj:121: max-range */
+            rng = a.miss_value;
           }
+          float z = __ldg(obsp + jb) - rng;
+          float pz1 = a.z_hit * expf(-(z * z) * a.inv2s2);
+          float pz2 = z < 0.0f ? __ldg(e2p + jb) : 0.0f; /* pz2's exponential and pz3 + pz4 */
+          float sum = (pz1 + pz2) + __ldg(p34p + jb);    /* depend on the beam only         */
+          if (a.s7) { /* sum of logs as the log of a running product, flushed before underflow */
+            prod *= sum;
+            if (!(prod >= 1.0e-30f)) { acc += logf(prod); prod = 1.0f; }
+          } else {
+            acc += (sum * sum) * sum; /* sensor.clj:162 (pow . 3) */
+          }
+          if (DIAG) {
+            int kk = hit ? k : kmax, jj = j;
+            n_rays++; n_cells += (unsigned)kk + 1u; n_probes += (unsigned)dg_probes; n_hits += hit ? 1u : 0u;
+            if (dbg) {
+              if (!hit) jj = ndx < 0 ? (int)((2ll * kk * dy - ndx) / (-2ll * ndx)) : 0;
+              int ca = dg_a0 + dg_xs * kk, cb2 = dg_b0 + dg_ys * jj;
+              int64_t o = (p - a.dbg_first) * nb + jb;
+              if (a.dbg_hit_x) a.dbg_hit_x[o] = dg_steep ? cb2 : ca;
+              if (a.dbg_hit_y) a.dbg_hit_y[o] = dg_steep ? ca : cb2;
+              if (a.dbg_steps) a.dbg_steps[o] = kk;
+              if (a.dbg_hit) a.dbg_hit[o] = (uint8_t)hit;
+              if (a.dbg_range) a.dbg_range[o] = rng;
+            }
+          }
+          have_ray = false;
+          jb++;
         }
-        pending = false;
-      }
-      /* ---- (2) idle lanes pull the next beams: sensor.clj:130-139 map-range ------------- */
-      if (nextb < nb) {
-        const uint32_t idle = __ballot_sync(FULL, !active);
-        const int jb = nextb + __popc(idle & lt_mask);
-        if (!active && jb < nb) {
+        /* ---- (2) set up the next beam: sensor.clj:130-139 map-range -------------------- */
+        if (jb < b_hi) {
           float cb = __ldg(cbp + jb), sb = __ldg(sbp + jb);
           float c = cb, s = sb;
           if (a.s1) { /* S1: theta + obs-bearing by the angle-addition identity */
@@ -205,10 +209,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
             a1 = a0; b1 = b0;
           }
           int xs = a0 < a1 ? 1 : -1, ys = b0 < b1 ? 1 : -1; /* sensor.clj:108-110, ties -> -1 */
-          int dx = abs(a0 - a1), dy = abs(b0 - b1);
+          int dx = abs(a0 - a1);
+          dy = abs(b0 - b1);
           /* the miss test runs AFTER the cell test at step k: S4=1 `x == max-x`;
            * S4=0 (sensor.clj:121) `x > max-x` */
-          int kmax;
           if (a.s4) kmax = dx;
           else if (xs > 0) kmax = dx + 1;
           else if (dx > 0) kmax = 0;
@@ -216,51 +220,51 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
             kmax = 0x3fffffff; dx = 1; dy = 1;
           }
           uint2 e = __ldg(a.divtab + min(dx, a.ndiv - 1)); /* dx < ndiv unless the start is out of range */
-          r.M = e.x; r.sh = e.y;
-          r.stepA = xs * (steep ? row : idx_scale);
-          r.stepB = ys * (steep ? idx_scale : row);
-          r.idx = idx0; r.k = 0; r.j = 0; r.err = 0;
-          r.ndx = -dx; r.dy = dy; r.kmax = kmax; r.beam = jb; r.d = 1;
+          M = e.x; sh = e.y;
+          stepA = xs * (steep ? row : idx_scale);
+          stepB = ys * (steep ? idx_scale : row);
+          idx = idx0; k = 0; j = 0; err = 0; ndx = -dx;
           if (DIAG) { dg_a0 = a0; dg_b0 = b0; dg_xs = xs; dg_ys = ys; dg_steep = steep; dg_probes = 0; }
-          active = true;
+          have_ray = true;
+          am = DMASK;
         }
-        nextb += __popc(idle);
       }
-      uint32_t act = __ballot_sync(FULL, active);
+      uint32_t act = __ballot_sync(FULL, am != 0);
       if (act == 0) break;
+      /* lanes that will need another set-up later; when none does, walk to the end */
+      const uint32_t more = __ballot_sync(FULL, jb + 1 < b_hi);
+      const int thresh = more ? a.refill : 1;
       /* ---- (3) walk: sensor.clj:112-128 extract-line, d cells per probe ------------------ */
-      const int thresh = nextb < nb ? a.refill : 1;
       do {
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
-          /* branch-free: every lane probes (a parked lane re-reads its last cell), the
-           * advance is committed only where the ray is still walking */
-          const uint32_t d = df_probe<MODE>(df, r.idx);
-          if (DIAG) dg_probes += active ? 1 : 0;
-          const int k2 = r.k + (int)d;
-          const bool fin = d == 0 || k2 > r.kmax; /* blocked cell, or all cells to the end free */
-          const int e2 = r.err + (int)d * r.dy;
-          const uint32_t t = (uint32_t)(2 * e2 - r.ndx);
-          const uint32_t jd = WIDE ? (__umulhi(t, r.M) >> r.sh) : __umulhi(t, r.M);
-          const bool adv = active && !fin;
-          if (active) r.d = d;
-          pending = pending || (active && fin);
-          r.k = adv ? k2 : r.k;
-          r.err = adv ? e2 + (int)jd * r.ndx : r.err;
-          r.j = adv ? r.j + (int)jd : r.j;
-          r.idx = adv ? r.idx + (int)d * r.stepA + (int)jd * r.stepB : r.idx;
-          active = adv;
+        for (int u = 0; u < PROBES_PER_VOTE; u++) {
+          /* branch-free: a parked lane reads d = 0, which makes every update a no-op */
+          const uint32_t d = df_probe<MODE>(df, idx, am);
+          if (DIAG) dg_probes += am ? 1 : 0;
+          k += (int)d;
+          const bool fin = d == 0 || k > kmax; /* blocked cell, or every cell to the end is free */
+          const int e2 = err + (int)d * dy;
+          const uint32_t t = (uint32_t)(2 * e2 - ndx);
+          const uint32_t jd = WIDE ? (__umulhi(t, M) >> sh) : __umulhi(t, M);
+          err = e2 + (int)jd * ndx;
+          j += (int)jd;
+          idx += (int)d * stepA + (int)jd * stepB;
+          am = fin ? 0u : am;
         }
-        act = __ballot_sync(FULL, active);
+        act = __ballot_sync(FULL, am != 0);
       } while (__popc(act) >= thresh);
     }
     if (a.s7) acc += logf(prod);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-    if (lane == 0 && a.raw) a.raw[p] = acc;
-    wmax = fmaxf(wmax, acc);
+    if (valid) {
+      if (a.raw) a.raw[(int64_t)chunk * a.n + p] = acc; /* chunk partials are summed by the caller */
+      wmax = fmaxf(wmax, acc);
+    }
   }
-  if (lane == 0 && a.rawmax_ord && wmax > -INFINITY) atomicMax(a.rawmax_ord, ord_of_float(wmax));
+  if (a.rawmax_ord && a.chunks == 1) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(FULL, wmax, o));
+    if (lane == 0 && wmax > -INFINITY) atomicMax(a.rawmax_ord, ord_of_float(wmax));
+  }
   if (DIAG && a.stats) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -278,6 +282,22 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
   }
 }
 
+// raw[p] = sum over chunks of the partial weights (fixed order), plus the max for the normaliser
+__global__ void __launch_bounds__(256)
+combine_kernel(const float *__restrict__ part, int chunks, int64_t n, float *__restrict__ raw,
+               uint32_t *rawmax_ord) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float v = -INFINITY;
+  if (i < n) {
+    v = __ldg(part + i);
+    for (int c = 1; c < chunks; c++) v += __ldg(part + (int64_t)c * n + i);
+    raw[i] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+  if ((threadIdx.x & 31) == 0 && rawmax_ord && v > -INFINITY) atomicMax(rawmax_ord, ord_of_float(v));
+}
+
 template <int MODE, bool DIAG, bool WIDE>
 static cudaError_t launch_t(const amclj_ctx *c, const SensorLaunch &a, cudaStream_t s) {
   auto kern = sensor_kernel<MODE, DIAG, WIDE>;
@@ -287,9 +307,10 @@ static cudaError_t launch_t(const amclj_ctx *c, const SensorLaunch &a, cudaStrea
     if (e != cudaSuccess) return e;
   }
   /* one CTA per SM (the staged field owns the SM's shared memory); warps sized to the work */
-  int64_t want_warps = (a.n + c->sm_count - 1) / c->sm_count;
+  int64_t ntasks = ((a.n + 31) / 32) * a.chunks;
+  int64_t want_warps = (ntasks + c->sm_count - 1) / c->sm_count;
   int wpb = (int)(want_warps < 4 ? 4 : (want_warps > 32 ? 32 : want_warps));
-  int64_t blocks = (a.n + wpb - 1) / wpb;
+  int64_t blocks = (ntasks + wpb - 1) / wpb;
   int per_sm = MODE == DF_SMEM4 ? 1 : 2;
   if (blocks > (int64_t)c->sm_count * per_sm) blocks = (int64_t)c->sm_count * per_sm;
   if (blocks < 1) blocks = 1;
@@ -304,15 +325,38 @@ static cudaError_t launch_m(const amclj_ctx *c, const SensorLaunch &a, bool diag
   return wide ? launch_t<MODE, false, true>(c, a, s) : launch_t<MODE, false, false>(c, a, s);
 }
 
-cudaError_t launch_sensor(const amclj_ctx *c, const SensorLaunch &a, int mode, bool diag,
+/* beams of one particle group are split into `chunks` warp tasks when there are too few
+ * particles to give every resident warp a few tasks */
+int sensor_chunks(const amclj_ctx *c, int64_t n, int nb) {
+  int64_t groups = (n + 31) / 32;
+  int64_t slots = (int64_t)c->sm_count * 32;
+  int64_t want = (4 * slots + groups - 1) / groups;
+  int64_t cap = nb / 16 > 0 ? nb / 16 : 1;
+  if (want > cap) want = cap;
+  if (want > 16) want = 16;
+  return want < 1 ? 1 : (int)want;
+}
+
+cudaError_t launch_sensor(const amclj_ctx *c, const SensorLaunch &a_in, int mode, bool diag,
                           cudaStream_t s) {
-  if (a.n <= 0 || a.nb <= 0) return cudaSuccess;
+  if (a_in.n <= 0 || a_in.nb <= 0) return cudaSuccess;
+  SensorLaunch a = a_in;
   bool wide = a.div_wide != 0;
+  float *final_raw = a.raw;
+  if (a.chunks > 1) a.raw = a.partials; /* [chunks][n] */
+  cudaError_t e;
   switch (mode) {
-    case DF_SMEM4: return launch_m<DF_SMEM4>(c, a, diag, wide, s);
-    case DF_GLOBAL8: return launch_m<DF_GLOBAL8>(c, a, diag, wide, s);
-    default: return launch_m<DF_GLOBAL4>(c, a, diag, wide, s);
+    case DF_SMEM4: e = launch_m<DF_SMEM4>(c, a, diag, wide, s); break;
+    case DF_GLOBAL8: e = launch_m<DF_GLOBAL8>(c, a, diag, wide, s); break;
+    default: e = launch_m<DF_GLOBAL4>(c, a, diag, wide, s); break;
   }
+  if (e != cudaSuccess) return e;
+  if (a.chunks > 1 && final_raw) {
+    combine_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a.partials, a.chunks, a.n, final_raw,
+                                                                 a.rawmax_ord);
+    e = cudaGetLastError();
+  }
+  return e;
 }
 
 }  // namespace amclj
