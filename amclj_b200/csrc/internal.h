@@ -57,7 +57,7 @@ struct SensorLaunch {
   int32_t div_wide;  // 1: j-step = umulhi(t, M) >> sh; 0: shift-free (short rays)
   int32_t refill;    // set up new beams when fewer lanes than this (of 32) are still walking
   int32_t chunks;    // beam chunks per particle group (warp tasks = groups x chunks)
-  float *partials;   // [chunks][n] partial weights when chunks > 1
+  long long *partials;  // [chunks][n] fixed-point partial weights when chunks > 1
   float R;            // ray length (S2)
   float miss_value;
   int32_t s1, s3, s4, s7, s10;
@@ -101,7 +101,7 @@ struct amclj_ctx {
   uint64_t *cdf = nullptr;
   int32_t *idx = nullptr;       // last resample's source indices
   float *normals = nullptr;     // staged injected normals [n][3]
-  float *partials = nullptr;    // sensor chunk partials
+  long long *partials = nullptr;  // sensor chunk partials (32.32 fixed point)
   int64_t partials_cap = 0;
   // scalars on the device
   uint32_t *rawmax_ord = nullptr;  // ordered-uint of max raw

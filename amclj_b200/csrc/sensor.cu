@@ -57,6 +57,18 @@ __device__ __forceinline__ uint32_t df_probe(const Field &f, int idx, uint32_t m
 
 constexpr int kMaxThreads = 1024;
 constexpr uint32_t FULL = 0xffffffffu;
+// Beams are scored in fixed segments of SEG beams; a segment's value (log of the running
+// product, or the partial sum of cubes) is rounded once to 32.32 fixed point and segments are
+// added as integers, so a particle's weight does not depend on how its beams were split into
+// warp tasks (1 GPU with many particles vs 8 GPUs with few must agree bit for bit).
+constexpr int SEG = 30;
+constexpr float FIX_SCALE = 4294967296.0f, FIX_FLOOR = -1.0e6f;
+
+__device__ __forceinline__ float fixed_to_raw(long long q) {
+  if (q <= (long long)(FIX_FLOOR * FIX_SCALE)) return -INFINITY; /* a zero-probability beam */
+  return __ll2float_rn(q) * (1.0f / FIX_SCALE);
+}
+
 #ifndef PROBES_PER_VOTE
 #define PROBES_PER_VOTE 3
 #endif
@@ -122,7 +134,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
     const int chunk = (int)(task / ngroups);
     const int64_t p = (task - (int64_t)chunk * ngroups) * 32 + lane;
     const bool valid = p < a.n;
-    const int b_lo = (int)((int64_t)nb * chunk / a.chunks), b_hi = (int)((int64_t)nb * (chunk + 1) / a.chunks);
+    const int nseg = (nb + SEG - 1) / SEG;
+    const int b_lo = (int)((int64_t)nseg * chunk / a.chunks) * SEG;
+    const int b_hi = min(nb, (int)((int64_t)nseg * (chunk + 1) / a.chunks) * SEG);
     float ox = 0.f, oy = 0.f, th = 0.f;
     if (valid) { ox = __ldg(a.x + p); oy = __ldg(a.y + p); th = __ldg(a.th + p); }
     float st, ct;
@@ -145,7 +159,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
     int dg_a0 = 0, dg_b0 = 0, dg_xs = 0, dg_ys = 0, dg_steep = 0, dg_probes = 0; /* DIAG only */
     bool have_ray = false;
     float acc = 0.0f, prod = 1.0f;
+    long long qacc = 0;
     int jb = valid ? b_lo : b_hi; /* this lane's current beam */
+    int seg_end = min(b_lo + SEG, b_hi);
 
     for (;;) {
       if (am == 0) {
@@ -185,6 +201,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
           }
           have_ray = false;
           jb++;
+          if (jb == seg_end) { /* close the segment: one rounding to fixed point */
+            float v = a.s7 ? acc + logf(prod) : acc;
+            qacc += __float2ll_rn(fmaxf(v, FIX_FLOOR) * FIX_SCALE);
+            acc = 0.0f; prod = 1.0f;
+            seg_end = min(seg_end + SEG, b_hi);
+          }
         }
         /* ---- (2) set up the next beam: sensor.clj:130-139 map-range -------------------- */
         if (jb < b_hi) {
@@ -254,10 +276,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
         act = __ballot_sync(FULL, am != 0);
       } while (__popc(act) >= thresh);
     }
-    if (a.s7) acc += logf(prod);
     if (valid) {
-      if (a.raw) a.raw[(int64_t)chunk * a.n + p] = acc; /* chunk partials are summed by the caller */
-      wmax = fmaxf(wmax, acc);
+      if (a.chunks > 1) {
+        a.partials[(int64_t)chunk * a.n + p] = qacc; /* summed (as integers) by combine_kernel */
+      } else {
+        float v = fixed_to_raw(qacc);
+        if (a.raw) a.raw[p] = v;
+        wmax = fmaxf(wmax, v);
+      }
     }
   }
   if (a.rawmax_ord && a.chunks == 1) {
@@ -282,15 +308,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
   }
 }
 
-// raw[p] = sum over chunks of the partial weights (fixed order), plus the max for the normaliser
+// raw[p] = sum over chunks of the fixed-point partial weights, plus the max for the normaliser
 __global__ void __launch_bounds__(256)
-combine_kernel(const float *__restrict__ part, int chunks, int64_t n, float *__restrict__ raw,
+combine_kernel(const long long *__restrict__ part, int chunks, int64_t n, float *__restrict__ raw,
                uint32_t *rawmax_ord) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float v = -INFINITY;
   if (i < n) {
-    v = __ldg(part + i);
-    for (int c = 1; c < chunks; c++) v += __ldg(part + (int64_t)c * n + i);
+    long long q = __ldg(part + i);
+    for (int c = 1; c < chunks; c++) q += __ldg(part + (int64_t)c * n + i);
+    v = fixed_to_raw(q);
     raw[i] = v;
   }
 #pragma unroll
@@ -331,7 +358,7 @@ int sensor_chunks(const amclj_ctx *c, int64_t n, int nb) {
   int64_t groups = (n + 31) / 32;
   int64_t slots = (int64_t)c->sm_count * 32;
   int64_t want = (4 * slots + groups - 1) / groups;
-  int64_t cap = nb / 16 > 0 ? nb / 16 : 1;
+  int64_t cap = (nb + SEG - 1) / SEG; /* a task is at least one segment of beams */
   if (want > cap) want = cap;
   if (want > 16) want = 16;
   return want < 1 ? 1 : (int)want;
@@ -343,7 +370,9 @@ cudaError_t launch_sensor(const amclj_ctx *c, const SensorLaunch &a_in, int mode
   SensorLaunch a = a_in;
   bool wide = a.div_wide != 0;
   float *final_raw = a.raw;
-  if (a.chunks > 1) a.raw = a.partials; /* [chunks][n] */
+  int nseg = (a.nb + SEG - 1) / SEG;
+  if (a.chunks > nseg) a.chunks = nseg;
+  if (a.chunks < 1 || !a.partials) a.chunks = 1;
   cudaError_t e;
   switch (mode) {
     case DF_SMEM4: e = launch_m<DF_SMEM4>(c, a, diag, wide, s); break;

@@ -263,20 +263,22 @@ def run_b200(args):
         e2e = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "note": "sharded particle sets stay device-resident between updates; see the N=1 line for the host-buffer call"}
 
+    # ---- diagnostic pass for the cell / probe counters (untimed; every rank takes part in
+    # the collectives of the sharded update) -------------------------------------------
+    ctx.set_params(_lib.params("NS", collect_stats=1))
+    restore()
+    if filt:
+        filt.stage_scan(s)
+        with torch.cuda.stream(stream):
+            filt.update(w.curr, w.prev, seed=1, u0=w.u0)
+    else:
+        ctx.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max)
+        ctx.filter_update_async(w.curr, w.prev, 1, w.u0)
+    ctx.synchronize()
+    st = ctx.stats()
     line = None
     if rank == 0:
         # ---- roofline of the dominant kernel (sensor: ray-cast + beam mixture) ---------
-        # diagnostic pass for the cell / probe counters (untimed)
-        ctx.set_params(_lib.params("NS", collect_stats=1))
-        restore()
-        if filt:
-            filt.stage_scan(s)
-            filt.update(w.curr, w.prev, seed=1, u0=w.u0)
-        else:
-            ctx.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max)
-            ctx.filter_update_async(w.curr, w.prev, 1, w.u0)
-        ctx.synchronize()
-        st = ctx.stats()
         peak, peak_src = peaks()
         k_ms = float(np.mean(sensor_ms))
         # sensor stage = read x,y,theta (12 B) + write raw (4 B) per particle;

@@ -1,0 +1,96 @@
+"""Sharded update on ONE GPU: G contexts stand for G ranks and the three exchanges of
+amclj_b200/sharded.py (max, totals, row rebalance) are done by hand, so the kernels and the
+planner of the N > 1 path are checked by the single-GPU gpu tier.  (NCCL itself is exercised by
+tools/sharded_check.py under torchrun on a multi-GPU box, and the choreography by the gloo
+test.)  The global particle list must equal the single-context update bit for bit."""
+import numpy as np
+import pytest
+
+from amclj_b200 import _lib, maps, workloads
+from amclj_b200.sharded import slots_of
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("world,n", [(2, 20_000), (3, 10_001), (8, 64_000)])
+def test_sharded_equals_single(world, n):
+    import torch
+
+    g = maps.lgfloor()
+    w = workloads.c3(n)
+    s = w.scan
+    ref = _lib.Context(0, "NS")
+    ref.set_map(g)
+    ref.set_particles(w.x, w.y, w.theta)
+    shards = []
+    for r in range(world):
+        lo, cnt = slots_of(r, world, n)
+        c = _lib.Context(0, "NS")
+        c.set_map(g)
+        c.set_shard(r, world, lo, n)
+        c.set_particles(w.x[lo:lo + cnt], w.y[lo:lo + cnt], w.theta[lo:lo + cnt])
+        c.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max)
+        shards.append((c, lo, cnt))
+    for it in range(2):
+        ref.filter_update(w.curr, w.prev, s.ranges, s.angle_min, s.angle_inc, s.range_max, w.u0, seed=9 + it)
+        # 1. motion + sensor, all-reduce(max)
+        for c, _, _ in shards:
+            c.shard_motion_sensor_async(w.curr, w.prev, 9 + it)
+            c.synchronize()
+        mx = max(float(c.device_tensor(_lib.BUF_RAW_MAX, (1,), "<f4").cpu()[0]) for c, _, _ in shards)
+        totals = []
+        for c, _, _ in shards:
+            c.device_tensor(_lib.BUF_RAW_MAX, (1,), "<f4").fill_(mx)
+            torch.cuda.synchronize()
+            c.shard_cdf_async()
+            c.synchronize()
+            totals.append(int(c.device_tensor(_lib.BUF_TOTAL, (1,), "<i8").cpu()[0]))
+        # 2. plan from the all-gathered totals
+        tot = np.array(totals, np.int64).view(np.uint64)
+        r, off, m_lo, m_cnt, send = _lib.plan_systematic(tot, n, w.u0)
+        T = int(tot.sum(dtype=np.uint64))
+        # 3. generate + rebalance (all-to-all by hand)
+        outs = []
+        for (c, _, _), rk in zip(shards, range(world)):
+            cnt = int(m_cnt[rk])
+            c.reserve_stage(max(cnt, slots_of(rk, world, n)[1]))
+            c.shard_generate_async(T, int(off[rk]), r, int(m_lo[rk]), cnt)
+            c.synchronize()
+            outs.append(c.device_tensor(_lib.BUF_STAGE_OUT, (cnt, 4), "<f4").clone() if cnt else torch.empty(0, 4, device="cuda"))
+        for d, (c, lo, cnt) in enumerate(shards):
+            parts = []
+            for src in range(world):
+                a = int(send[src, :d].sum())
+                parts.append(outs[src][a:a + int(send[src, d])])
+            inbox = torch.cat(parts, 0)
+            assert inbox.shape[0] == cnt
+            c.device_tensor(_lib.BUF_STAGE_IN, (cnt, 4), "<f4").copy_(inbox)
+            torch.cuda.synchronize()
+            c.shard_adopt_async(cnt)
+            c.synchronize()
+    rx, ry, rt, rw = ref.get_particles()
+    got = [c.get_particles() for c, _, _ in shards]
+    for k, refv in enumerate((rx, ry, rt)):
+        assert np.array_equal(np.concatenate([g_[k] for g_ in got]), refv)
+    np.testing.assert_allclose(np.concatenate([g_[3] for g_ in got]), rw, rtol=1e-7)
+    for c, _, _ in shards:
+        c.close()
+    ref.close()
+
+
+def test_weights_do_not_depend_on_task_split(monkeypatch):
+    """The same particles give bit-identical raw weights whether a particle's beams run as one
+    warp task or are split into chunks (fixed-point segment sums)."""
+    g = maps.lgfloor()
+    w = workloads.c3(5000)
+    s = w.scan
+    out = []
+    for chunks in ("1", "3", "12"):
+        monkeypatch.setenv("AMCLJ_CHUNKS", chunks)
+        c = _lib.Context(0, "NS")
+        c.set_map(g)
+        c.set_particles(w.x, w.y, w.theta)
+        c.sensor_update(s.ranges, s.angle_min, s.angle_inc, s.range_max)
+        out.append(c.raw_weights())
+        c.close()
+    assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
