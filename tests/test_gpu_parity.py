@@ -363,3 +363,25 @@ def test_errors_are_loud(ctx):
         ctx.resample(_lib.RESAMPLE_SYSTEMATIC, 0.5)
     with pytest.raises(_lib.AmcljError):
         _lib.Context(99)
+
+
+def test_host_mirror_of_reference_api(lg, golden, fixture_scan):
+    """amclj_b200.pf keeps the reference's function names (pf.clj, sensor.clj, motion.clj); the
+    dev-fixture particle of sensor.clj:69-74 scores the survey's REF weight through it."""
+    from amclj_b200 import pf
+    scan = workloads.Scan(fixture_scan["ranges"], fixture_scan["angle_min"], fixture_scan["angle_inc"],
+                          fixture_scan["range_max"])
+    cloud = pf.ParticleCloud(0, "REF")
+    e = golden["sensor"][0]
+    wgt = pf.likelihood_field_range_finder_model(scan, (e["x"], e["y"], e["theta"]), lg, cloud)
+    assert wgt == pytest.approx(e["ref"]["weight"], rel=RTOL)
+    pf.initialize_pf(cloud, lg, 1500, pose=workloads.TRUE_POSE, seed=3)
+    assert len(cloud) == pf.NUM_PARTICLES
+    pf.apply_motion_model([(0.2, 0.0, 0.1), (0.0, 0.0, 0.0)], cloud, seed=4)
+    pf.apply_sensor_model(scan, lg, cloud)
+    assert np.isfinite(pf.weights(cloud)).all()
+    idx = pf.roulette_selection(cloud, seed=5)
+    assert len(idx) == 1500 and idx.min() >= 0 and idx.max() < 1500
+    est = pf.pose_estimate(cloud)
+    assert abs(est["position"]["x"] - workloads.TRUE_POSE[0]) < 1.0
+    cloud.close()
