@@ -188,26 +188,27 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
   NEED(rcells < 4.0e6, AMCLJ_ERR_INVALID, "scan: ray of %.0f cells is too long", rcells);
   int step = beam_step(n, p.s6_max_beams);
   int nb = beams_used(n, p.s6_max_beams);
-  std::vector<float> h((size_t)nb * 5);
-  float *cb = h.data(), *sb = cb + nb, *obs = sb + nb, *e2 = obs + nb, *p34 = e2 + nb;
+  std::vector<float> h((size_t)nb * 6);
+  float *dir = h.data(), *mix = dir + 2 * (size_t)nb; /* float2 (cb, sb) | float4 (obs, e2, p34, 0) */
   float zshort = p.z_short, lam = p.lambda_short;
   int j = 0;
   for (int i = 0; i < n; i += step, j++) {
     /* sensor.clj:93-97 bearing: float32 message fields, double arithmetic */
     double a = (double)angle_min + (double)i * (double)angle_inc;
-    cb[j] = (float)cos(a);
-    sb[j] = (float)sin(a);
+    dir[2 * j] = (float)cos(a);
+    dir[2 * j + 1] = (float)sin(a);
     float o = ranges ? ranges[i] : 0.0f;
-    obs[j] = o;
-    e2[j] = zshort * lam * expf(-lam * o);                     /* sensor.clj:154-157 */
+    mix[4 * j] = o;
+    mix[4 * j + 1] = zshort * lam * expf(-lam * o);            /* sensor.clj:154-157 */
     float pz3 = o == range_max ? p.z_max : 0.0f;               /* sensor.clj:158-159 */
     float pz4 = o < range_max ? p.z_rand / range_max : 0.0f;   /* sensor.clj:160-161 */
-    p34[j] = pz3 + pz4;
+    mix[4 * j + 2] = pz3 + pz4;
+    mix[4 * j + 3] = 0.0f;
   }
   BeamTable &b = ctx->beams;
   if (nb > b.cap) {
     dfree(b.dev);
-    CK(dalloc(&b.dev, (size_t)nb * 5));
+    CK(dalloc(&b.dev, (size_t)nb * 6));
     b.cap = nb;
   }
   CK(cudaMemcpyAsync(b.dev, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice, ctx->stream));

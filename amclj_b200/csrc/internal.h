@@ -27,7 +27,7 @@ struct DeviceMap {
   bool fits_smem = false;
 };
 
-struct BeamTable {       // one float array of 5*nb: cb | sb | obs | e2 | p34
+struct BeamTable {       // float2 dir[nb] = (cb, sb) then float4 mix[nb] = (obs, e2, p34, 0)
   float *dev = nullptr;
   int32_t nb = 0, cap = 0;
   int32_t n_scan = 0;
@@ -52,7 +52,8 @@ struct SensorLaunch {
   float res;
   const float *beam;
   int32_t nb;
-  const uint2 *divtab;
+  const uint2 *divtab;   // (M, shift) per dx
+  int32_t tab_smem;      // 1: beam and reciprocal tables are staged into shared memory
   int32_t ndiv;
   int32_t div_wide;  // 1: j-step = umulhi(t, M) >> sh; 0: shift-free (short rays)
   int32_t refill;    // set up new beams when fewer lanes than this (of 32) are still walking
@@ -126,7 +127,7 @@ struct amclj_ctx {
   float last_wmax = 0.f;
   uint64_t last_total = 0;
   amclj_stats st;
-  int32_t refill = 10;
+  int32_t refill = 8;
   int32_t force_chunks = 0;
   void *pinned = nullptr;  // small pinned scratch for scalar readbacks
 };

@@ -55,6 +55,38 @@ __device__ __forceinline__ uint32_t df_probe(const Field &f, int idx, uint32_t m
   return (byte >> (idx & 4)) & mask;
 }
 
+// Beam tables: dir[jb] = (cos, sin) of the beam, mix[jb] = (obs, e2, p34, 0), and the magic
+// reciprocal per dx; staged into shared memory behind the field when they fit.
+struct Tables {
+  const float2 *dir;
+  const float4 *mix;
+  const uint2 *div;
+  uint32_t s_dir, s_mix, s_div;
+};
+template <bool TS>
+__device__ __forceinline__ float2 ld_dir(const Tables &t, int jb) {
+  if (!TS) return __ldg(t.dir + jb);
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(t.s_dir + (uint32_t)jb * 8u));
+  return v;
+}
+template <bool TS>
+__device__ __forceinline__ float4 ld_mix(const Tables &t, int jb) {
+  if (!TS) return __ldg(t.mix + jb);
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(t.s_mix + (uint32_t)jb * 16u));
+  return v;
+}
+template <bool TS>
+__device__ __forceinline__ uint2 ld_div(const Tables &t, int dx) {
+  if (!TS) return __ldg(t.div + dx);
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(t.s_div + (uint32_t)dx * 8u));
+  return v;
+}
+
 constexpr int kMaxThreads = 1024;
 constexpr uint32_t FULL = 0xffffffffu;
 // Beams are scored in fixed segments of SEG beams; a segment's value (log of the running
@@ -69,11 +101,40 @@ __device__ __forceinline__ float fixed_to_raw(long long q) {
   return __ll2float_rn(q) * (1.0f / FIX_SCALE);
 }
 
+// round(v / res) of map.clj:36-46 with the reciprocal hoisted out of the loop: q0 = v*r,
+// e = fma(-q0, res, v), q = fma(e, r, q0) with r = rcp(res) refined by one Newton step is the
+// compiler's own correctly-rounded fast path of an IEEE divide (what `v / res` emits for every
+// operand that passes its range check); operands outside a wide safe range take the real divide.
+struct ResDiv {
+  float res, r;
+  bool fast;
+};
+__device__ __forceinline__ ResDiv make_resdiv(float res) {
+  ResDiv d;
+  d.res = res;
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(res));
+  float e = fmaf(-res, r0, 1.0f);
+  d.r = fmaf(r0, e, r0);
+  d.fast = res > 1.0e-6f && res < 1.0e6f;
+  return d;
+}
+__device__ __forceinline__ int32_t round_cell_fast(float v, const ResDiv &d) {
+  float q0 = v * d.r;
+  float e = fmaf(-q0, d.res, v);
+  float q = fmaf(e, d.r, q0);
+  float a = fabsf(v);
+  if (!(d.fast && a < 1.0e18f && (a > 1.0e-18f || v == 0.0f))) q = v / d.res; /* rare: the real IEEE divide */
+  float t = floorf(q + 0.5f);
+  t = fminf(fmaxf(t, -1.0e9f), 1.0e9f); /* NaN -> -1e9 */
+  return (int32_t)t;
+}
+
 #ifndef PROBES_PER_VOTE
 #define PROBES_PER_VOTE 3
 #endif
 
-template <int MODE, bool DIAG, bool WIDE>
+template <int MODE, bool DIAG, bool WIDE, bool TS>
 __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaunch a) {
   extern __shared__ uint4 smem_dyn[];
   __shared__ uint64_t bar;
@@ -114,12 +175,27 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
     }
     df.s = smem_u32(sdf);
   }
+  Tables tb;
+  tb.dir = reinterpret_cast<const float2 *>(a.beam);
+  tb.mix = reinterpret_cast<const float4 *>(a.beam + 2 * (size_t)a.nb);
+  tb.div = a.divtab;
+  tb.s_dir = tb.s_mix = tb.s_div = 0;
+  if (TS) {
+    /* [field | mix float4[nb] | dir float2[nb] | div uint2[ndiv]] */
+    uint8_t *base = reinterpret_cast<uint8_t *>(smem_dyn) + (MODE == DF_SMEM4 ? a.df_bytes : 0);
+    float4 *smix = reinterpret_cast<float4 *>(base);
+    float2 *sdir = reinterpret_cast<float2 *>(smix + a.nb);
+    uint2 *sdiv = reinterpret_cast<uint2 *>(sdir + a.nb);
+    for (int i = threadIdx.x; i < a.nb; i += blockDim.x) { smix[i] = __ldg(tb.mix + i); sdir[i] = __ldg(tb.dir + i); }
+    for (int i = threadIdx.x; i < a.ndiv; i += blockDim.x) sdiv[i] = __ldg(tb.div + i);
+    tb.s_mix = smem_u32(smix); tb.s_dir = smem_u32(sdir); tb.s_div = smem_u32(sdiv);
+    __syncthreads();
+  }
+  const ResDiv rdv = make_resdiv(a.res);
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int64_t nwarps = (int64_t)gridDim.x * wpb;
   const int nb = a.nb;
-  const float *cbp = a.beam, *sbp = a.beam + nb, *obsp = a.beam + 2 * nb, *e2p = a.beam + 3 * nb,
-              *p34p = a.beam + 4 * nb;
   const int idx_scale = MODE == DF_GLOBAL8 ? 1 : 4;
   const uint32_t DMASK = MODE == DF_GLOBAL8 ? 255u : 15u;
   const int row = a.row_nib * idx_scale;
@@ -146,7 +222,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
       float ny = oy + fmaf(a.laser_x, st, a.laser_y * ct);
       ox = nx; oy = ny;
     }
-    const int x0 = round_cell(ox, a.res), y0 = round_cell(oy, a.res);
+    const int x0 = round_cell_fast(ox, rdv), y0 = round_cell_fast(oy, rdv);
     const bool start_in = (uint32_t)x0 < (uint32_t)a.W && (uint32_t)y0 < (uint32_t)a.H;
     /* padded field: cell (x, y) lives at (y+1)*row + (x+1); entry 0 is a ring cell (d = 0),
      * which makes an out-of-range start an immediate hit (the start cell is tested first) */
@@ -175,10 +251,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
           } else { /* sensor.clj:121: max-range */
             rng = a.miss_value;
           }
-          float z = __ldg(obsp + jb) - rng;
+          const float4 mx = ld_mix<TS>(tb, jb); /* obs, pz2's exponential, pz3 + pz4: beam-only terms */
+          float z = mx.x - rng;
           float pz1 = a.z_hit * expf(-(z * z) * a.inv2s2);
-          float pz2 = z < 0.0f ? __ldg(e2p + jb) : 0.0f; /* pz2's exponential and pz3 + pz4 */
-          float sum = (pz1 + pz2) + __ldg(p34p + jb);    /* depend on the beam only         */
+          float pz2 = z < 0.0f ? mx.y : 0.0f;
+          float sum = (pz1 + pz2) + mx.z;
           if (a.s7) { /* sum of logs as the log of a running product, flushed before underflow */
             prod *= sum;
             if (!(prod >= 1.0e-30f)) { acc += logf(prod); prod = 1.0f; }
@@ -210,15 +287,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
         }
         /* ---- (2) set up the next beam: sensor.clj:130-139 map-range -------------------- */
         if (jb < b_hi) {
-          float cb = __ldg(cbp + jb), sb = __ldg(sbp + jb);
+          const float2 bd = ld_dir<TS>(tb, jb);
+          float cb = bd.x, sb = bd.y;
           float c = cb, s = sb;
           if (a.s1) { /* S1: theta + obs-bearing by the angle-addition identity */
             c = fmaf(ct, cb, -(st * sb));
             s = fmaf(st, cb, ct * sb);
           }
           /* sensor.clj:99-103 project-pose, map.clj:36-46 world->map */
-          int x1 = round_cell(fmaf(a.R, c, ox), a.res);
-          int y1 = round_cell(fmaf(a.R, s, oy), a.res);
+          int x1 = round_cell_fast(fmaf(a.R, c, ox), rdv);
+          int y1 = round_cell_fast(fmaf(a.R, s, oy), rdv);
           int adx = abs(x1 - x0), ady = abs(y1 - y0);
           bool steep = ady > adx; /* sensor.clj:87-91 */
           int a0 = steep ? y0 : x0, b0 = steep ? x0 : y0;
@@ -241,7 +319,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
           else { /* dx = dy = 0: `2*err >= 0` always holds -> diagonal walk to a blocked cell */
             kmax = 0x3fffffff; dx = 1; dy = 1;
           }
-          uint2 e = __ldg(a.divtab + min(dx, a.ndiv - 1)); /* dx < ndiv unless the start is out of range */
+          uint2 e = ld_div<TS>(tb, min(dx, a.ndiv - 1)); /* dx < ndiv unless the start is out of range */
           M = e.x; sh = e.y;
           stepA = xs * (steep ? row : idx_scale);
           stepB = ys * (steep ? idx_scale : row);
@@ -325,10 +403,12 @@ combine_kernel(const long long *__restrict__ part, int chunks, int64_t n, float 
   if ((threadIdx.x & 31) == 0 && rawmax_ord && v > -INFINITY) atomicMax(rawmax_ord, ord_of_float(v));
 }
 
-template <int MODE, bool DIAG, bool WIDE>
+static size_t table_bytes(const SensorLaunch &a) { return (size_t)a.nb * 24 + (size_t)a.ndiv * 8; }
+
+template <int MODE, bool DIAG, bool WIDE, bool TS>
 static cudaError_t launch_t(const amclj_ctx *c, const SensorLaunch &a, cudaStream_t s) {
-  auto kern = sensor_kernel<MODE, DIAG, WIDE>;
-  size_t smem = MODE == DF_SMEM4 ? a.df_bytes : 0;
+  auto kern = sensor_kernel<MODE, DIAG, WIDE, TS>;
+  size_t smem = (MODE == DF_SMEM4 ? a.df_bytes : 0) + (TS ? table_bytes(a) : 0);
   if (smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -345,11 +425,19 @@ static cudaError_t launch_t(const amclj_ctx *c, const SensorLaunch &a, cudaStrea
   return cudaGetLastError();
 }
 
+template <int MODE, bool TS>
+static cudaError_t launch_w(const amclj_ctx *c, const SensorLaunch &a, bool diag, bool wide,
+                            cudaStream_t s) {
+  if (diag) return wide ? launch_t<MODE, true, true, TS>(c, a, s) : launch_t<MODE, true, false, TS>(c, a, s);
+  return wide ? launch_t<MODE, false, true, TS>(c, a, s) : launch_t<MODE, false, false, TS>(c, a, s);
+}
 template <int MODE>
 static cudaError_t launch_m(const amclj_ctx *c, const SensorLaunch &a, bool diag, bool wide,
                             cudaStream_t s) {
-  if (diag) return wide ? launch_t<MODE, true, true>(c, a, s) : launch_t<MODE, true, false>(c, a, s);
-  return wide ? launch_t<MODE, false, true>(c, a, s) : launch_t<MODE, false, false>(c, a, s);
+  /* tables ride in shared memory behind the field when the SM has room for them */
+  size_t need = (MODE == DF_SMEM4 ? a.df_bytes : 0) + table_bytes(a) + 64;
+  bool ts = need <= (size_t)c->max_smem_optin;
+  return ts ? launch_w<MODE, true>(c, a, diag, wide, s) : launch_w<MODE, false>(c, a, diag, wide, s);
 }
 
 /* beams of one particle group are split into `chunks` warp tasks when there are too few

@@ -385,3 +385,52 @@ def test_host_mirror_of_reference_api(lg, golden, fixture_scan):
     est = pf.pose_estimate(cloud)
     assert abs(est["position"]["x"] - workloads.TRUE_POSE[0]) < 1.0
     cloud.close()
+
+
+def test_c5_large_map_global_field():
+    """BASELINE config C5 shape: synthetic 8192 x 8192 grid (field too large for shared memory
+    -> byte field through L2), 1080-beam 270-degree scan, 30 m rays (600 cells).  Full GPU pass
+    on 20k particles; oracle on a sample: rays bit-exact, weights 1e-5."""
+    w = workloads.c5(20_000)
+    s = w.scan
+    pl, po = _pair("NS")
+    c = _lib.Context(0)
+    c.set_params(pl)
+    c.set_map(w.grid)
+    c.set_particles(w.x, w.y, w.theta)
+    dbg = c.raycast_debug(len(s.ranges), s.angle_min, s.angle_inc, s.range_max, 0, 64)
+    _, _, ref = oracle.sensor_f32(po, w.grid, s.ranges, s.angle_min, s.angle_inc, s.range_max,
+                                  w.x[:64], w.y[:64], w.theta[:64], debug=True, want_raw=False)
+    for k in ("hit", "hit_x", "hit_y", "steps", "range_m"):
+        assert np.array_equal(dbg[k], ref[k]), k
+    assert c.stats().map_in_smem == 0
+    c.sensor_update(s.ranges, s.angle_min, s.angle_inc, s.range_max)
+    raw = c.raw_weights()
+    sel = np.arange(0, w.n, 97)
+    rraw, _, _ = oracle.sensor_f32(po, w.grid, s.ranges, s.angle_min, s.angle_inc, s.range_max,
+                                   w.x[sel], w.y[sel], w.theta[sel])
+    np.testing.assert_allclose(raw[sel], rraw, rtol=RTOL)
+    c.close()
+
+
+def test_round_trip_properties_c3_size():
+    """Size-independent properties at BASELINE size C3 (1M particles): systematic indices are
+    non-decreasing, every source index is valid, the offspring count of a particle is within 1 of
+    N * w_i / sum(w), and resampling twice with the same u0 from the same weights is idempotent."""
+    n = 1_000_000
+    w = _weights(n, 21)
+    x = np.arange(n, dtype=np.float32)
+    c = _lib.Context(0, "NS")
+    c.set_particles(x, x, x, w)
+    total, wmax = c.normalize(from_raw=False)
+    idx = c.resample(_lib.RESAMPLE_SYSTEMATIC, 0.123456)
+    assert (np.diff(idx) >= 0).all() and idx[0] >= 0 and idx[-1] < n
+    counts = np.bincount(idx, minlength=n)
+    q, t2 = oracle.fixed_weights(w, oracle.wmax(w))
+    assert total == t2
+    expect = q.astype(np.float64) * n / float(total)
+    assert np.all(np.abs(counts - expect) <= 1.0 + 1e-9)
+    c.set_particles(x, x, x, w)
+    idx2 = c.resample(_lib.RESAMPLE_SYSTEMATIC, 0.123456)
+    assert np.array_equal(idx, idx2)
+    c.close()
