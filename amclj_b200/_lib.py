@@ -14,7 +14,10 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libamclj_b200.so"
+import os as _os
+
+# AMCLJ_LIB: load a differently-built copy of the library (kernel tuning experiments only)
+LIB_PATH = Path(_os.environ["AMCLJ_LIB"]) if _os.environ.get("AMCLJ_LIB") else _HERE / "libamclj_b200.so"
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM, ERR_NODEVICE = 0, -1, -2, -3, -4, -5
 PRESET_REF, PRESET_NS = 0, 1
@@ -30,7 +33,7 @@ SYMBOLS = [
     "amclj_motion_update", "amclj_sensor_update", "amclj_get_raw_weights", "amclj_raycast_debug",
     "amclj_beams_used", "amclj_normalize", "amclj_resample", "amclj_get_resample_indices",
     "amclj_filter_update", "amclj_stage_scan", "amclj_filter_update_async",
-    "amclj_filter_update_host", "amclj_pose_estimate", "amclj_get_stats",
+    "amclj_filter_update_host", "amclj_pose_estimate", "amclj_get_stats", "amclj_microbench",
     "amclj_shard_motion_sensor_async", "amclj_shard_cdf_async", "amclj_shard_generate_async",
     "amclj_shard_get_stage_idx", "amclj_shard_adopt_async", "amclj_plan_systematic",
     "amclj_device_ptr", "amclj_reserve_stage",
@@ -127,6 +130,7 @@ def lib():
                                       f32, f64], i32),
         "amclj_pose_estimate": ([vp, d3], i32),
         "amclj_get_stats": ([vp, C.POINTER(Stats)], i32),
+        "amclj_microbench": ([vp, i32, C.POINTER(f64)], i32),
         "amclj_shard_motion_sensor_async": ([vp, d3, d3, u64], i32),
         "amclj_shard_cdf_async": ([vp], i32),
         "amclj_shard_generate_async": ([vp, u64, u64, u64, i64, i64], i32),
@@ -354,6 +358,12 @@ class Context:
         s = Stats()
         self._ck(self._L.amclj_get_stats(self._h, C.byref(s)))
         return s
+
+    def microbench(self, which=0):
+        """Dependent-lookup ceiling (lookups/s): 0 = shared-memory nibble table, 1 = L2 byte table."""
+        v = C.c_double()
+        self._ck(self._L.amclj_microbench(self._h, int(which), C.byref(v)))
+        return float(v.value)
 
     # -- sharded building blocks ---------------------------------------------------------
     def shard_motion_sensor_async(self, curr, prev, seed):

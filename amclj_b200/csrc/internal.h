@@ -127,7 +127,7 @@ struct amclj_ctx {
   float last_wmax = 0.f;
   uint64_t last_total = 0;
   amclj_stats st;
-  int32_t refill = 8;
+  int32_t refill = 6;
   int32_t force_chunks = 0;
   void *pinned = nullptr;  // small pinned scratch for scalar readbacks
 };

@@ -131,7 +131,7 @@ __device__ __forceinline__ int32_t round_cell_fast(float v, const ResDiv &d) {
 }
 
 #ifndef PROBES_PER_VOTE
-#define PROBES_PER_VOTE 3
+#define PROBES_PER_VOTE 8
 #endif
 
 template <int MODE, bool DIAG, bool WIDE, bool TS>

@@ -292,12 +292,20 @@ def run_b200(args):
         sm_count = props.multi_processor_count
         sm_hz = 1e6 * float((clocks.summary().get("sm_mhz") or 1965))
         k_ms = float(np.mean(sensor_ms))
+        # measured ceiling of dependent distance-field lookups on this GPU (same placement as the map)
+        lookup_peak = ctx.microbench(0 if st.map_in_smem else 1)
+        traffic = None
+        tfile = ROOT / "profiles" / "sensor_traffic.json"
+        if tfile.exists():  # dram bytes per launch from the committed ncu --set full capture of this workload
+            t = json.loads(tfile.read_text())
+            if t.get("workload") == w.name and world == 1:
+                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
         # sensor stage = read x,y,theta (12 B) + write raw (4 B) per particle;
         # the map is staged once per CTA from L2 (not HBM after the first CTA)
         alg_bytes = 16.0 * w.n
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "kernel": "amclj::sensor_kernel",
+                    "traffic": traffic, "peak_source": peak_src, "kernel": "amclj::sensor_kernel",
                     "kernel_ms": k_ms, "kernel_share_of_step": k_ms / float(np.mean(total_ms_lib)),
                     "algorithmic_bytes_per_launch": alg_bytes,
                     "note": "HBM is not what binds this kernel (16 B/particle): it is issue / shared-memory-latency bound; see onchip",
@@ -308,11 +316,17 @@ def run_b200(args):
                                "probes_per_ray": st.probes / max(st.rays, 1),
                                "hit_fraction": st.hits / max(st.rays, 1),
                                "map_in_smem": int(st.map_in_smem),
+                               "lookup_peak_per_s": lookup_peak,
+                               "lookup_frac": (st.probes / (k_ms * 1e-3)) / lookup_peak,
+                               "lookup_peak_source": "amclj_microbench: dependent lookups, all SMs x 32 warps, "
+                                                     + ("128 KiB nibble table in shared memory" if st.map_in_smem
+                                                        else "64 MiB byte table in L2"),
+                               "issue_peak_warp_inst_per_s": sm_count * 4 * sm_hz,
                                "scheduler_cycles_per_ray": (k_ms * 1e-3) * sm_count * 4 * sm_hz / max(st.rays, 1),
                                "note": "scheduler_cycles_per_ray = kernel time x SMs x 4 schedulers x SM clock / rays: "
                                        "the issue-slot budget each ray consumed (ncu: ~80% of them issue an instruction)"}}
         cpu = None
-        if world == 1:
+        if world == 1 and not args.quick:
             from amclj_b200 import workloads as wl
             import oracle
             oracle.build()
@@ -347,6 +361,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--cpu-sample", type=int, default=100_000)
+    ap.add_argument("--quick", action="store_true", help="skip the CPU baseline leg (tuning sweeps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
