@@ -121,11 +121,7 @@ int ensure_particles(amclj_ctx *ctx, int64_t n) {
   CK(dalloc(&ctx->idx, (size_t)cap));
   dfree(ctx->normals);
   CK(dalloc(&ctx->normals, (size_t)cap * 3));
-  int64_t tiles = scan_tiles(cap) + 1;
-  if (tiles < (1 << 16)) tiles = 1 << 16; /* also serves the roulette compaction */
-  dfree(ctx->scan_state);
-  CK(dalloc(&ctx->scan_state, (size_t)tiles));
-  ctx->scan_state_cap = tiles;
+  NEED(scan_tiles(cap) <= ctx->scan_state_cap, AMCLJ_ERR_INVALID, "too many particles for one ctx");
   ctx->cap = cap;
   ctx->have_cdf = false;
   return AMCLJ_OK;
@@ -306,7 +302,16 @@ int enqueue_motion(amclj_ctx *ctx, const double curr[3], const double prev[3], b
   return AMCLJ_OK;
 }
 
-int enqueue_sensor(amclj_ctx *ctx) {
+/* clear the control block: everything (with_max) or only what the scan accumulates into */
+cudaError_t reset_ctrl(amclj_ctx *ctx, bool with_max) {
+  size_t words = (size_t)scan_tiles(ctx->n) + 2;
+  ctx->scan_clean = true;
+  if (with_max) return cudaMemsetAsync(ctx->ctrl, 0, sizeof(uint64_t) * (words + 1), ctx->stream);
+  return cudaMemsetAsync(ctx->ctrl + 1, 0, sizeof(uint64_t) * words, ctx->stream);
+}
+
+/* decode_max: also materialise the max as a float (AMCLJ_BUF_RAW_MAX) for a cross-rank all-reduce */
+int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
   NEED(ctx->beams.staged, AMCLJ_ERR_STATE, "sensor: no scan staged");
   NEED(ctx->n > 0, AMCLJ_ERR_STATE, "sensor: no particles");
   int mode = df_mode_of(ctx);
@@ -333,10 +338,11 @@ int enqueue_sensor(amclj_ctx *ctx) {
   }
   bool diag = ctx->p.collect_stats != 0;
   a.stats = diag ? ctx->stats : nullptr;
-  CK(cudaMemsetAsync(ctx->rawmax_ord, 0, sizeof(uint32_t), ctx->stream));
+  CK(reset_ctrl(ctx, true));
   if (diag) CK(cudaMemsetAsync(ctx->stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
   CK(launch_sensor(ctx, a, mode, diag, ctx->stream));
-  CK(launch_decode_max(ctx->rawmax_ord, ctx->rawmax, ctx->stream));
+  if (decode_max) CK(launch_decode_max(ctx->rawmax_ord, ctx->rawmax, ctx->stream));
+  ctx->max_in_ord = !decode_max;
   ctx->have_raw = true;
   ctx->have_cdf = false;
   ctx->st.map_in_smem = mode == DF_SMEM4;
@@ -349,9 +355,14 @@ int enqueue_sensor(amclj_ctx *ctx) {
 int enqueue_cdf(amclj_ctx *ctx, bool from_raw, bool max_known) {
   const float *v = from_raw ? ctx->raw : ctx->w;
   int is_log = from_raw && ctx->p.s7_log_weights;
-  if (!max_known) CK(launch_max(v, ctx->n, ctx->rawmax_ord, ctx->rawmax, ctx->sm_count, ctx->stream));
-  CK(launch_scan(v, ctx->rawmax, is_log, ctx->n, ctx->cdf, ctx->scan_state, ctx->scan_counter,
-                 ctx->total, ctx->stream));
+  if (!max_known) { /* launch_max clears and refills the max (ordered uint and float) */
+    CK(launch_max(v, ctx->n, ctx->rawmax_ord, ctx->rawmax, ctx->sm_count, ctx->stream));
+    ctx->max_in_ord = false;
+  }
+  if (!ctx->scan_clean || !max_known) CK(reset_ctrl(ctx, false));
+  CK(launch_scan(v, ctx->rawmax, ctx->max_in_ord ? ctx->rawmax_ord : nullptr, is_log, ctx->n, ctx->cdf,
+                 ctx->scan_state, ctx->scan_counter, ctx->total, ctx->stream));
+  ctx->scan_clean = false;
   ctx->have_cdf = true;
   ctx->cdf_from_raw = from_raw;
   return AMCLJ_OK;
@@ -365,14 +376,15 @@ void swap_particles(amclj_ctx *ctx) {
 }
 
 int enqueue_systematic(amclj_ctx *ctx, double u0) {
-  uint64_t bits = (uint64_t)ldexp(u0, 64); /* u0 in [0,1) as a 0.64 fraction */
-  CK(launch_plan(ctx->total, bits, ctx->n, ctx->plan, ctx->stream));
   GatherArgs g;
   memset(&g, 0, sizeof(g));
   g.cdf = ctx->cdf;
   g.n_local = ctx->n;
   g.cdf_offset = 0;
-  g.plan = ctx->plan;
+  g.plan = nullptr; /* derived in the kernel from the device-resident total */
+  g.total_ptr = ctx->total;
+  g.u0_bits = (uint64_t)ldexp(u0, 64); /* u0 in [0,1) as a 0.64 fraction */
+  g.n_global = ctx->n;
   g.m_lo = 0;
   g.count = ctx->n;
   g.x = ctx->x;
@@ -457,6 +469,7 @@ int run_roulette(amclj_ctx *ctx, const int32_t *h_sidx, const uint32_t *h_su, in
     a.tile_counter = ctx->scan_counter;
     a.accepted_out = cnt;
     a.last_attempt = cnt + 1;
+    ctx->scan_clean = false;
     cudaError_t e = launch_roulette(a, tiles, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -556,9 +569,19 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ctx->stream = ctx->own_stream;
   for (int i = 0; ok && i < 5; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
-  ok = ok && dalloc(&ctx->rawmax_ord, 1) == cudaSuccess && dalloc(&ctx->rawmax, 1) == cudaSuccess &&
-       dalloc(&ctx->total, 1) == cudaSuccess && dalloc(&ctx->stats, 8) == cudaSuccess &&
-       dalloc(&ctx->scan_counter, 1) == cudaSuccess && dalloc(&ctx->plan, 1) == cudaSuccess &&
+  /* control block: [0] ordered-uint max | [1] fixed-point total | [2] tile counter | [3..] tile
+   * descriptors of the scan (2^20 tiles = 2^31 particles; also serves the roulette compaction) */
+  ctx->scan_state_cap = 1 << 20;
+  ok = ok && dalloc(&ctx->ctrl, (size_t)ctx->scan_state_cap + 3) == cudaSuccess;
+  if (ok) {
+    ctx->rawmax_ord = reinterpret_cast<uint32_t *>(ctx->ctrl);
+    ctx->total = ctx->ctrl + 1;
+    ctx->scan_counter = reinterpret_cast<uint32_t *>(ctx->ctrl + 2);
+    ctx->scan_state = ctx->ctrl + 3;
+    ok = cudaMemset(ctx->ctrl, 0, sizeof(uint64_t) * ((size_t)ctx->scan_state_cap + 3)) == cudaSuccess;
+  }
+  ok = ok && dalloc(&ctx->rawmax, 1) == cudaSuccess && dalloc(&ctx->stats, 8) == cudaSuccess &&
+       dalloc(&ctx->plan, 1) == cudaSuccess &&
        dalloc(&ctx->pose_part, (size_t)pose_blocks() * 4) == cudaSuccess &&
        cudaMallocHost(&ctx->pinned, 4096) == cudaSuccess;
   if (ok) ok = cudaMemset(ctx->stats, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;
@@ -580,8 +603,8 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
   dfree(ctx->x); dfree(ctx->y); dfree(ctx->th); dfree(ctx->w); dfree(ctx->raw);
   dfree(ctx->x2); dfree(ctx->y2); dfree(ctx->th2); dfree(ctx->w2);
   dfree(ctx->cdf); dfree(ctx->idx); dfree(ctx->normals); dfree(ctx->partials);
-  dfree(ctx->rawmax_ord); dfree(ctx->rawmax); dfree(ctx->total); dfree(ctx->stats);
-  dfree(ctx->scan_state); dfree(ctx->scan_counter); dfree(ctx->pose_part); dfree(ctx->plan);
+  dfree(ctx->ctrl); dfree(ctx->rawmax); dfree(ctx->stats);
+  dfree(ctx->pose_part); dfree(ctx->plan);
   dfree(ctx->stage_out); dfree(ctx->stage_in); dfree(ctx->stage_idx);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int i = 0; i < 5; i++)
@@ -767,7 +790,7 @@ int32_t amclj_sensor_update(amclj_ctx *ctx, const float *ranges, int32_t n, floa
   int rc = stage_scan_impl(ctx, ranges, n, angle_min, angle_increment, range_max);
   if (rc) return rc;
   stamp(ctx, 1);
-  rc = enqueue_sensor(ctx);
+  rc = enqueue_sensor(ctx, true);
   if (rc) return rc;
   stamp(ctx, 2);
   CK(cudaStreamSynchronize(ctx->stream));
@@ -912,7 +935,7 @@ int32_t amclj_filter_update_async(amclj_ctx *ctx, const double curr[3], const do
   ctx->normals_staged = false;
   if (rc) return rc;
   stamp(ctx, 1);
-  rc = enqueue_sensor(ctx);
+  rc = enqueue_sensor(ctx, false);
   if (rc) return rc;
   stamp(ctx, 2);
   rc = enqueue_cdf(ctx, true, true);
@@ -947,7 +970,7 @@ int32_t amclj_filter_update(amclj_ctx *ctx, const double curr[3], const double p
   rc = enqueue_motion(ctx, curr, prev, normals != nullptr, seed);
   if (rc) return rc;
   stamp(ctx, 1);
-  rc = enqueue_sensor(ctx);
+  rc = enqueue_sensor(ctx, false);
   if (rc) return rc;
   stamp(ctx, 2);
   if (ctx->p.s8_resampler == AMCLJ_RESAMPLE_ROULETTE) {
@@ -1021,7 +1044,7 @@ int32_t amclj_shard_motion_sensor_async(amclj_ctx *ctx, const double curr[3], co
   int rc = enqueue_motion(ctx, curr, prev, false, seed);
   if (rc) return rc;
   stamp(ctx, 1);
-  rc = enqueue_sensor(ctx);
+  rc = enqueue_sensor(ctx, true);
   if (rc) return rc;
   stamp(ctx, 2);
   return AMCLJ_OK;

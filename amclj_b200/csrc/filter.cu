@@ -191,7 +191,8 @@ __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p) {
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_kernel(const float *__restrict__ v, const float *__restrict__ vmaxp, int is_log, int64_t n,
+scan_kernel(const float *__restrict__ v, const float *__restrict__ vmaxp,
+            const uint32_t *__restrict__ vmax_ord, int is_log, int64_t n,
             uint64_t *__restrict__ cdf, uint64_t *tile_state, uint32_t *tile_counter,
             uint64_t *total_out) {
   __shared__ uint64_t warp_sums[SCAN_THREADS / 32];
@@ -200,7 +201,15 @@ scan_kernel(const float *__restrict__ v, const float *__restrict__ vmaxp, int is
   if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
   __syncthreads();
   const uint32_t tile = s_tile;
-  const float vmax = *vmaxp;
+  /* the max arrives as a float (all-reduced across ranks) or as the ordered-uint the sensor
+   * kernel accumulated with atomicMax */
+  float vmax;
+  if (vmax_ord) {
+    uint32_t o = *vmax_ord;
+    vmax = o == 0 ? -INFINITY : float_of_ord(o);
+  } else {
+    vmax = *vmaxp;
+  }
   const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   uint64_t q[SCAN_ITEMS];
   if (base + SCAN_ITEMS <= n) { /* 128-bit loads: base is a multiple of 8 */
@@ -284,15 +293,14 @@ scan_kernel(const float *__restrict__ v, const float *__restrict__ vmaxp, int is
 
 int64_t scan_tiles(int64_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
 
-cudaError_t launch_scan(const float *v, const float *vmaxp, int is_log, int64_t n, uint64_t *cdf,
-                        uint64_t *tile_state, uint32_t *tile_counter, uint64_t *total_out,
-                        cudaStream_t s) {
+/* total_out, tile_counter and tile_state[0..tiles) must be zero (the ctx control block is
+ * cleared once per update) */
+cudaError_t launch_scan(const float *v, const float *vmaxp, const uint32_t *vmax_ord, int is_log,
+                        int64_t n, uint64_t *cdf, uint64_t *tile_state, uint32_t *tile_counter,
+                        uint64_t *total_out, cudaStream_t s) {
   int64_t tiles = scan_tiles(n);
-  cudaMemsetAsync(total_out, 0, sizeof(uint64_t), s);
-  if (tiles == 0) return cudaGetLastError();
-  cudaMemsetAsync(tile_state, 0, sizeof(uint64_t) * (size_t)tiles, s);
-  cudaMemsetAsync(tile_counter, 0, sizeof(uint32_t), s);
-  scan_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(v, vmaxp, is_log, n, cdf, tile_state,
+  if (tiles == 0) return cudaSuccess;
+  scan_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(v, vmaxp, vmax_ord, is_log, n, cdf, tile_state,
                                                         tile_counter, total_out);
   return cudaGetLastError();
 }
@@ -323,9 +331,24 @@ cudaError_t launch_set_plan(const SysPlan &p, SysPlan *out, cudaStream_t s) {
 }
 
 __global__ void __launch_bounds__(256) systematic_gather_kernel(const GatherArgs a) {
+  __shared__ SysPlan s_plan;
+  if (threadIdx.x == 0) {
+    if (a.plan) {
+      s_plan = *a.plan;
+    } else { /* r = floor(u0 * T) with u0 as a 0.64 fraction; T = a*N + b */
+      SysPlan p;
+      p.total = *a.total_ptr;
+      p.n = (uint64_t)a.n_global;
+      p.a = p.total / p.n;
+      p.b = p.total % p.n;
+      p.r = __umul64hi(a.u0_bits, p.total);
+      s_plan = p;
+    }
+  }
+  __syncthreads();
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= a.count) return;
-  const SysPlan plan = *a.plan;
+  const SysPlan plan = s_plan;
   uint64_t U = sys_threshold(plan, (uint64_t)(a.m_lo + k));
   uint64_t key = U - a.cdf_offset; /* caller guarantees U >= cdf_offset */
   int64_t lo = 0, hi = a.n_local;

@@ -104,7 +104,11 @@ struct amclj_ctx {
   float *normals = nullptr;     // staged injected normals [n][3]
   long long *partials = nullptr;  // sensor chunk partials (32.32 fixed point)
   int64_t partials_cap = 0;
-  // scalars on the device
+  // scalars on the device: one control block [ord | total | counter | tile_state...] so that a
+  // single memset per update clears everything the sensor max and the scan accumulate into
+  uint64_t *ctrl = nullptr;
+  bool scan_clean = false;
+  bool max_in_ord = false;  // the weight max of the last pass lives in rawmax_ord only
   uint32_t *rawmax_ord = nullptr;  // ordered-uint of max raw
   float *rawmax = nullptr;         // float[1] (AMCLJ_BUF_RAW_MAX)
   uint64_t *total = nullptr;       // u64[1]  (AMCLJ_BUF_TOTAL)
@@ -144,7 +148,10 @@ struct GatherArgs {
   const uint64_t *cdf;
   int64_t n_local;
   uint64_t cdf_offset;
-  const SysPlan *plan;  /* device pointer */
+  const SysPlan *plan;  /* device pointer, or null: derive it from total_ptr / u0_bits / n_global */
+  const uint64_t *total_ptr;
+  uint64_t u0_bits;
+  int64_t n_global;
   int64_t m_lo, count;
   const float *x, *y, *th;
   float *ox, *oy, *oth, *ow;  /* SoA outputs (single GPU) or null */
@@ -176,9 +183,9 @@ cudaError_t launch_max(const float *v, int64_t n, uint32_t *ord, float *out, int
                        cudaStream_t s);
 cudaError_t launch_decode_max(const uint32_t *ord, float *out, cudaStream_t s);
 int64_t scan_tiles(int64_t n);
-cudaError_t launch_scan(const float *v, const float *vmaxp, int is_log, int64_t n, uint64_t *cdf,
-                        uint64_t *tile_state, uint32_t *tile_counter, uint64_t *total_out,
-                        cudaStream_t s);
+cudaError_t launch_scan(const float *v, const float *vmaxp, const uint32_t *vmax_ord, int is_log,
+                        int64_t n, uint64_t *cdf, uint64_t *tile_state, uint32_t *tile_counter,
+                        uint64_t *total_out, cudaStream_t s);
 cudaError_t launch_plan(const uint64_t *total, uint64_t u0_bits, int64_t n_global, SysPlan *out,
                         cudaStream_t s);
 cudaError_t launch_set_plan(const SysPlan &p, SysPlan *out, cudaStream_t s);
