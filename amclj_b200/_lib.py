@@ -33,7 +33,8 @@ SYMBOLS = [
     "amclj_motion_update", "amclj_sensor_update", "amclj_get_raw_weights", "amclj_raycast_debug",
     "amclj_beams_used", "amclj_normalize", "amclj_resample", "amclj_get_resample_indices",
     "amclj_filter_update", "amclj_stage_scan", "amclj_filter_update_async",
-    "amclj_filter_update_host", "amclj_pose_estimate", "amclj_get_stats", "amclj_microbench",
+    "amclj_filter_update_host", "amclj_pose_estimate", "amclj_get_stats", "amclj_microbench", "amclj_median_weight",
+    "amclj_augmented_resample", "amclj_augment_state",
     "amclj_shard_motion_sensor_async", "amclj_shard_cdf_async", "amclj_shard_generate_async",
     "amclj_shard_get_stage_idx", "amclj_shard_adopt_async", "amclj_plan_systematic",
     "amclj_device_ptr", "amclj_reserve_stage",
@@ -63,7 +64,7 @@ class Stats(C.Structure):
         ("ms_motion", C.c_double), ("ms_sensor", C.c_double), ("ms_resample", C.c_double),
         ("ms_total", C.c_double), ("rays", C.c_uint64), ("cells_visited", C.c_uint64),
         ("probes", C.c_uint64), ("hits", C.c_uint64), ("n_particles", C.c_int64),
-        ("beams_used", C.c_int32), ("map_in_smem", C.c_int32),
+        ("beams_used", C.c_int32), ("map_in_smem", C.c_int32), ("oob_probes", C.c_uint64),
     ]
 
 
@@ -131,6 +132,9 @@ def lib():
         "amclj_pose_estimate": ([vp, d3], i32),
         "amclj_get_stats": ([vp, C.POINTER(Stats)], i32),
         "amclj_microbench": ([vp, i32, C.POINTER(f64)], i32),
+        "amclj_median_weight": ([vp, C.POINTER(f64)], i32),
+        "amclj_augmented_resample": ([vp, f64, f64, u64, vp], i32),
+        "amclj_augment_state": ([vp, d3, d3], i32),
         "amclj_shard_motion_sensor_async": ([vp, d3, d3, u64], i32),
         "amclj_shard_cdf_async": ([vp], i32),
         "amclj_shard_generate_async": ([vp, u64, u64, u64, i64, i64], i32),
@@ -358,6 +362,22 @@ class Context:
         s = Stats()
         self._ck(self._L.amclj_get_stats(self._h, C.byref(s)))
         return s
+
+    def median_weight(self):
+        v = C.c_double()
+        self._ck(self._L.amclj_median_weight(self._h, C.byref(v)))
+        return float(v.value)
+
+    def augmented_resample(self, alpha_slow=0.01, alpha_fast=0.1, seed=0):
+        idx = np.empty(self.n, np.int32)
+        self._ck(self._L.amclj_augmented_resample(self._h, alpha_slow, alpha_fast, int(seed), _vp(idx)))
+        return idx
+
+    def augment_state(self, set_to=None):
+        out = (C.c_double * 2)()
+        arg = None if set_to is None else (C.c_double * 2)(*set_to)
+        self._ck(self._L.amclj_augment_state(self._h, arg, out))
+        return float(out[0]), float(out[1])
 
     def microbench(self, which=0):
         """Dependent-lookup ceiling (lookups/s): 0 = shared-memory nibble table, 1 = L2 byte table."""

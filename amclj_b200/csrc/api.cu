@@ -339,7 +339,7 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
   bool diag = ctx->p.collect_stats != 0;
   a.stats = diag ? ctx->stats : nullptr;
   CK(reset_ctrl(ctx, true));
-  if (diag) CK(cudaMemsetAsync(ctx->stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  if (diag) CK(cudaMemsetAsync(ctx->stats, 0, 7 * sizeof(unsigned long long), ctx->stream));
   CK(launch_sensor(ctx, a, mode, diag, ctx->stream));
   if (decode_max) CK(launch_decode_max(ctx->rawmax_ord, ctx->rawmax, ctx->stream));
   ctx->max_in_ord = !decode_max;
@@ -604,7 +604,7 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
   dfree(ctx->x2); dfree(ctx->y2); dfree(ctx->th2); dfree(ctx->w2);
   dfree(ctx->cdf); dfree(ctx->idx); dfree(ctx->normals); dfree(ctx->partials);
   dfree(ctx->ctrl); dfree(ctx->rawmax); dfree(ctx->stats);
-  dfree(ctx->pose_part); dfree(ctx->plan);
+  dfree(ctx->pose_part); dfree(ctx->plan); dfree(ctx->hist);
   dfree(ctx->stage_out); dfree(ctx->stage_in); dfree(ctx->stage_idx);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int i = 0; i < 5; i++)
@@ -853,7 +853,7 @@ int32_t amclj_raycast_debug(amclj_ctx *ctx, int32_t n, float angle_min, float an
     a.stats = ctx->stats;
     ctx->st.map_in_smem = mode == DF_SMEM4;
     ctx->st.beams_used = ctx->beams.nb;
-    cudaMemsetAsync(ctx->stats, 0, 4 * sizeof(unsigned long long), ctx->stream);
+    cudaMemsetAsync(ctx->stats, 0, 7 * sizeof(unsigned long long), ctx->stream);
     e = launch_sensor(ctx, a, mode, true, ctx->stream);
   }
   auto back = [&](void *dst, const void *src, size_t bytes) {
@@ -1023,14 +1023,96 @@ int32_t amclj_get_stats(amclj_ctx *ctx, amclj_stats *out) {
   NEED(out, AMCLJ_ERR_INVALID, "get_stats: null");
   CK(cudaStreamSynchronize(ctx->stream));
   collect_times(ctx);
-  unsigned long long h[4] = {0, 0, 0, 0};
+  unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   CK(cudaMemcpy(h, ctx->stats, sizeof(h), cudaMemcpyDeviceToHost));
+  ctx->st.oob_probes = h[6];
   ctx->st.rays = h[0];
   ctx->st.cells_visited = h[1];
   ctx->st.probes = h[2];
   ctx->st.hits = h[3];
   ctx->st.n_particles = ctx->n;
   *out = ctx->st;
+  return AMCLJ_OK;
+}
+
+/* ---- augmented MCL: pf.clj:243-279 ---------------------------------------------------- */
+static int select_kth(amclj_ctx *ctx, const float *v, int64_t n, int64_t k, float *out) {
+  /* k-th smallest (0-based): four histogram passes, most significant byte first */
+  uint32_t prefix = 0, mask = 0;
+  uint32_t h[256];
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    CK(launch_select_hist(v, n, prefix, mask, shift, ctx->hist, ctx->sm_count, ctx->stream));
+    CK(cudaMemcpyAsync(h, ctx->hist, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int b = 0;
+    for (; b < 256; b++) {
+      if (k < (int64_t)h[b]) break;
+      k -= h[b];
+    }
+    NEED(b < 256, AMCLJ_ERR_STATE, "median: rank outside the histogram");
+    prefix |= (uint32_t)b << shift;
+    mask |= 255u << shift;
+  }
+  *out = ord_to_float_host(prefix);
+  return AMCLJ_OK;
+}
+
+int32_t amclj_median_weight(amclj_ctx *ctx, double *out) {
+  ENTER();
+  NEED(out, AMCLJ_ERR_INVALID, "median: null");
+  NEED(ctx->n > 0, AMCLJ_ERR_STATE, "median: no particles");
+  const float *v = ctx->have_raw ? ctx->raw : ctx->w;
+  if (!ctx->hist) CK(dalloc(&ctx->hist, 256));
+  float a = 0, b = 0;
+  int rc = select_kth(ctx, v, ctx->n, ctx->n / 2, &a);
+  if (rc) return rc;
+  if (ctx->n % 2 == 0) { /* even count: mean of the two middle order statistics */
+    rc = select_kth(ctx, v, ctx->n, ctx->n / 2 - 1, &b);
+    if (rc) return rc;
+    *out = ((double)a + (double)b) / 2.0;
+  } else {
+    *out = (double)a;
+  }
+  return AMCLJ_OK;
+}
+
+int32_t amclj_augmented_resample(amclj_ctx *ctx, double alpha_slow, double alpha_fast, uint64_t seed,
+                                 int32_t *idx_out) {
+  ENTER();
+  NEED(ctx->n > 0, AMCLJ_ERR_STATE, "augmented: no particles");
+  NEED(ctx->map.cells, AMCLJ_ERR_STATE, "augmented: no map set");
+  double w_avg = 0;
+  int rc = amclj_median_weight(ctx, &w_avg); /* pf.clj:271 */
+  if (rc) return rc;
+  ctx->w_slow += alpha_slow * (w_avg - ctx->w_slow); /* pf.clj:249-250 */
+  ctx->w_fast += alpha_fast * (w_avg - ctx->w_fast);
+  double thr = 1.0 - ctx->w_fast / ctx->w_slow;
+  if (!(thr > 0.0)) thr = 0.0; /* (max 0.0 ...) */
+  const float *wv = ctx->have_raw ? ctx->raw : ctx->w;
+  stamp(ctx, 2);
+  CK(launch_augmented(wv, ctx->x, ctx->y, ctx->th, ctx->n, (float)thr, ctx->map.cells, ctx->map.W,
+                      ctx->map.H, ctx->map.res, seed, ctx->x2, ctx->y2, ctx->th2, ctx->w2, ctx->idx,
+                      ctx->stream));
+  swap_particles(ctx);
+  ctx->have_raw = false;
+  ctx->have_cdf = false;
+  stamp(ctx, 3);
+  if (idx_out)
+    CK(cudaMemcpyAsync(idx_out, ctx->idx, sizeof(int32_t) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AMCLJ_OK;
+}
+
+int32_t amclj_augment_state(amclj_ctx *ctx, const double *set_slow_fast, double *get_slow_fast) {
+  if (!ctx) return AMCLJ_ERR_INVALID;
+  if (set_slow_fast) {
+    ctx->w_slow = set_slow_fast[0];
+    ctx->w_fast = set_slow_fast[1];
+  }
+  if (get_slow_fast) {
+    get_slow_fast[0] = ctx->w_slow;
+    get_slow_fast[1] = ctx->w_fast;
+  }
   return AMCLJ_OK;
 }
 

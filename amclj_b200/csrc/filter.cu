@@ -7,6 +7,8 @@
 // motion.clj:24-45; pf.clj:156-167 roulette-selection; pf.clj:182-195 tournament-selection;
 // pf.clj:67-84 pose-estimate; map.clj:59-84 uniform-initialization, :87-111
 // gaussian-initialization.
+#include <string.h>
+
 #include "internal.h"
 
 namespace amclj {
@@ -674,6 +676,102 @@ cudaError_t launch_init_gaussian(float mx, float my, float mth, float sd_xy, flo
   if (n <= 0) return cudaSuccess;
   init_gaussian_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mx, my, mth, sd_xy, sd_th, gid0,
                                                                   n, seed, x, y, th, w, w0);
+  return cudaGetLastError();
+}
+
+
+// ======================================================================================
+// pf.clj:243-279 augmented MCL (amcl*): w_avg = median of the weights; w_slow / w_fast are
+// exponential averages of it; every output slot either injects a fresh uniform particle
+// (map.clj:71-84) when Math/random > max(0, 1 - fast/slow) — the reference's inequality,
+// inverted relative to Probabilistic Robotics table 8.3 — or runs roulette-step
+// (pf.clj:169-180: rejection against the UN-normalised weights).
+// ======================================================================================
+constexpr uint32_t TAG_AUGMENT = 0x4155474du;
+
+// k-th smallest by radix select on the order-preserving uint image of the floats: one
+// 256-bin histogram pass per byte, most significant first.
+__global__ void __launch_bounds__(256)
+select_hist_kernel(const float *__restrict__ v, int64_t n, uint32_t prefix, uint32_t prefix_mask,
+                   int shift, uint32_t *__restrict__ hist) {
+  __shared__ uint32_t sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t o = ord_of_float(__ldg(v + i));
+    if ((o & prefix_mask) == prefix) atomicAdd(&sh[(o >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+cudaError_t launch_select_hist(const float *v, int64_t n, uint32_t prefix, uint32_t prefix_mask,
+                               int shift, uint32_t *hist, int sm_count, cudaStream_t s) {
+  cudaMemsetAsync(hist, 0, 256 * sizeof(uint32_t), s);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
+  select_hist_kernel<<<(unsigned)blocks, 256, 0, s>>>(v, n, prefix, prefix_mask, shift, hist);
+  return cudaGetLastError();
+}
+
+float ord_to_float_host(uint32_t o) {
+  uint32_t b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+}
+
+__global__ void __launch_bounds__(256)
+augmented_kernel(const float *__restrict__ wgt, const float *__restrict__ x,
+                 const float *__restrict__ y, const float *__restrict__ th, int64_t n,
+                 float inject_threshold, const int8_t *__restrict__ cells, int W, int H, float res,
+                 uint64_t seed, float *ox, float *oy, float *oth, float *ow, int32_t *oidx) {
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  uint32_t r[4];
+  auto draw = [&](uint32_t attempt) {
+    philox4x32_10((uint32_t)m, (uint32_t)((uint64_t)m >> 32), attempt, TAG_AUGMENT, (uint32_t)seed,
+                  (uint32_t)(seed >> 32), r);
+  };
+  draw(0u);
+  if (u24(r[0]) > inject_threshold) { /* pf.clj:254-256: a fresh particle from uniform-initialization */
+    for (uint32_t at = 1;; at++) {
+      draw(at);
+      float px = u24(r[0]) * (float)W, py = u24(r[1]) * (float)H;
+      int cx = (int)px, cy = (int)py;
+      bool bad = cx >= W || cy >= H || cx < 0 || cy < 0 || cells[(size_t)cy * W + cx] != 0;
+      if (at < 100000u && bad) continue;
+      ox[m] = px * res;
+      oy[m] = py * res;
+      oth[m] = sqrtf(-2.0f * logf(u24(r[2]))) * cosf(6.283185307179586f * u24(r[3])); /* map.clj:67-68 */
+      ow[m] = 0.0f;
+      oidx[m] = -1;
+      return;
+    }
+  }
+  for (uint32_t at = 1;; at++) { /* pf.clj:169-180 roulette-step */
+    draw(at);
+    int32_t i = (int32_t)(((uint64_t)r[0] * (uint64_t)n) >> 32);
+    float wi = __ldg(wgt + i);
+    if (wi > u24(r[1]) || at >= 100000u) {
+      ox[m] = __ldg(x + i);
+      oy[m] = __ldg(y + i);
+      oth[m] = __ldg(th + i);
+      ow[m] = wi;
+      oidx[m] = i;
+      return;
+    }
+  }
+}
+
+cudaError_t launch_augmented(const float *wgt, const float *x, const float *y, const float *th,
+                             int64_t n, float inject_threshold, const int8_t *cells, int W, int H,
+                             float res, uint64_t seed, float *ox, float *oy, float *oth, float *ow,
+                             int32_t *oidx, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  augmented_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wgt, x, y, th, n, inject_threshold, cells, W,
+                                                              H, res, seed, ox, oy, oth, ow, oidx);
   return cudaGetLastError();
 }
 

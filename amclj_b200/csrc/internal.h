@@ -132,6 +132,8 @@ struct amclj_ctx {
   uint64_t last_total = 0;
   amclj_stats st;
   int32_t refill = 6;
+  double w_slow = 1.0, w_fast = 1.0;  // pf.clj:243-244
+  uint32_t *hist = nullptr;           // 256-bin histogram of the radix select
   int32_t force_chunks = 0;
   void *pinned = nullptr;  // small pinned scratch for scalar readbacks
 };
@@ -201,6 +203,13 @@ cudaError_t launch_gather_idx(const int32_t *idx, int64_t n, const float *x, con
 cudaError_t launch_adopt(const float4 *rows, int64_t n, float *x, float *y, float *th, float *w,
                          cudaStream_t s);
 cudaError_t launch_fill(float *p, int64_t n, float v, cudaStream_t s);
+cudaError_t launch_select_hist(const float *v, int64_t n, uint32_t prefix, uint32_t prefix_mask,
+                               int shift, uint32_t *hist, int sm_count, cudaStream_t s);
+float ord_to_float_host(uint32_t o);
+cudaError_t launch_augmented(const float *wgt, const float *x, const float *y, const float *th,
+                             int64_t n, float inject_threshold, const int8_t *cells, int W, int H,
+                             float res, uint64_t seed, float *ox, float *oy, float *oth, float *ow,
+                             int32_t *oidx, cudaStream_t s);
 int pose_blocks();
 cudaError_t launch_pose(const float *x, const float *y, const float *th, int64_t n, double *part,
                         cudaStream_t s);

@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
   const int64_t ngroups = (a.n + 31) >> 5;
   const int64_t ntasks = ngroups * a.chunks;
   float wmax = -INFINITY;
-  unsigned long long n_cells = 0, n_probes = 0, n_hits = 0, n_rays = 0;
+  unsigned long long n_cells = 0, n_probes = 0, n_hits = 0, n_rays = 0, n_oob = 0;
+  const uint32_t idx_limit = (uint32_t)(a.df_bytes * (MODE == DF_GLOBAL8 ? 1u : 8u)); /* DIAG bounds check */
 
   /* task = 32 consecutive particles x one chunk of beams; chunk-major so that the warps of a
    * CTA work on neighbouring particles */
@@ -339,6 +340,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
 #pragma unroll
         for (int u = 0; u < PROBES_PER_VOTE; u++) {
           /* branch-free: a parked lane reads d = 0, which makes every update a no-op */
+          if (DIAG && (uint32_t)idx >= idx_limit) { n_oob++; idx = 0; } /* never taken: see tests */
           const uint32_t d = df_probe<MODE>(df, idx, am);
           if (DIAG) dg_probes += am ? 1 : 0;
           k += (int)d;
@@ -376,12 +378,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
       n_cells += __shfl_xor_sync(FULL, n_cells, o);
       n_probes += __shfl_xor_sync(FULL, n_probes, o);
       n_hits += __shfl_xor_sync(FULL, n_hits, o);
+      n_oob += __shfl_xor_sync(FULL, n_oob, o);
     }
     if (lane == 0) {
       atomicAdd(a.stats + 0, n_rays);
       atomicAdd(a.stats + 1, n_cells);
       atomicAdd(a.stats + 2, n_probes);
       atomicAdd(a.stats + 3, n_hits);
+      atomicAdd(a.stats + 6, n_oob);
     }
   }
 }

@@ -107,6 +107,7 @@ typedef struct amclj_stats {
   int64_t n_particles;
   int32_t beams_used;
   int32_t map_in_smem; /* 1 when the nibble-packed distance field fits shared memory */
+  uint64_t oob_probes; /* diagnostic passes only: probes outside the staged field (must be 0) */
 } amclj_stats;
 
 typedef struct amclj_ctx amclj_ctx;
@@ -204,6 +205,19 @@ int32_t amclj_filter_update_host(amclj_ctx *ctx, float *x, float *y, float *thet
                                  const float *normals, uint64_t seed, const float *ranges,
                                  int32_t n_ranges, float angle_min, float angle_increment,
                                  float range_max, double u0);
+
+/* ---- augmented MCL pf.clj:243-279 (amcl*; not wired into monte-carlo-localization) ------ */
+/* incanter median of the current weights (raw weights of the last sensor pass, else w). */
+int32_t amclj_median_weight(amclj_ctx *ctx, double *out);
+/* augmented-selection: w_avg = median weight, w_slow/w_fast updated with alpha_slow/alpha_fast
+ * (pf.clj:16-17: 0.01 / 0.1), then every slot injects a uniform particle when
+ * random > max(0, 1 - fast/slow) (pf.clj:254, the reference's inequality) or runs roulette-step
+ * (pf.clj:169-180).  Per-slot Philox streams keyed by `seed`.  idx_out: source index, -1 for an
+ * injected particle (host int32 [n], may be NULL). */
+int32_t amclj_augmented_resample(amclj_ctx *ctx, double alpha_slow, double alpha_fast, uint64_t seed,
+                                 int32_t *idx_out);
+/* The w-slow / w-fast atoms (pf.clj:243-244, both start at 1): either pointer may be NULL. */
+int32_t amclj_augment_state(amclj_ctx *ctx, const double *set_slow_fast, double *get_slow_fast);
 
 /* ---- pose-estimate pf.clj:67-84: unweighted mean of x, y, and of (qz, qw) ----------- */
 /* out = {mean x, mean y, mean qz, mean qw}.  On a shard (world > 1) out holds the local

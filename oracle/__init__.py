@@ -187,6 +187,11 @@ def lib():
     L.amclj_oracle_uniform_init.argtypes = [i8p, C.c_int32, C.c_int32, C.c_float, C.c_int64,
                                             C.c_int64, C.c_int32, C.c_uint64, f32p, f32p, f32p]
     L.amclj_oracle_threads.restype = C.c_int32
+    L.amclj_oracle_median.argtypes = [f32p, C.c_int64]
+    L.amclj_oracle_median.restype = C.c_double
+    L.amclj_oracle_augmented.argtypes = [f32p, f32p, f32p, f32p, C.c_int64, C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double), C.c_double, C.c_double, i8p, C.c_int32,
+                                         C.c_int32, C.c_float, C.c_uint64, f32p, f32p, f32p, f32p, i32p]
     L.amclj_oracle_expf_contract.argtypes = [C.c_float]
     L.amclj_oracle_expf_contract.restype = C.c_float
     L.amclj_oracle_linear_weights.argtypes = [f32p, C.c_int64, C.c_float, f32p]
@@ -412,6 +417,24 @@ def gaussian_init(mx, my, mth, sd_xy, sd_th, gid_first, n, seed):
     x, y, t = (np.zeros(n, np.float32) for _ in range(3))
     lib().amclj_oracle_gaussian_init(mx, my, mth, sd_xy, sd_th, gid_first, n, seed, x, y, t)
     return x, y, t
+
+
+def median(w):
+    w = np.ascontiguousarray(w, np.float32)
+    return float(lib().amclj_oracle_median(w, len(w)))
+
+
+def augmented(w, x, y, th, grid, slow, fast, alpha_slow, alpha_fast, seed):
+    """pf.clj:246-258.  Returns (x, y, theta, w, idx, slow', fast')."""
+    cells, W, H, res = _grid(grid)
+    w, x, y, th = (np.ascontiguousarray(a, np.float32) for a in (w, x, y, th))
+    n = len(w)
+    ox, oy, ot, ow = (np.zeros(n, np.float32) for _ in range(4))
+    oi = np.zeros(n, np.int32)
+    s, f = C.c_double(slow), C.c_double(fast)
+    lib().amclj_oracle_augmented(w, x, y, th, n, C.byref(s), C.byref(f), alpha_slow, alpha_fast, cells, W, H,
+                                 res, seed, ox, oy, ot, ow, oi)
+    return ox, oy, ot, ow, oi, s.value, f.value
 
 
 def to_heading(qx, qy, qz, qw):

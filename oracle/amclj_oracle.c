@@ -829,6 +829,80 @@ ORACLE_API void amclj_oracle_gaussian_init(float mx, float my, float mth, float 
   }
 }
 
+/* ------------------------------------------------------------------------------------
+ * pf.clj:243-279 augmented MCL.  w-avg = incanter stats/median of the weights (third party,
+ * incanter 1.5.4: restated as the textbook median, mean of the two middle order statistics for
+ * an even count); slow/fast are the w-slow/w-fast atoms (pf.clj:243-244, :249-250).  Slot m
+ * draws Math/random; `(> random (max 0.0 (- 1.0 (/ fast slow))))` injects a particle from
+ * uniform-initialization (map.clj:71-84; heading N(0,1), map.clj:67-68), otherwise roulette-step
+ * (pf.clj:169-180) rejection-samples against the UN-normalised weights.
+ * Injected streams: slot m owns Philox counters (m lo, m hi, attempt, TAG_AUGMENT); attempt 0
+ * word 0 is the inject draw; attempts 1.. are the proposals of whichever loop runs.
+ * ---------------------------------------------------------------------------------- */
+#define TAG_AUGMENT 0x4155474du
+
+static int cmp_float(const void *a, const void *b) {
+  float x = *(const float *)a, y = *(const float *)b;
+  return (x > y) - (x < y);
+}
+
+ORACLE_API double amclj_oracle_median(const float *w, int64_t n) {
+  float *t = (float *)malloc(sizeof(float) * (size_t)n);
+  memcpy(t, w, sizeof(float) * (size_t)n);
+  qsort(t, (size_t)n, sizeof(float), cmp_float);
+  double m = (n % 2) ? (double)t[n / 2] : ((double)t[n / 2] + (double)t[n / 2 - 1]) / 2.0;
+  free(t);
+  return m;
+}
+
+ORACLE_API void amclj_oracle_augmented(const float *w, const float *x, const float *y,
+                                       const float *th, int64_t n, double *slow, double *fast,
+                                       double alpha_slow, double alpha_fast, const int8_t *cells,
+                                       int32_t W, int32_t H, float res, uint64_t seed, float *ox,
+                                       float *oy, float *oth, float *ow, int32_t *oidx) {
+  oracle_map mp = {cells, W, H, res};
+  double w_avg = amclj_oracle_median(w, n);
+  *slow += alpha_slow * (w_avg - *slow);
+  *fast += alpha_fast * (w_avg - *fast);
+  double thr = 1.0 - *fast / *slow;
+  if (!(thr > 0.0)) thr = 0.0;
+  float fthr = (float)thr;
+  for (int64_t m = 0; m < n; m++) {
+    uint32_t r[4];
+#define DRAW(at) philox4x32_10((uint32_t)m, (uint32_t)((uint64_t)m >> 32), (at), TAG_AUGMENT, \
+                               (uint32_t)seed, (uint32_t)(seed >> 32), r)
+    DRAW(0u);
+    if (u24(r[0]) > fthr) {
+      for (uint32_t at = 1;; at++) {
+        DRAW(at);
+        float px = u24(r[0]) * (float)W, py = u24(r[1]) * (float)H;
+        int32_t cx = (int32_t)px, cy = (int32_t)py;
+        if (at < 100000u && (cx >= W || cy >= H || blocked(&mp, cx, cy))) continue;
+        ox[m] = px * res;
+        oy[m] = py * res;
+        oth[m] = sqrtf(-2.0f * logf(u24(r[2]))) * cosf(6.283185307179586f * u24(r[3]));
+        ow[m] = 0.0f;
+        oidx[m] = -1;
+        break;
+      }
+      continue;
+    }
+    for (uint32_t at = 1;; at++) {
+      DRAW(at);
+      int32_t i = (int32_t)(((uint64_t)r[0] * (uint64_t)n) >> 32);
+      if (w[i] > u24(r[1]) || at >= 100000u) {
+        ox[m] = x[i];
+        oy[m] = y[i];
+        oth[m] = th[i];
+        ow[m] = w[i];
+        oidx[m] = i;
+        break;
+      }
+    }
+#undef DRAW
+  }
+}
+
 ORACLE_API int32_t amclj_oracle_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -45,6 +45,7 @@ def _ray_parity(ctx, grid, x, y, th, scan, preset, **kw):
     assert np.array_equal(dbg["range_m"], ref["range_m"]), "range in metres is exact in the fp32 contract"
     s = ctx.stats()
     assert (s.rays, s.cells_visited, s.hits) == (st.rays, st.cells, st.hits)
+    assert s.oob_probes == 0  # every probe of every ray stayed inside the staged field
     return s
 
 
@@ -434,3 +435,34 @@ def test_round_trip_properties_c3_size():
     idx2 = c.resample(_lib.RESAMPLE_SYSTEMATIC, 0.123456)
     assert np.array_equal(idx, idx2)
     c.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 1001, 100_000])
+def test_median_weight(ctx, n):
+    w = _weights(n, 31)
+    z = np.zeros(n, np.float32)
+    ctx.set_particles(z, z, z, w)
+    assert ctx.median_weight() == oracle.median(w)
+
+
+@pytest.mark.parametrize("scale", [1.0, 0.02])
+def test_augmented_selection(ctx, lg, scale):
+    """pf.clj:246-258: w-slow/w-fast update, particle injection and roulette-step, slot by slot."""
+    n = 20_000
+    x, y, th = workloads.uniform_particles(lg, n, seed=5)
+    w = (_weights(n, 32) * scale).astype(np.float32)
+    ctx.set_map(lg)
+    ctx.set_particles(x, y, th, w)
+    ctx.augment_state((1.0, 1.0))
+    slow, fast = 1.0, 1.0
+    for it in range(3):  # the averages drift apart, so later rounds inject particles
+        gx0, gy0, gt0, gw0 = ctx.get_particles()
+        idx = ctx.augmented_resample(0.01, 0.1, seed=40 + it)
+        rx, ry, rt, rw, ridx, slow, fast = oracle.augmented(gw0, gx0, gy0, gt0, lg, slow, fast, 0.01, 0.1, 40 + it)
+        assert np.array_equal(idx, ridx)
+        gx, gy, gt, gw = ctx.get_particles()
+        assert np.array_equal(gx, rx) and np.array_equal(gy, ry) and np.array_equal(gw, rw)
+        np.testing.assert_allclose(gt, rt, rtol=RTOL, atol=1e-6)
+        s2, f2 = ctx.augment_state()
+        assert s2 == pytest.approx(slow, rel=1e-12) and f2 == pytest.approx(fast, rel=1e-12)
+    assert (idx == -1).any() or scale == 1.0
