@@ -22,7 +22,8 @@ LIB_PATH = Path(_os.environ["AMCLJ_LIB"]) if _os.environ.get("AMCLJ_LIB") else _
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM, ERR_NODEVICE = 0, -1, -2, -3, -4, -5
 PRESET_REF, PRESET_NS = 0, 1
 RESAMPLE_ROULETTE, RESAMPLE_SYSTEMATIC, RESAMPLE_TOURNAMENT = 0, 1, 2
-BUF_X, BUF_Y, BUF_THETA, BUF_W, BUF_RAW, BUF_RAW_MAX, BUF_TOTAL, BUF_STAGE_OUT, BUF_STAGE_IN, BUF_CDF = range(10)
+BUF_X, BUF_Y, BUF_THETA, BUF_W, BUF_RAW, BUF_RAW_MAX, BUF_TOTAL, BUF_STAGE_OUT, BUF_STAGE_IN, BUF_CDF, BUF_TOTALS_ALL = range(11)
+IPC_BYTES = 7 * 64
 
 # every symbol include/amclj_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -37,7 +38,8 @@ SYMBOLS = [
     "amclj_augmented_resample", "amclj_augment_state",
     "amclj_shard_motion_sensor_async", "amclj_shard_cdf_async", "amclj_shard_generate_async",
     "amclj_shard_get_stage_idx", "amclj_shard_adopt_async", "amclj_plan_systematic",
-    "amclj_device_ptr", "amclj_reserve_stage",
+    "amclj_device_ptr", "amclj_reserve_stage", "amclj_shard_export", "amclj_shard_import",
+    "amclj_shard_attach_local", "amclj_shard_pull_async",
 ]
 
 
@@ -143,6 +145,10 @@ def lib():
         "amclj_plan_systematic": ([vp, i32, i64, f64, C.POINTER(u64), vp, vp, vp, vp], i32),
         "amclj_device_ptr": ([vp, i32, C.POINTER(vp), C.POINTER(i64)], i32),
         "amclj_reserve_stage": ([vp, i64], i32),
+        "amclj_shard_export": ([vp, vp], i32),
+        "amclj_shard_import": ([vp, i32, vp, i64, i64], i32),
+        "amclj_shard_attach_local": ([vp, i32, vp], i32),
+        "amclj_shard_pull_async": ([vp, f64], i32),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -403,6 +409,21 @@ class Context:
 
     def shard_adopt_async(self, count):
         self._ck(self._L.amclj_shard_adopt_async(self._h, int(count)))
+
+    def shard_export(self) -> bytes:
+        buf = (C.c_uint8 * IPC_BYTES)()
+        self._ck(self._L.amclj_shard_export(self._h, buf))
+        return bytes(buf)
+
+    def shard_import(self, rank, handles: bytes, n_peer, peer_global_offset):
+        buf = (C.c_uint8 * IPC_BYTES).from_buffer_copy(handles)
+        self._ck(self._L.amclj_shard_import(self._h, int(rank), buf, int(n_peer), int(peer_global_offset)))
+
+    def shard_attach_local(self, rank, peer: "Context"):
+        self._ck(self._L.amclj_shard_attach_local(self._h, int(rank), peer._h))
+
+    def shard_pull_async(self, u0):
+        self._ck(self._L.amclj_shard_pull_async(self._h, float(u0)))
 
     def reserve_stage(self, rows):
         self._ck(self._L.amclj_reserve_stage(self._h, int(rows)))

@@ -103,6 +103,7 @@ int beams_used(int n, int max_beams) {
 
 int ensure_particles(amclj_ctx *ctx, int64_t n) {
   if (n <= ctx->cap) return AMCLJ_OK;
+  NEED(!ctx->frozen, AMCLJ_ERR_STATE, "particle buffers are exported to peers and cannot grow");
   int64_t cap = (n + 1023) / 1024 * 1024;
   float **bufs[] = {&ctx->x, &ctx->y, &ctx->th, &ctx->w, &ctx->raw, &ctx->x2, &ctx->y2, &ctx->th2, &ctx->w2};
   /* growing keeps the live particles */
@@ -581,7 +582,7 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
     ok = cudaMemset(ctx->ctrl, 0, sizeof(uint64_t) * ((size_t)ctx->scan_state_cap + 3)) == cudaSuccess;
   }
   ok = ok && dalloc(&ctx->rawmax, 1) == cudaSuccess && dalloc(&ctx->stats, 8) == cudaSuccess &&
-       dalloc(&ctx->plan, 1) == cudaSuccess &&
+       dalloc(&ctx->plan, 1) == cudaSuccess && dalloc(&ctx->totals_all, MAX_WORLD) == cudaSuccess &&
        dalloc(&ctx->pose_part, (size_t)pose_blocks() * 4) == cudaSuccess &&
        cudaMallocHost(&ctx->pinned, 4096) == cudaSuccess;
   if (ok) ok = cudaMemset(ctx->stats, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;
@@ -604,7 +605,10 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
   dfree(ctx->x2); dfree(ctx->y2); dfree(ctx->th2); dfree(ctx->w2);
   dfree(ctx->cdf); dfree(ctx->idx); dfree(ctx->normals); dfree(ctx->partials);
   dfree(ctx->ctrl); dfree(ctx->rawmax); dfree(ctx->stats);
-  dfree(ctx->pose_part); dfree(ctx->plan); dfree(ctx->hist);
+  dfree(ctx->pose_part); dfree(ctx->plan); dfree(ctx->hist); dfree(ctx->totals_all);
+  for (int g = 0; g < MAX_WORLD; g++)
+    for (int k = 0; k < 7; k++)
+      if (ctx->ipc_opened[g][k]) cudaIpcCloseMemHandle(ctx->ipc_opened[g][k]);
   dfree(ctx->stage_out); dfree(ctx->stage_in); dfree(ctx->stage_idx);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int i = 0; i < 5; i++)
@@ -1194,6 +1198,97 @@ int32_t amclj_shard_adopt_async(amclj_ctx *ctx, int64_t count) {
   return AMCLJ_OK;
 }
 
+/* ---- peer-memory resampling -------------------------------------------------------------- */
+static void local_views(amclj_ctx *c, PeerView *a, PeerView *b) {
+  /* A = the buffers that are current now (flip accounts for swaps since export) */
+  float *cx = c->flip ? c->x2 : c->x, *cy = c->flip ? c->y2 : c->y, *ct = c->flip ? c->th2 : c->th;
+  float *ax = c->flip ? c->x : c->x2, *ay = c->flip ? c->y : c->y2, *at = c->flip ? c->th : c->th2;
+  a->x = cx; a->y = cy; a->th = ct; a->cdf = c->cdf; a->n = c->n; a->gid0 = c->global_offset;
+  b->x = ax; b->y = ay; b->th = at; b->cdf = c->cdf; b->n = c->n; b->gid0 = c->global_offset;
+}
+
+int32_t amclj_shard_export(amclj_ctx *ctx, uint8_t *handles) {
+  ENTER();
+  NEED(handles, AMCLJ_ERR_INVALID, "shard_export: null");
+  NEED(ctx->n > 0 && ctx->cdf, AMCLJ_ERR_STATE, "shard_export: no particles");
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->flip = 0;
+  ctx->frozen = true;
+  void *bufs[7] = {ctx->x, ctx->y, ctx->th, ctx->x2, ctx->y2, ctx->th2, ctx->cdf};
+  for (int k = 0; k < 7; k++) {
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, bufs[k]));
+    memcpy(handles + (size_t)k * AMCLJ_IPC_HANDLE_BYTES, &h, sizeof(h));
+  }
+  return AMCLJ_OK;
+}
+
+int32_t amclj_shard_import(amclj_ctx *ctx, int32_t rank, const uint8_t *handles, int64_t n_peer,
+                           int64_t peer_global_offset) {
+  ENTER();
+  NEED(handles && rank >= 0 && rank < MAX_WORLD && n_peer > 0, AMCLJ_ERR_INVALID, "shard_import: bad arguments");
+  void *p[7];
+  for (int k = 0; k < 7; k++) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)k * AMCLJ_IPC_HANDLE_BYTES, sizeof(h));
+    if (ctx->ipc_opened[rank][k]) cudaIpcCloseMemHandle(ctx->ipc_opened[rank][k]);
+    CK(cudaIpcOpenMemHandle(&p[k], h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->ipc_opened[rank][k] = p[k];
+  }
+  PeerView a = {(float *)p[0], (float *)p[1], (float *)p[2], (uint64_t *)p[6], n_peer, peer_global_offset};
+  PeerView b = {(float *)p[3], (float *)p[4], (float *)p[5], (uint64_t *)p[6], n_peer, peer_global_offset};
+  ctx->peers[0][rank] = a;
+  ctx->peers[1][rank] = b;
+  ctx->peer_set[rank] = true;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_shard_attach_local(amclj_ctx *ctx, int32_t rank, amclj_ctx *peer) {
+  ENTER();
+  NEED(peer && rank >= 0 && rank < MAX_WORLD && peer->n > 0, AMCLJ_ERR_INVALID, "shard_attach_local: bad arguments");
+  if (peer == ctx) {
+    ctx->flip = 0;
+    ctx->frozen = true;
+  }
+  NEED(peer->flip == 0, AMCLJ_ERR_STATE, "shard_attach_local: attach before the first pull");
+  peer->frozen = true;
+  local_views(peer, &ctx->peers[0][rank], &ctx->peers[1][rank]);
+  ctx->peer_set[rank] = true;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_shard_pull_async(amclj_ctx *ctx, double u0) {
+  ENTER();
+  NEED(ctx->have_cdf, AMCLJ_ERR_STATE, "shard_pull: no CDF");
+  NEED(u0 >= 0.0 && u0 < 1.0, AMCLJ_ERR_INVALID, "shard_pull: u0 must be in [0,1)");
+  NEED(ctx->world <= MAX_WORLD, AMCLJ_ERR_INVALID, "shard_pull: world > %d", MAX_WORLD);
+  PullArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int g = 0; g < ctx->world; g++) {
+    NEED(ctx->peer_set[g], AMCLJ_ERR_STATE, "shard_pull: rank %d not imported", g);
+    a.peer[g] = ctx->peers[ctx->flip][g];
+  }
+  a.world = ctx->world;
+  a.totals = ctx->totals_all;
+  a.u0_bits = (uint64_t)ldexp(u0, 64);
+  a.n_global = ctx->n_global;
+  a.slot0 = ctx->global_offset;
+  a.count = ctx->n;
+  a.ox = ctx->x2;
+  a.oy = ctx->y2;
+  a.oth = ctx->th2;
+  a.ow = ctx->w2;
+  a.oidx64 = ctx->stage_idx && ctx->stage_cap >= ctx->n ? ctx->stage_idx : nullptr;
+  a.wout = 1.0f / (float)ctx->n_global;
+  a.zero_flag = ctx->stats + 5;
+  CK(launch_pull(a, ctx->stream));
+  swap_particles(ctx);
+  ctx->flip ^= 1;
+  ctx->have_raw = ctx->have_cdf = false;
+  stamp(ctx, 3);
+  return AMCLJ_OK;
+}
+
 int32_t amclj_plan_systematic(const uint64_t *totals, int32_t world, int64_t n_global, double u0,
                               uint64_t *r_out, uint64_t *cdf_offsets, int64_t *m_lo,
                               int64_t *m_cnt, int64_t *send_matrix) {
@@ -1258,6 +1353,7 @@ int32_t amclj_device_ptr(amclj_ctx *ctx, int32_t which, void **ptr, int64_t *byt
     case AMCLJ_BUF_STAGE_OUT: p = ctx->stage_out; b = 16 * ctx->stage_cap; break;
     case AMCLJ_BUF_STAGE_IN: p = ctx->stage_in; b = 16 * ctx->stage_cap; break;
     case AMCLJ_BUF_CDF: p = ctx->cdf; b = 8 * ctx->cap; break;
+    case AMCLJ_BUF_TOTALS_ALL: p = ctx->totals_all; b = 8 * MAX_WORLD; break;
     default: return fail(ctx, AMCLJ_ERR_INVALID, "device_ptr: unknown buffer %d", which);
   }
   *ptr = p;

@@ -775,4 +775,68 @@ cudaError_t launch_augmented(const float *wgt, const float *x, const float *y, c
   return cudaGetLastError();
 }
 
+
+// ======================================================================================
+// Sharded systematic resampling as a PULL over peer memory: every rank fills its own output
+// slots [slot0, slot0 + count).  Slot m's threshold U_m falls into the CDF interval of exactly
+// one rank g (exclusive prefix of the all-gathered totals); the thread binary-searches rank g's
+// CDF and copies that particle — plain loads on rank g's memory, local or across NVLink/NVSwitch
+// (IPC-mapped peer pointers).  No staging rows, no all-to-all, no host round trip; with evenly
+// spread weights almost every slot resolves locally.  Same integer arithmetic as the single-GPU
+// gather, so the global list is identical.
+// ======================================================================================
+__global__ void __launch_bounds__(256) pull_kernel(const PullArgs a) {
+  __shared__ SysPlan s_plan;
+  __shared__ uint64_t s_off[MAX_WORLD + 1];
+  if (threadIdx.x == 0) {
+    uint64_t T = 0;
+    for (int g = 0; g < a.world; g++) {
+      s_off[g] = T;
+      T += a.totals[g];
+    }
+    s_off[a.world] = T;
+    SysPlan p;
+    p.total = T;
+    p.n = (uint64_t)a.n_global;
+    p.a = T / p.n;
+    p.b = T % p.n;
+    p.r = __umul64hi(a.u0_bits, T);
+    s_plan = p;
+    if (T == 0 && blockIdx.x == 0) *a.zero_flag = 1ull;
+  }
+  __syncthreads();
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.count) return;
+  const SysPlan plan = s_plan;
+  const int64_t m = a.slot0 + k;
+  int g = 0;
+  int64_t i = 0;
+  if (plan.total == 0) { /* degenerate: all weights zero -> keep the particle that sits in the slot */
+    for (g = 0; g + 1 < a.world && m >= a.peer[g + 1].gid0; g++) {}
+    i = m - a.peer[g].gid0;
+  } else {
+    const uint64_t U = sys_threshold(plan, (uint64_t)m);
+    for (g = 0; g + 1 < a.world && U >= s_off[g + 1]; g++) {}
+    const uint64_t key = U - s_off[g];
+    const uint64_t *cdf = a.peer[g].cdf;
+    int64_t lo = 0, hi = a.peer[g].n;
+    while (lo < hi) { /* first i with cdf[i] > key */
+      int64_t mid = (lo + hi) >> 1;
+      if (cdf[mid] > key) hi = mid; else lo = mid + 1;
+    }
+    i = lo < a.peer[g].n ? lo : a.peer[g].n - 1;
+  }
+  a.ox[k] = a.peer[g].x[i];
+  a.oy[k] = a.peer[g].y[i];
+  a.oth[k] = a.peer[g].th[i];
+  a.ow[k] = a.wout;
+  if (a.oidx64) a.oidx64[k] = a.peer[g].gid0 + i;
+}
+
+cudaError_t launch_pull(const PullArgs &a, cudaStream_t s) {
+  if (a.count <= 0) return cudaSuccess;
+  pull_kernel<<<(unsigned)((a.count + 255) / 256), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
 }  // namespace amclj

@@ -82,6 +82,12 @@ struct MotionLaunch {
   float rot1, trans, rot2, sd1, sdt, sd2;
 };
 
+constexpr int MAX_WORLD = 16;
+struct PeerView {   /* one rank's shard as seen from this GPU (own memory or NVLink peer memory) */
+  const float *x, *y, *th;
+  const uint64_t *cdf;
+  int64_t n, gid0;
+};
 }  // namespace amclj
 
 struct amclj_ctx {
@@ -124,6 +130,13 @@ struct amclj_ctx {
   // sharding
   int32_t rank = 0, world = 1;
   int64_t global_offset = 0, n_global = 0;
+  // peer-memory resampling: both particle buffer sets of every rank (A = current at export)
+  amclj::PeerView peers[2][amclj::MAX_WORLD];
+  bool peer_set[amclj::MAX_WORLD] = {};
+  void *ipc_opened[amclj::MAX_WORLD][7] = {};
+  int flip = 0;            // swaps since export, mod 2
+  bool frozen = false;     // buffers exported: no reallocation
+  uint64_t *totals_all = nullptr;  // [MAX_WORLD] all-gathered totals
   float4 *stage_out = nullptr, *stage_in = nullptr;
   int64_t stage_cap = 0;
   int64_t *stage_idx = nullptr;
@@ -163,6 +176,19 @@ struct GatherArgs {
   int64_t gid0;
   float wout;
 };
+struct PullArgs {
+  PeerView peer[MAX_WORLD];
+  int32_t world;
+  const uint64_t *totals;  /* device [world]: every rank's fixed-point weight total */
+  uint64_t u0_bits;
+  int64_t n_global, slot0, count;
+  float *ox, *oy, *oth, *ow;
+  int64_t *oidx64;
+  float wout;
+  unsigned long long *zero_flag;
+};
+cudaError_t launch_pull(const PullArgs &a, cudaStream_t s);
+
 struct RouletteArgs {
   const uint64_t *cdf;
   int64_t n;

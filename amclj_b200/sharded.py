@@ -8,7 +8,13 @@ One update needs exactly three exchanges:
   2. all-gather of the per-rank fixed-point weight totals   -> every rank derives the global
      total T, its exclusive prefix and, in closed form, the contiguous range of output slots
      whose systematic thresholds fall into its CDF interval (amclj_plan_systematic)
-  3. all-to-all of the generated offspring rows             -> slot m lives on rank m / (N/G)
+  3. the particles themselves, in one of two ways:
+     "pull" (default on GPUs): every rank fills its own output slots by reading the owning
+         rank's CDF and particles through NVLink peer pointers inside one kernel
+         (amclj_shard_pull_async; CUDA IPC handles are exchanged once) — no staging, no
+         all-to-all, no host round trip;
+     "a2a": each rank generates the offspring of its CDF interval and an NCCL all-to-all moves
+         the rows to the ranks that own the slots (slot m lives on rank m / (N/G)).
 
 The resulting global index list is identical to the single-GPU one (integer CDF).  The
 reference has no counterpart (single-threaded Clojure, pf.clj:222-240); this is the
@@ -63,6 +69,25 @@ class CudaShard:
     def empty(self, *shape, dtype):
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
+    # -- peer-memory ("pull") variant ---------------------------------------------------------
+    def connect_peers(self, rank, world, n_global, group=None):
+        """Exchange CUDA IPC handles once; afterwards every rank can read every shard."""
+        mine = self.ctx.shard_export()
+        handles = [None] * world
+        dist.all_gather_object(handles, mine, group=group)
+        for g in range(world):
+            lo, cnt = slots_of(g, world, n_global)
+            if g == rank:
+                self.ctx.shard_attach_local(g, self.ctx)
+            else:
+                self.ctx.shard_import(g, handles[g], cnt, lo)
+
+    def totals_all(self, world) -> torch.Tensor:
+        return self.ctx.device_tensor(_lib.BUF_TOTALS_ALL, (16,), "<i8")[:world]
+
+    def pull(self, u0):
+        self.ctx.shard_pull_async(u0)
+
 
 def slots_of(rank, world, n_global):
     """Output slots owned by ``rank``: n_global / world each, the remainder to the low ranks."""
@@ -72,15 +97,25 @@ def slots_of(rank, world, n_global):
 
 
 class ShardedFilter:
-    def __init__(self, ctx, rank, world, n_global, device, stream=None, backend=None, group=None):
+    def __init__(self, ctx, rank, world, n_global, device, stream=None, backend=None, group=None,
+                 mode=None):
         self.rank, self.world, self.n_global, self.group = rank, world, int(n_global), group
         self.backend = backend if backend is not None else CudaShard(ctx, device)
         self.ctx = ctx
         self.stream = stream
         self.slot0, self.n_slots = slots_of(rank, world, self.n_global)
         self.backend.set_shard(rank, world, self.slot0, self.n_global)
-        self.backend.reserve(max(self.n_slots, 1))
+        self.mode = mode or ("pull" if backend is None and world <= 16 else "a2a")
+        self.connected = False
+        if self.mode == "a2a":
+            self.backend.reserve(max(self.n_slots, 1))
         self.last_plan = None
+
+    def connect(self):
+        """Pull mode: map the peers' buffers (call once, after the particles are in place)."""
+        if self.mode == "pull" and not self.connected:
+            self.backend.connect_peers(self.rank, self.world, self.n_global, self.group)
+            self.connected = True
 
     def stage_scan(self, scan):
         self.ctx.stage_scan(scan.ranges, scan.angle_min, scan.angle_inc, scan.range_max)
@@ -94,6 +129,11 @@ class ShardedFilter:
         mx = b.raw_max()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
         tot = b.cdf()
+        if self.mode == "pull":
+            self.connect()
+            dist.all_gather_into_tensor(b.totals_all(self.world), tot, group=self.group)
+            b.pull(u0)  # reads the peers' CDFs and particles over NVLink; no host round trip
+            return None
         totals = b.empty(self.world, dtype=torch.int64)
         dist.all_gather_into_tensor(totals, tot, group=self.group)
         h = totals.cpu().numpy().view(np.uint64)  # the one host round trip of the update

@@ -196,10 +196,12 @@ def run_b200(args):
     ctx.set_map(w.grid)
     ctx.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max) if world == 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    filt = ShardedFilter(ctx, rank, world, w.n * world, dev) if world > 1 else None
-    if filt:
+    filt = None
+    if world > 1:
         ctx.set_particles(w.x, w.y, w.theta)
+        filt = ShardedFilter(ctx, rank, world, w.n * world, dev, mode=args.shard_mode)
         filt.stage_scan(s)
+        filt.connect()
 
     def one_step(k):
         if filt:
@@ -361,6 +363,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--cpu-sample", type=int, default=100_000)
+    ap.add_argument("--shard-mode", default="pull", choices=["pull", "a2a"])
     ap.add_argument("--quick", action="store_true", help="skip the CPU baseline leg (tuning sweeps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -248,6 +248,23 @@ int32_t amclj_shard_generate_async(amclj_ctx *ctx, uint64_t total_global, uint64
 int32_t amclj_shard_get_stage_idx(amclj_ctx *ctx, int64_t *idx_out, int64_t count);
 /* Stage 4: adopt `count` float4 rows from AMCLJ_BUF_STAGE_IN as the new local particles. */
 int32_t amclj_shard_adopt_async(amclj_ctx *ctx, int64_t count);
+/* Peer-memory variant of stages 3-4 (no staging rows, no all-to-all, no host round trip): every
+ * rank PULLS its own output slots from whichever rank's CDF interval holds the slot's threshold,
+ * reading that rank's CDF and particles through NVLink peer pointers.
+ *   export: CUDA IPC handles (AMCLJ_IPC_BUFFERS x AMCLJ_IPC_HANDLE_BYTES) of this ctx's particle
+ *           and CDF buffers; freezes their size.  import: map rank `rank`'s buffers (n_peer
+ *           particles starting at global id peer_global_offset).  attach_local: the same for a ctx
+ *           of this process (also used for the ctx's own rank).
+ *   pull:   needs the all-gathered totals in AMCLJ_BUF_TOTALS_ALL (uint64[world]) and the CDF of
+ *           stage 2; fills this rank's slots [global_offset, global_offset + n) and swaps them in.
+ * Every rank must call pull the same number of times (the buffer sets alternate in lock step). */
+#define AMCLJ_IPC_HANDLE_BYTES 64
+#define AMCLJ_IPC_BUFFERS 7
+int32_t amclj_shard_export(amclj_ctx *ctx, uint8_t *handles);
+int32_t amclj_shard_import(amclj_ctx *ctx, int32_t rank, const uint8_t *handles, int64_t n_peer,
+                           int64_t peer_global_offset);
+int32_t amclj_shard_attach_local(amclj_ctx *ctx, int32_t rank, amclj_ctx *peer);
+int32_t amclj_shard_pull_async(amclj_ctx *ctx, double u0);
 /* Host-only planning (no GPU needed): for per-rank totals T_g, systematic offset
  * r = floor(u0 * T), and slots split evenly (n_global / world per rank, remainder to the
  * low ranks) computes m_lo[g], m_cnt[g] and the world x world send matrix (row = source). */
@@ -265,6 +282,7 @@ int32_t amclj_plan_systematic(const uint64_t *totals, int32_t world, int64_t n_g
 #define AMCLJ_BUF_STAGE_OUT 7 /* float4[capacity] */
 #define AMCLJ_BUF_STAGE_IN 8  /* float4[capacity] */
 #define AMCLJ_BUF_CDF 9       /* uint64[n] */
+#define AMCLJ_BUF_TOTALS_ALL 10 /* uint64[16]: all-gather target for the per-rank totals */
 /* Raw device pointer + size in bytes of a library-owned buffer, for zero-copy interop
  * with the host framework's collectives (the pointer stays valid until the particle count
  * changes or the ctx is destroyed). */

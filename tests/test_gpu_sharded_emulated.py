@@ -94,3 +94,57 @@ def test_weights_do_not_depend_on_task_split(monkeypatch):
         out.append(c.raw_weights())
         c.close()
     assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
+
+
+@pytest.mark.parametrize("world,n", [(2, 20_000), (3, 10_001), (8, 64_000)])
+def test_sharded_pull_equals_single(world, n):
+    """Peer-memory variant (amclj_shard_pull_async): every rank fills its own slots by reading
+    the owning rank's CDF and particles; here the 'peers' are contexts of one process."""
+    import torch
+
+    g = maps.lgfloor()
+    w = workloads.c3(n)
+    s = w.scan
+    ref = _lib.Context(0, "NS")
+    ref.set_map(g)
+    ref.set_particles(w.x, w.y, w.theta)
+    shards = []
+    for r in range(world):
+        lo, cnt = slots_of(r, world, n)
+        c = _lib.Context(0, "NS")
+        c.set_map(g)
+        c.set_shard(r, world, lo, n)
+        c.set_particles(w.x[lo:lo + cnt], w.y[lo:lo + cnt], w.theta[lo:lo + cnt])
+        c.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max)
+        shards.append(c)
+    for c in shards:
+        for r, peer in enumerate(shards):
+            c.shard_attach_local(r, peer)
+    for it in range(3):
+        ref.filter_update(w.curr, w.prev, s.ranges, s.angle_min, s.angle_inc, s.range_max, w.u0, seed=9 + it)
+        for c in shards:
+            c.shard_motion_sensor_async(w.curr, w.prev, 9 + it)
+            c.synchronize()
+        mx = max(float(c.device_tensor(_lib.BUF_RAW_MAX, (1,), "<f4").cpu()[0]) for c in shards)
+        totals = []
+        for c in shards:
+            c.device_tensor(_lib.BUF_RAW_MAX, (1,), "<f4").fill_(mx)
+            torch.cuda.synchronize()
+            c.shard_cdf_async()
+            c.synchronize()
+            totals.append(int(c.device_tensor(_lib.BUF_TOTAL, (1,), "<i8").cpu()[0]))
+        tot = torch.tensor(totals, dtype=torch.int64, device="cuda")
+        for c in shards:
+            c.device_tensor(_lib.BUF_TOTALS_ALL, (16,), "<i8")[:world].copy_(tot)
+        torch.cuda.synchronize()
+        for c in shards:
+            c.shard_pull_async(w.u0)
+            c.synchronize()
+    rx, ry, rt, rw = ref.get_particles()
+    got = [c.get_particles() for c in shards]
+    for k, refv in enumerate((rx, ry, rt)):
+        assert np.array_equal(np.concatenate([g_[k] for g_ in got]), refv)
+    np.testing.assert_allclose(np.concatenate([g_[3] for g_ in got]), rw, rtol=1e-7)
+    for c in shards:
+        c.close()
+    ref.close()

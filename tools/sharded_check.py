@@ -22,6 +22,7 @@ from amclj_b200.sharded import ShardedFilter, slots_of  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
+    mode = sys.argv[2] if len(sys.argv) > 2 else "pull"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -36,7 +37,7 @@ def main():
     ctx.set_shard(rank, world, lo, n)
     ctx.set_particles(w.x[lo:lo + cnt], w.y[lo:lo + cnt], w.theta[lo:lo + cnt])
     with torch.cuda.stream(stream):
-        f = ShardedFilter(ctx, rank, world, n, dev)
+        f = ShardedFilter(ctx, rank, world, n, dev, mode=mode)
         f.stage_scan(s)
         for it in range(2):  # two consecutive updates: the second starts from rebalanced shards
             f.update(w.curr, w.prev, seed=77 + it, u0=w.u0)
@@ -56,7 +57,7 @@ def main():
         full = np.concatenate(got, axis=0)
         ok = (np.array_equal(full[:, 0], rx) and np.array_equal(full[:, 1], ry) and np.array_equal(full[:, 2], rt)
               and np.allclose(full[:, 3], rw))
-        print(f"SHARDED_GPU_{'OK' if ok else 'MISMATCH'} world={world} n={n} "
+        print(f"SHARDED_GPU_{'OK' if ok else 'MISMATCH'} mode={mode} world={world} n={n} "
               f"mismatching_slots={(full[:, 0] != rx).sum()}", flush=True)
         ref.close()
     dist.barrier()
