@@ -6,8 +6,9 @@ normalise -> systematic resample) on synthetic inputs of BASELINE.json's configu
 
 N = 1: config C2 (lgfloor, 100k particles x 360 beams, pose tracking).  N > 1 (torchrun, one
 rank per GPU): the C4 workload (10M particles x 360 beams over 8 GPUs) at its per-GPU share,
-1.25M particles per rank, weak scaling; NCCL all-reduce(max) + all-gather(totals) +
-all-to-all particle rebalance per update.
+1.25M particles per rank, weak scaling; per update an NCCL all-reduce(max) and all-gather(totals),
+then every rank pulls its resampled slots from the owning rank over NVLink peer memory
+(--shard-mode a2a: generate + NCCL all-to-all instead).
 
 Prints ONE JSON line (rank 0).  `value` = beam evaluations per second with the particle set
 resident in HBM; `e2e` = the same through the host-buffer C-ABI call
@@ -36,7 +37,7 @@ if str(ROOT) not in sys.path:
 METRIC = "beam_evals_per_s"
 UNIT = "beam-evals/s"
 PER_GPU_SHARDED = 1_250_000  # C4: 10M particles over 8 GPUs
-KERNELS_PER_UPDATE = 6       # motion, sensor, decode-max, scan, plan, gather
+KERNELS_PER_UPDATE = 5       # 1 GPU: motion, sensor, combine, scan, gather; sharded: motion, sensor, decode-max, scan, pull
 
 
 def peaks():
