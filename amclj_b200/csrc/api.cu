@@ -169,6 +169,7 @@ int df_mode_of(const amclj_ctx *ctx) {
     case 1: return ctx->map.fits_smem ? DF_SMEM4 : -1;
     case 2: return ctx->map.df8 ? DF_GLOBAL8 : -1;
     case 3: return DF_GLOBAL4;
+    case 4: return ctx->map.wedge ? DF_WEDGE8 : -1;
     default: return ctx->map.fits_smem ? DF_SMEM4 : (ctx->map.df8 ? DF_GLOBAL8 : DF_GLOBAL4);
   }
 }
@@ -220,7 +221,7 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
   int ndiv = (int)ceil(rcells) + 8;
   int mode = df_mode_of(ctx);
   NEED(mode >= 0, AMCLJ_ERR_INVALID, "scan: df_mode %d unavailable for this map", ctx->p.df_mode);
-  int dcap = mode == DF_GLOBAL8 ? 255 : 15;
+  int dcap = (mode == DF_GLOBAL8 || mode == DF_WEDGE8) ? 255 : 15;
   uint64_t Dmax = 2ull * (uint64_t)(ndiv - 1);
   int wide = (uint64_t)(dcap + 1) * Dmax * Dmax > (1ull << 32);
   DivTable &d = ctx->divs;
@@ -256,7 +257,12 @@ void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode) {
   a.W = m.W;
   a.H = m.H;
   a.res = m.res;
-  if (mode == DF_GLOBAL8) {
+  if (mode == DF_WEDGE8) {
+    a.df = m.wedge;
+    a.row_nib = m.pitch8;
+    a.df_bytes = m.wedge_plane * WEDGE_CLASSES;
+    a.wedge_plane = (int32_t)m.wedge_plane;
+  } else if (mode == DF_GLOBAL8) {
     a.df = m.df8;
     a.row_nib = m.pitch8;
     a.df_bytes = m.bytes8;
@@ -270,7 +276,7 @@ void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode) {
   a.divtab = ctx->divs.dev;
   a.ndiv = ctx->divs.n;
   a.div_wide = ctx->divs.wide;
-  a.refill = ctx->refill;
+  a.refill = mode == DF_WEDGE8 ? ctx->refill_wedge : ctx->refill;
   a.chunks = 1;
   a.R = p.s2_use_scan_range_max ? ctx->beams.range_max : p.max_range;
   a.miss_value = a.R; /* sensor.clj:121 returns max-range on a miss */
@@ -305,10 +311,11 @@ int enqueue_motion(amclj_ctx *ctx, const double curr[3], const double prev[3], b
 
 /* clear the control block: everything (with_max) or only what the scan accumulates into */
 cudaError_t reset_ctrl(amclj_ctx *ctx, bool with_max) {
+  /* layout: [0..1] particle bounding box | [2] max | [3] total | [4] tile counter | [5..] tiles */
   size_t words = (size_t)scan_tiles(ctx->n) + 2;
   ctx->scan_clean = true;
-  if (with_max) return cudaMemsetAsync(ctx->ctrl, 0, sizeof(uint64_t) * (words + 1), ctx->stream);
-  return cudaMemsetAsync(ctx->ctrl + 1, 0, sizeof(uint64_t) * words, ctx->stream);
+  if (with_max) return cudaMemsetAsync(ctx->ctrl, 0, sizeof(uint64_t) * (words + 3), ctx->stream);
+  return cudaMemsetAsync(ctx->ctrl + 3, 0, sizeof(uint64_t) * words, ctx->stream);
 }
 
 /* decode_max: also materialise the max as a float (AMCLJ_BUF_RAW_MAX) for a cross-rank all-reduce */
@@ -340,8 +347,32 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
   bool diag = ctx->p.collect_stats != 0;
   a.stats = diag ? ctx->stats : nullptr;
   CK(reset_ctrl(ctx, true));
-  if (diag) CK(cudaMemsetAsync(ctx->stats, 0, 7 * sizeof(unsigned long long), ctx->stream));
-  CK(launch_sensor(ctx, a, mode, diag, ctx->stream));
+  if (diag) {
+    CK(cudaMemsetAsync(ctx->stats, 0, 7 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->stats + 8, 0, sizeof(unsigned long long), ctx->stream));
+  }
+  /* df_mode 0 on a map with both field sets: the directional fields win when the particles sit
+   * close together (their probes share a small L1 working set), the shared-memory field when they
+   * are spread out.  Both kernels are launched; each looks at the particle bounding box and the
+   * one that is not selected returns at once.  The results are identical either way. */
+  bool both = ctx->p.df_mode == 0 && mode == DF_SMEM4 && ctx->map.wedge != nullptr;
+  if (both) {
+    CK(launch_bbox(ctx->x, ctx->y, ctx->n, ctx->bbox, ctx->sm_count, ctx->stream));
+    a.bbox = ctx->bbox;
+    a.compact_m = ctx->compact_cells * ctx->map.res;
+    a.auto_sel = 2; /* run when NOT compact */
+    a.skip_combine = 1; /* the chunk partials are combined once, after the second launch */
+    CK(launch_sensor(ctx, a, DF_SMEM4, diag, ctx->stream));
+    SensorLaunch b;
+    fill_sensor_args(ctx, b, DF_WEDGE8);
+    b.x = a.x; b.y = a.y; b.th = a.th; b.raw = a.raw; b.n = a.n; b.rawmax_ord = a.rawmax_ord;
+    b.chunks = a.chunks; b.partials = a.partials; b.stats = a.stats;
+    b.bbox = ctx->bbox; b.compact_m = a.compact_m;
+    b.auto_sel = 1; /* run when compact */
+    CK(launch_sensor(ctx, b, DF_WEDGE8, diag, ctx->stream));
+  } else {
+    CK(launch_sensor(ctx, a, mode, diag, ctx->stream));
+  }
   if (decode_max) CK(launch_decode_max(ctx->rawmax_ord, ctx->rawmax, ctx->stream));
   ctx->max_in_ord = !decode_max;
   ctx->have_raw = true;
@@ -566,26 +597,30 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
     if (v >= 1 && v <= 32) ctx->refill = v;
   }
   if (const char *e = getenv("AMCLJ_CHUNKS")) ctx->force_chunks = atoi(e);
+  if (const char *e = getenv("AMCLJ_REFILL_WEDGE")) ctx->refill_wedge = atoi(e);
+  if (const char *e = getenv("AMCLJ_COMPACT_CELLS")) ctx->compact_cells = (float)atof(e);
   memset(&ctx->st, 0, sizeof(ctx->st));
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ctx->stream = ctx->own_stream;
   for (int i = 0; ok && i < 5; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
-  /* control block: [0] ordered-uint max | [1] fixed-point total | [2] tile counter | [3..] tile
-   * descriptors of the scan (2^20 tiles = 2^31 particles; also serves the roulette compaction) */
+  /* control block: [0..1] particle bounding box (4 ordered-uint maxima) | [2] ordered-uint max
+   * weight | [3] fixed-point total | [4] tile counter | [5..] tile descriptors of the scan (2^20
+   * tiles = 2^31 particles; also serves the roulette compaction) */
   ctx->scan_state_cap = 1 << 20;
-  ok = ok && dalloc(&ctx->ctrl, (size_t)ctx->scan_state_cap + 3) == cudaSuccess;
+  ok = ok && dalloc(&ctx->ctrl, (size_t)ctx->scan_state_cap + 5) == cudaSuccess;
   if (ok) {
-    ctx->rawmax_ord = reinterpret_cast<uint32_t *>(ctx->ctrl);
-    ctx->total = ctx->ctrl + 1;
-    ctx->scan_counter = reinterpret_cast<uint32_t *>(ctx->ctrl + 2);
-    ctx->scan_state = ctx->ctrl + 3;
-    ok = cudaMemset(ctx->ctrl, 0, sizeof(uint64_t) * ((size_t)ctx->scan_state_cap + 3)) == cudaSuccess;
+    ctx->bbox = reinterpret_cast<uint32_t *>(ctx->ctrl);
+    ctx->rawmax_ord = reinterpret_cast<uint32_t *>(ctx->ctrl + 2);
+    ctx->total = ctx->ctrl + 3;
+    ctx->scan_counter = reinterpret_cast<uint32_t *>(ctx->ctrl + 4);
+    ctx->scan_state = ctx->ctrl + 5;
+    ok = cudaMemset(ctx->ctrl, 0, sizeof(uint64_t) * ((size_t)ctx->scan_state_cap + 5)) == cudaSuccess;
   }
-  ok = ok && dalloc(&ctx->rawmax, 1) == cudaSuccess && dalloc(&ctx->stats, 8) == cudaSuccess &&
+  ok = ok && dalloc(&ctx->rawmax, 1) == cudaSuccess && dalloc(&ctx->stats, 12) == cudaSuccess &&
        dalloc(&ctx->plan, 1) == cudaSuccess && dalloc(&ctx->totals_all, MAX_WORLD) == cudaSuccess &&
        dalloc(&ctx->pose_part, (size_t)pose_blocks() * 4) == cudaSuccess &&
        cudaMallocHost(&ctx->pinned, 4096) == cudaSuccess;
-  if (ok) ok = cudaMemset(ctx->stats, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;
+  if (ok) ok = cudaMemset(ctx->stats, 0, 12 * sizeof(unsigned long long)) == cudaSuccess;
   if (!ok) {
     amclj_destroy(ctx);
     return AMCLJ_ERR_CUDA;
@@ -599,7 +634,7 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
   if (!ctx) return AMCLJ_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  dfree(ctx->map.cells); dfree(ctx->map.df4); dfree(ctx->map.df8);
+  dfree(ctx->map.cells); dfree(ctx->map.df4); dfree(ctx->map.df8); dfree(ctx->map.wedge);
   dfree(ctx->beams.dev); dfree(ctx->divs.dev);
   dfree(ctx->x); dfree(ctx->y); dfree(ctx->th); dfree(ctx->w); dfree(ctx->raw);
   dfree(ctx->x2); dfree(ctx->y2); dfree(ctx->th2); dfree(ctx->w2);
@@ -636,7 +671,12 @@ int32_t amclj_synchronize(amclj_ctx *ctx) {
 int32_t amclj_set_params(amclj_ctx *ctx, const amclj_params *p) {
   ENTER();
   NEED(p, AMCLJ_ERR_INVALID, "set_params: null");
-  NEED(p->df_mode >= 0 && p->df_mode <= 3, AMCLJ_ERR_INVALID, "set_params: df_mode %d", p->df_mode);
+  NEED(p->df_mode >= 0 && p->df_mode <= 4, AMCLJ_ERR_INVALID, "set_params: df_mode %d", p->df_mode);
+  if (p->df_mode == 4 && ctx->map.cells && !ctx->map.wedge) { /* directional fields are built on demand */
+    NEED((size_t)ctx->map.pitch8 * (ctx->map.H + 2) * WEDGE_CLASSES <= (512ull << 20), AMCLJ_ERR_INVALID,
+         "set_params: map too large for directional fields");
+    CK(build_wedge_fields(ctx, ctx->stream));
+  }
   NEED(p->s8_resampler >= 0 && p->s8_resampler <= 2, AMCLJ_ERR_INVALID, "set_params: resampler %d", p->s8_resampler);
   ctx->p = *p;
   ctx->beams.staged = false; /* the beam table bakes S2/S5/S6 and the mixture constants */
@@ -670,7 +710,7 @@ int32_t amclj_set_map(amclj_ctx *ctx, const int8_t *cells, int32_t width, int32_
   NEED(isfinite(resolution) && resolution > 0.f, AMCLJ_ERR_INVALID, "set_map: bad resolution");
   CK(cudaStreamSynchronize(ctx->stream));
   DeviceMap &m = ctx->map;
-  dfree(m.cells); dfree(m.df4); dfree(m.df8);
+  dfree(m.cells); dfree(m.df4); dfree(m.df8); dfree(m.wedge);
   m.W = width;
   m.H = height;
   m.res = resolution;
@@ -686,6 +726,12 @@ int32_t amclj_set_map(amclj_ctx *ctx, const int8_t *cells, int32_t width, int32_
   m.bytes8 = (size_t)m.pitch8 * (height + 2);
   if (want8) CK(dalloc(&m.df8, m.bytes8));
   CK(build_distance_fields(ctx, want8, ctx->stream));
+  if (ctx->p.df_mode == 4) {
+    NEED(m.bytes8 * WEDGE_CLASSES <= (512ull << 20), AMCLJ_ERR_INVALID, "set_map: map too large for directional fields");
+    CK(build_wedge_fields(ctx, ctx->stream));
+  } else if (ctx->p.df_mode == 0 && m.fits_smem && m.bytes8 * WEDGE_CLASSES <= (64ull << 20)) {
+    CK(build_wedge_fields(ctx, ctx->stream)); /* auto: both field sets, chosen per update */
+  }
   ctx->beams.staged = false;
   ctx->divs.n = 0;
   ctx->st.map_in_smem = m.fits_smem;
@@ -1027,9 +1073,10 @@ int32_t amclj_get_stats(amclj_ctx *ctx, amclj_stats *out) {
   NEED(out, AMCLJ_ERR_INVALID, "get_stats: null");
   CK(cudaStreamSynchronize(ctx->stream));
   collect_times(ctx);
-  unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long h[12] = {0};
   CK(cudaMemcpy(h, ctx->stats, sizeof(h), cudaMemcpyDeviceToHost));
   ctx->st.oob_probes = h[6];
+  if (h[8]) ctx->st.map_in_smem = (int)h[8] - 1 == DF_SMEM4; /* the placement that actually ran */
   ctx->st.rays = h[0];
   ctx->st.cells_visited = h[1];
   ctx->st.probes = h[2];

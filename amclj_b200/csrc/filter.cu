@@ -175,6 +175,40 @@ cudaError_t launch_decode_max(const uint32_t *ord, float *out, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// bounding box of the particle set as four maxima (x, -x, y, -y) in ordered-uint form, so that
+// a zeroed control block is the identity and a NaN coordinate poisons the box (-> "not compact")
+__global__ void __launch_bounds__(256)
+bbox_kernel(const float *__restrict__ x, const float *__restrict__ y, int64_t n, uint32_t *bbox) {
+  uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float px = __ldg(x + i), py = __ldg(y + i);
+    m0 = max(m0, ord_of_float(px));
+    m1 = max(m1, ord_of_float(-px));
+    m2 = max(m2, ord_of_float(py));
+    m3 = max(m3, ord_of_float(-py));
+  }
+  m0 = __reduce_max_sync(0xffffffffu, m0);
+  m1 = __reduce_max_sync(0xffffffffu, m1);
+  m2 = __reduce_max_sync(0xffffffffu, m2);
+  m3 = __reduce_max_sync(0xffffffffu, m3);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(bbox + 0, m0);
+    atomicMax(bbox + 1, m1);
+    atomicMax(bbox + 2, m2);
+    atomicMax(bbox + 3, m3);
+  }
+}
+
+cudaError_t launch_bbox(const float *x, const float *y, int64_t n, uint32_t *bbox, int sm_count,
+                        cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  int64_t blocks = (n + 1023) / 1024;
+  if (blocks > (int64_t)sm_count * 4) blocks = (int64_t)sm_count * 4;
+  bbox_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, y, n, bbox);
+  return cudaGetLastError();
+}
+
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
@@ -837,6 +871,56 @@ cudaError_t launch_pull(const PullArgs &a, cudaStream_t s) {
   if (a.count <= 0) return cudaSuccess;
   pull_kernel<<<(unsigned)((a.count + 255) / 256), 256, 0, s>>>(a);
   return cudaGetLastError();
+}
+
+
+// ======================================================================================
+// Directional ("wedge") distance fields.  For a direction class (steep, x step, y step, slope
+// bin [lo, hi]) and a free cell c, w(c) is the smallest k >= 1 such that some cell a Bresenham
+// line of that class could occupy k steps after c is blocked: major offset k, minor offset in
+// [floor(k*lo), floor(k*hi) + 1]  (the line's own offset is floor(k*s) or floor(k*s) + 1 for its
+// slope s in [lo, hi], whatever its error state at c).  All cells of the line at steps 1..w-1 are
+// therefore free, so the walk may jump w steps — the same exactness argument as for the isotropic
+// field, but obstacles beside or behind the ray no longer shorten the jump.
+// ======================================================================================
+__global__ void __launch_bounds__(128)
+wedge_build_kernel(const int8_t *__restrict__ cells, int W, int H, int pitch, size_t plane,
+                   uint8_t *__restrict__ out) {
+  const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y, cls = blockIdx.z;
+  if (px >= W + 2) return;
+  const int bin = cls % WEDGE_BINS, ysn = (cls / WEDGE_BINS) & 1, xsn = (cls / (2 * WEDGE_BINS)) & 1,
+            steep = (cls / (4 * WEDGE_BINS)) & 1;
+  const int xs = xsn ? -1 : 1, ys = ysn ? -1 : 1;
+  auto blocked = [&](int qx, int qy) -> bool { /* padded coordinates */
+    if (qx <= 0 || qx >= W + 1 || qy <= 0 || qy >= H + 1) return true;
+    return cells[(size_t)(qy - 1) * W + (qx - 1)] != 0;
+  };
+  int d = 0;
+  if (!blocked(px, py)) {
+    d = 255;
+    for (int k = 1; k < 255 && d == 255; k++) {
+      int jlo = (k * bin) / WEDGE_BINS, jhi = (k * (bin + 1)) / WEDGE_BINS + 1;
+      for (int j = jlo; j <= jhi; j++) {
+        int da = xs * k, db = ys * j;
+        int qx = steep ? px + db : px + da, qy = steep ? py + da : py + db;
+        if (blocked(qx, qy)) { d = k; break; }
+      }
+    }
+  }
+  out[(size_t)cls * plane + (size_t)py * pitch + px] = (uint8_t)d;
+}
+
+cudaError_t build_wedge_fields(amclj_ctx *c, cudaStream_t s) {
+  DeviceMap &m = c->map;
+  m.wedge_plane = (size_t)m.pitch8 * (m.H + 2);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&m.wedge), m.wedge_plane * WEDGE_CLASSES);
+  if (e != cudaSuccess) return e;
+  cudaMemsetAsync(m.wedge, 0, m.wedge_plane * WEDGE_CLASSES, s);
+  dim3 g((m.W + 2 + 127) / 128, m.H + 2, WEDGE_CLASSES);
+  wedge_build_kernel<<<g, 128, 0, s>>>(m.cells, m.W, m.H, m.pitch8, m.wedge_plane, m.wedge);
+  e = cudaGetLastError();
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  return e != cudaSuccess ? e : e2;
 }
 
 }  // namespace amclj

@@ -24,6 +24,8 @@ struct DeviceMap {
   int32_t row_bytes4 = 0;    // multiple of 16
   int32_t pitch8 = 0;
   size_t bytes4 = 0, bytes8 = 0;
+  uint8_t *wedge = nullptr;  // WEDGE_CLASSES planes of (H+2) x pitch8 bytes: directional distance fields
+  size_t wedge_plane = 0;
   bool fits_smem = false;
 };
 
@@ -47,6 +49,7 @@ struct SensorLaunch {
   int64_t n;
   const uint8_t *df;
   int32_t row_nib;   // nibbles (df4) or bytes (df8) per padded row
+  int32_t wedge_plane;  // bytes per direction class (DF_WEDGE8)
   int32_t W, H;
   size_t df_bytes;
   float res;
@@ -59,6 +62,10 @@ struct SensorLaunch {
   int32_t refill;    // set up new beams when fewer lanes than this (of 32) are still walking
   int32_t chunks;    // beam chunks per particle group (warp tasks = groups x chunks)
   long long *partials;  // [chunks][n] fixed-point partial weights when chunks > 1
+  const uint32_t *bbox;  // particle bounding box (auto policy), see launch_bbox
+  float compact_m;       // bounding-box side (metres) up to which the particle set counts as compact
+  int32_t auto_sel;      // 0: always run; 1: run only when compact; 2: only when not compact
+  int32_t skip_combine;  // leave the chunk partials to a later launch
   float R;            // ray length (S2)
   float miss_value;
   int32_t s1, s3, s4, s7, s10;
@@ -144,7 +151,9 @@ struct amclj_ctx {
   float last_wmax = 0.f;
   uint64_t last_total = 0;
   amclj_stats st;
-  int32_t refill = 6;
+  int32_t refill = 6, refill_wedge = 12;
+  float compact_cells = 64.f;  // auto policy: directional fields when the particle bounding box is this small
+  uint32_t *bbox = nullptr;    // 4 ordered-uint maxima: x, -x, y, -y (inside ctrl)
   double w_slow = 1.0, w_fast = 1.0;  // pf.clj:243-244
   uint32_t *hist = nullptr;           // 256-bin histogram of the radix select
   int32_t force_chunks = 0;
@@ -155,7 +164,10 @@ namespace amclj {
 // sensor.cu
 cudaError_t launch_sensor(const amclj_ctx *c, const SensorLaunch &a, int mode, bool diag,
                           cudaStream_t s);
-enum { DF_SMEM4 = 0, DF_GLOBAL8 = 1, DF_GLOBAL4 = 2 };
+enum { DF_SMEM4 = 0, DF_GLOBAL8 = 1, DF_GLOBAL4 = 2, DF_WEDGE8 = 3 };
+constexpr int WEDGE_BINS = 2;                   /* slope bins per octant */
+constexpr int WEDGE_CLASSES = 8 * WEDGE_BINS;   /* steep x xs x ys x bin */
+cudaError_t build_wedge_fields(amclj_ctx *c, cudaStream_t s);
 int sensor_chunks(const amclj_ctx *c, int64_t n, int nb);
 
 // filter.cu
@@ -206,6 +218,8 @@ struct RouletteArgs {
   unsigned long long *last_attempt; /* attempt index (+1) of the acceptance filling slot n-1 */
 };
 cudaError_t launch_motion(const MotionLaunch &a, cudaStream_t s);
+cudaError_t launch_bbox(const float *x, const float *y, int64_t n, uint32_t *bbox, int sm_count,
+                        cudaStream_t s);
 cudaError_t build_distance_fields(amclj_ctx *c, bool want8, cudaStream_t s);
 cudaError_t launch_max(const float *v, int64_t n, uint32_t *ord, float *out, int sm_count,
                        cudaStream_t s);

@@ -45,7 +45,7 @@ struct Field {
 
 template <int MODE>
 __device__ __forceinline__ uint32_t df_probe(const Field &f, int idx, uint32_t mask) {
-  if (MODE == DF_GLOBAL8) return (uint32_t)__ldg(f.g + idx) & mask;
+  if (MODE == DF_GLOBAL8 || MODE == DF_WEDGE8) return (uint32_t)__ldg(f.g + idx) & mask;
   uint32_t byte;
   if (MODE == DF_SMEM4) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(byte) : "r"(f.s + (uint32_t)(idx >> 3)));
@@ -133,11 +133,20 @@ __device__ __forceinline__ int32_t round_cell_fast(float v, const ResDiv &d) {
 #ifndef PROBES_PER_VOTE
 #define PROBES_PER_VOTE 8
 #endif
+#ifndef PROBES_PER_VOTE_WEDGE
+#define PROBES_PER_VOTE_WEDGE 4
+#endif
 
 template <int MODE, bool DIAG, bool WIDE, bool TS>
 __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaunch a) {
   extern __shared__ uint4 smem_dyn[];
   __shared__ uint64_t bar;
+  if (a.auto_sel) { /* two field placements were launched: only the one that suits the particle spread runs */
+    auto dec = [](uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); };
+    float wx = dec(a.bbox[0]) + dec(a.bbox[1]), wy = dec(a.bbox[2]) + dec(a.bbox[3]); /* max - min */
+    bool compact = wx <= a.compact_m && wy <= a.compact_m; /* NaN -> not compact */
+    if (compact != (a.auto_sel == 1)) return;
+  }
   Field df;
   df.g = a.df;
   df.s = 0;
@@ -196,14 +205,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
   const int wpb = blockDim.x >> 5;
   const int64_t nwarps = (int64_t)gridDim.x * wpb;
   const int nb = a.nb;
-  const int idx_scale = MODE == DF_GLOBAL8 ? 1 : 4;
-  const uint32_t DMASK = MODE == DF_GLOBAL8 ? 255u : 15u;
+  constexpr bool BYTES = MODE == DF_GLOBAL8 || MODE == DF_WEDGE8;
+  const int idx_scale = BYTES ? 1 : 4;
+  const uint32_t DMASK = BYTES ? 255u : 15u;
   const int row = a.row_nib * idx_scale;
   const int64_t ngroups = (a.n + 31) >> 5;
   const int64_t ntasks = ngroups * a.chunks;
   float wmax = -INFINITY;
   unsigned long long n_cells = 0, n_probes = 0, n_hits = 0, n_rays = 0, n_oob = 0;
-  const uint32_t idx_limit = (uint32_t)(a.df_bytes * (MODE == DF_GLOBAL8 ? 1u : 8u)); /* DIAG bounds check */
+  const uint32_t idx_limit = (uint32_t)(a.df_bytes * (BYTES ? 1u : 8u)); /* DIAG bounds check */
 
   /* task = 32 consecutive particles x one chunk of beams; chunk-major so that the warps of a
    * CTA work on neighbouring particles */
@@ -325,6 +335,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
           stepA = xs * (steep ? row : idx_scale);
           stepB = ys * (steep ? idx_scale : row);
           idx = idx0; k = 0; j = 0; err = 0; ndx = -dx;
+          if (MODE == DF_WEDGE8 && start_in) { /* the plane of this ray's direction class */
+            int bin = min(WEDGE_BINS - 1, (dy * WEDGE_BINS) / dx);
+            int cls = ((steep ? 1 : 0) * 4 + (xs < 0 ? 2 : 0) + (ys < 0 ? 1 : 0)) * WEDGE_BINS + bin;
+            idx += cls * a.wedge_plane;
+          }
           if (DIAG) { dg_a0 = a0; dg_b0 = b0; dg_xs = xs; dg_ys = ys; dg_steep = steep; dg_probes = 0; }
           have_ray = true;
           am = DMASK;
@@ -338,7 +353,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
       /* ---- (3) walk: sensor.clj:112-128 extract-line, d cells per probe ------------------ */
       do {
 #pragma unroll
-        for (int u = 0; u < PROBES_PER_VOTE; u++) {
+        for (int u = 0; u < (MODE == DF_WEDGE8 ? PROBES_PER_VOTE_WEDGE : PROBES_PER_VOTE); u++) {
           /* branch-free: a parked lane reads d = 0, which makes every update a no-op */
           if (DIAG && (uint32_t)idx >= idx_limit) { n_oob++; idx = 0; } /* never taken: see tests */
           const uint32_t d = df_probe<MODE>(df, idx, am);
@@ -381,6 +396,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
       n_oob += __shfl_xor_sync(FULL, n_oob, o);
     }
     if (lane == 0) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) a.stats[8] = (unsigned long long)MODE + 1ull;
       atomicAdd(a.stats + 0, n_rays);
       atomicAdd(a.stats + 1, n_cells);
       atomicAdd(a.stats + 2, n_probes);
@@ -469,10 +485,11 @@ cudaError_t launch_sensor(const amclj_ctx *c, const SensorLaunch &a_in, int mode
   switch (mode) {
     case DF_SMEM4: e = launch_m<DF_SMEM4>(c, a, diag, wide, s); break;
     case DF_GLOBAL8: e = launch_m<DF_GLOBAL8>(c, a, diag, wide, s); break;
+    case DF_WEDGE8: e = launch_m<DF_WEDGE8>(c, a, diag, wide, s); break;
     default: e = launch_m<DF_GLOBAL4>(c, a, diag, wide, s); break;
   }
   if (e != cudaSuccess) return e;
-  if (a.chunks > 1 && final_raw) {
+  if (a.chunks > 1 && final_raw && !a.skip_combine) {
     combine_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a.partials, a.chunks, a.n, final_raw,
                                                                  a.rawmax_ord);
     e = cudaGetLastError();

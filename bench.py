@@ -184,6 +184,9 @@ def run_b200(args):
 
     if world == 1:
         w = workloads.c2() if args.workload == "c2" else getattr(workloads, args.workload)()
+        if args.sd_xy is not None and args.workload == "c2":
+            w.x, w.y, w.theta = workloads.gaussian_particles(w.n, sd_xy=args.sd_xy)
+            w.name += f" (sd_xy {args.sd_xy} m)"
     else:
         w = workloads.c3(PER_GPU_SHARDED * world)
         lo = rank * PER_GPU_SHARDED
@@ -192,6 +195,7 @@ def run_b200(args):
     s = w.scan
     nb = len(s.ranges)
     ctx = _lib.Context(local, "NS")
+    ctx.set_params(_lib.params("NS", df_mode=args.df_mode))
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_map(w.grid)
@@ -276,7 +280,7 @@ def run_b200(args):
 
     # ---- diagnostic pass for the cell / probe counters (untimed; every rank takes part in
     # the collectives of the sharded update) -------------------------------------------
-    ctx.set_params(_lib.params("NS", collect_stats=1))
+    ctx.set_params(_lib.params("NS", collect_stats=1, df_mode=args.df_mode))
     restore()
     if filt:
         filt.stage_scan(s)
@@ -365,6 +369,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--cpu-sample", type=int, default=100_000)
     ap.add_argument("--shard-mode", default="pull", choices=["pull", "a2a"])
+    ap.add_argument("--sd-xy", type=float, default=None, help="C2 only: std-dev of the particle cloud in metres (policy experiments)")
+    ap.add_argument("--df-mode", type=int, default=0, help="amclj_params.df_mode (0 auto)")
     ap.add_argument("--quick", action="store_true", help="skip the CPU baseline leg (tuning sweeps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

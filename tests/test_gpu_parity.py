@@ -91,9 +91,10 @@ def test_raycast_switch_matrix(ctx, lg, switches):
     _ray_parity(ctx, lg, x, y, th, scan, "NS", **switches)
 
 
-@pytest.mark.parametrize("df_mode", [1, 2, 3])
+@pytest.mark.parametrize("df_mode", [1, 2, 3, 4])
 def test_raycast_all_field_placements(ctx, lg, df_mode):
-    """Shared-memory nibbles, global bytes and global nibbles give the same answers."""
+    """Shared-memory nibbles, global bytes, global nibbles and the directional (wedge) fields
+    give the same answers."""
     x, y, th = workloads.uniform_particles(lg, 1500, seed=13)
     ctx.set_params(_lib.params("NS", df_mode=df_mode))
     ctx.set_map(lg)
@@ -466,3 +467,51 @@ def test_augmented_selection(ctx, lg, scale):
         s2, f2 = ctx.augment_state()
         assert s2 == pytest.approx(slow, rel=1e-12) and f2 == pytest.approx(fast, rel=1e-12)
     assert (idx == -1).any() or scale == 1.0
+
+
+@pytest.mark.parametrize("preset,switches", [("NS", {}), ("REF", {}), ("NS", dict(s4_endpoint_termination=0)),
+                                             ("NS", dict(s3_proper_endpoint=0, s4_endpoint_termination=0)),
+                                             ("NS", dict(s1_use_heading=0, s10_apply_laser_offset=1))])
+def test_raycast_directional_fields_exact(ctx, lg, preset, switches):
+    """df_mode 4: the walk jumps by direction-class (wedge) distances; cells, steps and ranges
+    stay bit-identical to the reference's cell-by-cell Bresenham in every semantic mode."""
+    x, y, th = workloads.uniform_particles(lg, 4000, seed=17)
+    res = float(lg.info.resolution)
+    W, H = lg.info.width, lg.info.height
+    ex = np.array([-1.0, (W + 3) * res, 5.0, 0.0, (W - 0.6) * res, np.nan, 1e12], np.float32)
+    ey = np.array([5.0, 5.0, -2.0, 0.0, (H - 0.6) * res, 3.0, -1e12], np.float32)
+    x, y, th = np.concatenate([x, ex]), np.concatenate([y, ey]), np.concatenate([th, np.zeros(len(ex), np.float32)])
+    ctx.set_map(lg)
+    scan = workloads.make_scan(lg, workloads.TRUE_POSE, 360, -math.pi, 2 * math.pi / 360, 5.6)
+    s = _ray_parity(ctx, lg, x, y, th, scan, preset, df_mode=4, **switches)
+    assert s.map_in_smem == 0
+    if preset == "NS" and not switches:
+        assert s.probes < 0.7 * 7.4 * s.rays  # fewer probes than the isotropic field needs
+
+
+def test_auto_field_selection_by_particle_spread(lg):
+    """df_mode 0 on a map that has both field sets: a compact particle cloud runs on the
+    directional fields, a spread-out one on the shared-memory field; weights agree with the oracle
+    either way (and with each other bit for bit, since both walks are exact)."""
+    c = _lib.Context(0)
+    pl, po = _pair("NS", collect_stats=1)
+    c.set_params(pl)
+    c.set_map(lg)
+    scan = workloads.make_scan(lg, workloads.TRUE_POSE, 360, -math.pi, 2 * math.pi / 360, 5.6)
+    for spread, in_smem in ((False, 0), (True, 1)):
+        x, y, th = workloads.uniform_particles(lg, 3000, seed=3) if spread else workloads.gaussian_particles(3000)
+        c.set_particles(x, y, th)
+        c.sensor_update(scan.ranges, scan.angle_min, scan.angle_inc, scan.range_max)
+        assert c.stats().map_in_smem == in_smem
+        raw = c.raw_weights()
+        ref, _, _ = oracle.sensor_f32(po, lg, scan.ranges, scan.angle_min, scan.angle_inc, scan.range_max, x, y, th)
+        np.testing.assert_allclose(raw, ref, rtol=RTOL)
+        for forced in (1, 4):
+            c2 = _lib.Context(0)
+            c2.set_params(_lib.params("NS", df_mode=forced))
+            c2.set_map(lg)
+            c2.set_particles(x, y, th)
+            c2.sensor_update(scan.ranges, scan.angle_min, scan.angle_inc, scan.range_max)
+            assert np.array_equal(c2.raw_weights(), raw)
+            c2.close()
+    c.close()
