@@ -152,7 +152,7 @@ struct amclj_ctx {
   uint64_t last_total = 0;
   amclj_stats st;
   int32_t refill = 6, refill_wedge = 12;
-  float compact_cells = 64.f;  // auto policy: directional fields when the particle bounding box is this small
+  float compact_cells = 320.f;  // auto policy: directional fields when the particle bounding box is this small
   uint32_t *bbox = nullptr;    // 4 ordered-uint maxima: x, -x, y, -y (inside ctrl)
   double w_slow = 1.0, w_fast = 1.0;  // pf.clj:243-244
   uint32_t *hist = nullptr;           // 256-bin histogram of the radix select

@@ -134,7 +134,7 @@ __device__ __forceinline__ int32_t round_cell_fast(float v, const ResDiv &d) {
 #define PROBES_PER_VOTE 8
 #endif
 #ifndef PROBES_PER_VOTE_WEDGE
-#define PROBES_PER_VOTE_WEDGE 4
+#define PROBES_PER_VOTE_WEDGE 6
 #endif
 
 template <int MODE, bool DIAG, bool WIDE, bool TS>
