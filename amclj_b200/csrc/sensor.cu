@@ -336,7 +336,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
           stepB = ys * (steep ? idx_scale : row);
           idx = idx0; k = 0; j = 0; err = 0; ndx = -dx;
           if (MODE == DF_WEDGE8 && start_in) { /* the plane of this ray's direction class */
-            int bin = min(WEDGE_BINS - 1, (dy * WEDGE_BINS) / dx);
+            int bin = 0; /* = min(BINS - 1, floor(dy * BINS / dx)) without the division */
+#pragma unroll
+            for (int t = 1; t < WEDGE_BINS; t++) bin += (dy * WEDGE_BINS >= t * dx) ? 1 : 0;
             int cls = ((steep ? 1 : 0) * 4 + (xs < 0 ? 2 : 0) + (ys < 0 ? 1 : 0)) * WEDGE_BINS + bin;
             idx += cls * a.wedge_plane;
           }
