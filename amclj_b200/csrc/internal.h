@@ -165,7 +165,7 @@ namespace amclj {
 cudaError_t launch_sensor(const amclj_ctx *c, const SensorLaunch &a, int mode, bool diag,
                           cudaStream_t s);
 enum { DF_SMEM4 = 0, DF_GLOBAL8 = 1, DF_GLOBAL4 = 2, DF_WEDGE8 = 3 };
-constexpr int WEDGE_BINS = 2;                   /* slope bins per octant */
+constexpr int WEDGE_BINS = 4;                   /* slope bins per octant */
 constexpr int WEDGE_CLASSES = 8 * WEDGE_BINS;   /* steep x xs x ys x bin */
 cudaError_t build_wedge_fields(amclj_ctx *c, cudaStream_t s);
 int sensor_chunks(const amclj_ctx *c, int64_t n, int nb);

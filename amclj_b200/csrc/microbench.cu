@@ -64,11 +64,11 @@ extern "C" int32_t amclj_microbench(amclj_ctx *ctx, int32_t which, double *looku
   if (!ctx || !lookups_per_s) return AMCLJ_ERR_INVALID;
   cudaSetDevice(ctx->device);
   const bool smem = which == 0;
-  const size_t bytes = smem ? (128u << 10) : (64u << 20);
+  const size_t bytes = smem ? (128u << 10) : (which == 2 ? (64u << 10) : (64u << 20));
   uint8_t *tab = nullptr;
   if (cudaMalloc(&tab, bytes) != cudaSuccess) return AMCLJ_ERR_NOMEM;
   fill_random_kernel<<<(unsigned)((bytes + 255) / 256), 256, 0, ctx->stream>>>(tab, bytes, 12345u);
-  const int iters = smem ? 2048 : 256;
+  const int iters = smem || which == 2 ? 2048 : 256;
   const int blocks = ctx->sm_count;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);

@@ -37,7 +37,8 @@ if str(ROOT) not in sys.path:
 METRIC = "beam_evals_per_s"
 UNIT = "beam-evals/s"
 PER_GPU_SHARDED = 1_250_000  # C4: 10M particles over 8 GPUs
-KERNELS_PER_UPDATE = 5       # 1 GPU: motion, sensor, combine, scan, gather; sharded: motion, sensor, decode-max, scan, pull
+KERNELS_PER_UPDATE = 7       # motion, bounding box, sensor x2 (one returns at once), combine, scan, gather
+KERNELS_PER_UPDATE_SHARDED = 5  # motion, sensor, decode-max, scan, pull (+ 2 NCCL collectives)
 
 
 def peaks():
@@ -48,25 +49,52 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md): NVML every few
+    milliseconds (nvidia-smi as a fallback)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.sm, self.reasons, self.max_mhz, self._stop = index, [], set(), None, threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            uuid = None
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
 
     def _run(self):
         while not self._stop.is_set():
             try:
+                if self._nvml is not None:
+                    n = self._nvml
+                    self.sm.append(int(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h)) if hasattr(
+                        n, "nvmlDeviceGetCurrentClocksEventReasons") else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                    self.reasons |= {k for k, b in self.BITS.items() if mask & b}
+                    self._stop.wait(0.004)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                if out.strip():
-                    self.rows.append([c.strip() for c in out.strip().split(",")])
+                r = [c.strip() for c in out.strip().split(",")]
+                if r and r[0].isdigit():
+                    self.sm.append(int(r[0]))
+                    self.max_mhz = int(r[1]) if r[1].isdigit() else self.max_mhz
+                    self.reasons |= {k for j, k in enumerate(["hw_slowdown", "hw_thermal_slowdown",
+                                                              "sw_thermal_slowdown", "sw_power_cap"])
+                                     if r[2 + j].lower().startswith("active")}
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t.start()
@@ -77,14 +105,11 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["clock sampling unavailable"]}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def cpu_pass(w, sample, threads=0):
@@ -300,7 +325,10 @@ def run_b200(args):
         sm_hz = 1e6 * float((clocks.summary().get("sm_mhz") or 1965))
         k_ms = float(np.mean(sensor_ms))
         # measured ceiling of dependent distance-field lookups on this GPU (same placement as the map)
-        lookup_peak = ctx.microbench(0 if st.map_in_smem else 1)
+        # placement of the field the kernel actually ran on: shared memory, L1 (directional planes of a
+        # compact particle cloud: ncu shows a 99 % L1 hit rate) or L2 (large maps)
+        placement = 0 if st.map_in_smem else (2 if w.grid.info.width * w.grid.info.height < (1 << 22) else 1)
+        lookup_peak = ctx.microbench(placement)
         traffic = None
         tfile = ROOT / "profiles" / "sensor_traffic.json"
         if tfile.exists():  # dram bytes per launch from the committed ncu --set full capture of this workload
@@ -315,7 +343,7 @@ def run_b200(args):
                     "traffic": traffic, "peak_source": peak_src, "kernel": "amclj::sensor_kernel",
                     "kernel_ms": k_ms, "kernel_share_of_step": k_ms / float(np.mean(total_ms_lib)),
                     "algorithmic_bytes_per_launch": alg_bytes,
-                    "note": "HBM is not what binds this kernel (16 B/particle): it is issue / shared-memory-latency bound; see onchip",
+                    "note": "HBM is not what binds this kernel (16 B/particle): it is instruction-issue bound (ncu: ~82 % of scheduler cycles issue); see onchip",
                     "onchip": {"rays_per_s": st.rays / (k_ms * 1e-3),
                                "reference_cells_per_s": st.cells_visited / (k_ms * 1e-3),
                                "probes_per_s": st.probes / (k_ms * 1e-3),
@@ -326,8 +354,8 @@ def run_b200(args):
                                "lookup_peak_per_s": lookup_peak,
                                "lookup_frac": (st.probes / (k_ms * 1e-3)) / lookup_peak,
                                "lookup_peak_source": "amclj_microbench: dependent lookups, all SMs x 32 warps, "
-                                                     + ("128 KiB nibble table in shared memory" if st.map_in_smem
-                                                        else "64 MiB byte table in L2"),
+                                                     + ["128 KiB nibble table in shared memory", "64 MiB byte table in L2",
+                                                        "64 KiB byte table in L1"][placement],
                                "issue_peak_warp_inst_per_s": sm_count * 4 * sm_hz,
                                "scheduler_cycles_per_ray": (k_ms * 1e-3) * sm_count * 4 * sm_hz / max(st.rays, 1),
                                "note": "scheduler_cycles_per_ray = kernel time x SMs x 4 schedulers x SM clock / rays: "
@@ -348,7 +376,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_of(args, w, extra={"parallelism": f"particles sharded x{world}, map replicated"}),
             "updates_per_s": 1e3 / ms_per_step, "particles_total": n_total,
-            "e2e": e2e, "gpu_launches": KERNELS_PER_UPDATE * args.steps + (2 * args.steps if world > 1 else 0),
+            "e2e": e2e, "gpu_launches": (KERNELS_PER_UPDATE if world == 1 else KERNELS_PER_UPDATE_SHARDED) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
             "wall_s_timed_loop": t_wall,
             "stage_ms": {"motion": None, "sensor": k_ms, "total_lib_events": float(np.mean(total_ms_lib))},

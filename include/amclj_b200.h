@@ -227,8 +227,9 @@ int32_t amclj_pose_estimate(amclj_ctx *ctx, double out[4]);
 
 int32_t amclj_get_stats(amclj_ctx *ctx, amclj_stats *out);
 /* Measured ceiling of the ray caster's inner operation on this GPU: dependent distance-field
- * lookups per second from shared memory (which = 0, 128 KiB nibble table) or from an
- * L2-resident 64 MiB byte table (which = 1), all SMs, 32 warps each. */
+ * lookups per second from shared memory (which = 0, 128 KiB nibble table), from an L2-resident
+ * 64 MiB byte table (which = 1) or from an L1-resident 64 KiB byte table (which = 2), all SMs,
+ * 32 warps each. */
 int32_t amclj_microbench(amclj_ctx *ctx, int32_t which, double *lookups_per_s);
 
 /* ---- sharded (multi-GPU) building blocks, SURVEY 8e --------------------------------- */
