@@ -186,8 +186,17 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
   NEED(rcells < 4.0e6, AMCLJ_ERR_INVALID, "scan: ray of %.0f cells is too long", rcells);
   int step = beam_step(n, p.s6_max_beams);
   int nb = beams_used(n, p.s6_max_beams);
-  std::vector<float> h((size_t)nb * 6);
-  float *dir = h.data(), *mix = dir + 2 * (size_t)nb; /* float2 (cb, sb) | float4 (obs, e2, p34, 0) */
+  /* host staging in pinned memory, guarded by an event, so the upload needs no synchronisation */
+  size_t tab_bytes = sizeof(float) * (size_t)nb * 6;
+  if (tab_bytes > ctx->pin_tab_bytes) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->pin_tab) cudaFreeHost(ctx->pin_tab);
+    ctx->pin_tab = nullptr;
+    CK(cudaMallocHost(&ctx->pin_tab, tab_bytes));
+    ctx->pin_tab_bytes = tab_bytes;
+  }
+  CK(cudaEventSynchronize(ctx->ev[4])); /* the previous upload from this buffer has finished */
+  float *dir = reinterpret_cast<float *>(ctx->pin_tab), *mix = dir + 2 * (size_t)nb; /* float2 (cb, sb) | float4 (obs, e2, p34, 0) */
   float zshort = p.z_short, lam = p.lambda_short;
   int j = 0;
   for (int i = 0; i < n; i += step, j++) {
@@ -209,7 +218,8 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
     CK(dalloc(&b.dev, (size_t)nb * 6));
     b.cap = nb;
   }
-  CK(cudaMemcpyAsync(b.dev, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(b.dev, ctx->pin_tab, tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   b.nb = nb;
   b.n_scan = n;
   b.angle_min = angle_min;
@@ -221,7 +231,8 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
   int ndiv = (int)ceil(rcells) + 8;
   int mode = df_mode_of(ctx);
   NEED(mode >= 0, AMCLJ_ERR_INVALID, "scan: df_mode %d unavailable for this map", ctx->p.df_mode);
-  int dcap = (mode == DF_GLOBAL8 || mode == DF_WEDGE8) ? 255 : 15;
+  /* the directional planes (also when the auto policy may pick them) and the byte field jump up to 255 */
+  int dcap = (mode == DF_GLOBAL8 || mode == DF_WEDGE8 || (ctx->p.df_mode == 0 && ctx->map.wedge)) ? 255 : 15;
   uint64_t Dmax = 2ull * (uint64_t)(ndiv - 1);
   int wide = (uint64_t)(dcap + 1) * Dmax * Dmax > (1ull << 32);
   DivTable &d = ctx->divs;
@@ -245,7 +256,6 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
     d.wide = wide;
     d.dcap = dcap;
   }
-  CK(cudaStreamSynchronize(ctx->stream)); /* the host vectors go out of scope */
   b.staged = true;
   return AMCLJ_OK;
 }
@@ -625,7 +635,7 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
     amclj_destroy(ctx);
     return AMCLJ_ERR_CUDA;
   }
-  for (int i = 0; i < 4; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
+  for (int i = 0; i < 5; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
   *out = ctx;
   return AMCLJ_OK;
 }
@@ -646,6 +656,7 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
       if (ctx->ipc_opened[g][k]) cudaIpcCloseMemHandle(ctx->ipc_opened[g][k]);
   dfree(ctx->stage_out); dfree(ctx->stage_in); dfree(ctx->stage_idx);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->pin_tab) cudaFreeHost(ctx->pin_tab);
   for (int i = 0; i < 5; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1042,12 +1053,44 @@ int32_t amclj_filter_update_host(amclj_ctx *ctx, float *x, float *y, float *thet
                                  const float *normals, uint64_t seed, const float *ranges,
                                  int32_t n_ranges, float angle_min, float angle_increment,
                                  float range_max, double u0) {
-  int rc = amclj_set_particles(ctx, x, y, theta, nullptr, n);
+  ENTER();
+  NEED(x && y && theta && n > 0 && n <= (1ll << 31) - 1, AMCLJ_ERR_INVALID, "filter_update_host: bad arguments");
+  NEED(curr && prev && ranges, AMCLJ_ERR_INVALID, "filter_update_host: null argument");
+  if (ctx->p.s8_resampler != AMCLJ_RESAMPLE_SYSTEMATIC) { /* host-in-the-loop resamplers: plain composition */
+    int rc = amclj_set_particles(ctx, x, y, theta, nullptr, n);
+    if (rc) return rc;
+    rc = amclj_filter_update(ctx, curr, prev, normals, seed, ranges, n_ranges, angle_min, angle_increment,
+                             range_max, u0);
+    if (rc) return rc;
+    return amclj_get_particles(ctx, x, y, theta, w);
+  }
+  /* upload -> update -> download enqueued back to back, one synchronisation at the end */
+  NEED(u0 >= 0.0 && u0 < 1.0, AMCLJ_ERR_INVALID, "filter_update: u0 must be in [0,1)");
+  int64_t keep = ctx->n;
+  ctx->n = 0;
+  int rc = ensure_particles(ctx, n);
+  if (rc) { ctx->n = keep; return rc; }
+  size_t b = sizeof(float) * (size_t)n;
+  CK(cudaMemcpyAsync(ctx->x, x, b, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->y, y, b, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->th, theta, b, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->n = n;
+  if (ctx->world == 1) { ctx->n_global = n; ctx->global_offset = 0; }
+  ctx->have_raw = ctx->have_cdf = false;
+  rc = stage_scan_impl(ctx, ranges, n_ranges, angle_min, angle_increment, range_max);
   if (rc) return rc;
-  rc = amclj_filter_update(ctx, curr, prev, normals, seed, ranges, n_ranges, angle_min,
-                           angle_increment, range_max, u0);
+  rc = upload_normals(ctx, normals);
   if (rc) return rc;
-  return amclj_get_particles(ctx, x, y, theta, w);
+  ctx->normals_staged = normals != nullptr;
+  rc = amclj_filter_update_async(ctx, curr, prev, seed, u0);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(x, ctx->x, b, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(y, ctx->y, b, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(theta, ctx->th, b, cudaMemcpyDeviceToHost, ctx->stream));
+  if (w) CK(cudaMemcpyAsync(w, ctx->w, b, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  collect_times(ctx);
+  return AMCLJ_OK;
 }
 
 int32_t amclj_pose_estimate(amclj_ctx *ctx, double out[4]) {

@@ -158,6 +158,8 @@ struct amclj_ctx {
   uint32_t *hist = nullptr;           // 256-bin histogram of the radix select
   int32_t force_chunks = 0;
   void *pinned = nullptr;  // small pinned scratch for scalar readbacks
+  void *pin_tab = nullptr; // pinned staging of the beam table
+  size_t pin_tab_bytes = 0;
 };
 
 namespace amclj {
