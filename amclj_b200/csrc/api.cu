@@ -415,6 +415,7 @@ void swap_particles(amclj_ctx *ctx) {
   std::swap(ctx->y, ctx->y2);
   std::swap(ctx->th, ctx->th2);
   std::swap(ctx->w, ctx->w2);
+  ctx->flip ^= 1; /* peers that mapped both buffer sets follow the alternation */
 }
 
 int enqueue_systematic(amclj_ctx *ctx, double u0) {
@@ -1373,7 +1374,6 @@ int32_t amclj_shard_pull_async(amclj_ctx *ctx, double u0) {
   a.zero_flag = ctx->stats + 5;
   CK(launch_pull(a, ctx->stream));
   swap_particles(ctx);
-  ctx->flip ^= 1;
   ctx->have_raw = ctx->have_cdf = false;
   stamp(ctx, 3);
   return AMCLJ_OK;

@@ -107,7 +107,7 @@ __device__ __forceinline__ float fixed_to_raw(long long q) {
 // operand that passes its range check); operands outside a wide safe range take the real divide.
 struct ResDiv {
   float res, r;
-  bool fast;
+  float lim; /* |v| below this takes the fast path (-1: never) */
 };
 __device__ __forceinline__ ResDiv make_resdiv(float res) {
   ResDiv d;
@@ -116,15 +116,16 @@ __device__ __forceinline__ ResDiv make_resdiv(float res) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(res));
   float e = fmaf(-res, r0, 1.0f);
   d.r = fmaf(r0, e, r0);
-  d.fast = res > 1.0e-6f && res < 1.0e6f;
+  d.lim = (res > 1.0e-6f && res < 1.0e6f) ? 1.0e18f : -1.0f;
   return d;
 }
 __device__ __forceinline__ int32_t round_cell_fast(float v, const ResDiv &d) {
   float q0 = v * d.r;
   float e = fmaf(-q0, d.res, v);
   float q = fmaf(e, d.r, q0);
-  float a = fabsf(v);
-  if (!(d.fast && a < 1.0e18f && (a > 1.0e-18f || v == 0.0f))) q = v / d.res; /* rare: the real IEEE divide */
+  /* huge, infinite and NaN operands take the real IEEE divide; tiny ones need no care: whatever
+   * rounding a subnormal quotient gets, floor(q + 0.5) is 0 */
+  if (!(fabsf(v) < d.lim)) q = v / d.res;
   float t = floorf(q + 0.5f);
   t = fminf(fmaxf(t, -1.0e9f), 1.0e9f); /* NaN -> -1e9 */
   return (int32_t)t;
@@ -336,11 +337,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
           stepB = ys * (steep ? idx_scale : row);
           idx = idx0; k = 0; j = 0; err = 0; ndx = -dx;
           if (MODE == DF_WEDGE8 && start_in) { /* the plane of this ray's direction class */
-            int bin = 0; /* = min(BINS - 1, floor(dy * BINS / dx)) without the division */
+            /* plane = ((steep*4 + (xs<0)*2 + (ys<0)) * BINS + bin), bin = min(BINS-1, floor(dy*BINS/dx))
+             * without a division; accumulated directly as a byte offset */
+            const int P = a.wedge_plane;
+            int off = steep ? 4 * WEDGE_BINS * P : 0;
+            off += xs < 0 ? 2 * WEDGE_BINS * P : 0;
+            off += ys < 0 ? WEDGE_BINS * P : 0;
+            const int dyb = dy * WEDGE_BINS;
 #pragma unroll
-            for (int t = 1; t < WEDGE_BINS; t++) bin += (dy * WEDGE_BINS >= t * dx) ? 1 : 0;
-            int cls = ((steep ? 1 : 0) * 4 + (xs < 0 ? 2 : 0) + (ys < 0 ? 1 : 0)) * WEDGE_BINS + bin;
-            idx += cls * a.wedge_plane;
+            for (int t = 1; t < WEDGE_BINS; t++) off += (dyb >= t * dx) ? P : 0;
+            idx += off;
           }
           if (DIAG) { dg_a0 = a0; dg_b0 = b0; dg_xs = xs; dg_ys = ys; dg_steep = steep; dg_probes = 0; }
           have_ray = true;

@@ -316,6 +316,26 @@ def run_b200(args):
         ctx.filter_update_async(w.curr, w.prev, 1, w.u0)
     ctx.synchronize()
     st = ctx.stats()
+    same_share = None
+    if world > 1:
+        # the same per-GPU share as a plain single-GPU update (no collectives), so that the sharded
+        # line can be read against an N = 1 run of the SAME workload (the N = 1 bench line is C2)
+        ctx.set_params(_lib.params("NS", df_mode=args.df_mode))
+        ctx.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max)
+        ss = []
+        for k in range(3 + min(args.steps, 10)):
+            ctx.set_particles(w.x, w.y, w.theta)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                ctx.filter_update_async(w.curr, w.prev, 900 + k, w.u0)
+                e1.record(stream)
+            torch.cuda.synchronize()
+            ss.append(e0.elapsed_time(e1))
+        t = torch.tensor([float(np.mean(ss[3:]))], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        same_share = float(t.item())
     line = None
     if rank == 0:
         # ---- roofline of the dominant kernel (sensor: ray-cast + beam mixture) ---------
@@ -379,6 +399,11 @@ def run_b200(args):
             "e2e": e2e, "gpu_launches": (KERNELS_PER_UPDATE if world == 1 else KERNELS_PER_UPDATE_SHARDED) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
             "wall_s_timed_loop": t_wall,
+            "same_share_single_gpu": None if same_share is None else {
+                "ms_per_step": same_share, "value_per_gpu": w.n * nb / (same_share * 1e-3),
+                "sharded_over_single": same_share / ms_per_step,
+                "note": "each rank's share run as a plain 1-GPU update (no collectives); the ratio is the "
+                        "efficiency of the sharded update against the same per-GPU work"},
             "stage_ms": {"motion": None, "sensor": k_ms, "total_lib_events": float(np.mean(total_ms_lib))},
         }
         print(json.dumps(line), flush=True)
