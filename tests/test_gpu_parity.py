@@ -515,3 +515,32 @@ def test_auto_field_selection_by_particle_spread(lg):
             assert np.array_equal(c2.raw_weights(), raw)
             c2.close()
     c.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_raycast_random_small_maps(seed):
+    """Random small maps of awkward shapes (1-cell-wide, odd widths, coarse and fine resolutions),
+    random scans and switches; every field placement against the oracle, ray by ray."""
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    W = int(rng.choice([1, 2, 3, 7, 16, 33, 64, 129]))
+    H = int(rng.choice([1, 2, 5, 9, 31, 64, 100]))
+    res = float(rng.choice([0.05, 0.1, 0.25, 1.0, 2.5]))
+    g = np.where(rng.random((H, W)) < 0.12, 100, 0).astype(np.int8)
+    g[rng.random((H, W)) < 0.05] = -1
+    grid = maps.OccupancyGrid(maps.MapMetaData(np.float32(res), W, H), g)
+    n = 600
+    x = (rng.uniform(-1.5, W + 1.5, n) * res).astype(np.float32)
+    y = (rng.uniform(-1.5, H + 1.5, n) * res).astype(np.float32)
+    th = rng.uniform(-7, 7, n).astype(np.float32)
+    nbeams = int(rng.choice([1, 2, 17, 64, 181]))
+    rmax = float(rng.choice([0.3, 2.0, 11.0])) * res * 10
+    scan = workloads.Scan((rng.uniform(0, rmax, nbeams)).astype(np.float32), float(np.float32(rng.uniform(-3.2, 0))),
+                          float(np.float32(rng.uniform(0.001, 6.3 / max(nbeams, 2)))), float(np.float32(rmax)))
+    preset = "NS" if seed % 2 == 0 else "REF"
+    switches = {} if seed % 3 else dict(s4_endpoint_termination=seed % 2, s3_proper_endpoint=(seed // 2) % 2)
+    c = _lib.Context(0)
+    for df_mode in (1, 2, 3, 4, 0):
+        c.set_params(_lib.params(preset, df_mode=df_mode, **switches))
+        c.set_map(grid)
+        _ray_parity(c, grid, x, y, th, scan, preset, df_mode=df_mode, **switches)
+    c.close()
