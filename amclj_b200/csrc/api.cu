@@ -196,7 +196,8 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
     ctx->pin_tab_bytes = tab_bytes;
   }
   CK(cudaEventSynchronize(ctx->ev[4])); /* the previous upload from this buffer has finished */
-  float *dir = reinterpret_cast<float *>(ctx->pin_tab), *mix = dir + 2 * (size_t)nb; /* float2 (cb, sb) | float4 (obs, e2, p34, 0) */
+  /* float4 (obs, e2, p34, 0) first so that it stays 16-byte aligned for any beam count | float2 (cb, sb) */
+  float *mix = reinterpret_cast<float *>(ctx->pin_tab), *dir = mix + 4 * (size_t)nb;
   float zshort = p.z_short, lam = p.lambda_short;
   int j = 0;
   for (int i = 0; i < n; i += step, j++) {

@@ -29,7 +29,7 @@ struct DeviceMap {
   bool fits_smem = false;
 };
 
-struct BeamTable {       // float2 dir[nb] = (cb, sb) then float4 mix[nb] = (obs, e2, p34, 0)
+struct BeamTable {       // float4 mix[nb] = (obs, e2, p34, 0) then float2 dir[nb] = (cb, sb)
   float *dev = nullptr;
   int32_t nb = 0, cap = 0;
   int32_t n_scan = 0;

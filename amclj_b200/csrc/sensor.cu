@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
     df.s = smem_u32(sdf);
   }
   Tables tb;
-  tb.dir = reinterpret_cast<const float2 *>(a.beam);
-  tb.mix = reinterpret_cast<const float4 *>(a.beam + 2 * (size_t)a.nb);
+  tb.mix = reinterpret_cast<const float4 *>(a.beam);
+  tb.dir = reinterpret_cast<const float2 *>(a.beam + 4 * (size_t)a.nb);
   tb.div = a.divtab;
   tb.s_dir = tb.s_mix = tb.s_div = 0;
   if (TS) {
