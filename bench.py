@@ -212,6 +212,9 @@ def run_b200(args):
         if args.sd_xy is not None and args.workload == "c2":
             w.x, w.y, w.theta = workloads.gaussian_particles(w.n, sd_xy=args.sd_xy)
             w.name += f" (sd_xy {args.sd_xy} m)"
+        if args.random_heading and args.workload == "c2":
+            w.theta = np.random.Generator(np.random.PCG64(9)).uniform(-math.pi, math.pi, w.n).astype(np.float32)
+            w.name += " (random headings)"
     else:
         w = workloads.c3(PER_GPU_SHARDED * world)
         lo = rank * PER_GPU_SHARDED
@@ -423,6 +426,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=100_000)
     ap.add_argument("--shard-mode", default="pull", choices=["pull", "a2a"])
     ap.add_argument("--sd-xy", type=float, default=None, help="C2 only: std-dev of the particle cloud in metres (policy experiments)")
+    ap.add_argument("--random-heading", action="store_true", help="C2 only: uniform random headings (locality experiments)")
     ap.add_argument("--df-mode", type=int, default=0, help="amclj_params.df_mode (0 auto)")
     ap.add_argument("--quick", action="store_true", help="skip the CPU baseline leg (tuning sweeps)")
     args = ap.parse_args()

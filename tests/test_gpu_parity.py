@@ -544,3 +544,34 @@ def test_raycast_random_small_maps(seed):
         c.set_map(grid)
         _ray_parity(c, grid, x, y, th, scan, preset, df_mode=df_mode, **switches)
     c.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_resample_random_weight_patterns(ctx, seed):
+    """Odd particle counts and hostile weight vectors (NaN, negative, infinities, one survivor,
+    all equal, denormals): fixed-point CDF, systematic and tournament lists match the oracle."""
+    rng = np.random.Generator(np.random.PCG64(500 + seed))
+    n = int(rng.choice([1, 2, 3, 31, 33, 257, 2047, 2049, 4097, 70_001]))
+    w = (rng.random(n) ** rng.choice([1, 4, 20])).astype(np.float32)
+    kind = seed % 6
+    if kind == 1:
+        w[:] = 0.0
+        w[rng.integers(0, n)] = 3.5
+    elif kind == 2:
+        w[:] = 0.125
+    elif kind == 3 and n > 3:
+        w[0], w[1], w[2] = np.nan, -1.0, 1e-42
+    elif kind == 4 and n > 2:
+        w[rng.integers(0, n)] = 1e30
+    z = np.zeros(n, np.float32)
+    ctx.set_particles(z, z, z, w)
+    total, wmax = ctx.normalize(from_raw=False)
+    q, rtotal = oracle.fixed_weights(w, oracle.wmax(w))
+    assert total == rtotal and np.array_equal(ctx.cdf(), np.cumsum(q, dtype=np.uint64))
+    if rtotal > 0:
+        u0 = float(rng.random())
+        idx = ctx.resample(_lib.RESAMPLE_SYSTEMATIC, u0)
+        assert np.array_equal(idx.astype(np.int64), oracle.systematic_resample(w, u0))
+    wt = np.nan_to_num(w, nan=0.0)
+    ctx.set_particles(z, z, z, wt)
+    assert np.array_equal(ctx.resample(_lib.RESAMPLE_TOURNAMENT, 0.0, seed=seed), oracle.tournament_philox(wt, seed))
