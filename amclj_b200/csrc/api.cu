@@ -120,6 +120,8 @@ int ensure_particles(amclj_ctx *ctx, int64_t n) {
   CK(dalloc(&ctx->cdf, (size_t)cap));
   dfree(ctx->idx);
   CK(dalloc(&ctx->idx, (size_t)cap));
+  dfree(ctx->perm);
+  CK(dalloc(&ctx->perm, (size_t)cap));
   dfree(ctx->normals);
   CK(dalloc(&ctx->normals, (size_t)cap * 3));
   NEED(scan_tiles(cap) <= ctx->scan_state_cap, AMCLJ_ERR_INVALID, "too many particles for one ctx");
@@ -170,6 +172,7 @@ int df_mode_of(const amclj_ctx *ctx) {
     case 2: return ctx->map.df8 ? DF_GLOBAL8 : -1;
     case 3: return DF_GLOBAL4;
     case 4: return ctx->map.wedge ? DF_WEDGE8 : -1;
+    case 5: return ctx->map.wedge ? DF_WEDGE8 : -1; /* directional planes, particles walked in tile order */
     default: return ctx->map.fits_smem ? DF_SMEM4 : (ctx->map.df8 ? DF_GLOBAL8 : DF_GLOBAL4);
   }
 }
@@ -362,28 +365,28 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
     CK(cudaMemsetAsync(ctx->stats, 0, 7 * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->stats + 8, 0, sizeof(unsigned long long), ctx->stream));
   }
-  /* df_mode 0 on a map with both field sets: the directional fields win when the particles sit
-   * close together (their probes share a small L1 working set), the shared-memory field when they
-   * are spread out.  Both kernels are launched; each looks at the particle bounding box and the
-   * one that is not selected returns at once.  The results are identical either way. */
-  bool both = ctx->p.df_mode == 0 && mode == DF_SMEM4 && ctx->map.wedge != nullptr;
-  if (both) {
-    CK(launch_bbox(ctx->x, ctx->y, ctx->n, ctx->bbox, ctx->sm_count, ctx->stream));
-    a.bbox = ctx->bbox;
-    a.compact_m = ctx->compact_cells * ctx->map.res;
-    a.auto_sel = 2; /* run when NOT compact */
-    a.skip_combine = 1; /* the chunk partials are combined once, after the second launch */
-    CK(launch_sensor(ctx, a, DF_SMEM4, diag, ctx->stream));
+  /* df_mode 0 on a map that has the directional planes: they are used for every cloud.  A compact
+   * cloud is local as it is; a spread-out one is walked in map-tile order so that each CTA's probes
+   * share an L1-sized neighbourhood.  A 5 us bounding-box kernel leaves the decision on the device
+   * (the tile-order kernels return at once for a compact cloud, and the sensor kernel ignores the
+   * permutation); either way the results are identical. */
+  bool directional = ctx->p.df_mode == 0 && mode == DF_SMEM4 && ctx->map.wedge != nullptr;
+  if (directional) {
+    mode = DF_WEDGE8;
     SensorLaunch b;
     fill_sensor_args(ctx, b, DF_WEDGE8);
     b.x = a.x; b.y = a.y; b.th = a.th; b.raw = a.raw; b.n = a.n; b.rawmax_ord = a.rawmax_ord;
     b.chunks = a.chunks; b.partials = a.partials; b.stats = a.stats;
-    b.bbox = ctx->bbox; b.compact_m = a.compact_m;
-    b.auto_sel = 1; /* run when compact */
-    CK(launch_sensor(ctx, b, DF_WEDGE8, diag, ctx->stream));
-  } else {
-    CK(launch_sensor(ctx, a, mode, diag, ctx->stream));
+    a = b;
+    if (!ctx->tile_counters) CK(dalloc(&ctx->tile_counters, (size_t)tile_count(ctx->map.W, ctx->map.H) + 1));
+    CK(launch_bbox(ctx->x, ctx->y, ctx->n, ctx->bbox, ctx->sm_count, ctx->stream));
+    a.bbox = ctx->bbox;
+    a.compact_m = ctx->compact_cells * ctx->map.res;
+    CK(launch_tile_order(ctx->x, ctx->y, ctx->n, ctx->map.res, ctx->map.W, ctx->map.H, ctx->tile_counters,
+                         ctx->perm, ctx->bbox, a.compact_m, ctx->stream));
+    a.perm = ctx->perm;
   }
+  CK(launch_sensor(ctx, a, mode, diag, ctx->stream));
   if (decode_max) CK(launch_decode_max(ctx->rawmax_ord, ctx->rawmax, ctx->stream));
   ctx->max_in_ord = !decode_max;
   ctx->have_raw = true;
@@ -650,7 +653,7 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
   dfree(ctx->beams.dev); dfree(ctx->divs.dev);
   dfree(ctx->x); dfree(ctx->y); dfree(ctx->th); dfree(ctx->w); dfree(ctx->raw);
   dfree(ctx->x2); dfree(ctx->y2); dfree(ctx->th2); dfree(ctx->w2);
-  dfree(ctx->cdf); dfree(ctx->idx); dfree(ctx->normals); dfree(ctx->partials);
+  dfree(ctx->cdf); dfree(ctx->idx); dfree(ctx->normals); dfree(ctx->partials); dfree(ctx->perm); dfree(ctx->tile_counters);
   dfree(ctx->ctrl); dfree(ctx->rawmax); dfree(ctx->stats);
   dfree(ctx->pose_part); dfree(ctx->plan); dfree(ctx->hist); dfree(ctx->totals_all);
   for (int g = 0; g < MAX_WORLD; g++)
@@ -684,8 +687,8 @@ int32_t amclj_synchronize(amclj_ctx *ctx) {
 int32_t amclj_set_params(amclj_ctx *ctx, const amclj_params *p) {
   ENTER();
   NEED(p, AMCLJ_ERR_INVALID, "set_params: null");
-  NEED(p->df_mode >= 0 && p->df_mode <= 4, AMCLJ_ERR_INVALID, "set_params: df_mode %d", p->df_mode);
-  if (p->df_mode == 4 && ctx->map.cells && !ctx->map.wedge) { /* directional fields are built on demand */
+  NEED(p->df_mode >= 0 && p->df_mode <= 5, AMCLJ_ERR_INVALID, "set_params: df_mode %d", p->df_mode);
+  if (p->df_mode >= 4 && ctx->map.cells && !ctx->map.wedge) { /* directional fields are built on demand */
     NEED((size_t)ctx->map.pitch8 * (ctx->map.H + 2) * WEDGE_CLASSES <= (512ull << 20), AMCLJ_ERR_INVALID,
          "set_params: map too large for directional fields");
     CK(build_wedge_fields(ctx, ctx->stream));
@@ -723,7 +726,7 @@ int32_t amclj_set_map(amclj_ctx *ctx, const int8_t *cells, int32_t width, int32_
   NEED(isfinite(resolution) && resolution > 0.f, AMCLJ_ERR_INVALID, "set_map: bad resolution");
   CK(cudaStreamSynchronize(ctx->stream));
   DeviceMap &m = ctx->map;
-  dfree(m.cells); dfree(m.df4); dfree(m.df8); dfree(m.wedge);
+  dfree(m.cells); dfree(m.df4); dfree(m.df8); dfree(m.wedge); dfree(ctx->tile_counters);
   m.W = width;
   m.H = height;
   m.res = resolution;
@@ -739,7 +742,7 @@ int32_t amclj_set_map(amclj_ctx *ctx, const int8_t *cells, int32_t width, int32_
   m.bytes8 = (size_t)m.pitch8 * (height + 2);
   if (want8) CK(dalloc(&m.df8, m.bytes8));
   CK(build_distance_fields(ctx, want8, ctx->stream));
-  if (ctx->p.df_mode == 4) {
+  if (ctx->p.df_mode >= 4) {
     NEED(m.bytes8 * WEDGE_CLASSES <= (512ull << 20), AMCLJ_ERR_INVALID, "set_map: map too large for directional fields");
     CK(build_wedge_fields(ctx, ctx->stream));
   } else if (ctx->p.df_mode == 0 && m.fits_smem && m.bytes8 * WEDGE_CLASSES <= (64ull << 20)) {

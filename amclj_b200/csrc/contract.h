@@ -125,4 +125,14 @@ AMCLJ_HD bool roulette_accept(uint64_t q, uint32_t u, uint64_t total) {
 #endif
 }
 
+#if defined(__CUDACC__)
+// Particle bounding box kept on the device as four ordered-uint maxima (x, -x, y, -y): is the
+// cloud's box at most `compact_m` metres on a side?  (NaN coordinates poison the box: not compact.)
+__device__ __forceinline__ bool cloud_is_compact(const uint32_t *bbox, float compact_m) {
+  auto dec = [](uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); };
+  float wx = dec(bbox[0]) + dec(bbox[1]), wy = dec(bbox[2]) + dec(bbox[3]); /* max - min */
+  return wx <= compact_m && wy <= compact_m;
+}
+#endif
+
 }  // namespace amclj

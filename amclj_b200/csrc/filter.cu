@@ -209,6 +209,64 @@ cudaError_t launch_bbox(const float *x, const float *y, int64_t n, uint32_t *bbo
   return cudaGetLastError();
 }
 
+// Walking order for spread-out clouds: a counting sort of the particle indices by 8x8-cell map
+// tile (row-major tiles).  The order inside a tile is whatever the atomics give — it only decides
+// which lanes walk together, never a result.  Skipped (the kernels return) for a compact cloud.
+constexpr int TILE_SHIFT = 3;
+int tile_count(int W, int H) { return ((W >> TILE_SHIFT) + 1) * ((H >> TILE_SHIFT) + 1); }
+
+__device__ __forceinline__ int tile_of(float px, float py, float res, int W, int H) {
+  int cx = min(max(round_cell(px, res), 0), W - 1), cy = min(max(round_cell(py, res), 0), H - 1);
+  return (cy >> TILE_SHIFT) * ((W >> TILE_SHIFT) + 1) + (cx >> TILE_SHIFT);
+}
+
+__global__ void __launch_bounds__(256)
+tile_hist_kernel(const float *__restrict__ x, const float *__restrict__ y, int64_t n, float res, int W,
+                 int H, uint32_t *counters, const uint32_t *bbox, float compact_m) {
+  if (bbox && cloud_is_compact(bbox, compact_m)) return;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&counters[tile_of(__ldg(x + i), __ldg(y + i), res, W, H)], 1u);
+}
+
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(uint32_t *counters, int ntiles, const uint32_t *bbox, float compact_m) {
+  if (bbox && cloud_is_compact(bbox, compact_m)) return;
+  __shared__ uint32_t part[1024];
+  const int per = (ntiles + 1023) / 1024, lo = threadIdx.x * per, hi = min(lo + per, ntiles);
+  uint32_t sum = 0;
+  for (int t = lo; t < hi; t++) sum += counters[t];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) { /* 1024 partial sums: a serial pass is fine */
+    uint32_t run = 0;
+    for (int t = 0; t < 1024; t++) { uint32_t v = part[t]; part[t] = run; run += v; }
+  }
+  __syncthreads();
+  uint32_t run = part[threadIdx.x];
+  for (int t = lo; t < hi; t++) { uint32_t v = counters[t]; counters[t] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(256)
+tile_scatter_kernel(const float *__restrict__ x, const float *__restrict__ y, int64_t n, float res, int W,
+                    int H, uint32_t *cursors, int32_t *perm, const uint32_t *bbox, float compact_m) {
+  if (bbox && cloud_is_compact(bbox, compact_m)) return;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) perm[atomicAdd(&cursors[tile_of(__ldg(x + i), __ldg(y + i), res, W, H)], 1u)] = (int32_t)i;
+}
+
+cudaError_t launch_tile_order(const float *x, const float *y, int64_t n, float res, int W, int H,
+                              uint32_t *counters, int32_t *perm, const uint32_t *bbox, float compact_m,
+                              cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  int ntiles = tile_count(W, H);
+  cudaMemsetAsync(counters, 0, sizeof(uint32_t) * (size_t)ntiles, s);
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  tile_hist_kernel<<<blocks, 256, 0, s>>>(x, y, n, res, W, H, counters, bbox, compact_m);
+  tile_scan_kernel<<<1, 1024, 0, s>>>(counters, ntiles, bbox, compact_m);
+  tile_scatter_kernel<<<blocks, 256, 0, s>>>(x, y, n, res, W, H, counters, perm, bbox, compact_m);
+  return cudaGetLastError();
+}
+
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;

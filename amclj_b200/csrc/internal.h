@@ -66,6 +66,7 @@ struct SensorLaunch {
   float compact_m;       // bounding-box side (metres) up to which the particle set counts as compact
   int32_t auto_sel;      // 0: always run; 1: run only when compact; 2: only when not compact
   int32_t skip_combine;  // leave the chunk partials to a later launch
+  const int32_t *perm;   // walking order (particle indices sorted by map tile), or null
   float R;            // ray length (S2)
   float miss_value;
   int32_t s1, s3, s4, s7, s10;
@@ -116,6 +117,8 @@ struct amclj_ctx {
   int32_t *idx = nullptr;       // last resample's source indices
   float *normals = nullptr;     // staged injected normals [n][3]
   long long *partials = nullptr;  // sensor chunk partials (32.32 fixed point)
+  int32_t *perm = nullptr;        // walking order of the particles (sorted by map tile)
+  uint32_t *tile_counters = nullptr;
   int64_t partials_cap = 0;
   // scalars on the device: one control block [ord | total | counter | tile_state...] so that a
   // single memset per update clears everything the sensor max and the scan accumulate into
@@ -220,6 +223,10 @@ struct RouletteArgs {
   unsigned long long *last_attempt; /* attempt index (+1) of the acceptance filling slot n-1 */
 };
 cudaError_t launch_motion(const MotionLaunch &a, cudaStream_t s);
+cudaError_t launch_tile_order(const float *x, const float *y, int64_t n, float res, int W, int H,
+                              uint32_t *counters, int32_t *perm, const uint32_t *bbox, float compact_m,
+                              cudaStream_t s);
+int tile_count(int W, int H);
 cudaError_t launch_bbox(const float *x, const float *y, int64_t n, uint32_t *bbox, int sm_count,
                         cudaStream_t s);
 cudaError_t build_distance_fields(amclj_ctx *c, bool want8, cudaStream_t s);

@@ -143,11 +143,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
   extern __shared__ uint4 smem_dyn[];
   __shared__ uint64_t bar;
   if (a.auto_sel) { /* two field placements were launched: only the one that suits the particle spread runs */
-    auto dec = [](uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); };
-    float wx = dec(a.bbox[0]) + dec(a.bbox[1]), wy = dec(a.bbox[2]) + dec(a.bbox[3]); /* max - min */
-    bool compact = wx <= a.compact_m && wy <= a.compact_m; /* NaN -> not compact */
-    if (compact != (a.auto_sel == 1)) return;
+    if (cloud_is_compact(a.bbox, a.compact_m) != (a.auto_sel == 1)) return;
   }
+  /* spread-out clouds are walked in spatial (tile) order so that a CTA's probes share an L1-sized
+   * neighbourhood; a compact cloud is local as it is */
+  const int32_t *perm = a.perm;
+  if (perm && a.bbox && cloud_is_compact(a.bbox, a.compact_m)) perm = nullptr;
   Field df;
   df.g = a.df;
   df.s = 0;
@@ -216,12 +217,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaun
   unsigned long long n_cells = 0, n_probes = 0, n_hits = 0, n_rays = 0, n_oob = 0;
   const uint32_t idx_limit = (uint32_t)(a.df_bytes * (BYTES ? 1u : 8u)); /* DIAG bounds check */
 
-  /* task = 32 consecutive particles x one chunk of beams; chunk-major so that the warps of a
-   * CTA work on neighbouring particles */
-  for (int64_t task = (int64_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x; task < ntasks; task += nwarps) {
+  /* task = 32 consecutive particles (in walking order) x one chunk of beams; the warps of a CTA
+   * take consecutive tasks, i.e. neighbouring particles */
+  for (int64_t task = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); task < ntasks; task += nwarps) {
     const int chunk = (int)(task / ngroups);
-    const int64_t p = (task - (int64_t)chunk * ngroups) * 32 + lane;
-    const bool valid = p < a.n;
+    const int64_t slot = (task - (int64_t)chunk * ngroups) * 32 + lane;
+    const bool valid = slot < a.n;
+    const int64_t p = valid && perm ? (int64_t)__ldg(perm + slot) : slot;
     const int nseg = (nb + SEG - 1) / SEG;
     const int b_lo = (int)((int64_t)nseg * chunk / a.chunks) * SEG;
     const int b_hi = min(nb, (int)((int64_t)nseg * (chunk + 1) / a.chunks) * SEG);

@@ -78,7 +78,8 @@ typedef struct amclj_params {
   int32_t collect_stats; /* count cells visited / probes (small cost) */
   /* distance-field placement: 0 auto (shared memory when the nibble-packed field fits,
    * else one byte per cell in L2), 1 shared nibbles, 2 global bytes, 3 global nibbles,
-   * 4 directional byte fields (16 direction classes) through L1/L2 */
+   * 4 directional byte fields (32 direction classes) through L1/L2, 5 the same with the particles
+   * walked in map-tile order (spread-out clouds) */
   int32_t df_mode;
   float max_range;    /* sensor.clj:12  (-1.0) */
   float z_hit;        /* sensor.clj:14 */

@@ -91,7 +91,7 @@ def test_raycast_switch_matrix(ctx, lg, switches):
     _ray_parity(ctx, lg, x, y, th, scan, "NS", **switches)
 
 
-@pytest.mark.parametrize("df_mode", [1, 2, 3, 4])
+@pytest.mark.parametrize("df_mode", [1, 2, 3, 4, 5])
 def test_raycast_all_field_placements(ctx, lg, df_mode):
     """Shared-memory nibbles, global bytes, global nibbles and the directional (wedge) fields
     give the same answers."""
@@ -489,30 +489,31 @@ def test_raycast_directional_fields_exact(ctx, lg, preset, switches):
         assert s.probes < 0.7 * 7.4 * s.rays  # fewer probes than the isotropic field needs
 
 
-def test_auto_field_selection_by_particle_spread(lg):
-    """df_mode 0 on a map that has both field sets: a compact particle cloud runs on the
-    directional fields, a spread-out one on the shared-memory field; weights agree with the oracle
-    either way (and with each other bit for bit, since both walks are exact)."""
+def test_auto_field_policy_matches_every_placement(lg):
+    """df_mode 0 on a small map walks the directional planes — in place for a compact particle
+    cloud, in map-tile order for a spread-out one (decided on the device from the bounding box).
+    Weights agree with the oracle and, bit for bit, with every forced placement."""
     c = _lib.Context(0)
     pl, po = _pair("NS", collect_stats=1)
     c.set_params(pl)
     c.set_map(lg)
     scan = workloads.make_scan(lg, workloads.TRUE_POSE, 360, -math.pi, 2 * math.pi / 360, 5.6)
-    for spread, in_smem in ((False, 0), (True, 1)):
+    for spread in (False, True):
         x, y, th = workloads.uniform_particles(lg, 3000, seed=3) if spread else workloads.gaussian_particles(3000)
         c.set_particles(x, y, th)
         c.sensor_update(scan.ranges, scan.angle_min, scan.angle_inc, scan.range_max)
-        assert c.stats().map_in_smem == in_smem
+        st = c.stats()
+        assert st.map_in_smem == 0 and st.probes < 5 * st.rays
         raw = c.raw_weights()
         ref, _, _ = oracle.sensor_f32(po, lg, scan.ranges, scan.angle_min, scan.angle_inc, scan.range_max, x, y, th)
         np.testing.assert_allclose(raw, ref, rtol=RTOL)
-        for forced in (1, 4):
+        for forced in (1, 2, 4, 5):
             c2 = _lib.Context(0)
             c2.set_params(_lib.params("NS", df_mode=forced))
             c2.set_map(lg)
             c2.set_particles(x, y, th)
             c2.sensor_update(scan.ranges, scan.angle_min, scan.angle_inc, scan.range_max)
-            assert np.array_equal(c2.raw_weights(), raw)
+            assert np.array_equal(c2.raw_weights(), raw), forced
             c2.close()
     c.close()
 
@@ -539,7 +540,7 @@ def test_raycast_random_small_maps(seed):
     preset = "NS" if seed % 2 == 0 else "REF"
     switches = {} if seed % 3 else dict(s4_endpoint_termination=seed % 2, s3_proper_endpoint=(seed // 2) % 2)
     c = _lib.Context(0)
-    for df_mode in (1, 2, 3, 4, 0):
+    for df_mode in (1, 2, 3, 4, 5, 0):
         c.set_params(_lib.params(preset, df_mode=df_mode, **switches))
         c.set_map(grid)
         _ray_parity(c, grid, x, y, th, scan, preset, df_mode=df_mode, **switches)
