@@ -382,7 +382,7 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
     CK(launch_bbox(ctx->x, ctx->y, ctx->n, ctx->bbox, ctx->sm_count, ctx->stream));
     a.bbox = ctx->bbox;
     a.compact_m = ctx->compact_cells * ctx->map.res;
-    CK(launch_tile_order(ctx->x, ctx->y, ctx->n, ctx->map.res, ctx->map.W, ctx->map.H, ctx->tile_counters,
+    CK(launch_tile_order(ctx->x, ctx->y, ctx->th, ctx->n, ctx->map.res, ctx->map.W, ctx->map.H, ctx->tile_counters,
                          ctx->perm, ctx->bbox, a.compact_m, ctx->stream));
     a.perm = ctx->perm;
   }

@@ -212,20 +212,28 @@ cudaError_t launch_bbox(const float *x, const float *y, int64_t n, uint32_t *bbo
 // Walking order for spread-out clouds: a counting sort of the particle indices by 8x8-cell map
 // tile (row-major tiles).  The order inside a tile is whatever the atomics give — it only decides
 // which lanes walk together, never a result.  Skipped (the kernels return) for a compact cloud.
-constexpr int TILE_SHIFT = 3;
-int tile_count(int W, int H) { return ((W >> TILE_SHIFT) + 1) * ((H >> TILE_SHIFT) + 1); }
+#ifndef AMCLJ_TILE_SHIFT
+#define AMCLJ_TILE_SHIFT 3
+#endif
+constexpr int TILE_SHIFT = AMCLJ_TILE_SHIFT;
+#ifndef AMCLJ_HEADING_BINS
+#define AMCLJ_HEADING_BINS 8
+#endif
+constexpr int HEADING_BINS = AMCLJ_HEADING_BINS; /* power of two: secondary key, heading sector */
+int tile_count(int W, int H) { return ((W >> TILE_SHIFT) + 1) * ((H >> TILE_SHIFT) + 1) * HEADING_BINS; }
 
-__device__ __forceinline__ int tile_of(float px, float py, float res, int W, int H) {
+__device__ __forceinline__ int tile_of(float px, float py, float pth, float res, int W, int H) {
   int cx = min(max(round_cell(px, res), 0), W - 1), cy = min(max(round_cell(py, res), 0), H - 1);
-  return (cy >> TILE_SHIFT) * ((W >> TILE_SHIFT) + 1) + (cx >> TILE_SHIFT);
+  int hb = __float2int_rd(pth * (HEADING_BINS / 6.283185307179586f)) & (HEADING_BINS - 1);
+  return ((cy >> TILE_SHIFT) * ((W >> TILE_SHIFT) + 1) + (cx >> TILE_SHIFT)) * HEADING_BINS + hb;
 }
 
 __global__ void __launch_bounds__(256)
-tile_hist_kernel(const float *__restrict__ x, const float *__restrict__ y, int64_t n, float res, int W,
-                 int H, uint32_t *counters, const uint32_t *bbox, float compact_m) {
+tile_hist_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th,
+                 int64_t n, float res, int W, int H, uint32_t *counters, const uint32_t *bbox, float compact_m) {
   if (bbox && cloud_is_compact(bbox, compact_m)) return;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(&counters[tile_of(__ldg(x + i), __ldg(y + i), res, W, H)], 1u);
+  if (i < n) atomicAdd(&counters[tile_of(__ldg(x + i), __ldg(y + i), __ldg(th + i), res, W, H)], 1u);
 }
 
 __global__ void __launch_bounds__(1024)
@@ -247,23 +255,23 @@ tile_scan_kernel(uint32_t *counters, int ntiles, const uint32_t *bbox, float com
 }
 
 __global__ void __launch_bounds__(256)
-tile_scatter_kernel(const float *__restrict__ x, const float *__restrict__ y, int64_t n, float res, int W,
-                    int H, uint32_t *cursors, int32_t *perm, const uint32_t *bbox, float compact_m) {
+tile_scatter_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th,
+                    int64_t n, float res, int W, int H, uint32_t *cursors, int32_t *perm, const uint32_t *bbox, float compact_m) {
   if (bbox && cloud_is_compact(bbox, compact_m)) return;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) perm[atomicAdd(&cursors[tile_of(__ldg(x + i), __ldg(y + i), res, W, H)], 1u)] = (int32_t)i;
+  if (i < n) perm[atomicAdd(&cursors[tile_of(__ldg(x + i), __ldg(y + i), __ldg(th + i), res, W, H)], 1u)] = (int32_t)i;
 }
 
-cudaError_t launch_tile_order(const float *x, const float *y, int64_t n, float res, int W, int H,
+cudaError_t launch_tile_order(const float *x, const float *y, const float *th, int64_t n, float res, int W, int H,
                               uint32_t *counters, int32_t *perm, const uint32_t *bbox, float compact_m,
                               cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   int ntiles = tile_count(W, H);
   cudaMemsetAsync(counters, 0, sizeof(uint32_t) * (size_t)ntiles, s);
   unsigned blocks = (unsigned)((n + 255) / 256);
-  tile_hist_kernel<<<blocks, 256, 0, s>>>(x, y, n, res, W, H, counters, bbox, compact_m);
+  tile_hist_kernel<<<blocks, 256, 0, s>>>(x, y, th, n, res, W, H, counters, bbox, compact_m);
   tile_scan_kernel<<<1, 1024, 0, s>>>(counters, ntiles, bbox, compact_m);
-  tile_scatter_kernel<<<blocks, 256, 0, s>>>(x, y, n, res, W, H, counters, perm, bbox, compact_m);
+  tile_scatter_kernel<<<blocks, 256, 0, s>>>(x, y, th, n, res, W, H, counters, perm, bbox, compact_m);
   return cudaGetLastError();
 }
 

@@ -223,7 +223,8 @@ struct RouletteArgs {
   unsigned long long *last_attempt; /* attempt index (+1) of the acceptance filling slot n-1 */
 };
 cudaError_t launch_motion(const MotionLaunch &a, cudaStream_t s);
-cudaError_t launch_tile_order(const float *x, const float *y, int64_t n, float res, int W, int H,
+cudaError_t launch_tile_order(const float *x, const float *y, const float *th, int64_t n, float res, int W,
+                              int H,
                               uint32_t *counters, int32_t *perm, const uint32_t *bbox, float compact_m,
                               cudaStream_t s);
 int tile_count(int W, int H);

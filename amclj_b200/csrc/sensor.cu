@@ -139,7 +139,12 @@ __device__ __forceinline__ int32_t round_cell_fast(float v, const ResDiv &d) {
 #endif
 
 template <int MODE, bool DIAG, bool WIDE, bool TS>
-__global__ void __launch_bounds__(kMaxThreads, 1) sensor_kernel(const SensorLaunch a) {
+#ifndef WEDGE_THREADS
+#define WEDGE_THREADS 1024
+#define WEDGE_CTAS 1
+#endif
+__global__ void __launch_bounds__(MODE == DF_WEDGE8 ? WEDGE_THREADS : kMaxThreads, MODE == DF_WEDGE8 ? WEDGE_CTAS : 1)
+sensor_kernel(const SensorLaunch a) {
   extern __shared__ uint4 smem_dyn[];
   __shared__ uint64_t bar;
   if (a.auto_sel) { /* two field placements were launched: only the one that suits the particle spread runs */
@@ -446,9 +451,10 @@ static cudaError_t launch_t(const amclj_ctx *c, const SensorLaunch &a, cudaStrea
   /* one CTA per SM (the staged field owns the SM's shared memory); warps sized to the work */
   int64_t ntasks = ((a.n + 31) / 32) * a.chunks;
   int64_t want_warps = (ntasks + c->sm_count - 1) / c->sm_count;
-  int wpb = (int)(want_warps < 4 ? 4 : (want_warps > 32 ? 32 : want_warps));
+  const int max_wpb = MODE == DF_WEDGE8 ? WEDGE_THREADS / 32 : 32;
+  int wpb = (int)(want_warps < 4 ? 4 : (want_warps > max_wpb ? max_wpb : want_warps));
   int64_t blocks = (ntasks + wpb - 1) / wpb;
-  int per_sm = MODE == DF_SMEM4 ? 1 : 2;
+  int per_sm = MODE == DF_SMEM4 ? 1 : (MODE == DF_WEDGE8 ? WEDGE_CTAS : 2);
   if (blocks > (int64_t)c->sm_count * per_sm) blocks = (int64_t)c->sm_count * per_sm;
   if (blocks < 1) blocks = 1;
   kern<<<(unsigned)blocks, wpb * 32, smem, s>>>(a);
