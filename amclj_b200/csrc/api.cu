@@ -319,6 +319,11 @@ int enqueue_motion(amclj_ctx *ctx, const double curr[3], const double prev[3], b
   m.gid0 = ctx->global_offset;
   m.normals = injected ? ctx->normals : nullptr;
   m.seed = seed;
+  m.bbox = nullptr;
+  if (ctx->ctrl_fresh && !m.is_static && ctx->p.df_mode == 0 && ctx->map.wedge) {
+    m.bbox = ctx->bbox; /* the moved cloud's bounding box comes for free */
+    ctx->bbox_done = true;
+  }
   CK(launch_motion(m, ctx->stream));
   return AMCLJ_OK;
 }
@@ -360,7 +365,11 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
   }
   bool diag = ctx->p.collect_stats != 0;
   a.stats = diag ? ctx->stats : nullptr;
-  CK(reset_ctrl(ctx, true));
+  if (!ctx->ctrl_fresh) {
+    CK(reset_ctrl(ctx, true));
+    ctx->bbox_done = false;
+  }
+  ctx->ctrl_fresh = false;
   if (diag) {
     CK(cudaMemsetAsync(ctx->stats, 0, 7 * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->stats + 8, 0, sizeof(unsigned long long), ctx->stream));
@@ -379,12 +388,19 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
     b.chunks = a.chunks; b.partials = a.partials; b.stats = a.stats;
     a = b;
     if (!ctx->tile_counters) CK(dalloc(&ctx->tile_counters, (size_t)tile_count(ctx->map.W, ctx->map.H) + 1));
-    CK(launch_bbox(ctx->x, ctx->y, ctx->n, ctx->bbox, ctx->sm_count, ctx->stream));
+    if (!ctx->bbox_done) CK(launch_bbox(ctx->x, ctx->y, ctx->n, ctx->bbox, ctx->sm_count, ctx->stream));
+    ctx->bbox_done = false;
     a.bbox = ctx->bbox;
     a.compact_m = ctx->compact_cells * ctx->map.res;
-    CK(launch_tile_order(ctx->x, ctx->y, ctx->th, ctx->n, ctx->map.res, ctx->map.W, ctx->map.H, ctx->tile_counters,
-                         ctx->perm, ctx->bbox, a.compact_m, ctx->stream));
-    a.perm = ctx->perm;
+    a.decision = const_cast<int32_t *>(ctx->pin_decision); /* pinned host memory: the kernel stores straight into it */
+    /* the previous update's verdict, which the kernel left in pinned host memory, is only a hint: when the
+     * cloud was compact the tile-order kernels are not even launched (a wrong guess costs speed
+     * for one update, never a result) */
+    if (*ctx->pin_decision != 1) {
+      CK(launch_tile_order(ctx->x, ctx->y, ctx->th, ctx->n, ctx->map.res, ctx->map.W, ctx->map.H,
+                           ctx->tile_counters, ctx->perm, ctx->bbox, a.compact_m, ctx->stream));
+      a.perm = ctx->perm;
+    }
   }
   CK(launch_sensor(ctx, a, mode, diag, ctx->stream));
   if (decode_max) CK(launch_decode_max(ctx->rawmax_ord, ctx->rawmax, ctx->stream));
@@ -632,9 +648,14 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
     ok = cudaMemset(ctx->ctrl, 0, sizeof(uint64_t) * ((size_t)ctx->scan_state_cap + 5)) == cudaSuccess;
   }
   ok = ok && dalloc(&ctx->rawmax, 1) == cudaSuccess && dalloc(&ctx->stats, 12) == cudaSuccess &&
-       dalloc(&ctx->plan, 1) == cudaSuccess && dalloc(&ctx->totals_all, MAX_WORLD) == cudaSuccess &&
+       dalloc(&ctx->plan, 1) == cudaSuccess && dalloc(&ctx->decision, 1) == cudaSuccess && dalloc(&ctx->totals_all, MAX_WORLD) == cudaSuccess &&
        dalloc(&ctx->pose_part, (size_t)pose_blocks() * 4) == cudaSuccess &&
        cudaMallocHost(&ctx->pinned, 4096) == cudaSuccess;
+  if (ok) {
+    ctx->pin_decision = reinterpret_cast<volatile int32_t *>(reinterpret_cast<char *>(ctx->pinned) + 2048);
+    *ctx->pin_decision = -1;
+    ok = cudaMemset(ctx->decision, 0xff, sizeof(int32_t)) == cudaSuccess;
+  }
   if (ok) ok = cudaMemset(ctx->stats, 0, 12 * sizeof(unsigned long long)) == cudaSuccess;
   if (!ok) {
     amclj_destroy(ctx);
@@ -655,7 +676,7 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
   dfree(ctx->x2); dfree(ctx->y2); dfree(ctx->th2); dfree(ctx->w2);
   dfree(ctx->cdf); dfree(ctx->idx); dfree(ctx->normals); dfree(ctx->partials); dfree(ctx->perm); dfree(ctx->tile_counters);
   dfree(ctx->ctrl); dfree(ctx->rawmax); dfree(ctx->stats);
-  dfree(ctx->pose_part); dfree(ctx->plan); dfree(ctx->hist); dfree(ctx->totals_all);
+  dfree(ctx->pose_part); dfree(ctx->plan); dfree(ctx->hist); dfree(ctx->totals_all); dfree(ctx->decision);
   for (int g = 0; g < MAX_WORLD; g++)
     for (int k = 0; k < 7; k++)
       if (ctx->ipc_opened[g][k]) cudaIpcCloseMemHandle(ctx->ipc_opened[g][k]);
@@ -997,6 +1018,9 @@ int32_t amclj_filter_update_async(amclj_ctx *ctx, const double curr[3], const do
        "filter_update_async: only the systematic resampler runs without a host round trip");
   NEED(u0 >= 0.0 && u0 < 1.0, AMCLJ_ERR_INVALID, "filter_update: u0 must be in [0,1)");
   stamp(ctx, 0);
+  CK(reset_ctrl(ctx, true)); /* one clear per update: bounding box, max, total, scan tiles */
+  ctx->ctrl_fresh = true;
+  ctx->bbox_done = false;
   int rc = enqueue_motion(ctx, curr, prev, ctx->normals_staged, seed);
   ctx->normals_staged = false;
   if (rc) return rc;
@@ -1033,6 +1057,9 @@ int32_t amclj_filter_update(amclj_ctx *ctx, const double curr[3], const double p
   /* roulette / tournament need the host in the loop (pf.clj:156-167 has an unbounded
    * attempt count) */
   stamp(ctx, 0);
+  CK(reset_ctrl(ctx, true)); /* one clear per update: bounding box, max, total, scan tiles */
+  ctx->ctrl_fresh = true;
+  ctx->bbox_done = false;
   rc = enqueue_motion(ctx, curr, prev, normals != nullptr, seed);
   if (rc) return rc;
   stamp(ctx, 1);
@@ -1222,6 +1249,9 @@ int32_t amclj_shard_motion_sensor_async(amclj_ctx *ctx, const double curr[3], co
   NEED(curr && prev, AMCLJ_ERR_INVALID, "shard: null control");
   NEED(ctx->n > 0, AMCLJ_ERR_STATE, "shard: no particles");
   stamp(ctx, 0);
+  CK(reset_ctrl(ctx, true)); /* one clear per update: bounding box, max, total, scan tiles */
+  ctx->ctrl_fresh = true;
+  ctx->bbox_done = false;
   int rc = enqueue_motion(ctx, curr, prev, false, seed);
   if (rc) return rc;
   stamp(ctx, 1);

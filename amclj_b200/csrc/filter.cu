@@ -18,6 +18,11 @@ namespace amclj {
 // are launch-uniform (computed once on the host, motion.clj:68-79 did it per particle);
 // per particle: three normals, one sincos, three FMAs.  24 B/particle of HBM traffic.
 // ======================================================================================
+__device__ __forceinline__ uint32_t ord_of_float_m(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
 __device__ __forceinline__ void philox_normals3(uint64_t seed, uint64_t gid, uint32_t tag,
                                                 float &n1, float &n2, float &n3) {
   uint32_t r[4];
@@ -32,24 +37,46 @@ __device__ __forceinline__ void philox_normals3(uint64_t seed, uint64_t gid, uin
 
 __global__ void __launch_bounds__(256) motion_kernel(const MotionLaunch a) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
-  float n1, n2, n3;
-  if (a.normals) {
-    n1 = __ldg(a.normals + 3 * i);
-    n2 = __ldg(a.normals + 3 * i + 1);
-    n3 = __ldg(a.normals + 3 * i + 2);
-  } else {
-    philox_normals3(a.seed, (uint64_t)(a.gid0 + i), TAG_MOTION, n1, n2, n3);
+  const bool valid = i < a.n;
+  uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+  if (valid) {
+    float n1, n2, n3;
+    if (a.normals) {
+      n1 = __ldg(a.normals + 3 * i);
+      n2 = __ldg(a.normals + 3 * i + 1);
+      n3 = __ldg(a.normals + 3 * i + 2);
+    } else {
+      philox_normals3(a.seed, (uint64_t)(a.gid0 + i), TAG_MOTION, n1, n2, n3);
+    }
+    float th = a.th[i];
+    float r1 = fmaf(-n1, a.sd1, a.rot1);                          /* motion.clj:35 */
+    float tr = a.trans_zero ? 0.0f : fmaf(-n2, a.sdt, a.trans);   /* motion.clj:36-37 */
+    float r2 = fmaf(-n3, a.sd2, a.rot2);                          /* motion.clj:38 */
+    float sn, cs;
+    sincos_det(th + r1, sn, cs);
+    float nx = fmaf(tr, cs, a.x[i]), ny = fmaf(tr, sn, a.y[i]); /* motion.clj:39-44 */
+    a.x[i] = nx;
+    a.y[i] = ny;
+    a.th[i] = th + (r1 + r2);      /* quat/rotate by rot1* + rot2* */
+    m0 = ord_of_float_m(nx); m1 = ord_of_float_m(-nx); m2 = ord_of_float_m(ny); m3 = ord_of_float_m(-ny);
   }
-  float th = a.th[i];
-  float r1 = fmaf(-n1, a.sd1, a.rot1);                          /* motion.clj:35 */
-  float tr = a.trans_zero ? 0.0f : fmaf(-n2, a.sdt, a.trans);   /* motion.clj:36-37 */
-  float r2 = fmaf(-n3, a.sd2, a.rot2);                          /* motion.clj:38 */
-  float sn, cs;
-  sincos_det(th + r1, sn, cs);
-  a.x[i] = fmaf(tr, cs, a.x[i]); /* motion.clj:39-44 */
-  a.y[i] = fmaf(tr, sn, a.y[i]);
-  a.th[i] = th + (r1 + r2);      /* quat/rotate by rot1* + rot2* */
+  if (a.bbox) { /* bounding box of the moved cloud, for the sensor stage's walking-order decision */
+    m0 = __reduce_max_sync(0xffffffffu, m0);
+    m1 = __reduce_max_sync(0xffffffffu, m1);
+    m2 = __reduce_max_sync(0xffffffffu, m2);
+    m3 = __reduce_max_sync(0xffffffffu, m3);
+    __shared__ uint32_t sm[4];
+    if (threadIdx.x < 4) sm[threadIdx.x] = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { /* block-level first: the four global words are shared by everyone */
+      atomicMax(&sm[0], m0);
+      atomicMax(&sm[1], m1);
+      atomicMax(&sm[2], m2);
+      atomicMax(&sm[3], m3);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) atomicMax(a.bbox + threadIdx.x, sm[threadIdx.x]);
+  }
 }
 
 cudaError_t launch_motion(const MotionLaunch &a, cudaStream_t s) {

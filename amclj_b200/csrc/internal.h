@@ -67,6 +67,7 @@ struct SensorLaunch {
   int32_t auto_sel;      // 0: always run; 1: run only when compact; 2: only when not compact
   int32_t skip_combine;  // leave the chunk partials to a later launch
   const int32_t *perm;   // walking order (particle indices sorted by map tile), or null
+  int32_t *decision;     // out: 1 when the cloud was compact (host hint for the next update)
   float R;            // ray length (S2)
   float miss_value;
   int32_t s1, s3, s4, s7, s10;
@@ -87,6 +88,7 @@ struct MotionLaunch {
   const float *normals;  // [n][3] or null -> Philox
   uint64_t seed;
   int32_t is_static, trans_zero;
+  uint32_t *bbox;  // when set: accumulate the bounding box of the moved cloud (4 ordered-uint maxima)
   float rot1, trans, rot2, sd1, sdt, sd2;
 };
 
@@ -124,6 +126,10 @@ struct amclj_ctx {
   // single memset per update clears everything the sensor max and the scan accumulate into
   uint64_t *ctrl = nullptr;
   bool scan_clean = false;
+  bool ctrl_fresh = false;   // control block cleared for this update already
+  bool bbox_done = false;    // the motion kernel of this update left the bounding box
+  int32_t *decision = nullptr;      // device flag: the last cloud was compact
+  volatile int32_t *pin_decision = nullptr;  // its (asynchronously refreshed) host copy: a hint only
   bool max_in_ord = false;  // the weight max of the last pass lives in rawmax_ord only
   uint32_t *rawmax_ord = nullptr;  // ordered-uint of max raw
   float *rawmax = nullptr;         // float[1] (AMCLJ_BUF_RAW_MAX)

@@ -153,7 +153,11 @@ sensor_kernel(const SensorLaunch a) {
   /* spread-out clouds are walked in spatial (tile) order so that a CTA's probes share an L1-sized
    * neighbourhood; a compact cloud is local as it is */
   const int32_t *perm = a.perm;
-  if (perm && a.bbox && cloud_is_compact(a.bbox, a.compact_m)) perm = nullptr;
+  if (a.bbox) {
+    const bool compact = cloud_is_compact(a.bbox, a.compact_m);
+    if (compact) perm = nullptr;
+    if (a.decision && blockIdx.x == 0 && threadIdx.x == 0) *a.decision = compact ? 1 : 0;
+  }
   Field df;
   df.g = a.df;
   df.s = 0;
