@@ -405,6 +405,7 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
   CK(launch_sensor(ctx, a, mode, diag, ctx->stream));
   if (decode_max) CK(launch_decode_max(ctx->rawmax_ord, ctx->rawmax, ctx->stream));
   ctx->max_in_ord = !decode_max;
+  ctx->last_diag = diag;
   ctx->have_raw = true;
   ctx->have_cdf = false;
   ctx->st.map_in_smem = mode == DF_SMEM4;
@@ -939,6 +940,7 @@ int32_t amclj_raycast_debug(amclj_ctx *ctx, int32_t n, float angle_min, float an
     a.dbg_range = d_rng;
     a.stats = ctx->stats;
     ctx->st.map_in_smem = mode == DF_SMEM4;
+    ctx->last_diag = true;
     ctx->st.beams_used = ctx->beams.nb;
     cudaMemsetAsync(ctx->stats, 0, 7 * sizeof(unsigned long long), ctx->stream);
     e = launch_sensor(ctx, a, mode, true, ctx->stream);
@@ -1151,7 +1153,7 @@ int32_t amclj_get_stats(amclj_ctx *ctx, amclj_stats *out) {
   unsigned long long h[12] = {0};
   CK(cudaMemcpy(h, ctx->stats, sizeof(h), cudaMemcpyDeviceToHost));
   ctx->st.oob_probes = h[6];
-  if (h[8]) ctx->st.map_in_smem = (int)h[8] - 1 == DF_SMEM4; /* the placement that actually ran */
+  if (h[8] && ctx->last_diag) ctx->st.map_in_smem = (int)h[8] - 1 == DF_SMEM4; /* the placement that actually ran */
   ctx->st.rays = h[0];
   ctx->st.cells_visited = h[1];
   ctx->st.probes = h[2];

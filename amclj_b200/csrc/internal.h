@@ -130,6 +130,7 @@ struct amclj_ctx {
   bool bbox_done = false;    // the motion kernel of this update left the bounding box
   int32_t *decision = nullptr;      // device flag: the last cloud was compact
   volatile int32_t *pin_decision = nullptr;  // its (asynchronously refreshed) host copy: a hint only
+  bool last_diag = false;   // the last sensor pass ran the diagnostic kernel (stats are fresh)
   bool max_in_ord = false;  // the weight max of the last pass lives in rawmax_ord only
   uint32_t *rawmax_ord = nullptr;  // ordered-uint of max raw
   float *rawmax = nullptr;         // float[1] (AMCLJ_BUF_RAW_MAX)
