@@ -379,7 +379,7 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
    * share an L1-sized neighbourhood.  A 5 us bounding-box kernel leaves the decision on the device
    * (the tile-order kernels return at once for a compact cloud, and the sensor kernel ignores the
    * permutation); either way the results are identical. */
-  bool directional = ctx->p.df_mode == 0 && mode == DF_SMEM4 && ctx->map.wedge != nullptr;
+  bool directional = ctx->p.df_mode == 0 && ctx->map.wedge != nullptr;
   if (directional) {
     mode = DF_WEDGE8;
     SensorLaunch b;
@@ -629,6 +629,7 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
     if (v >= 1 && v <= 32) ctx->refill = v;
   }
   if (const char *e = getenv("AMCLJ_CHUNKS")) ctx->force_chunks = atoi(e);
+  if (const char *e = getenv("AMCLJ_WEDGE_BUDGET_MB")) ctx->wedge_budget = (size_t)atoll(e) << 20;
   if (const char *e = getenv("AMCLJ_REFILL_WEDGE")) ctx->refill_wedge = atoi(e);
   if (const char *e = getenv("AMCLJ_COMPACT_CELLS")) ctx->compact_cells = (float)atof(e);
   memset(&ctx->st, 0, sizeof(ctx->st));
@@ -711,7 +712,7 @@ int32_t amclj_set_params(amclj_ctx *ctx, const amclj_params *p) {
   NEED(p, AMCLJ_ERR_INVALID, "set_params: null");
   NEED(p->df_mode >= 0 && p->df_mode <= 5, AMCLJ_ERR_INVALID, "set_params: df_mode %d", p->df_mode);
   if (p->df_mode >= 4 && ctx->map.cells && !ctx->map.wedge) { /* directional fields are built on demand */
-    NEED((size_t)ctx->map.pitch8 * (ctx->map.H + 2) * WEDGE_CLASSES <= (512ull << 20), AMCLJ_ERR_INVALID,
+    NEED((size_t)ctx->map.pitch8 * (ctx->map.H + 2) * WEDGE_CLASSES <= (8ull << 30), AMCLJ_ERR_INVALID,
          "set_params: map too large for directional fields");
     CK(build_wedge_fields(ctx, ctx->stream));
   }
@@ -765,9 +766,10 @@ int32_t amclj_set_map(amclj_ctx *ctx, const int8_t *cells, int32_t width, int32_
   if (want8) CK(dalloc(&m.df8, m.bytes8));
   CK(build_distance_fields(ctx, want8, ctx->stream));
   if (ctx->p.df_mode >= 4) {
-    NEED(m.bytes8 * WEDGE_CLASSES <= (512ull << 20), AMCLJ_ERR_INVALID, "set_map: map too large for directional fields");
+    NEED(m.bytes8 * WEDGE_CLASSES <= (8ull << 30), AMCLJ_ERR_INVALID, "set_map: map too large for directional fields");
     CK(build_wedge_fields(ctx, ctx->stream));
-  } else if (ctx->p.df_mode == 0 && m.fits_smem && m.bytes8 * WEDGE_CLASSES <= (64ull << 20)) {
+  } else if (ctx->p.df_mode == 0 && m.bytes8 * WEDGE_CLASSES <= ctx->wedge_budget &&
+             m.bytes8 * WEDGE_CLASSES < (1ull << 32)) {
     CK(build_wedge_fields(ctx, ctx->stream)); /* auto: both field sets, chosen per update */
   }
   ctx->beams.staged = false;

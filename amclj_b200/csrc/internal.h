@@ -162,6 +162,7 @@ struct amclj_ctx {
   uint64_t last_total = 0;
   amclj_stats st;
   int32_t refill = 6, refill_wedge = 12;
+  size_t wedge_budget = 64ull << 20;  // auto policy: build the directional planes when they fit this
   float compact_cells = 320.f;  // auto policy: directional fields when the particle bounding box is this small
   uint32_t *bbox = nullptr;    // 4 ordered-uint maxima: x, -x, y, -y (inside ctrl)
   double w_slow = 1.0, w_fast = 1.0;  // pf.clj:243-244

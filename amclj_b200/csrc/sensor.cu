@@ -44,7 +44,7 @@ struct Field {
 };
 
 template <int MODE>
-__device__ __forceinline__ uint32_t df_probe(const Field &f, int idx, uint32_t mask) {
+__device__ __forceinline__ uint32_t df_probe(const Field &f, uint32_t idx, uint32_t mask) {
   if (MODE == DF_GLOBAL8 || MODE == DF_WEDGE8) return (uint32_t)__ldg(f.g + idx) & mask;
   uint32_t byte;
   if (MODE == DF_SMEM4) {
@@ -253,7 +253,8 @@ sensor_kernel(const SensorLaunch a) {
     const bool dbg = DIAG && a.dbg_count > 0 && valid && p >= a.dbg_first && p < a.dbg_first + a.dbg_count;
 
     /* the ray in flight; a parked lane (am == 0) turns every update below into a no-op */
-    int idx = 0, k = 0, j = 0, err = 0, dy = 0, ndx = 0, kmax = 0, stepA = 0, stepB = 0;
+    uint32_t idx = 0; /* unsigned: 32 byte planes of a large map reach past 2^31 */
+    int k = 0, j = 0, err = 0, dy = 0, ndx = 0, kmax = 0, stepA = 0, stepB = 0;
     uint32_t M = 0, sh = 0, am = 0;
     int dg_a0 = 0, dg_b0 = 0, dg_xs = 0, dg_ys = 0, dg_steep = 0, dg_probes = 0; /* DIAG only */
     bool have_ray = false;
@@ -350,8 +351,8 @@ sensor_kernel(const SensorLaunch a) {
           if (MODE == DF_WEDGE8 && start_in) { /* the plane of this ray's direction class */
             /* plane = ((steep*4 + (xs<0)*2 + (ys<0)) * BINS + bin), bin = min(BINS-1, floor(dy*BINS/dx))
              * without a division; accumulated directly as a byte offset */
-            const int P = a.wedge_plane;
-            int off = steep ? 4 * WEDGE_BINS * P : 0;
+            const uint32_t P = (uint32_t)a.wedge_plane;
+            uint32_t off = steep ? 4 * WEDGE_BINS * P : 0;
             off += xs < 0 ? 2 * WEDGE_BINS * P : 0;
             off += ys < 0 ? WEDGE_BINS * P : 0;
             const int dyb = dy * WEDGE_BINS;
@@ -374,7 +375,7 @@ sensor_kernel(const SensorLaunch a) {
 #pragma unroll
         for (int u = 0; u < (MODE == DF_WEDGE8 ? PROBES_PER_VOTE_WEDGE : PROBES_PER_VOTE); u++) {
           /* branch-free: a parked lane reads d = 0, which makes every update a no-op */
-          if (DIAG && (uint32_t)idx >= idx_limit) { n_oob++; idx = 0; } /* never taken: see tests */
+          if (DIAG && idx >= idx_limit) { n_oob++; idx = 0; } /* never taken: see tests */
           const uint32_t d = df_probe<MODE>(df, idx, am);
           if (DIAG) dg_probes += am ? 1 : 0;
           k += (int)d;
@@ -384,7 +385,7 @@ sensor_kernel(const SensorLaunch a) {
           const uint32_t jd = WIDE ? (__umulhi(t, M) >> sh) : __umulhi(t, M);
           err = e2 + (int)jd * ndx;
           j += (int)jd;
-          idx += (int)d * stepA + (int)jd * stepB;
+          idx += (uint32_t)((int)d * stepA + (int)jd * stepB);
           am = fin ? 0u : am;
         }
         act = __ballot_sync(FULL, am != 0);
