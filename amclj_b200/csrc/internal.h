@@ -64,8 +64,6 @@ struct SensorLaunch {
   long long *partials;  // [chunks][n] fixed-point partial weights when chunks > 1
   const uint32_t *bbox;  // particle bounding box (auto policy), see launch_bbox
   float compact_m;       // bounding-box side (metres) up to which the particle set counts as compact
-  int32_t auto_sel;      // 0: always run; 1: run only when compact; 2: only when not compact
-  int32_t skip_combine;  // leave the chunk partials to a later launch
   const int32_t *perm;   // walking order (particle indices sorted by map tile), or null
   int32_t *decision;     // out: 1 when the cloud was compact (host hint for the next update)
   float R;            // ray length (S2)

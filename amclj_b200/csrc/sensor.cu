@@ -147,9 +147,6 @@ __global__ void __launch_bounds__(MODE == DF_WEDGE8 ? WEDGE_THREADS : kMaxThread
 sensor_kernel(const SensorLaunch a) {
   extern __shared__ uint4 smem_dyn[];
   __shared__ uint64_t bar;
-  if (a.auto_sel) { /* two field placements were launched: only the one that suits the particle spread runs */
-    if (cloud_is_compact(a.bbox, a.compact_m) != (a.auto_sel == 1)) return;
-  }
   /* spread-out clouds are walked in spatial (tile) order so that a CTA's probes share an L1-sized
    * neighbourhood; a compact cloud is local as it is */
   const int32_t *perm = a.perm;
@@ -510,7 +507,7 @@ cudaError_t launch_sensor(const amclj_ctx *c, const SensorLaunch &a_in, int mode
     default: e = launch_m<DF_GLOBAL4>(c, a, diag, wide, s); break;
   }
   if (e != cudaSuccess) return e;
-  if (a.chunks > 1 && final_raw && !a.skip_combine) {
+  if (a.chunks > 1 && final_raw) {
     combine_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a.partials, a.chunks, a.n, final_raw,
                                                                  a.rawmax_ord);
     e = cudaGetLastError();

@@ -37,7 +37,8 @@ if str(ROOT) not in sys.path:
 METRIC = "beam_evals_per_s"
 UNIT = "beam-evals/s"
 PER_GPU_SHARDED = 1_250_000  # C4: 10M particles over 8 GPUs
-KERNELS_PER_UPDATE = 7       # motion, bounding box, sensor x2 (one returns at once), combine, scan, gather
+KERNELS_PER_UPDATE = 5       # motion (+ bounding box), sensor, combine, scan, gather; the 3 tile-order kernels of a
+                             # spread-out cloud come on top (a compact cloud skips their launches after its first update)
 KERNELS_PER_UPDATE_SHARDED = 5  # motion, sensor, decode-max, scan, pull (+ 2 NCCL collectives)
 
 

@@ -76,8 +76,10 @@ typedef struct amclj_params {
   /* S10 sensor.clj:78-81,142 — 0: base->laser offset ignored (REF and NS default) */
   int32_t s10_apply_laser_offset;
   int32_t collect_stats; /* count cells visited / probes (small cost) */
-  /* distance-field placement: 0 auto (shared memory when the nibble-packed field fits,
-   * else one byte per cell in L2), 1 shared nibbles, 2 global bytes, 3 global nibbles,
+  /* distance-field placement: 0 auto (maps whose 32 directional planes fit 64 MB: the planes,
+   * walked in place for a compact particle cloud and in map-tile order for a spread-out one;
+   * larger maps: one byte per cell in L2), 1 isotropic nibbles in shared memory, 2 isotropic bytes
+   * in global memory, 3 isotropic nibbles in global memory,
    * 4 directional byte fields (32 direction classes) through L1/L2, 5 the same with the particles
    * walked in map-tile order (spread-out clouds) */
   int32_t df_mode;
@@ -108,7 +110,7 @@ typedef struct amclj_stats {
   uint64_t hits;
   int64_t n_particles;
   int32_t beams_used;
-  int32_t map_in_smem; /* 1 when the nibble-packed distance field fits shared memory */
+  int32_t map_in_smem; /* 1 when the last sensor pass walked the shared-memory field */
   uint64_t oob_probes; /* diagnostic passes only: probes outside the staged field (must be 0) */
 } amclj_stats;
 
