@@ -518,7 +518,7 @@ def test_auto_field_policy_matches_every_placement(lg):
     c.close()
 
 
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", range(20))
 def test_raycast_random_small_maps(seed):
     """Random small maps of awkward shapes (1-cell-wide, odd widths, coarse and fine resolutions),
     random scans and switches; every field placement against the oracle, ray by ray."""
@@ -576,3 +576,26 @@ def test_resample_random_weight_patterns(ctx, seed):
     wt = np.nan_to_num(w, nan=0.0)
     ctx.set_particles(z, z, z, wt)
     assert np.array_equal(ctx.resample(_lib.RESAMPLE_TOURNAMENT, 0.0, seed=seed), oracle.tournament_philox(wt, seed))
+
+
+@pytest.mark.parametrize("preset", ["NS", "REF"])
+def test_raycast_very_long_rays_use_the_shifted_reciprocal(preset):
+    """Rays of 20,000 cells (fine resolution, long range) push the minor-axis division past the
+    shift-free reciprocal's exact range: the table switches to the shifted form; still bit-exact."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    W, H, res = 300, 200, 0.005
+    g = np.where(rng.random((H, W)) < 0.002, 100, 0).astype(np.int8)
+    grid = maps.OccupancyGrid(maps.MapMetaData(np.float32(res), W, H), g)
+    n = 800
+    x = (rng.uniform(0, W, n) * res).astype(np.float32)
+    y = (rng.uniform(0, H, n) * res).astype(np.float32)
+    th = rng.uniform(-3.2, 3.2, n).astype(np.float32)
+    scan = workloads.Scan(rng.uniform(0, 2, 90).astype(np.float32), float(np.float32(-3.1)), float(np.float32(0.07)),
+                          float(np.float32(100.0)))
+    c = _lib.Context(0)
+    for df_mode in (1, 2, 4, 0):
+        kw = dict(df_mode=df_mode, max_range=-100.0) if preset == "REF" else dict(df_mode=df_mode)
+        c.set_params(_lib.params(preset, **kw))
+        c.set_map(grid)
+        _ray_parity(c, grid, x, y, th, scan, preset, **kw)
+    c.close()
