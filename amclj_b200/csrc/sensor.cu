@@ -131,6 +131,32 @@ __device__ __forceinline__ int32_t round_cell_fast(float v, const ResDiv &d) {
   return (int32_t)t;
 }
 
+/* both coordinates of a point at once: one range check for the pair */
+__device__ __forceinline__ void round_cell2_fast(float vx, float vy, const ResDiv &d, int &cx, int &cy) {
+  float qx0 = vx * d.r, qy0 = vy * d.r;
+  float qx = fmaf(fmaf(-qx0, d.res, vx), d.r, qx0);
+  float qy = fmaf(fmaf(-qy0, d.res, vy), d.r, qy0);
+  if (!(fmaxf(fabsf(vx), fabsf(vy)) < d.lim)) { /* huge / infinite (a NaN falls through as NaN either way) */
+    qx = vx / d.res;
+    qy = vy / d.res;
+  }
+  float tx = fminf(fmaxf(floorf(qx + 0.5f), -1.0e9f), 1.0e9f);
+  float ty = fminf(fmaxf(floorf(qy + 0.5f), -1.0e9f), 1.0e9f);
+  cx = (int32_t)tx;
+  cy = (int32_t)ty;
+}
+
+/* sqrt of an exact integer 1 <= d2 <= 2^32, correctly rounded: the compiler's own fast path of
+ * sqrt.rn (rsqrt, one Newton step on g = x*y with the exact residual) without its range
+ * scaffolding, which these operands never need */
+__device__ __forceinline__ float sqrt_int(uint32_t d2) {
+  float x = __uint2float_rn(d2), y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  float g = x * y, h = 0.5f * y;
+  g = fmaf(fmaf(-g, g, x), h, g);
+  return d2 ? g : 0.0f;
+}
+
 #ifndef PROBES_PER_VOTE
 #define PROBES_PER_VOTE 8
 #endif
@@ -242,7 +268,8 @@ sensor_kernel(const SensorLaunch a) {
       float ny = oy + fmaf(a.laser_x, st, a.laser_y * ct);
       ox = nx; oy = ny;
     }
-    const int x0 = round_cell_fast(ox, rdv), y0 = round_cell_fast(oy, rdv);
+    int x0, y0;
+    round_cell2_fast(ox, oy, rdv, x0, y0);
     const bool start_in = (uint32_t)x0 < (uint32_t)a.W && (uint32_t)y0 < (uint32_t)a.H;
     /* padded field: cell (x, y) lives at (y+1)*row + (x+1); entry 0 is a ring cell (d = 0),
      * which makes an out-of-range start an immediate hit (the start cell is tested first) */
@@ -268,7 +295,7 @@ sensor_kernel(const SensorLaunch a) {
           float rng;
           if (hit) { /* sensor.clj:118-120: hypot(x - x0, y - y0) * resolution */
             uint32_t d2 = (uint32_t)k * (uint32_t)k + (uint32_t)j * (uint32_t)j;
-            rng = __fmul_rn(__fsqrt_rn(__uint2float_rn(d2)), a.res);
+            rng = __fmul_rn(sqrt_int(d2), a.res);
           } else { /* sensor.clj:121: max-range */
             rng = a.miss_value;
           }
@@ -316,8 +343,8 @@ sensor_kernel(const SensorLaunch a) {
             s = fmaf(st, cb, ct * sb);
           }
           /* sensor.clj:99-103 project-pose, map.clj:36-46 world->map */
-          int x1 = round_cell_fast(fmaf(a.R, c, ox), rdv);
-          int y1 = round_cell_fast(fmaf(a.R, s, oy), rdv);
+          int x1, y1;
+          round_cell2_fast(fmaf(a.R, c, ox), fmaf(a.R, s, oy), rdv, x1, y1);
           int adx = abs(x1 - x0), ady = abs(y1 - y0);
           bool steep = ady > adx; /* sensor.clj:87-91 */
           int a0 = steep ? y0 : x0, b0 = steep ? x0 : y0;
