@@ -146,6 +146,19 @@ __device__ __forceinline__ void round_cell2_fast(float vx, float vy, const ResDi
   cy = (int32_t)ty;
 }
 
+/* endpoint of a ray whose start already passed the range check (|R| is bounded by the host), so
+ * the quotient cannot overflow; a start that failed it is out of range, hits at step 0 and never
+ * looks at its endpoint */
+__device__ __forceinline__ void round_cell2_inrange(float vx, float vy, const ResDiv &d, int &cx, int &cy) {
+  float qx0 = vx * d.r, qy0 = vy * d.r;
+  float qx = fmaf(fmaf(-qx0, d.res, vx), d.r, qx0);
+  float qy = fmaf(fmaf(-qy0, d.res, vy), d.r, qy0);
+  float tx = fminf(fmaxf(floorf(qx + 0.5f), -1.0e9f), 1.0e9f);
+  float ty = fminf(fmaxf(floorf(qy + 0.5f), -1.0e9f), 1.0e9f);
+  cx = (int32_t)tx;
+  cy = (int32_t)ty;
+}
+
 /* sqrt of an exact integer 1 <= d2 <= 2^32, correctly rounded: the compiler's own fast path of
  * sqrt.rn (rsqrt, one Newton step on g = x*y with the exact residual) without its range
  * scaffolding, which these operands never need */
@@ -292,13 +305,10 @@ sensor_kernel(const SensorLaunch a) {
         /* ---- (1) score the ray that has ended: sensor.clj:149-162 beam mixture ---------- */
         if (have_ray) {
           const bool hit = k <= kmax; /* a miss leaves k beyond the last cell to test */
-          float rng;
-          if (hit) { /* sensor.clj:118-120: hypot(x - x0, y - y0) * resolution */
-            uint32_t d2 = (uint32_t)k * (uint32_t)k + (uint32_t)j * (uint32_t)j;
-            rng = __fmul_rn(sqrt_int(d2), a.res);
-          } else { /* sensor.clj:121: max-range */
-            rng = a.miss_value;
-          }
+          /* sensor.clj:118-120 hypot(x - x0, y - y0) * resolution on a hit, :121 max-range on a miss
+           * (branch-free: the root of a miss's leftover counters is computed and dropped) */
+          const uint32_t d2 = (uint32_t)k * (uint32_t)k + (uint32_t)j * (uint32_t)j;
+          const float rng = hit ? __fmul_rn(sqrt_int(d2), a.res) : a.miss_value;
           const float4 mx = ld_mix<TS>(tb, jb); /* obs, pz2's exponential, pz3 + pz4: beam-only terms */
           float z = mx.x - rng;
           float pz1 = a.z_hit * expf(-(z * z) * a.inv2s2);
@@ -344,7 +354,8 @@ sensor_kernel(const SensorLaunch a) {
           }
           /* sensor.clj:99-103 project-pose, map.clj:36-46 world->map */
           int x1, y1;
-          round_cell2_fast(fmaf(a.R, c, ox), fmaf(a.R, s, oy), rdv, x1, y1);
+          if (rdv.lim > 0.0f) round_cell2_inrange(fmaf(a.R, c, ox), fmaf(a.R, s, oy), rdv, x1, y1);
+          else round_cell2_fast(fmaf(a.R, c, ox), fmaf(a.R, s, oy), rdv, x1, y1); /* odd resolutions: real divides */
           int adx = abs(x1 - x0), ady = abs(y1 - y0);
           bool steep = ady > adx; /* sensor.clj:87-91 */
           int a0 = steep ? y0 : x0, b0 = steep ? x0 : y0;
