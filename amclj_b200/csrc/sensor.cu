@@ -245,6 +245,9 @@ sensor_kernel(const SensorLaunch a) {
     for (int i = threadIdx.x; i < a.nb; i += blockDim.x) { smix[i] = __ldg(tb.mix + i); sdir[i] = __ldg(tb.dir + i); }
     for (int i = threadIdx.x; i < a.ndiv; i += blockDim.x) sdiv[i] = __ldg(tb.div + i);
     tb.s_mix = smem_u32(smix); tb.s_dir = smem_u32(sdir); tb.s_div = smem_u32(sdiv);
+    /* keep the three window addresses in registers: left alone, the compiler rebuilds each of
+     * them from SR_CgaCtaId at every use */
+    asm volatile("" : "+r"(tb.s_mix), "+r"(tb.s_dir), "+r"(tb.s_div));
     __syncthreads();
   }
   const ResDiv rdv = make_resdiv(a.res);
