@@ -45,7 +45,11 @@ struct Field {
 
 template <int MODE>
 __device__ __forceinline__ uint32_t df_probe(const Field &f, uint32_t idx, uint32_t mask) {
-  if (MODE == DF_GLOBAL8 || MODE == DF_WEDGE8) return (uint32_t)__ldg(f.g + idx) & mask;
+  if (MODE == DF_GLOBAL8 || MODE == DF_WEDGE8) {
+    uint32_t v; /* zero-extending byte load through the read-only path: no second mask needed */
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(f.g + idx));
+    return v & mask;
+  }
   uint32_t byte;
   if (MODE == DF_SMEM4) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(byte) : "r"(f.s + (uint32_t)(idx >> 3)));
