@@ -290,7 +290,7 @@ void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode) {
   a.divtab = ctx->divs.dev;
   a.ndiv = ctx->divs.n;
   a.div_wide = ctx->divs.wide;
-  a.refill = mode == DF_WEDGE8 ? ctx->refill_wedge : ctx->refill;
+  a.refill = mode == DF_WEDGE8 ? ctx->refill_wedge : (mode == DF_SMEM4 ? ctx->refill : ctx->refill_global);
   a.chunks = 1;
   a.R = p.s2_use_scan_range_max ? ctx->beams.range_max : p.max_range;
   a.miss_value = a.R; /* sensor.clj:121 returns max-range on a miss */
@@ -320,7 +320,7 @@ int enqueue_motion(amclj_ctx *ctx, const double curr[3], const double prev[3], b
   m.normals = injected ? ctx->normals : nullptr;
   m.seed = seed;
   m.bbox = nullptr;
-  if (ctx->ctrl_fresh && !m.is_static && ctx->p.df_mode == 0 && ctx->map.wedge) {
+  if (ctx->ctrl_fresh && !m.is_static && ctx->p.df_mode == 0 && (ctx->map.wedge || ctx->order_large_maps)) {
     m.bbox = ctx->bbox; /* the moved cloud's bounding box comes for free */
     ctx->bbox_done = true;
   }
@@ -380,6 +380,9 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
    * (the tile-order kernels return at once for a compact cloud, and the sensor kernel ignores the
    * permutation); either way the results are identical. */
   bool directional = ctx->p.df_mode == 0 && ctx->map.wedge != nullptr;
+  /* large maps (byte field through L2) get the tile-order walk too: it is what keeps a CTA's
+   * probes in L1 */
+  bool ordered = directional || (ctx->p.df_mode == 0 && mode == DF_GLOBAL8 && ctx->order_large_maps);
   if (directional) {
     mode = DF_WEDGE8;
     SensorLaunch b;
@@ -387,6 +390,8 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
     b.x = a.x; b.y = a.y; b.th = a.th; b.raw = a.raw; b.n = a.n; b.rawmax_ord = a.rawmax_ord;
     b.chunks = a.chunks; b.partials = a.partials; b.stats = a.stats;
     a = b;
+  }
+  if (ordered) {
     if (!ctx->tile_counters) CK(dalloc(&ctx->tile_counters, (size_t)tile_count(ctx->map.W, ctx->map.H) + 1));
     if (!ctx->bbox_done) CK(launch_bbox(ctx->x, ctx->y, ctx->n, ctx->bbox, ctx->sm_count, ctx->stream));
     ctx->bbox_done = false;
@@ -629,8 +634,10 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
     if (v >= 1 && v <= 32) ctx->refill = v;
   }
   if (const char *e = getenv("AMCLJ_CHUNKS")) ctx->force_chunks = atoi(e);
+  if (const char *e = getenv("AMCLJ_ORDER_LARGE")) ctx->order_large_maps = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_WEDGE_BUDGET_MB")) ctx->wedge_budget = (size_t)atoll(e) << 20;
   if (const char *e = getenv("AMCLJ_REFILL_WEDGE")) ctx->refill_wedge = atoi(e);
+  if (const char *e = getenv("AMCLJ_REFILL_GLOBAL")) ctx->refill_global = atoi(e);
   if (const char *e = getenv("AMCLJ_COMPACT_CELLS")) ctx->compact_cells = (float)atof(e);
   memset(&ctx->st, 0, sizeof(ctx->st));
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;

@@ -159,7 +159,8 @@ struct amclj_ctx {
   float last_wmax = 0.f;
   uint64_t last_total = 0;
   amclj_stats st;
-  int32_t refill = 6, refill_wedge = 12;
+  int32_t refill = 6, refill_wedge = 12, refill_global = 16;
+  bool order_large_maps = true;       // auto policy: tile-order walk on the L2 byte field as well
   size_t wedge_budget = 64ull << 20;  // auto policy: build the directional planes when they fit this
   float compact_cells = 320.f;  // auto policy: directional fields when the particle bounding box is this small
   uint32_t *bbox = nullptr;    // 4 ordered-uint maxima: x, -x, y, -y (inside ctrl)
