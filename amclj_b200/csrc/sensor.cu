@@ -181,12 +181,22 @@ __device__ __forceinline__ float sqrt_int(uint32_t d2) {
 #define PROBES_PER_VOTE_WEDGE 6
 #endif
 
-template <int MODE, bool DIAG, bool WIDE, bool TS>
 #ifndef WEDGE_THREADS
 #define WEDGE_THREADS 1024
 #define WEDGE_CTAS 1
 #endif
-__global__ void __launch_bounds__(MODE == DF_WEDGE8 ? WEDGE_THREADS : kMaxThreads, MODE == DF_WEDGE8 ? WEDGE_CTAS : 1)
+/* the L1/L2 byte field is latency bound: 2 CTAs of 24 warps (40 registers) hide more of it than
+ * one of 32 (C5: 107.5 -> 97.8 ms) */
+#ifndef GLOBAL_THREADS
+#define GLOBAL_THREADS 768
+#define GLOBAL_CTAS 2
+#endif
+constexpr int mode_threads(int mode) {
+  return mode == DF_WEDGE8 ? WEDGE_THREADS : (mode == DF_SMEM4 ? kMaxThreads : GLOBAL_THREADS);
+}
+constexpr int mode_ctas(int mode) { return mode == DF_WEDGE8 ? WEDGE_CTAS : (mode == DF_SMEM4 ? 1 : GLOBAL_CTAS); }
+template <int MODE, bool DIAG, bool WIDE, bool TS>
+__global__ void __launch_bounds__(mode_threads(MODE), mode_ctas(MODE))
 sensor_kernel(const SensorLaunch a) {
   extern __shared__ uint4 smem_dyn[];
   __shared__ uint64_t bar;
@@ -498,10 +508,10 @@ static cudaError_t launch_t(const amclj_ctx *c, const SensorLaunch &a, cudaStrea
   /* one CTA per SM (the staged field owns the SM's shared memory); warps sized to the work */
   int64_t ntasks = ((a.n + 31) / 32) * a.chunks;
   int64_t want_warps = (ntasks + c->sm_count - 1) / c->sm_count;
-  const int max_wpb = MODE == DF_WEDGE8 ? WEDGE_THREADS / 32 : 32;
+  const int max_wpb = mode_threads(MODE) / 32;
   int wpb = (int)(want_warps < 4 ? 4 : (want_warps > max_wpb ? max_wpb : want_warps));
   int64_t blocks = (ntasks + wpb - 1) / wpb;
-  int per_sm = MODE == DF_SMEM4 ? 1 : (MODE == DF_WEDGE8 ? WEDGE_CTAS : 2);
+  int per_sm = MODE == DF_SMEM4 ? 1 : (MODE == DF_WEDGE8 ? WEDGE_CTAS : (GLOBAL_CTAS > 2 ? GLOBAL_CTAS : 2));
   if (blocks > (int64_t)c->sm_count * per_sm) blocks = (int64_t)c->sm_count * per_sm;
   if (blocks < 1) blocks = 1;
   kern<<<(unsigned)blocks, wpb * 32, smem, s>>>(a);
