@@ -67,6 +67,7 @@ class Stats(C.Structure):
         ("ms_total", C.c_double), ("rays", C.c_uint64), ("cells_visited", C.c_uint64),
         ("probes", C.c_uint64), ("hits", C.c_uint64), ("n_particles", C.c_int64),
         ("beams_used", C.c_int32), ("map_in_smem", C.c_int32), ("oob_probes", C.c_uint64),
+        ("table_cells", C.c_uint64), ("table_particles", C.c_uint64), ("table_misses", C.c_uint64),
     ]
 
 

@@ -173,8 +173,116 @@ int df_mode_of(const amclj_ctx *ctx) {
     case 3: return DF_GLOBAL4;
     case 4: return ctx->map.wedge ? DF_WEDGE8 : -1;
     case 5: return ctx->map.wedge ? DF_WEDGE8 : -1; /* directional planes, particles walked in tile order */
+    case 6: return ctx->map.wedge ? DF_WEDGE8 : (ctx->map.df8 ? DF_GLOBAL8 : DF_GLOBAL4); /* ray tables, filled over these */
     default: return ctx->map.fits_smem ? DF_SMEM4 : (ctx->map.df8 ? DF_GLOBAL8 : DF_GLOBAL4);
   }
+}
+
+/* End-cell ring of a ray of r cells (raytable.cu): a start and an end cell are rounded
+ * independently (map.clj:36-46), so (x1 - x0, y1 - y0) = r (cos, sin) + delta with |delta| < 1 per
+ * axis: an offset (ex, ey) is reachable only when the square of half-side 1 around it meets the
+ * circle of radius r.  The ring keeps every cell whose square of half-side 1.05 does (the 0.05
+ * covers the fp32 arithmetic of the end point, ~1e-4 cells); per row the admissible |ex| form one
+ * interval.  An end cell outside the ring (never seen) makes the kernel walk that ray instead. */
+int stage_ring(amclj_ctx *ctx, double r) {
+  RayTables &t = ctx->rt;
+  t.available = false;
+  if (!ctx->rt_enable || !(ctx->p.df_mode == 0 || ctx->p.df_mode == 6)) return AMCLJ_OK;
+  if (t.r_cells == r && t.rows) {
+    t.available = t.n_entries > 0;
+    return AMCLJ_OK;
+  }
+  t.r_cells = r;
+  t.n_entries = 0;
+  const double half = 1.05;
+  if (!(r + 2.0 * half < 30000.0)) return AMCLJ_OK; /* offsets are stored as 16-bit values */
+  const int E = (int)ceil(r + half);
+  std::vector<uint4> rows;
+  std::vector<short2> ents;
+  rows.reserve((size_t)2 * E + 1);
+  uint32_t base = 0;
+  for (int ey = -E; ey <= E; ey++) {
+    const double ay = fabs((double)ey), ny = fmax(0.0, ay - half), fy = ay + half;
+    int lo = -1, hi = -1;
+    for (int a = 0; a <= E + 1; a++) {
+      double nearest = hypot(fmax(0.0, (double)a - half), ny), farthest = hypot((double)a + half, fy);
+      if (nearest <= r && r <= farthest) {
+        if (lo < 0) lo = a;
+        hi = a;
+      }
+    }
+    uint32_t cnt = lo < 0 ? 0u : (uint32_t)(hi - lo + 1);
+    if (lo < 0) lo = 0;
+    rows.push_back(make_uint4(base, (uint32_t)lo, cnt, base + cnt));
+    for (uint32_t k = 0; k < cnt; k++) ents.push_back(make_short2((short)(lo + (int)k), (short)ey));
+    for (uint32_t k = 0; k < cnt; k++) {
+      int a = lo + (int)k;
+      ents.push_back(make_short2(a == 0 ? (short)-32768 : (short)-a, (short)ey));
+    }
+    base += 2 * cnt;
+    if (base > (1u << 20)) return AMCLJ_OK; /* a table per cell would not pay */
+  }
+  if (ents.empty()) return AMCLJ_OK;
+  CK(cudaStreamSynchronize(ctx->stream));
+  if ((int)rows.size() > t.rows_cap) {
+    dfree(t.rows);
+    CK(dalloc(&t.rows, rows.size()));
+    t.rows_cap = (int)rows.size();
+  }
+  if ((int)ents.size() > t.ents_cap) {
+    dfree(t.ents);
+    CK(dalloc(&t.ents, ents.size()));
+    t.ents_cap = (int)ents.size();
+  }
+  CK(cudaMemcpyAsync(t.rows, rows.data(), sizeof(uint4) * rows.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(t.ents, ents.data(), sizeof(short2) * ents.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  t.nrows = (int)rows.size();
+  t.E = E;
+  t.n_entries = (int)ents.size();
+  t.available = true;
+  return AMCLJ_OK;
+}
+
+/* particles per start cell from which filling a table beats walking the cell's rays: a table is
+ * n_entries rays, a looked-up ray costs about a fifth of a walked one */
+int rt_threshold(const amclj_ctx *ctx, bool forced) {
+  if (forced) return 1;
+  if (ctx->rt.thr > 0) return ctx->rt.thr;
+  int nb = ctx->beams.nb > 0 ? ctx->beams.nb : 1;
+  int thr = (int)ceil(2.5 * (double)ctx->rt.n_entries / (double)nb);
+  return thr < 4 ? 4 : thr;
+}
+
+/* scratch of the ray-table path, sized for this particle count */
+int ensure_rt_scratch(amclj_ctx *ctx, int64_t n, bool diag, int thr, int *max_slots, int *max_items) {
+  RayTables &t = ctx->rt;
+  if (!t.bins) {
+    CK(rt_prepare_device());
+    CK(dalloc(&t.bins, (size_t)RT_BIN_CAP));
+    CK(dalloc(&t.slots, (size_t)RT_BIN_CAP));
+    CK(dalloc(&t.item0, (size_t)RT_BIN_CAP + 1));
+    CK(dalloc(&t.ctl, 1));
+    CK(cudaMemsetAsync(t.ctl, 0, sizeof(RtCtl), ctx->stream));
+  }
+  int64_t items = (n + RT_PI - 1) / RT_PI + RT_BIN_CAP + 1;
+  size_t table_bytes = (size_t)t.n_entries * (diag ? 16 : 4);
+  int64_t slots = (int64_t)(t.budget / table_bytes);
+  if (slots > RT_BIN_CAP) slots = RT_BIN_CAP;
+  if (slots > n / thr + 1) slots = n / thr + 1;
+  if (slots < 1) slots = 1;
+  size_t need = (size_t)slots * table_bytes;
+  if (need > t.tables_bytes) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (t.tables) cudaFree(t.tables);
+    t.tables = nullptr;
+    t.tables_bytes = 0;
+    CK(cudaMalloc(&t.tables, need));
+    t.tables_bytes = need;
+  }
+  *max_slots = (int)slots;
+  *max_items = (int)(items > 0x7fffffff ? 0x7fffffff : items);
+  return AMCLJ_OK;
 }
 
 int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min, float angle_inc,
@@ -260,6 +368,8 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
     d.wide = wide;
     d.dcap = dcap;
   }
+  int rrc = stage_ring(ctx, rcells);
+  if (rrc) return rrc;
   b.staged = true;
   return AMCLJ_OK;
 }
@@ -302,6 +412,7 @@ void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode) {
   a.z_hit = p.z_hit;
   float sig = p.s5_use_sigma_hit ? p.sigma_hit : p.z_hit; /* S5, sensor.clj:151-153 */
   a.inv2s2 = 1.0f / (2.0f * sig * sig);
+  a.k2 = (float)((double)a.inv2s2 * 1.4426950408889634);
   a.laser_x = p.laser_x;
   a.laser_y = p.laser_y;
 }
@@ -320,7 +431,8 @@ int enqueue_motion(amclj_ctx *ctx, const double curr[3], const double prev[3], b
   m.normals = injected ? ctx->normals : nullptr;
   m.seed = seed;
   m.bbox = nullptr;
-  if (ctx->ctrl_fresh && !m.is_static && ctx->p.df_mode == 0 && (ctx->map.wedge || ctx->order_large_maps)) {
+  if (ctx->ctrl_fresh && !m.is_static &&
+      ((ctx->p.df_mode == 0 && (ctx->map.wedge || ctx->order_large_maps || ctx->rt_enable)) || ctx->p.df_mode == 6)) {
     m.bbox = ctx->bbox; /* the moved cloud's bounding box comes for free */
     ctx->bbox_done = true;
   }
@@ -335,6 +447,38 @@ cudaError_t reset_ctrl(amclj_ctx *ctx, bool with_max) {
   ctx->scan_clean = true;
   if (with_max) return cudaMemsetAsync(ctx->ctrl, 0, sizeof(uint64_t) * (words + 3), ctx->stream);
   return cudaMemsetAsync(ctx->ctrl + 3, 0, sizeof(uint64_t) * words, ctx->stream);
+}
+
+/* the ray-table path over the particles of `base` (raytable.cu); results land in base.raw */
+int enqueue_raytable(amclj_ctx *ctx, const SensorLaunch &base, bool diag, int must_run) {
+  const bool forced = must_run == 2;
+  int fill_mode = ctx->map.wedge ? DF_WEDGE8 : (df_mode_of(ctx) == DF_GLOBAL8 ? DF_GLOBAL8 : DF_GLOBAL4);
+  RtLaunch L;
+  memset(&L, 0, sizeof(L));
+  fill_sensor_args(ctx, L.s, fill_mode);
+  L.s.x = base.x; L.s.y = base.y; L.s.th = base.th; L.s.raw = base.raw; L.s.n = base.n;
+  L.s.rawmax_ord = base.rawmax_ord; L.s.stats = base.stats;
+  L.s.bbox = base.bbox; L.s.compact_m = base.compact_m; L.s.decision = base.decision;
+  L.s.dbg_first = base.dbg_first; L.s.dbg_count = base.dbg_count;
+  L.s.dbg_hit_x = base.dbg_hit_x; L.s.dbg_hit_y = base.dbg_hit_y; L.s.dbg_steps = base.dbg_steps;
+  L.s.dbg_hit = base.dbg_hit; L.s.dbg_range = base.dbg_range;
+  const RayTables &t = ctx->rt;
+  L.thr = rt_threshold(ctx, forced);
+  int rc = ensure_rt_scratch(ctx, base.n, diag, L.thr, &L.max_slots, &L.max_items);
+  if (rc) return rc;
+  L.rows = t.rows; L.ents = t.ents; L.nrows = t.nrows; L.E = t.E; L.n_entries = t.n_entries;
+  L.bins = t.bins; L.slots = t.slots; L.item0 = t.item0; L.tables = t.tables; L.ctl = t.ctl;
+  if (base.n > ctx->partials_cap) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx->partials);
+    CK(dalloc(&ctx->partials, (size_t)base.n));
+    ctx->partials_cap = base.n;
+  }
+  L.qacc = ctx->partials;
+  L.perm = ctx->perm;
+  L.must_run = must_run;
+  CK(launch_raytable(ctx, L, fill_mode, diag, ctx->stream));
+  return AMCLJ_OK;
 }
 
 /* decode_max: also materialise the max as a float (AMCLJ_BUF_RAW_MAX) for a cross-rank all-reduce */
@@ -372,7 +516,7 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
   ctx->ctrl_fresh = false;
   if (diag) {
     CK(cudaMemsetAsync(ctx->stats, 0, 7 * sizeof(unsigned long long), ctx->stream));
-    CK(cudaMemsetAsync(ctx->stats + 8, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->stats + 8, 0, 4 * sizeof(unsigned long long), ctx->stream));
   }
   /* df_mode 0 on a map that has the directional planes: they are used for every cloud.  A compact
    * cloud is local as it is; a spread-out one is walked in map-tile order so that each CTA's probes
@@ -383,6 +527,18 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
   /* large maps (byte field through L2) get the tile-order walk too: it is what keeps a CTA's
    * probes in L1 */
   bool ordered = directional || (ctx->p.df_mode == 0 && mode == DF_GLOBAL8 && ctx->order_large_maps);
+  /* dense clouds (pose tracking: thousands of particles per start cell) go through per-cell ray
+   * tables (raytable.cu).  Whether the cloud is dense is decided on the device, every update; the
+   * verdict of the previous update, left in pinned host memory, only picks which kernels are
+   * launched at all: 0 spread out -> walk kernel only; 1 compact / -1 unknown -> both, the device flag
+   * picks one; 2 dense -> ray tables only (they take any cloud, a sparse one slowly). */
+  const bool rt_forced = ctx->p.df_mode == 6;
+  const bool rt_auto = ctx->p.df_mode == 0 && ctx->rt_enable && ctx->rt.available && !ctx->p.s10_apply_laser_offset;
+  NEED(!rt_forced || ctx->rt.available, AMCLJ_ERR_INVALID, "sensor: df_mode 6 (ray tables) unavailable for rays of %.0f cells",
+       ctx->rt.r_cells);
+  const int hint = *ctx->pin_decision;
+  const bool use_rt = rt_forced || (rt_auto && hint != 0);
+  const bool only_rt = rt_forced || (rt_auto && hint == 2);
   if (directional) {
     mode = DF_WEDGE8;
     SensorLaunch b;
@@ -391,29 +547,35 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
     b.chunks = a.chunks; b.partials = a.partials; b.stats = a.stats;
     a = b;
   }
-  if (ordered) {
-    if (!ctx->tile_counters) CK(dalloc(&ctx->tile_counters, (size_t)tile_count(ctx->map.W, ctx->map.H) + 1));
+  if (ordered || use_rt) {
     if (!ctx->bbox_done) CK(launch_bbox(ctx->x, ctx->y, ctx->n, ctx->bbox, ctx->sm_count, ctx->stream));
     ctx->bbox_done = false;
     a.bbox = ctx->bbox;
     a.compact_m = ctx->compact_cells * ctx->map.res;
     a.decision = const_cast<int32_t *>(ctx->pin_decision); /* pinned host memory: the kernel stores straight into it */
-    /* the previous update's verdict, which the kernel left in pinned host memory, is only a hint: when the
-     * cloud was compact the tile-order kernels are not even launched (a wrong guess costs speed
-     * for one update, never a result) */
-    if (*ctx->pin_decision != 1) {
+  }
+  if (ordered && !only_rt) {
+    if (!ctx->tile_counters) CK(dalloc(&ctx->tile_counters, (size_t)tile_count(ctx->map.W, ctx->map.H) + 1));
+    /* the previous update's verdict is only a hint: when the cloud was compact the tile-order
+     * kernels are not even launched (a wrong guess costs speed for one update, never a result) */
+    if (hint != 1) {
       CK(launch_tile_order(ctx->x, ctx->y, ctx->th, ctx->n, ctx->map.res, ctx->map.W, ctx->map.H,
                            ctx->tile_counters, ctx->perm, ctx->bbox, a.compact_m, ctx->stream));
       a.perm = ctx->perm;
     }
   }
-  CK(launch_sensor(ctx, a, mode, diag, ctx->stream));
+  if (use_rt) {
+    int rrc = enqueue_raytable(ctx, a, diag, rt_forced ? 2 : (only_rt ? 1 : 0));
+    if (rrc) return rrc;
+    a.skip_flag = &ctx->rt.ctl->dense;
+  }
+  if (!only_rt) CK(launch_sensor(ctx, a, mode, diag, ctx->stream));
   if (decode_max) CK(launch_decode_max(ctx->rawmax_ord, ctx->rawmax, ctx->stream));
   ctx->max_in_ord = !decode_max;
   ctx->last_diag = diag;
   ctx->have_raw = true;
   ctx->have_cdf = false;
-  ctx->st.map_in_smem = mode == DF_SMEM4;
+  ctx->st.map_in_smem = mode == DF_SMEM4 && !only_rt;
   ctx->st.beams_used = ctx->beams.nb;
   ctx->st.n_particles = ctx->n;
   return AMCLJ_OK;
@@ -639,6 +801,9 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
   if (const char *e = getenv("AMCLJ_REFILL_WEDGE")) ctx->refill_wedge = atoi(e);
   if (const char *e = getenv("AMCLJ_REFILL_GLOBAL")) ctx->refill_global = atoi(e);
   if (const char *e = getenv("AMCLJ_COMPACT_CELLS")) ctx->compact_cells = (float)atof(e);
+  if (const char *e = getenv("AMCLJ_RAYTABLE")) ctx->rt_enable = atoi(e) != 0;
+  if (const char *e = getenv("AMCLJ_RT_THR")) ctx->rt.thr = atoi(e);
+  if (const char *e = getenv("AMCLJ_RT_BUDGET_MB")) ctx->rt.budget = (size_t)atoll(e) << 20;
   memset(&ctx->st, 0, sizeof(ctx->st));
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ctx->stream = ctx->own_stream;
@@ -690,6 +855,8 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
     for (int k = 0; k < 7; k++)
       if (ctx->ipc_opened[g][k]) cudaIpcCloseMemHandle(ctx->ipc_opened[g][k]);
   dfree(ctx->stage_out); dfree(ctx->stage_in); dfree(ctx->stage_idx);
+  dfree(ctx->rt.rows); dfree(ctx->rt.ents); dfree(ctx->rt.bins); dfree(ctx->rt.item0); dfree(ctx->rt.slots); dfree(ctx->rt.ctl);
+  if (ctx->rt.tables) cudaFree(ctx->rt.tables);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->pin_tab) cudaFreeHost(ctx->pin_tab);
   for (int i = 0; i < 5; i++)
@@ -717,8 +884,8 @@ int32_t amclj_synchronize(amclj_ctx *ctx) {
 int32_t amclj_set_params(amclj_ctx *ctx, const amclj_params *p) {
   ENTER();
   NEED(p, AMCLJ_ERR_INVALID, "set_params: null");
-  NEED(p->df_mode >= 0 && p->df_mode <= 5, AMCLJ_ERR_INVALID, "set_params: df_mode %d", p->df_mode);
-  if (p->df_mode >= 4 && ctx->map.cells && !ctx->map.wedge) { /* directional fields are built on demand */
+  NEED(p->df_mode >= 0 && p->df_mode <= 6, AMCLJ_ERR_INVALID, "set_params: df_mode %d", p->df_mode);
+  if ((p->df_mode == 4 || p->df_mode == 5) && ctx->map.cells && !ctx->map.wedge) { /* directional fields are built on demand */
     NEED((size_t)ctx->map.pitch8 * (ctx->map.H + 2) * WEDGE_CLASSES <= (8ull << 30), AMCLJ_ERR_INVALID,
          "set_params: map too large for directional fields");
     CK(build_wedge_fields(ctx, ctx->stream));
@@ -772,15 +939,16 @@ int32_t amclj_set_map(amclj_ctx *ctx, const int8_t *cells, int32_t width, int32_
   m.bytes8 = (size_t)m.pitch8 * (height + 2);
   if (want8) CK(dalloc(&m.df8, m.bytes8));
   CK(build_distance_fields(ctx, want8, ctx->stream));
-  if (ctx->p.df_mode >= 4) {
+  if (ctx->p.df_mode == 4 || ctx->p.df_mode == 5) {
     NEED(m.bytes8 * WEDGE_CLASSES <= (8ull << 30), AMCLJ_ERR_INVALID, "set_map: map too large for directional fields");
     CK(build_wedge_fields(ctx, ctx->stream));
-  } else if (ctx->p.df_mode == 0 && m.bytes8 * WEDGE_CLASSES <= ctx->wedge_budget &&
+  } else if ((ctx->p.df_mode == 0 || ctx->p.df_mode == 6) && m.bytes8 * WEDGE_CLASSES <= ctx->wedge_budget &&
              m.bytes8 * WEDGE_CLASSES < (1ull << 32)) {
     CK(build_wedge_fields(ctx, ctx->stream)); /* auto: both field sets, chosen per update */
   }
   ctx->beams.staged = false;
   ctx->divs.n = 0;
+  *ctx->pin_decision = -1; /* a new map: no hint about the cloud */
   ctx->st.map_in_smem = m.fits_smem;
   return AMCLJ_OK;
 }
@@ -951,8 +1119,23 @@ int32_t amclj_raycast_debug(amclj_ctx *ctx, int32_t n, float angle_min, float an
     ctx->st.map_in_smem = mode == DF_SMEM4;
     ctx->last_diag = true;
     ctx->st.beams_used = ctx->beams.nb;
-    cudaMemsetAsync(ctx->stats, 0, 7 * sizeof(unsigned long long), ctx->stream);
-    e = launch_sensor(ctx, a, mode, true, ctx->stream);
+    cudaMemsetAsync(ctx->stats, 0, 12 * sizeof(unsigned long long), ctx->stream);
+    if (ctx->p.df_mode == 6) { /* parity probe through the ray tables: every occupied cell gets a table */
+      if (!ctx->rt.available) {
+        status = fail(ctx, AMCLJ_ERR_INVALID, "raycast_debug: df_mode 6 unavailable for rays of %.0f cells", ctx->rt.r_cells);
+      } else {
+        cudaMemsetAsync(ctx->bbox, 0, 4 * sizeof(uint32_t), ctx->stream);
+        e = launch_bbox(a.x, a.y, a.n, ctx->bbox, ctx->sm_count, ctx->stream);
+        a.bbox = ctx->bbox;
+        a.compact_m = ctx->compact_cells * ctx->map.res;
+        ctx->ctrl_fresh = false;
+        ctx->bbox_done = false;
+        ctx->st.map_in_smem = 0;
+        if (e == cudaSuccess) status = enqueue_raytable(ctx, a, true, 2);
+      }
+    } else {
+      e = launch_sensor(ctx, a, mode, true, ctx->stream);
+    }
   }
   auto back = [&](void *dst, const void *src, size_t bytes) {
     if (e == cudaSuccess && dst) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
@@ -963,7 +1146,7 @@ int32_t amclj_raycast_debug(amclj_ctx *ctx, int32_t n, float angle_min, float an
   back(hit, d_hit, rays);
   back(range_m, d_rng, rays * 4);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (e != cudaSuccess) status = fail(ctx, AMCLJ_ERR_CUDA, "raycast_debug: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess && status == AMCLJ_OK) status = fail(ctx, AMCLJ_ERR_CUDA, "raycast_debug: %s", cudaGetErrorString(e));
   dfree(d_hx); dfree(d_hy); dfree(d_st); dfree(d_hit); dfree(d_rng);
   return status;
 }
@@ -1167,6 +1350,9 @@ int32_t amclj_get_stats(amclj_ctx *ctx, amclj_stats *out) {
   ctx->st.cells_visited = h[1];
   ctx->st.probes = h[2];
   ctx->st.hits = h[3];
+  ctx->st.table_cells = ctx->last_diag ? h[9] : 0;
+  ctx->st.table_particles = ctx->last_diag ? h[10] : 0;
+  ctx->st.table_misses = ctx->last_diag ? h[11] : 0;
   ctx->st.n_particles = ctx->n;
   *out = ctx->st;
   return AMCLJ_OK;

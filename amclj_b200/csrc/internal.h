@@ -66,10 +66,12 @@ struct SensorLaunch {
   float compact_m;       // bounding-box side (metres) up to which the particle set counts as compact
   const int32_t *perm;   // walking order (particle indices sorted by map tile), or null
   int32_t *decision;     // out: 1 when the cloud was compact (host hint for the next update)
+  const int32_t *skip_flag;  // when set and *skip_flag == 1 the ray-table path took this update: return at once
   float R;            // ray length (S2)
   float miss_value;
   int32_t s1, s3, s4, s7, s10;
   float z_hit, inv2s2, laser_x, laser_y;
+  float k2;  // inv2s2 * log2(e): the hit Gaussian is one ex2
   uint32_t *rawmax_ord;          // ordered-uint max of raw (may be null)
   unsigned long long *stats;     // rays, cells, probes, hits (may be null)
   // parity probe
@@ -88,6 +90,54 @@ struct MotionLaunch {
   int32_t is_static, trans_zero;
   uint32_t *bbox;  // when set: accumulate the bounding box of the moved cloud (4 ordered-uint maxima)
   float rot1, trans, rot2, sd1, sdt, sd2;
+};
+
+// ---------------------------------------------------------------------------------------
+// ray tables (raytable.cu): for a dense cloud many particles share a start cell, and a ray's
+// result is a function of its integer start and end cells only (sensor.clj:130-139).
+// ---------------------------------------------------------------------------------------
+constexpr int RT_PI = 32;           // particles per work item: one warp, lane = particle
+constexpr int RT_BIN_CAP = 16384;   // start cells the cloud's bounding box may cover (128 x 128)
+struct RtSlot { int32_t cx, cy, first, cnt; };  // a dense start cell: its particles are perm[first, first + cnt)
+struct RtCtl {
+  int32_t dense;    // 1: this update runs on the ray tables
+  int32_t n_dense;  // particles in dense cells (they come first in the walking order)
+  int32_t n_items;  // work items over dense cells
+  int32_t n_cells;  // dense cells = tables to fill
+  int32_t cx0, cy0, bw, bh;
+  uint32_t pad[8];
+};
+struct RayTables {
+  // end-cell ring of a ray of r cells, built on the host per scan geometry: row ey + E ->
+  // {base, lo, cnt, base + cnt}: |ex| in [lo, lo + cnt) is entry base + (|ex| - lo) (+ cnt when ex < 0)
+  uint4 *rows = nullptr;
+  short2 *ents = nullptr;   // entry -> (ex, ey); x = -32768 marks the unused slot of a merged row
+  int32_t nrows = 0, E = 0, n_entries = 0, rows_cap = 0, ents_cap = 0;
+  double r_cells = -1.0;
+  bool available = false;
+  uint32_t *bins = nullptr;   // [RT_BIN_CAP] particles per start cell, then write cursors
+  RtSlot *slots = nullptr;    // [RT_BIN_CAP] the dense cells, one table each
+  int32_t *item0 = nullptr;   // [RT_BIN_CAP + 1] first work item of each dense cell
+  void *tables = nullptr;     // [max_slots][n_entries] float range (diagnostic passes: float4)
+  size_t tables_bytes = 0;
+  RtCtl *ctl = nullptr;
+  int32_t thr = 0;            // particles per cell from which a table pays (0: derived)
+  size_t budget = 256ull << 20;
+};
+struct RtLaunch {
+  SensorLaunch s;
+  const uint4 *rows;
+  const short2 *ents;
+  int32_t nrows, E, n_entries;
+  uint32_t *bins;
+  RtSlot *slots;
+  int32_t *item0;
+  void *tables;
+  RtCtl *ctl;
+  int32_t *perm;
+  long long *qacc;   // [n] 32.32 fixed-point weight accumulators
+  int32_t thr, max_slots, max_items;
+  int32_t must_run;  // 1: the walk kernel is not launched for this update, so this path takes every particle
 };
 
 constexpr int MAX_WORLD = 16;
@@ -167,6 +217,8 @@ struct amclj_ctx {
   double w_slow = 1.0, w_fast = 1.0;  // pf.clj:243-244
   uint32_t *hist = nullptr;           // 256-bin histogram of the radix select
   int32_t force_chunks = 0;
+  amclj::RayTables rt;
+  bool rt_enable = true;   // auto policy may take the ray-table path (AMCLJ_RAYTABLE=0 turns it off)
   void *pinned = nullptr;  // small pinned scratch for scalar readbacks
   void *pin_tab = nullptr; // pinned staging of the beam table
   size_t pin_tab_bytes = 0;
@@ -177,6 +229,9 @@ namespace amclj {
 cudaError_t launch_sensor(const amclj_ctx *c, const SensorLaunch &a, int mode, bool diag,
                           cudaStream_t s);
 enum { DF_SMEM4 = 0, DF_GLOBAL8 = 1, DF_GLOBAL4 = 2, DF_WEDGE8 = 3 };
+// raytable.cu
+cudaError_t launch_raytable(const amclj_ctx *c, const RtLaunch &L, int mode, bool diag, cudaStream_t s);
+cudaError_t rt_prepare_device();
 constexpr int WEDGE_BINS = 4;                   /* slope bins per octant */
 constexpr int WEDGE_CLASSES = 8 * WEDGE_BINS;   /* steep x xs x ys x bin */
 cudaError_t build_wedge_fields(amclj_ctx *c, cudaStream_t s);

@@ -81,7 +81,8 @@ typedef struct amclj_params {
    * larger maps: one byte per cell in L2), 1 isotropic nibbles in shared memory, 2 isotropic bytes
    * in global memory, 3 isotropic nibbles in global memory,
    * 4 directional byte fields (32 direction classes) through L1/L2, 5 the same with the particles
-   * walked in map-tile order (spread-out clouds) */
+   * walked in map-tile order (spread-out clouds), 6 per-start-cell ray tables for every occupied cell
+   * (mode 0 takes them by itself when most particles share their start cell with many others) */
   int32_t df_mode;
   float max_range;    /* sensor.clj:12  (-1.0) */
   float z_hit;        /* sensor.clj:14 */
@@ -112,6 +113,9 @@ typedef struct amclj_stats {
   int32_t beams_used;
   int32_t map_in_smem; /* 1 when the last sensor pass walked the shared-memory field */
   uint64_t oob_probes; /* diagnostic passes only: probes outside the staged field (must be 0) */
+  uint64_t table_cells;     /* diagnostic passes only: start cells that got a ray table (0: the walk kernel ran) */
+  uint64_t table_particles; /* ... and the particles standing on them */
+  uint64_t table_misses;    /* ... and their rays whose end cell was not in the table (walked instead; expected 0) */
 } amclj_stats;
 
 typedef struct amclj_ctx amclj_ctx;

@@ -91,7 +91,7 @@ def test_raycast_switch_matrix(ctx, lg, switches):
     _ray_parity(ctx, lg, x, y, th, scan, "NS", **switches)
 
 
-@pytest.mark.parametrize("df_mode", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("df_mode", [1, 2, 3, 4, 5, 6])
 def test_raycast_all_field_placements(ctx, lg, df_mode):
     """Shared-memory nibbles, global bytes, global nibbles and the directional (wedge) fields
     give the same answers."""
@@ -507,7 +507,7 @@ def test_auto_field_policy_matches_every_placement(lg):
         raw = c.raw_weights()
         ref, _, _ = oracle.sensor_f32(po, lg, scan.ranges, scan.angle_min, scan.angle_inc, scan.range_max, x, y, th)
         np.testing.assert_allclose(raw, ref, rtol=RTOL)
-        for forced in (1, 2, 4, 5):
+        for forced in (1, 2, 4, 5, 6):
             c2 = _lib.Context(0)
             c2.set_params(_lib.params("NS", df_mode=forced))
             c2.set_map(lg)
@@ -540,7 +540,7 @@ def test_raycast_random_small_maps(seed):
     preset = "NS" if seed % 2 == 0 else "REF"
     switches = {} if seed % 3 else dict(s4_endpoint_termination=seed % 2, s3_proper_endpoint=(seed // 2) % 2)
     c = _lib.Context(0)
-    for df_mode in (1, 2, 3, 4, 5, 0):
+    for df_mode in (1, 2, 3, 4, 5, 6, 0):
         c.set_params(_lib.params(preset, df_mode=df_mode, **switches))
         c.set_map(grid)
         _ray_parity(c, grid, x, y, th, scan, preset, df_mode=df_mode, **switches)
@@ -593,7 +593,7 @@ def test_raycast_very_long_rays_use_the_shifted_reciprocal(preset):
     scan = workloads.Scan(rng.uniform(0, 2, 90).astype(np.float32), float(np.float32(-3.1)), float(np.float32(0.07)),
                           float(np.float32(100.0)))
     c = _lib.Context(0)
-    for df_mode in (1, 2, 4, 0):
+    for df_mode in (1, 2, 4, 6, 0):
         kw = dict(df_mode=df_mode, max_range=-100.0) if preset == "REF" else dict(df_mode=df_mode)
         c.set_params(_lib.params(preset, **kw))
         c.set_map(grid)
