@@ -223,6 +223,7 @@ int stage_ring(amclj_ctx *ctx, double r) {
     if (base > (1u << 20)) return AMCLJ_OK; /* a table per cell would not pay */
   }
   if (ents.empty()) return AMCLJ_OK;
+  ents.push_back(make_short2((short)-32767, 0)); /* last entry: the NaN the fast path reads for an end cell off the ring */
   CK(cudaStreamSynchronize(ctx->stream));
   if ((int)rows.size() > t.rows_cap) {
     dfree(t.rows);
@@ -250,7 +251,7 @@ int rt_threshold(const amclj_ctx *ctx, bool forced) {
   if (forced) return 1;
   if (ctx->rt.thr > 0) return ctx->rt.thr;
   int nb = ctx->beams.nb > 0 ? ctx->beams.nb : 1;
-  int thr = (int)ceil(2.5 * (double)ctx->rt.n_entries / (double)nb);
+  int thr = (int)ceil(1.75 * (double)ctx->rt.n_entries / (double)nb);
   return thr < 4 ? 4 : thr;
 }
 
@@ -266,6 +267,13 @@ int ensure_rt_scratch(amclj_ctx *ctx, int64_t n, bool diag, int thr, int *max_sl
     CK(cudaMemsetAsync(t.ctl, 0, sizeof(RtCtl), ctx->stream));
   }
   int64_t items = (n + RT_PI - 1) / RT_PI + RT_BIN_CAP + 1;
+  if (n > t.pstate_cap) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    dfree(t.pstate);
+    t.pstate_cap = 0;
+    CK(dalloc(&t.pstate, (size_t)n));
+    t.pstate_cap = n;
+  }
   size_t table_bytes = (size_t)t.n_entries * (diag ? 16 : 4);
   int64_t slots = (int64_t)(t.budget / table_bytes);
   if (slots > RT_BIN_CAP) slots = RT_BIN_CAP;
@@ -476,7 +484,9 @@ int enqueue_raytable(amclj_ctx *ctx, const SensorLaunch &base, bool diag, int mu
   }
   L.qacc = ctx->partials;
   L.perm = ctx->perm;
+  L.pstate = t.pstate;
   L.must_run = must_run;
+  L.tail_pct = t.tail_pct;
   CK(launch_raytable(ctx, L, fill_mode, diag, ctx->stream));
   return AMCLJ_OK;
 }
@@ -803,6 +813,8 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
   if (const char *e = getenv("AMCLJ_COMPACT_CELLS")) ctx->compact_cells = (float)atof(e);
   if (const char *e = getenv("AMCLJ_RAYTABLE")) ctx->rt_enable = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_RT_THR")) ctx->rt.thr = atoi(e);
+  if (const char *e = getenv("AMCLJ_RT_WAVES")) ctx->rt.waves = atoi(e);
+  if (const char *e = getenv("AMCLJ_RT_TAIL_PCT")) ctx->rt.tail_pct = atoi(e) < 0 ? 0 : (atoi(e) > 100 ? 100 : atoi(e));
   if (const char *e = getenv("AMCLJ_RT_BUDGET_MB")) ctx->rt.budget = (size_t)atoll(e) << 20;
   memset(&ctx->st, 0, sizeof(ctx->st));
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -855,7 +867,7 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
     for (int k = 0; k < 7; k++)
       if (ctx->ipc_opened[g][k]) cudaIpcCloseMemHandle(ctx->ipc_opened[g][k]);
   dfree(ctx->stage_out); dfree(ctx->stage_in); dfree(ctx->stage_idx);
-  dfree(ctx->rt.rows); dfree(ctx->rt.ents); dfree(ctx->rt.bins); dfree(ctx->rt.item0); dfree(ctx->rt.slots); dfree(ctx->rt.ctl);
+  dfree(ctx->rt.rows); dfree(ctx->rt.ents); dfree(ctx->rt.pstate); dfree(ctx->rt.bins); dfree(ctx->rt.item0); dfree(ctx->rt.slots); dfree(ctx->rt.ctl);
   if (ctx->rt.tables) cudaFree(ctx->rt.tables);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->pin_tab) cudaFreeHost(ctx->pin_tab);

@@ -105,7 +105,9 @@ struct RtCtl {
   int32_t n_items;  // work items over dense cells
   int32_t n_cells;  // dense cells = tables to fill
   int32_t cx0, cy0, bw, bh;
-  uint32_t pad[8];
+  uint32_t hist_done;  // CTAs of the histogram that have finished (the last one plans)
+  uint32_t next_tail;  // next unit of the look-up kernel's common tail
+  uint32_t pad[6];
 };
 struct RayTables {
   // end-cell ring of a ray of r cells, built on the host per scan geometry: row ey + E ->
@@ -121,8 +123,12 @@ struct RayTables {
   void *tables = nullptr;     // [max_slots][n_entries] float range (diagnostic passes: float4)
   size_t tables_bytes = 0;
   RtCtl *ctl = nullptr;
+  float4 *pstate = nullptr;   // [pstate_cap] per-particle look-up state in walking order
+  int64_t pstate_cap = 0;
   int32_t thr = 0;            // particles per cell from which a table pays (0: derived)
   size_t budget = 256ull << 20;
+  int32_t tail_pct = 10;
+  int32_t waves = 1;          // look-up grid = resident CTAs x waves (smaller CTAs balance better)
 };
 struct RtLaunch {
   SensorLaunch s;
@@ -135,8 +141,10 @@ struct RtLaunch {
   void *tables;
   RtCtl *ctl;
   int32_t *perm;
+  float4 *pstate;    // [n] (origin x, origin y, sin, cos) of the particles in walking order
   long long *qacc;   // [n] 32.32 fixed-point weight accumulators
   int32_t thr, max_slots, max_items;
+  int32_t tail_pct;  // share of the dense units handed out dynamically at the end of the look-up kernel
   int32_t must_run;  // 1: the walk kernel is not launched for this update, so this path takes every particle
 };
 

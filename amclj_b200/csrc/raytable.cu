@@ -9,14 +9,17 @@
 // A tracking cloud puts thousands of particles on each start cell, and every end cell of a ray of
 // r cells lies in a thin ring around it (|(ex, ey)| within sqrt(2) of r: both ends are rounded
 // independently).  Per update:
-//   1. counting sort of the particles by start cell (histogram over the cloud's bounding box,
-//      one-CTA plan, scatter) — cells holding at least `thr` particles are "dense";
-//   2. rt_fill_kernel walks ONE ray per (dense cell, ring entry) with the same distance-field
-//      walk as sensor.cu and stores its range: a table per dense cell (lgfloor: 3,262 entries);
+//   1. rt_hist_plan_kernel: histogram of the particles over the start cells of the cloud's bounding
+//      box; its last CTA plans the update — cells holding at least `thr` particles are "dense" and
+//      get a table, and the walking order is [dense cells, cell by cell | the rest];
+//   2. rt_scatter_fill_kernel: the first CTAs finish the counting sort, the others walk ONE ray per
+//      (dense cell, ring entry) with the same distance-field walk as sensor.cu and store its range:
+//      a table per dense cell (lgfloor, 5.6 m rays: 1,922 entries = 7.7 KB);
 //   3. rt_lookup_kernel scores every (particle, beam): rotate the beam by the particle's heading,
 //      round the end point exactly as sensor.cu does, look the range up, beam mixture.  Particles of
-//      sparse cells, and any end cell outside the ring (never seen; the ring is 1.5 cells wide each
-//      side), walk their ray directly — the table is an accelerator, never an approximation.
+//      sparse cells, and any end cell outside the ring (never seen; tests assert it), walk their ray
+//      directly — the table is an accelerator, never an approximation;
+//   4. rt_finish_kernel: fixed-point accumulators -> raw weights and their maximum.
 // Nothing is kept from one update to the next: tables are rebuilt from the map every time.
 // Weights are accumulated per 30-beam segment in 32.32 fixed point exactly as in sensor.cu, so the
 // two paths agree bit for bit and the policy that picks one never changes a result.
@@ -146,18 +149,106 @@ __device__ __forceinline__ int bin_of(float px, float py, float res, int cx0, in
 constexpr int RT_SORT_THREADS = 512, RT_SORT_PER_THREAD = 4;
 constexpr int RT_SORT_TILE = RT_SORT_THREADS * RT_SORT_PER_THREAD;
 
+struct PlanArgs {
+  int64_t n;
+  int32_t thr, max_slots, max_items, force;
+  RtSlot *slots;
+  int32_t *item0;
+  RtCtl *ctl;
+};
+
+// The plan (run by the last CTA of the histogram): classify the cells, decide, and lay the walking
+// order out as [particles of dense cells, cell by cell | particles of sparse cells].  Dense cell k
+// gets table slot k and the work items [item0[k], item0[k+1]) of 32 particles each.
+__device__ void rt_plan(const PlanArgs &pa, uint32_t *bins, int cx0, int cy0, int bw, int bh, int4 *s_warp, int4 *s_total) {
+  const int nthreads = blockDim.x, nbins = bw * bh, per = (nbins + nthreads - 1) / nthreads;
+  const int lo = min((int)threadIdx.x * per, nbins), hi = min(lo + per, nbins);
+  int4 v = make_int4(0, 0, 0, 0); /* dense particles, dense items, dense cells, sparse particles */
+  for (int b = lo; b < hi; b++) {
+    int c = (int)__ldcg(bins + b); /* the other CTAs' counts, straight from L2 */
+    if (c >= pa.thr) { v.x += c; v.y += (c + RT_PI - 1) / RT_PI; v.z += 1; }
+    else v.w += c;
+  }
+  /* block-wide exclusive scan of the four counters */
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = nthreads >> 5;
+  int4 inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int tx = __shfl_up_sync(0xffffffffu, inc.x, o), ty = __shfl_up_sync(0xffffffffu, inc.y, o);
+    int tz = __shfl_up_sync(0xffffffffu, inc.z, o), tw = __shfl_up_sync(0xffffffffu, inc.w, o);
+    if (lane >= o) { inc.x += tx; inc.y += ty; inc.z += tz; inc.w += tw; }
+  }
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int4 w = lane < nwarps ? s_warp[lane] : make_int4(0, 0, 0, 0), wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int tx = __shfl_up_sync(0xffffffffu, wi.x, o), ty = __shfl_up_sync(0xffffffffu, wi.y, o);
+      int tz = __shfl_up_sync(0xffffffffu, wi.z, o), tw = __shfl_up_sync(0xffffffffu, wi.w, o);
+      if (lane >= o) { wi.x += tx; wi.y += ty; wi.z += tz; wi.w += tw; }
+    }
+    if (lane == 31) *s_total = wi;
+    s_warp[lane] = make_int4(wi.x - w.x, wi.y - w.y, wi.z - w.z, wi.w - w.w);
+  }
+  __syncthreads();
+  const int4 base = s_warp[wid], tot = *s_total;
+  int run_dn = base.x + inc.x - v.x, run_di = base.y + inc.y - v.y, run_dc = base.z + inc.z - v.z,
+      run_sn = base.w + inc.w - v.w;
+  /* tables pay when most particles sit in dense cells (or when the caller forces the path) */
+  const bool dense = tot.z > 0 && tot.z <= pa.max_slots && tot.y <= pa.max_items &&
+                     (pa.force || 2ll * tot.x >= (long long)pa.n);
+  RtCtl *ctl = pa.ctl;
+  if (threadIdx.x == 0) {
+    ctl->dense = dense ? 1 : 0;
+    ctl->n_dense = dense ? tot.x : 0;
+    ctl->n_items = dense ? tot.y : 0;
+    ctl->n_cells = dense ? tot.z : 0;
+    ctl->cx0 = cx0; ctl->cy0 = cy0; ctl->bw = bw; ctl->bh = bh;
+    ctl->hist_done = 0; /* ready for the next update */
+    ctl->next_tail = 0;
+    if (dense) pa.item0[tot.z] = tot.y;
+  }
+  if (!dense) return;
+  for (int b = lo; b < hi; b++) {
+    int c = (int)__ldcg(bins + b);
+    if (c >= pa.thr) {
+      RtSlot sl;
+      sl.cx = cx0 + b % bw; sl.cy = cy0 + b / bw; sl.first = run_dn; sl.cnt = c;
+      pa.slots[run_dc] = sl;
+      pa.item0[run_dc] = run_di;
+      bins[b] = (uint32_t)run_dn;
+      run_dn += c;
+      run_di += (c + RT_PI - 1) / RT_PI;
+      run_dc++;
+    } else {
+      bins[b] = (uint32_t)(tot.x + run_sn);
+      run_sn += c;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(RT_SORT_THREADS)
-rt_hist_kernel(const float *__restrict__ x, const float *__restrict__ y, int64_t n, float res,
-               const uint32_t *__restrict__ bbox, uint32_t *bins, long long *qacc) {
+rt_hist_plan_kernel(const float *__restrict__ x, const float *__restrict__ y, float res,
+                    const uint32_t *__restrict__ bbox, uint32_t *bins, long long *qacc, const PlanArgs pa) {
   extern __shared__ uint32_t sh_bins[];
-  const int64_t base = (int64_t)blockIdx.x * RT_SORT_TILE;
+  __shared__ int4 s_warp[32];
+  __shared__ int4 s_total;
+  __shared__ uint32_t s_ticket;
+  const int64_t n = pa.n, base = (int64_t)blockIdx.x * RT_SORT_TILE;
 #pragma unroll
   for (int k = 0; k < RT_SORT_PER_THREAD; k++) { /* the weight accumulators of this update */
     int64_t i = base + k * RT_SORT_THREADS + threadIdx.x;
     if (i < n) qacc[i] = 0;
   }
   int cx0, cy0, bw, bh;
-  if (!cell_box(bbox, res, cx0, cy0, bw, bh)) return;
+  if (!cell_box(bbox, res, cx0, cy0, bw, bh)) { /* every CTA sees the same box */
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      RtCtl *ctl = pa.ctl;
+      ctl->dense = 0; ctl->n_dense = 0; ctl->n_items = 0; ctl->n_cells = 0; ctl->next_tail = 0;
+    }
+    return;
+  }
   const int nbins = bw * bh;
   for (int b = threadIdx.x; b < nbins; b += RT_SORT_THREADS) sh_bins[b] = 0;
   __syncthreads();
@@ -171,131 +262,82 @@ rt_hist_kernel(const float *__restrict__ x, const float *__restrict__ y, int64_t
     uint32_t c = sh_bins[b];
     if (c) atomicAdd(&bins[b], c);
   }
+  /* the last CTA to get here has every count in L2 and plans the update */
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&pa.ctl->hist_done, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  rt_plan(pa, bins, cx0, cy0, bw, bh, s_warp, &s_total);
 }
 
-// One CTA: classify the cells, decide, and lay the walking order out as
-// [particles of dense cells, cell by cell | particles of sparse cells].  Dense cell k gets table
-// slot k and the work items [item0[k], item0[k+1]) of 32 particles each.
-__global__ void __launch_bounds__(1024)
-rt_plan_kernel(const uint32_t *__restrict__ bbox, float res, int64_t n, int thr, int max_slots, int max_items,
-               int force, uint32_t *bins, RtSlot *slots, int32_t *item0, RtCtl *ctl) {
-  __shared__ int4 s_warp[32];
-  __shared__ int4 s_total;
-  int cx0 = 0, cy0 = 0, bw = 0, bh = 0;
-  const bool ok = cell_box(bbox, res, cx0, cy0, bw, bh);
-  if (!ok) {
-    if (threadIdx.x == 0) { ctl->dense = 0; ctl->n_dense = 0; ctl->n_items = 0; ctl->n_cells = 0; }
-    return;
-  }
-  const int nbins = bw * bh, per = (nbins + 1023) / 1024;
-  const int lo = min((int)threadIdx.x * per, nbins), hi = min(lo + per, nbins);
-  int4 v = make_int4(0, 0, 0, 0); /* dense particles, dense items, dense cells, sparse particles */
-  for (int b = lo; b < hi; b++) {
-    int c = (int)bins[b];
-    if (c >= thr) { v.x += c; v.y += (c + RT_PI - 1) / RT_PI; v.z += 1; }
-    else v.w += c;
-  }
-  /* block-wide exclusive scan of the four counters */
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int4 inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int tx = __shfl_up_sync(0xffffffffu, inc.x, o), ty = __shfl_up_sync(0xffffffffu, inc.y, o);
-    int tz = __shfl_up_sync(0xffffffffu, inc.z, o), tw = __shfl_up_sync(0xffffffffu, inc.w, o);
-    if (lane >= o) { inc.x += tx; inc.y += ty; inc.z += tz; inc.w += tw; }
-  }
-  if (lane == 31) s_warp[wid] = inc;
-  __syncthreads();
-  if (wid == 0) {
-    int4 w = s_warp[lane], wi = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int tx = __shfl_up_sync(0xffffffffu, wi.x, o), ty = __shfl_up_sync(0xffffffffu, wi.y, o);
-      int tz = __shfl_up_sync(0xffffffffu, wi.z, o), tw = __shfl_up_sync(0xffffffffu, wi.w, o);
-      if (lane >= o) { wi.x += tx; wi.y += ty; wi.z += tz; wi.w += tw; }
-    }
-    if (lane == 31) s_total = wi;
-    s_warp[lane] = make_int4(wi.x - w.x, wi.y - w.y, wi.z - w.z, wi.w - w.w);
-  }
-  __syncthreads();
-  const int4 base = s_warp[wid], tot = s_total;
-  int run_dn = base.x + inc.x - v.x, run_di = base.y + inc.y - v.y, run_dc = base.z + inc.z - v.z,
-      run_sn = base.w + inc.w - v.w;
-  /* tables pay when most particles sit in dense cells (or when the caller forces the path) */
-  const bool dense = tot.z > 0 && tot.z <= max_slots && tot.y <= max_items &&
-                     (force || 2ll * tot.x >= (long long)n);
-  if (threadIdx.x == 0) {
-    ctl->dense = dense ? 1 : 0;
-    ctl->n_dense = dense ? tot.x : 0;
-    ctl->n_items = dense ? tot.y : 0;
-    ctl->n_cells = dense ? tot.z : 0;
-    ctl->cx0 = cx0; ctl->cy0 = cy0; ctl->bw = bw; ctl->bh = bh;
-    if (dense) item0[tot.z] = tot.y;
-  }
-  if (!dense) return;
-  for (int b = lo; b < hi; b++) {
-    int c = (int)bins[b];
-    if (c >= thr) {
-      RtSlot sl;
-      sl.cx = cx0 + b % bw; sl.cy = cy0 + b / bw; sl.first = run_dn; sl.cnt = c;
-      slots[run_dc] = sl;
-      item0[run_dc] = run_di;
-      bins[b] = (uint32_t)run_dn;
-      run_dn += c;
-      run_di += (c + RT_PI - 1) / RT_PI;
-      run_dc++;
-    } else {
-      bins[b] = (uint32_t)(tot.x + run_sn);
-      run_sn += c;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(RT_SORT_THREADS)
-rt_scatter_kernel(const float *__restrict__ x, const float *__restrict__ y, int64_t n, float res,
-                  uint32_t *cursors, const RtCtl *__restrict__ ctl, int32_t *perm) {
-  if (ctl->dense != 1) return;
-  extern __shared__ uint32_t sh_bins[];
-  const int cx0 = ctl->cx0, cy0 = ctl->cy0, bw = ctl->bw, bh = ctl->bh, nbins = bw * bh;
-  for (int b = threadIdx.x; b < nbins; b += RT_SORT_THREADS) sh_bins[b] = 0;
-  __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * RT_SORT_TILE;
-  int bin[RT_SORT_PER_THREAD];
-  uint32_t rank[RT_SORT_PER_THREAD];
-#pragma unroll
-  for (int k = 0; k < RT_SORT_PER_THREAD; k++) { /* rank inside this CTA's share of the cell */
-    int64_t i = base + k * RT_SORT_THREADS + threadIdx.x;
-    bin[k] = -1;
-    if (i < n) {
-      bin[k] = bin_of(__ldg(x + i), __ldg(y + i), res, cx0, cy0, bw, bh);
-      rank[k] = atomicAdd(&sh_bins[bin[k]], 1u);
-    }
-  }
-  __syncthreads();
-  for (int b = threadIdx.x; b < nbins; b += RT_SORT_THREADS) { /* one reservation per occupied cell */
-    uint32_t c = sh_bins[b];
-    if (c) sh_bins[b] = atomicAdd(&cursors[b], c);
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < RT_SORT_PER_THREAD; k++)
-    if (bin[k] >= 0) perm[sh_bins[bin[k]] + rank[k]] = (int32_t)(base + k * RT_SORT_THREADS + threadIdx.x);
-}
-
-// One ray per (dense cell, ring entry).  Neighbouring threads take neighbouring end cells of the
-// same start cell: near-identical rays, converged warps, probes that share cache lines.
+// Second half of the sort (the first CTAs) and the table fill (the others) in one launch: both
+// need only the plan.  Scatter: rank inside this CTA's share of each cell in shared memory, one
+// reservation per occupied cell.  Fill: one ray per (dense cell, ring entry); neighbouring threads
+// take neighbouring end cells of the same start cell: near-identical rays, converged warps, probes
+// that share cache lines.
 template <int MODE, bool WIDE, bool DIAG>
-__global__ void __launch_bounds__(RT_THREADS, RT_CTAS)
-rt_fill_kernel(const RtLaunch L) {
+__global__ void __launch_bounds__(RT_SORT_THREADS, 2)
+rt_scatter_fill_kernel(const __grid_constant__ RtLaunch L, int scatter_blocks) {
   const RtCtl *ctl = L.ctl;
   if (ctl->dense != 1) return;
   const SensorLaunch &a = L.s;
+  if ((int)blockIdx.x < scatter_blocks) {
+    extern __shared__ uint32_t sh_bins[];
+    const int cx0 = ctl->cx0, cy0 = ctl->cy0, bw = ctl->bw, bh = ctl->bh, nbins = bw * bh;
+    for (int b = threadIdx.x; b < nbins; b += RT_SORT_THREADS) sh_bins[b] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RT_SORT_TILE;
+    int bin[RT_SORT_PER_THREAD];
+    uint32_t rank[RT_SORT_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < RT_SORT_PER_THREAD; k++) {
+      int64_t i = base + k * RT_SORT_THREADS + threadIdx.x;
+      bin[k] = -1;
+      if (i < a.n) {
+        bin[k] = bin_of(__ldg(a.x + i), __ldg(a.y + i), a.res, cx0, cy0, bw, bh);
+        rank[k] = atomicAdd(&sh_bins[bin[k]], 1u);
+      }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += RT_SORT_THREADS) {
+      uint32_t c = sh_bins[b];
+      if (c) sh_bins[b] = atomicAdd(&L.bins[b], c);
+    }
+    __syncthreads();
+    /* walking order, and next to it what every look-up of the particle starts from: the ray origin
+     * (S10: the laser, sensor.clj:78-81) and the heading's sine and cosine, once instead of per segment */
+#pragma unroll
+    for (int k = 0; k < RT_SORT_PER_THREAD; k++) {
+      if (bin[k] < 0) continue;
+      const int64_t i = base + k * RT_SORT_THREADS + threadIdx.x;
+      const uint32_t pos = sh_bins[bin[k]] + rank[k];
+      float ox = __ldg(a.x + i), oy = __ldg(a.y + i), st, ct;
+      sincos_det(__ldg(a.th + i), st, ct);
+      if (a.s10) {
+        float nx = ox + fmaf(a.laser_x, ct, -(a.laser_y * st));
+        float ny = oy + fmaf(a.laser_x, st, a.laser_y * ct);
+        ox = nx; oy = ny;
+      }
+      L.perm[pos] = (int32_t)i;
+      L.pstate[pos] = make_float4(ox, oy, st, ct);
+    }
+    return;
+  }
   const int64_t total = (int64_t)ctl->n_cells * L.n_entries;
+  const int64_t stride = (int64_t)(gridDim.x - scatter_blocks) * blockDim.x;
   unsigned long long n_probes = 0, n_oob = 0;
-  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t w = (int64_t)(blockIdx.x - scatter_blocks) * blockDim.x + threadIdx.x; w < total; w += stride) {
     const int slot = (int)(w / L.n_entries), e = (int)(w - (int64_t)slot * L.n_entries);
     const short2 en = __ldg(L.ents + e);
     if (en.x == -32768) continue; /* the unused slot of a merged row */
+    if (en.x == -32767) { /* the sentinel behind the ring: what the fast path reads for an end cell off it */
+      const float nanv = __int_as_float(0x7fc00000);
+      if (DIAG) reinterpret_cast<float4 *>(L.tables)[w] = make_float4(nanv, nanv, nanv, nanv);
+      else reinterpret_cast<float *>(L.tables)[w] = nanv;
+      continue;
+    }
     const int cx = L.slots[slot].cx, cy = L.slots[slot].cy;
     RayOut o;
     const float rng = cast_ray<MODE, WIDE, DIAG>(a, a.df, cx, cy, cx + en.x, cy + en.y, o);
@@ -348,25 +390,24 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
 }
 
 // One 30-beam segment of one particle, every range from the table of the particle's start cell.
-// Straight-line per beam (the compiler interleaves two beams): an end cell outside the ring only
-// raises `bad`, and the caller then redoes the segment on the general path.
+// Straight-line per beam (the compiler interleaves two beams): an end cell outside the ring reads
+// the table's NaN entry, the segment comes back NaN and the caller redoes it on the general path
+// (a NaN scan range takes the same detour and gets the same answer as before, only slower).
 template <bool S7, bool TS>
 __device__ __forceinline__ float table_segment(const SensorLaunch &a, const RtLaunch &L, const ResDiv &rdv,
                                                const float *__restrict__ table, uint32_t s_mix, uint32_t s_dir,
                                                uint32_t s_rows, const float4 *mixt, const float2 *dirt, float ox, float oy,
-                                               float st, float ct, int x0, int y0, int jb0, int jb1, bool &bad_out) {
+                                               float st, float ct, int x0, int y0, int jb0, int jb1) {
   float acc = 0.0f, prod = 1.0f;
-  bool bad = false;
-  const uint32_t last_row = (uint32_t)L.nrows - 1u;
+  int pexp = 0;
+  const uint32_t last_row = (uint32_t)L.nrows - 1u, nan_entry = (uint32_t)L.n_entries - 1u;
   const int xoff = 0x4B400000 + x0, yoff = 0x4B400000 + y0 - L.E;
+  /* S1 off = rotation by zero: fma(1, cb, -(0 * sb)) and fma(0, cb, 1 * sb) give back (cb, sb) */
+  const float rc = a.s1 ? ct : 1.0f, rs = a.s1 ? st : 0.0f;
 #pragma unroll 2
   for (int jb = jb0; jb < jb1; jb++) {
     const float2 bd = TS ? lds_f2(s_dir + (uint32_t)jb * 8u) : __ldg(dirt + jb);
-    float c = bd.x, s = bd.y;
-    if (a.s1) { /* S1: theta + obs-bearing by the angle-addition identity */
-      c = fmaf(ct, bd.x, -(st * bd.y));
-      s = fmaf(st, bd.x, ct * bd.y);
-    }
+    const float c = fmaf(rc, bd.x, -(rs * bd.y)), s = fmaf(rs, bd.x, rc * bd.y); /* S1: angle addition */
     /* sensor.clj:130-135: end point of the beam to its cell: map.clj:36-46 round(v / res) as in
      * round_cell2_inrange; a start inside a table cell keeps the quotient far from the int32 range,
      * so the clamps (and their NaN duty) are not needed */
@@ -378,13 +419,12 @@ __device__ __forceinline__ float table_segment(const SensorLaunch &a, const RtLa
      * the mantissa (exact for |q| < 2^22; the caller keeps table cells inside 2^21) */
     const int ex = __float_as_int(__fadd_rd(qx + 0.5f, 12582912.0f)) - xoff;
     const uint32_t ry = (uint32_t)(__float_as_int(__fadd_rd(qy + 0.5f, 12582912.0f)) - yoff);
-    /* ring entry of the end cell */
+    /* ring entry of the end cell; off the ring: the NaN entry, which poisons the segment */
     const uint32_t ryc = min(ry, last_row);
     const uint4 rw = TS ? lds_u4(s_rows + ryc * 16u) : __ldg(L.rows + ryc);
     const uint32_t tt = (uint32_t)abs(ex) - rw.y; /* row = {first entry, lo, cnt, first entry of the negative arc} */
     const bool ok = tt < rw.z && ry <= last_row;
-    bad |= !ok;
-    const uint32_t ent = ok ? tt + (ex < 0 ? rw.w : rw.x) : 0u;
+    const uint32_t ent = ok ? tt + (ex < 0 ? rw.w : rw.x) : nan_entry;
     const float rng = __ldg(table + ent);
     /* sensor.clj:149-162 beam mixture, exactly as in sensor.cu */
     const float4 mx = TS ? lds_f4(s_mix + (uint32_t)jb * 16u) : __ldg(mixt + jb);
@@ -392,15 +432,10 @@ __device__ __forceinline__ float table_segment(const SensorLaunch &a, const RtLa
     const float pz1 = hit_gauss(z, a.k2, a.z_hit);
     const float pz2 = z < 0.0f ? mx.y : 0.0f;
     const float sum = (pz1 + pz2) + mx.z;
-    if (S7) {
-      prod *= sum;
-      if (!(prod >= 1.0e-30f)) { acc += logf(prod); prod = 1.0f; }
-    } else {
-      acc += (sum * sum) * sum;
-    }
+    if (S7) logprod_mul(acc, prod, pexp, sum);
+    else acc += (sum * sum) * sum;
   }
-  bad_out = bad;
-  return S7 ? acc + logf(prod) : acc;
+  return S7 ? logprod_close(acc, prod, pexp) : acc;
 }
 
 // Warp task ("unit") = 32 particles x one 30-beam segment; lane = particle.  Units over dense cells
@@ -441,7 +476,9 @@ rt_lookup_kernel(const __grid_constant__ RtLaunch L) {
   const int64_t n_sparse_items = (a.n - n_dense + RT_PI - 1) / RT_PI;
   const int64_t ud = n_items_dense * nseg, us = n_sparse_items * nseg;
   const int64_t G = gridDim.x, bid = blockIdx.x;
-  const int64_t d_lo = ud * bid / G, d_hi = ud * (bid + 1) / G;
+  /* the last few percent of the dense units are a common tail: whoever finishes first takes it */
+  const int64_t ud_static = ud - ud * L.tail_pct / 100;
+  const int64_t d_lo = ud_static * bid / G, d_hi = ud_static * (bid + 1) / G;
   const int64_t ns_mine = us > bid ? (us - bid + G - 1) / G : 0; /* sparse units bid, bid + G, ... */
   const int64_t n_mine = ns_mine + (d_hi - d_lo);
   const ResDiv rdv = make_resdiv(a.res);
@@ -450,40 +487,59 @@ rt_lookup_kernel(const __grid_constant__ RtLaunch L) {
   const int lane = threadIdx.x & 31;
   unsigned long long n_cells = 0, n_probes = 0, n_hits = 0, n_rays = 0, n_oob = 0, n_miss = 0;
 
+  int c_slot = 0, c_i0 = 0, c_i1 = 0; /* the dense cell of the previous unit: [c_i0, c_i1) are its items */
   for (;;) {
     int k = 0;
     if (lane == 0) k = atomicAdd(&s_next, 1);
     k = __shfl_sync(FULL, k, 0);
-    if (k >= n_mine) break;
-    const int64_t u = k < ns_mine ? ud + bid + (int64_t)k * G : d_lo + (k - ns_mine);
+    int64_t u;
+    if (k < n_mine) {
+      u = k < ns_mine ? ud + bid + (int64_t)k * G : d_lo + (k - ns_mine);
+    } else { /* this CTA's share is done: help with the common tail */
+      uint32_t t = 0;
+      if (lane == 0) t = atomicAdd(&L.ctl->next_tail, 1u);
+      t = __shfl_sync(FULL, t, 0);
+      if ((int64_t)t >= ud - ud_static) break;
+      u = ud_static + t;
+    }
     const int64_t item = u / nseg;
     const int sgm = (int)(u - item * nseg);
     int64_t first;
     int cnt, cx = 0, cy = 0;
     const float *table = nullptr;
     if (item < n_items_dense) {
-      /* the dense cell this item belongs to: last slot whose first item is <= item */
-      int lo_s = 0, hi_s = n_tabs;
-      while (hi_s - lo_s > 1) {
-        const int mid = (lo_s + hi_s) >> 1;
-        if ((int64_t)__ldg(L.item0 + mid) <= item) lo_s = mid; else hi_s = mid;
+      if (item < c_i0 || item >= c_i1) { /* last slot whose first item is <= item */
+        int lo_s = 0, hi_s = n_tabs;
+        while (hi_s - lo_s > 1) {
+          const int mid = (lo_s + hi_s) >> 1;
+          if ((int64_t)__ldg(L.item0 + mid) <= item) lo_s = mid; else hi_s = mid;
+        }
+        c_slot = lo_s; c_i0 = __ldg(L.item0 + lo_s); c_i1 = __ldg(L.item0 + lo_s + 1);
       }
-      const RtSlot sl = L.slots[lo_s];
-      const int off = (int)(item - __ldg(L.item0 + lo_s)) * RT_PI;
+      const RtSlot sl = L.slots[c_slot];
+      const int off = (int)(item - c_i0) * RT_PI;
       first = sl.first + off; cnt = min(RT_PI, sl.cnt - off); cx = sl.cx; cy = sl.cy;
-      table = reinterpret_cast<const float *>(L.tables) + (size_t)lo_s * L.n_entries * (DIAG ? 4 : 1);
+      table = reinterpret_cast<const float *>(L.tables) + (size_t)c_slot * L.n_entries * (DIAG ? 4 : 1);
     } else {
       first = n_dense + (item - n_items_dense) * RT_PI;
       cnt = (int)min((int64_t)RT_PI, a.n - first);
     }
     if (lane >= cnt) continue;
-    const int64_t p = dense ? (int64_t)__ldg(L.perm + first + lane) : first + lane;
-    float ox = __ldg(a.x + p), oy = __ldg(a.y + p), st, ct;
-    sincos_det(__ldg(a.th + p), st, ct);
-    if (a.s10) { /* S10: base->laser offset (sensor.clj:78-81), off by default */
-      float nx = ox + fmaf(a.laser_x, ct, -(a.laser_y * st));
-      float ny = oy + fmaf(a.laser_x, st, a.laser_y * ct);
-      ox = nx; oy = ny;
+    int64_t p;
+    float ox, oy, st, ct;
+    if (dense) { /* the sort left the ray origin and the heading's sine / cosine in walking order */
+      p = (int64_t)__ldg(L.perm + first + lane);
+      const float4 ps = __ldg(L.pstate + first + lane);
+      ox = ps.x; oy = ps.y; st = ps.z; ct = ps.w;
+    } else {
+      p = first + lane;
+      ox = __ldg(a.x + p); oy = __ldg(a.y + p);
+      sincos_det(__ldg(a.th + p), st, ct);
+      if (a.s10) { /* S10: base->laser offset (sensor.clj:78-81), off by default */
+        float nx = ox + fmaf(a.laser_x, ct, -(a.laser_y * st));
+        float ny = oy + fmaf(a.laser_x, st, a.laser_y * ct);
+        ox = nx; oy = ny;
+      }
     }
     int x0, y0;
     round_cell2_fast(ox, oy, rdv, x0, y0);
@@ -494,12 +550,14 @@ rt_lookup_kernel(const __grid_constant__ RtLaunch L) {
     float v = 0.0f;
     bool general = DIAG || !use_table;
     if (!general) {
-      v = a.s7 ? table_segment<true, TS>(a, L, rdv, table, s_mix, s_dir, s_rows, mixt, dirt, ox, oy, st, ct, x0, y0, jb0, jb1, general)
-               : table_segment<false, TS>(a, L, rdv, table, s_mix, s_dir, s_rows, mixt, dirt, ox, oy, st, ct, x0, y0, jb0, jb1, general);
+      v = a.s7 ? table_segment<true, TS>(a, L, rdv, table, s_mix, s_dir, s_rows, mixt, dirt, ox, oy, st, ct, x0, y0, jb0, jb1)
+               : table_segment<false, TS>(a, L, rdv, table, s_mix, s_dir, s_rows, mixt, dirt, ox, oy, st, ct, x0, y0, jb0, jb1);
+      general = v != v;
     }
     if (general) { /* sparse cells, diagnostics, and the segments the fast path gave back */
       const bool dbg = DIAG && a.dbg_count > 0 && p >= a.dbg_first && p < a.dbg_first + a.dbg_count;
       float acc = 0.0f, prod = 1.0f;
+      int pexp = 0;
       for (int jb = jb0; jb < jb1; jb++) {
         const float2 bd = TS ? lds_f2(s_dir + (uint32_t)jb * 8u) : __ldg(dirt + jb);
         float c = bd.x, s = bd.y;
@@ -545,12 +603,8 @@ rt_lookup_kernel(const __grid_constant__ RtLaunch L) {
         const float pz1 = hit_gauss(z, a.k2, a.z_hit);
         const float pz2 = z < 0.0f ? mx.y : 0.0f;
         const float sum = (pz1 + pz2) + mx.z;
-        if (a.s7) {
-          prod *= sum;
-          if (!(prod >= 1.0e-30f)) { acc += logf(prod); prod = 1.0f; }
-        } else {
-          acc += (sum * sum) * sum;
-        }
+        if (a.s7) logprod_mul(acc, prod, pexp, sum);
+        else acc += (sum * sum) * sum;
         if (DIAG) {
           n_rays++; n_cells += (unsigned)o.kk + 1u; n_probes += (unsigned)o.probes; n_hits += (unsigned)o.hit;
           n_oob += (unsigned)o.oob;
@@ -564,7 +618,7 @@ rt_lookup_kernel(const __grid_constant__ RtLaunch L) {
           }
         }
       }
-      v = a.s7 ? acc + logf(prod) : acc;
+      v = a.s7 ? logprod_close(acc, prod, pexp) : acc;
     }
     /* close the segment: one rounding to fixed point; segments add as integers */
     atomicAdd(reinterpret_cast<unsigned long long *>(L.qacc) + p,
@@ -617,18 +671,24 @@ template <int MODE, bool WIDE, bool DIAG>
 static cudaError_t launch_rt_t(const amclj_ctx *c, const RtLaunch &L, cudaStream_t s) {
   /* persistent grids: the amount of work is decided on the device */
   const int64_t grid = (int64_t)c->sm_count * RT_CTAS;
-  rt_fill_kernel<MODE, WIDE, DIAG><<<(unsigned)grid, RT_THREADS, 0, s>>>(L);
+  const int64_t grid_lookup = grid * (c->rt.waves > 0 ? c->rt.waves : 1);
+  const int scatter_blocks = (int)((L.s.n + RT_SORT_TILE - 1) / RT_SORT_TILE);
+  const size_t sort_smem = sizeof(uint32_t) * RT_BIN_CAP;
+  auto sf = rt_scatter_fill_kernel<MODE, WIDE, DIAG>;
+  cudaError_t e = cudaFuncSetAttribute(sf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
+  if (e != cudaSuccess) return e;
+  sf<<<(unsigned)(scatter_blocks + c->sm_count * 2), RT_SORT_THREADS, sort_smem, s>>>(L, scatter_blocks);
   /* beam tables and ring rows ride in shared memory when RT_CTAS CTAs of them fit the SM */
   const size_t smem = (size_t)L.s.nb * 24 + (size_t)L.nrows * 16;
   if (smem * RT_CTAS + 4096 <= (size_t)c->max_smem_optin) {
     auto kern = rt_lookup_kernel<MODE, WIDE, DIAG, true>;
     if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
     }
-    kern<<<(unsigned)grid, RT_THREADS, smem, s>>>(L);
+    kern<<<(unsigned)grid_lookup, RT_THREADS, smem, s>>>(L);
   } else {
-    rt_lookup_kernel<MODE, WIDE, DIAG, false><<<(unsigned)grid, RT_THREADS, 0, s>>>(L);
+    rt_lookup_kernel<MODE, WIDE, DIAG, false><<<(unsigned)grid_lookup, RT_THREADS, 0, s>>>(L);
   }
   rt_finish_kernel<<<(unsigned)((L.s.n + 255) / 256), 256, 0, s>>>(L);
   return cudaGetLastError();
@@ -640,12 +700,10 @@ static cudaError_t launch_rt_m(const amclj_ctx *c, const RtLaunch &L, bool diag,
   return wide ? launch_rt_t<MODE, true, false>(c, L, s) : launch_rt_t<MODE, false, false>(c, L, s);
 }
 
-/* once per device: the sort kernels take 64 KB of dynamic shared memory */
+/* once per device: the histogram takes 64 KB of dynamic shared memory */
 cudaError_t rt_prepare_device() {
   const int sort_smem = (int)(sizeof(uint32_t) * RT_BIN_CAP);
-  cudaError_t e = cudaFuncSetAttribute(rt_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sort_smem);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(rt_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sort_smem);
+  return cudaFuncSetAttribute(rt_hist_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sort_smem);
 }
 
 cudaError_t launch_raytable(const amclj_ctx *c, const RtLaunch &L, int mode, bool diag, cudaStream_t s) {
@@ -654,10 +712,10 @@ cudaError_t launch_raytable(const amclj_ctx *c, const RtLaunch &L, int mode, boo
   cudaMemsetAsync(L.bins, 0, sizeof(uint32_t) * RT_BIN_CAP, s);
   const size_t sort_smem = sizeof(uint32_t) * RT_BIN_CAP; /* a counter per cell of the largest box */
   const unsigned blocks = (unsigned)((a.n + RT_SORT_TILE - 1) / RT_SORT_TILE);
-  rt_hist_kernel<<<blocks, RT_SORT_THREADS, sort_smem, s>>>(a.x, a.y, a.n, a.res, a.bbox, L.bins, L.qacc);
-  rt_plan_kernel<<<1, 1024, 0, s>>>(a.bbox, a.res, a.n, L.thr, L.max_slots, L.max_items, L.must_run == 2 ? 1 : 0,
-                                    L.bins, L.slots, L.item0, L.ctl);
-  rt_scatter_kernel<<<blocks, RT_SORT_THREADS, sort_smem, s>>>(a.x, a.y, a.n, a.res, L.bins, L.ctl, L.perm);
+  PlanArgs pa;
+  pa.n = a.n; pa.thr = L.thr; pa.max_slots = L.max_slots; pa.max_items = L.max_items; pa.force = L.must_run == 2 ? 1 : 0;
+  pa.slots = L.slots; pa.item0 = L.item0; pa.ctl = L.ctl;
+  rt_hist_plan_kernel<<<blocks, RT_SORT_THREADS, sort_smem, s>>>(a.x, a.y, a.res, a.bbox, L.bins, L.qacc, pa);
   const bool wide = a.div_wide != 0;
   switch (mode) {
     case DF_WEDGE8: return launch_rt_m<DF_WEDGE8>(c, L, diag, wide, s);

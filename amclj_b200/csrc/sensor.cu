@@ -167,6 +167,7 @@ sensor_kernel(const SensorLaunch a) {
     int dg_a0 = 0, dg_b0 = 0, dg_xs = 0, dg_ys = 0, dg_steep = 0, dg_probes = 0; /* DIAG only */
     bool have_ray = false;
     float acc = 0.0f, prod = 1.0f;
+    int pexp = 0;
     long long qacc = 0;
     int jb = valid ? b_lo : b_hi; /* this lane's current beam */
     int seg_end = min(b_lo + SEG, b_hi);
@@ -186,8 +187,7 @@ sensor_kernel(const SensorLaunch a) {
           float pz2 = z < 0.0f ? mx.y : 0.0f;
           float sum = (pz1 + pz2) + mx.z;
           if (a.s7) { /* sum of logs as the log of a running product, flushed before underflow */
-            prod *= sum;
-            if (!(prod >= 1.0e-30f)) { acc += logf(prod); prod = 1.0f; }
+            logprod_mul(acc, prod, pexp, sum);
           } else {
             acc += (sum * sum) * sum; /* sensor.clj:162 (pow . 3) */
           }
@@ -208,9 +208,9 @@ sensor_kernel(const SensorLaunch a) {
           have_ray = false;
           jb++;
           if (jb == seg_end) { /* close the segment: one rounding to fixed point */
-            float v = a.s7 ? acc + logf(prod) : acc;
+            float v = a.s7 ? logprod_close(acc, prod, pexp) : acc;
             qacc += __float2ll_rn(fmaxf(v, FIX_FLOOR) * FIX_SCALE);
-            acc = 0.0f; prod = 1.0f;
+            acc = 0.0f; prod = 1.0f; pexp = 0;
             seg_end = min(seg_end + SEG, b_hi);
           }
         }

@@ -113,7 +113,7 @@ def test_auto_policy_takes_the_tables_for_a_dense_cloud_only(lg):
         w.set_map(lg)
         clouds = [workloads.gaussian_particles(30_000, sd_theta=0.05), workloads.uniform_particles(lg, 5000, seed=3),
                   workloads.gaussian_particles(30_000, sd_theta=0.05, seed=8), workloads.gaussian_particles(30_000, seed=9),
-                  workloads.gaussian_particles(600, seed=10)]
+                  workloads.gaussian_particles(150, seed=10)]
         took = []
         for x, y, th in clouds:
             for ctx in (c, w):
