@@ -32,7 +32,7 @@ SYMBOLS = [
     "amclj_get_params", "amclj_set_shard", "amclj_set_map", "amclj_set_particles",
     "amclj_get_particles", "amclj_num_particles", "amclj_init_uniform", "amclj_init_gaussian",
     "amclj_motion_update", "amclj_sensor_update", "amclj_get_raw_weights", "amclj_raycast_debug",
-    "amclj_beams_used", "amclj_normalize", "amclj_resample", "amclj_get_resample_indices",
+    "amclj_beams_used", "amclj_ray_table_entries", "amclj_normalize", "amclj_resample", "amclj_get_resample_indices",
     "amclj_filter_update", "amclj_stage_scan", "amclj_filter_update_async",
     "amclj_filter_update_host", "amclj_pose_estimate", "amclj_get_stats", "amclj_microbench", "amclj_median_weight",
     "amclj_augmented_resample", "amclj_augment_state",
@@ -68,6 +68,7 @@ class Stats(C.Structure):
         ("probes", C.c_uint64), ("hits", C.c_uint64), ("n_particles", C.c_int64),
         ("beams_used", C.c_int32), ("map_in_smem", C.c_int32), ("oob_probes", C.c_uint64),
         ("table_cells", C.c_uint64), ("table_particles", C.c_uint64), ("table_misses", C.c_uint64),
+        ("ms_sensor_main", C.c_double), ("sensor_path", C.c_int32), ("kernels_launched", C.c_int32),
     ]
 
 
@@ -124,6 +125,7 @@ def lib():
         "amclj_get_raw_weights": ([vp, vp], i32),
         "amclj_raycast_debug": ([vp, i32, f32, f32, f32, i64, i64, vp, vp, vp, vp, vp], i32),
         "amclj_beams_used": ([vp, i32], i32),
+        "amclj_ray_table_entries": ([vp], i32),
         "amclj_normalize": ([vp, i32, C.POINTER(u64), C.POINTER(f32)], i32),
         "amclj_resample": ([vp, i32, f64, vp, vp, i64, u64, vp], i32),
         "amclj_get_resample_indices": ([vp, vp], i32),
@@ -294,6 +296,9 @@ class Context:
         raw = np.empty(self.n, np.float32)
         self._ck(self._L.amclj_get_raw_weights(self._h, _vp(raw)))
         return raw
+
+    def ray_table_entries(self):
+        return int(self._L.amclj_ray_table_entries(self._h))
 
     def beams_used(self, n_scan):
         return int(self._L.amclj_beams_used(self._h, int(n_scan)))

@@ -445,6 +445,7 @@ int enqueue_motion(amclj_ctx *ctx, const double curr[3], const double prev[3], b
     ctx->bbox_done = true;
   }
   CK(launch_motion(m, ctx->stream));
+  ctx->launches += 1;
   return AMCLJ_OK;
 }
 
@@ -488,6 +489,7 @@ int enqueue_raytable(amclj_ctx *ctx, const SensorLaunch &base, bool diag, int mu
   L.must_run = must_run;
   L.tail_pct = t.tail_pct;
   CK(launch_raytable(ctx, L, fill_mode, diag, ctx->stream));
+  ctx->launches += 4; /* histogram + plan, scatter + fill, look-up, finish */
   return AMCLJ_OK;
 }
 
@@ -517,7 +519,8 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
     }
     a.partials = ctx->partials;
   }
-  bool diag = ctx->p.collect_stats != 0;
+  bool diag = (ctx->p.collect_stats & 1) != 0;
+  ctx->time_main = ctx->time_main_env || (ctx->p.collect_stats & 2) != 0;
   a.stats = diag ? ctx->stats : nullptr;
   if (!ctx->ctrl_fresh) {
     CK(reset_ctrl(ctx, true));
@@ -558,7 +561,10 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
     a = b;
   }
   if (ordered || use_rt) {
-    if (!ctx->bbox_done) CK(launch_bbox(ctx->x, ctx->y, ctx->n, ctx->bbox, ctx->sm_count, ctx->stream));
+    if (!ctx->bbox_done) {
+      CK(launch_bbox(ctx->x, ctx->y, ctx->n, ctx->bbox, ctx->sm_count, ctx->stream));
+      ctx->launches += 1;
+    }
     ctx->bbox_done = false;
     a.bbox = ctx->bbox;
     a.compact_m = ctx->compact_cells * ctx->map.res;
@@ -571,6 +577,7 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
     if (hint != 1) {
       CK(launch_tile_order(ctx->x, ctx->y, ctx->th, ctx->n, ctx->map.res, ctx->map.W, ctx->map.H,
                            ctx->tile_counters, ctx->perm, ctx->bbox, a.compact_m, ctx->stream));
+      ctx->launches += 3;
       a.perm = ctx->perm;
     }
   }
@@ -579,8 +586,14 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
     if (rrc) return rrc;
     a.skip_flag = &ctx->rt.ctl->dense;
   }
-  if (!only_rt) CK(launch_sensor(ctx, a, mode, diag, ctx->stream));
-  if (decode_max) CK(launch_decode_max(ctx->rawmax_ord, ctx->rawmax, ctx->stream));
+  if (!only_rt) {
+    CK(launch_sensor(ctx, a, mode, diag, ctx->stream));
+    ctx->launches += a.chunks > 1 ? 2 : 1;
+  }
+  if (decode_max) {
+    CK(launch_decode_max(ctx->rawmax_ord, ctx->rawmax, ctx->stream));
+    ctx->launches += 1;
+  }
   ctx->max_in_ord = !decode_max;
   ctx->last_diag = diag;
   ctx->have_raw = true;
@@ -597,11 +610,13 @@ int enqueue_cdf(amclj_ctx *ctx, bool from_raw, bool max_known) {
   int is_log = from_raw && ctx->p.s7_log_weights;
   if (!max_known) { /* launch_max clears and refills the max (ordered uint and float) */
     CK(launch_max(v, ctx->n, ctx->rawmax_ord, ctx->rawmax, ctx->sm_count, ctx->stream));
+    ctx->launches += 2;
     ctx->max_in_ord = false;
   }
   if (!ctx->scan_clean || !max_known) CK(reset_ctrl(ctx, false));
   CK(launch_scan(v, ctx->rawmax, ctx->max_in_ord ? ctx->rawmax_ord : nullptr, is_log, ctx->n, ctx->cdf,
                  ctx->scan_state, ctx->scan_counter, ctx->total, ctx->stream));
+  ctx->launches += 1;
   ctx->scan_clean = false;
   ctx->have_cdf = true;
   ctx->cdf_from_raw = from_raw;
@@ -638,6 +653,7 @@ int enqueue_systematic(amclj_ctx *ctx, double u0) {
   g.oidx = ctx->idx;
   g.wout = 1.0f / (float)ctx->n;
   CK(launch_systematic(g, ctx->stream));
+  ctx->launches += 1;
   swap_particles(ctx);
   ctx->have_raw = false;
   ctx->have_cdf = false;
@@ -759,7 +775,11 @@ int upload_normals(amclj_ctx *ctx, const float *normals) {
   return AMCLJ_OK;
 }
 
-void stamp(amclj_ctx *ctx, int k) { cudaEventRecord(ctx->ev[k], ctx->stream); }
+void stamp(amclj_ctx *ctx, int k) {
+  cudaEventRecord(ctx->ev[k], ctx->stream);
+  if (k == 0) ctx->launches = 0; /* a new update */
+  ctx->st.kernels_launched = ctx->launches;
+}
 
 void collect_times(amclj_ctx *ctx) {
   float a = 0, b = 0, c = 0, t = 0;
@@ -772,6 +792,11 @@ void collect_times(amclj_ctx *ctx) {
   ctx->st.ms_sensor = b;
   ctx->st.ms_resample = c;
   ctx->st.ms_total = t;
+  float m = 0;
+  if (cudaEventElapsedTime(&m, ctx->ev[5], ctx->ev[6]) != cudaSuccess || m < 0) m = 0;
+  (void)cudaGetLastError();
+  ctx->st.ms_sensor_main = m;
+  ctx->st.sensor_path = *ctx->pin_decision;
 }
 
 }  // namespace
@@ -812,6 +837,7 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
   if (const char *e = getenv("AMCLJ_REFILL_GLOBAL")) ctx->refill_global = atoi(e);
   if (const char *e = getenv("AMCLJ_COMPACT_CELLS")) ctx->compact_cells = (float)atof(e);
   if (const char *e = getenv("AMCLJ_RAYTABLE")) ctx->rt_enable = atoi(e) != 0;
+  if (const char *e = getenv("AMCLJ_TIME_MAIN")) ctx->time_main_env = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_RT_THR")) ctx->rt.thr = atoi(e);
   if (const char *e = getenv("AMCLJ_RT_WAVES")) ctx->rt.waves = atoi(e);
   if (const char *e = getenv("AMCLJ_RT_TAIL_PCT")) ctx->rt.tail_pct = atoi(e) < 0 ? 0 : (atoi(e) > 100 ? 100 : atoi(e));
@@ -819,7 +845,7 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
   memset(&ctx->st, 0, sizeof(ctx->st));
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ctx->stream = ctx->own_stream;
-  for (int i = 0; ok && i < 5; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+  for (int i = 0; ok && i < 7; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
   /* control block: [0..1] particle bounding box (4 ordered-uint maxima) | [2] ordered-uint max
    * weight | [3] fixed-point total | [4] tile counter | [5..] tile descriptors of the scan (2^20
    * tiles = 2^31 particles; also serves the roulette compaction) */
@@ -847,7 +873,7 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
     amclj_destroy(ctx);
     return AMCLJ_ERR_CUDA;
   }
-  for (int i = 0; i < 5; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
+  for (int i = 0; i < 7; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
   *out = ctx;
   return AMCLJ_OK;
 }
@@ -871,7 +897,7 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
   if (ctx->rt.tables) cudaFree(ctx->rt.tables);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->pin_tab) cudaFreeHost(ctx->pin_tab);
-  for (int i = 0; i < 5; i++)
+  for (int i = 0; i < 7; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -1084,6 +1110,10 @@ int32_t amclj_get_raw_weights(amclj_ctx *ctx, float *raw) {
   CK(cudaMemcpyAsync(raw, ctx->raw, sizeof(float) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return AMCLJ_OK;
+}
+
+int32_t amclj_ray_table_entries(const amclj_ctx *ctx) {
+  return ctx && ctx->rt.available ? ctx->rt.n_entries : 0;
 }
 
 int32_t amclj_beams_used(const amclj_ctx *ctx, int32_t n) {
@@ -1507,6 +1537,7 @@ int32_t amclj_shard_generate_async(amclj_ctx *ctx, uint64_t total_global, uint64
   g.gid0 = ctx->global_offset;
   g.wout = 1.0f / (float)ctx->n_global;
   CK(launch_systematic(g, ctx->stream));
+  ctx->launches += 1;
   return AMCLJ_OK;
 }
 
@@ -1526,6 +1557,7 @@ int32_t amclj_shard_adopt_async(amclj_ctx *ctx, int64_t count) {
   int rc = ensure_particles(ctx, count);
   if (rc) return rc;
   CK(launch_adopt(ctx->stage_in, count, ctx->x, ctx->y, ctx->th, ctx->w, ctx->stream));
+  ctx->launches += 1;
   ctx->n = count;
   ctx->have_raw = ctx->have_cdf = false;
   stamp(ctx, 3);
@@ -1616,6 +1648,7 @@ int32_t amclj_shard_pull_async(amclj_ctx *ctx, double u0) {
   a.wout = 1.0f / (float)ctx->n_global;
   a.zero_flag = ctx->stats + 5;
   CK(launch_pull(a, ctx->stream));
+  ctx->launches += 1;
   swap_particles(ctx);
   ctx->have_raw = ctx->have_cdf = false;
   stamp(ctx, 3);

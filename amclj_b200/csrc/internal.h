@@ -127,7 +127,7 @@ struct RayTables {
   int64_t pstate_cap = 0;
   int32_t thr = 0;            // particles per cell from which a table pays (0: derived)
   size_t budget = 256ull << 20;
-  int32_t tail_pct = 10;
+  int32_t tail_pct = 30;
   int32_t waves = 1;          // look-up grid = resident CTAs x waves (smaller CTAs balance better)
 };
 struct RtLaunch {
@@ -161,7 +161,9 @@ struct amclj_ctx {
   int sm_count = 0;
   int max_smem_optin = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [5], [6]: around the dominant sensor kernel
+  bool time_main = false, time_main_env = false;  // collect_stats bit 1 (or AMCLJ_TIME_MAIN=1): events around that kernel
+  int32_t launches = 0;   // kernels enqueued by the update in progress
   std::string err;
   amclj_params p;
   amclj::DeviceMap map;

@@ -680,6 +680,7 @@ static cudaError_t launch_rt_t(const amclj_ctx *c, const RtLaunch &L, cudaStream
   sf<<<(unsigned)(scatter_blocks + c->sm_count * 2), RT_SORT_THREADS, sort_smem, s>>>(L, scatter_blocks);
   /* beam tables and ring rows ride in shared memory when RT_CTAS CTAs of them fit the SM */
   const size_t smem = (size_t)L.s.nb * 24 + (size_t)L.nrows * 16;
+  if (c->time_main) cudaEventRecord(c->ev[5], s);
   if (smem * RT_CTAS + 4096 <= (size_t)c->max_smem_optin) {
     auto kern = rt_lookup_kernel<MODE, WIDE, DIAG, true>;
     if (smem > 48 * 1024) {
@@ -690,6 +691,7 @@ static cudaError_t launch_rt_t(const amclj_ctx *c, const RtLaunch &L, cudaStream
   } else {
     rt_lookup_kernel<MODE, WIDE, DIAG, false><<<(unsigned)grid_lookup, RT_THREADS, 0, s>>>(L);
   }
+  if (c->time_main) cudaEventRecord(c->ev[6], s);
   rt_finish_kernel<<<(unsigned)((L.s.n + 255) / 256), 256, 0, s>>>(L);
   return cudaGetLastError();
 }

@@ -369,7 +369,9 @@ static cudaError_t launch_t(const amclj_ctx *c, const SensorLaunch &a, cudaStrea
   int per_sm = MODE == DF_SMEM4 ? 1 : (MODE == DF_WEDGE8 ? WEDGE_CTAS : (GLOBAL_CTAS > 2 ? GLOBAL_CTAS : 2));
   if (blocks > (int64_t)c->sm_count * per_sm) blocks = (int64_t)c->sm_count * per_sm;
   if (blocks < 1) blocks = 1;
+  if (c->time_main) cudaEventRecord(c->ev[5], s);
   kern<<<(unsigned)blocks, wpb * 32, smem, s>>>(a);
+  if (c->time_main) cudaEventRecord(c->ev[6], s);
   return cudaGetLastError();
 }
 

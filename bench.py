@@ -37,9 +37,13 @@ if str(ROOT) not in sys.path:
 METRIC = "beam_evals_per_s"
 UNIT = "beam-evals/s"
 PER_GPU_SHARDED = 1_250_000  # C4: 10M particles over 8 GPUs
-KERNELS_PER_UPDATE = 5       # motion (+ bounding box), sensor, combine, scan, gather; the 3 tile-order kernels of a
-                             # spread-out cloud come on top (a compact cloud skips their launches after its first update)
-KERNELS_PER_UPDATE_SHARDED = 5  # motion, sensor, decode-max, scan, pull (+ 2 NCCL collectives)
+# kernels per update are counted by the library (amclj_stats.kernels_launched): dense cloud on the ray
+# tables = motion, histogram+plan, scatter+fill, look-up, finish, scan, gather = 7; walk kernel = motion,
+# sensor, combine, scan, gather = 5 (+ 3 tile-order kernels for a spread-out cloud); sharded: + decode-max,
+# pull instead of gather, and 2 NCCL collectives that are not counted
+SENSOR_PATHS = {-1: "unknown", 0: "walk kernel, particles in map-tile order (spread-out cloud)",
+                1: "walk kernel, particles in place (compact cloud)",
+                2: "ray tables (dense cloud: one walk per (start cell, end cell), looked up per particle-beam)"}
 
 
 def peaks():
@@ -177,6 +181,11 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def ctx_ring_entries(ctx):
+    """Ray-table entries per start cell for the staged scan geometry (0 when the path is unavailable)."""
+    return int(ctx.ray_table_entries())
+
+
 def config_of(args, w, sample_note=None, extra=None):
     c = {"workload": w.name, "map": f"{w.grid.info.width}x{w.grid.info.height}@{float(w.grid.info.resolution):.2f}m",
          "particles_per_gpu": w.n, "beams": len(w.scan.ranges), "range_max_m": w.scan.range_max,
@@ -259,7 +268,7 @@ def run_b200(args):
             one_step(k)
         barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        sensor_ms, total_ms_lib = [], []
+        sensor_ms, total_ms_lib, main_ms, launches, paths = [], [], [], [], []
         with ClockSampler(local) as clocks:
             t_wall0 = time.perf_counter()
             for k in range(args.steps):
@@ -273,6 +282,8 @@ def run_b200(args):
                 st = ctx.stats()
                 sensor_ms.append(st.ms_sensor)
                 total_ms_lib.append(st.ms_total)
+                launches.append(st.kernels_launched)
+                paths.append(st.sensor_path)
             t_wall = time.perf_counter() - t_wall0
         step_ms = [a.elapsed_time(b) for a, b in ev]
     dev_ms = float(np.sum(step_ms))
@@ -283,6 +294,28 @@ def run_b200(args):
     ms_per_step = dev_ms / args.steps
     n_total = w.n * world
     value = n_total * nb / (ms_per_step * 1e-3)
+
+    # ---- the dominant sensor kernel alone: the same K steps again with two more event records
+    # around that launch (collect_stats bit 1; they cost ~3 % of a C2 update, so the headline loop
+    # above runs without them) ----------------------------------------------------------------
+    ctx.set_params(_lib.params("NS", collect_stats=2, df_mode=args.df_mode))
+    if filt:
+        filt.stage_scan(s)
+    else:
+        ctx.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max)
+    with torch.cuda.stream(stream):
+        for k in range(args.steps):
+            restore()
+            flush.fill_(k & 0xff)
+            barrier()
+            one_step(args.warmup + k)
+            barrier()
+            main_ms.append(ctx.stats().ms_sensor_main)
+    ctx.set_params(_lib.params("NS", df_mode=args.df_mode))
+    if filt:
+        filt.stage_scan(s)
+    else:
+        ctx.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max)
 
     # ---- e2e: host PoseArray in, resampled PoseArray out, through the C ABI ------------
     e2e = None
@@ -347,43 +380,62 @@ def run_b200(args):
         props = torch.cuda.get_device_properties(dev)
         sm_count = props.multi_processor_count
         sm_hz = 1e6 * float((clocks.summary().get("sm_mhz") or 1965))
-        k_ms = float(np.mean(sensor_ms))
-        # measured ceiling of dependent distance-field lookups on this GPU (same placement as the map)
-        # placement of the field the kernel actually ran on: shared memory, L1 (directional planes of a
-        # compact particle cloud: ncu shows a 99 % L1 hit rate) or L2 (large maps)
-        placement = 0 if st.map_in_smem else (2 if w.grid.info.width * w.grid.info.height < (1 << 22) else 1)
+        stage_ms = float(np.mean(sensor_ms))          # the whole sensor stage (sort + fill + look-up + finish, or walk + combine)
+        k_ms = float(np.mean(main_ms)) or stage_ms      # its dominant kernel alone (events around that launch)
+        path = int(paths[-1]) if paths else -1
+        tables = path == 2
+        # measured ceiling of dependent lookups on this GPU, placed like what the kernel reads:
+        # shared memory, L1 (directional planes of a compact cloud, per-cell ray tables) or L2 (large maps)
+        placement = 0 if st.map_in_smem else (2 if (tables or w.grid.info.width * w.grid.info.height < (1 << 22)) else 1)
         lookup_peak = ctx.microbench(placement)
         traffic = None
         tfile = ROOT / "profiles" / "sensor_traffic.json"
         if tfile.exists():  # dram bytes per launch from the committed ncu --set full capture of this workload
             t = json.loads(tfile.read_text())
-            if t.get("workload") == w.name and world == 1:
+            if t.get("workload") == w.name and world == 1 and t.get("kernel", "").endswith("rt_lookup_kernel") == tables:
                 traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
         # sensor stage = read x,y,theta (12 B) + write raw (4 B) per particle;
-        # the map is staged once per CTA from L2 (not HBM after the first CTA)
+        # map, tables and beam constants are served on chip
         alg_bytes = 16.0 * w.n
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        n_rays = st.rays if st.rays else w.n * nb
+        onchip = {"rays_per_s": n_rays / (k_ms * 1e-3),
+                  "reference_cells_per_s": st.cells_visited / (k_ms * 1e-3),
+                  "cells_per_ray": st.cells_visited / max(st.rays, 1),
+                  "hit_fraction": st.hits / max(st.rays, 1),
+                  "map_in_smem": int(st.map_in_smem),
+                  "issue_peak_warp_inst_per_s": sm_count * 4 * sm_hz,
+                  "scheduler_cycles_per_ray": (k_ms * 1e-3) * sm_count * 4 * sm_hz / max(n_rays, 1),
+                  "note": "scheduler_cycles_per_ray = kernel time x SMs x 4 schedulers x SM clock / rays: "
+                          "the issue-slot budget each ray consumed"}
+        if tables:
+            onchip.update({
+                "table_cells": int(st.table_cells), "table_particles": int(st.table_particles),
+                "table_misses": int(st.table_misses),
+                "table_entries_per_cell": ctx_ring_entries(ctx),
+                "rays_walked_for_tables_per_update": int(st.table_cells) * ctx_ring_entries(ctx),
+                "walk_probes_per_update": int(st.probes),
+                "table_lookups_per_s": n_rays / (k_ms * 1e-3),
+                "lookup_peak_per_s": lookup_peak,
+                "lookup_frac": (n_rays / (k_ms * 1e-3)) / lookup_peak,
+                "lookup_peak_source": "amclj_microbench: dependent byte lookups, all SMs x 32 warps, 64 KiB table in L1 "
+                                      "(each table look-up here carries ~55 more instructions: end point, ring index, mixture)"})
+        else:
+            onchip.update({
+                "probes_per_s": st.probes / (k_ms * 1e-3), "probes_per_ray": st.probes / max(st.rays, 1),
+                "lookup_peak_per_s": lookup_peak, "lookup_frac": (st.probes / (k_ms * 1e-3)) / lookup_peak,
+                "lookup_peak_source": "amclj_microbench: dependent lookups, all SMs x 32 warps, "
+                                      + ["128 KiB nibble table in shared memory", "64 MiB byte table in L2",
+                                         "64 KiB byte table in L1"][placement]})
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "kernel": "amclj::sensor_kernel",
+                    "traffic": traffic, "peak_source": peak_src,
+                    "kernel": "amclj::rt_lookup_kernel" if tables else "amclj::sensor_kernel",
                     "kernel_ms": k_ms, "kernel_share_of_step": k_ms / float(np.mean(total_ms_lib)),
+                    "sensor_stage_ms": stage_ms, "sensor_path": SENSOR_PATHS.get(path, str(path)),
                     "algorithmic_bytes_per_launch": alg_bytes,
-                    "note": "HBM is not what binds this kernel (16 B/particle): it is instruction-issue bound (ncu: ~82 % of scheduler cycles issue); see onchip",
-                    "onchip": {"rays_per_s": st.rays / (k_ms * 1e-3),
-                               "reference_cells_per_s": st.cells_visited / (k_ms * 1e-3),
-                               "probes_per_s": st.probes / (k_ms * 1e-3),
-                               "cells_per_ray": st.cells_visited / max(st.rays, 1),
-                               "probes_per_ray": st.probes / max(st.rays, 1),
-                               "hit_fraction": st.hits / max(st.rays, 1),
-                               "map_in_smem": int(st.map_in_smem),
-                               "lookup_peak_per_s": lookup_peak,
-                               "lookup_frac": (st.probes / (k_ms * 1e-3)) / lookup_peak,
-                               "lookup_peak_source": "amclj_microbench: dependent lookups, all SMs x 32 warps, "
-                                                     + ["128 KiB nibble table in shared memory", "64 MiB byte table in L2",
-                                                        "64 KiB byte table in L1"][placement],
-                               "issue_peak_warp_inst_per_s": sm_count * 4 * sm_hz,
-                               "scheduler_cycles_per_ray": (k_ms * 1e-3) * sm_count * 4 * sm_hz / max(st.rays, 1),
-                               "note": "scheduler_cycles_per_ray = kernel time x SMs x 4 schedulers x SM clock / rays: "
-                                       "the issue-slot budget each ray consumed (ncu: ~80% of them issue an instruction)"}}
+                    "note": "HBM is not what binds this kernel (16 B/particle): it is instruction-issue bound "
+                            "(ncu, profiles/: 71-85 % of scheduler cycles issue); see onchip",
+                    "onchip": onchip}
         cpu = None
         if world == 1 and not args.quick:
             from amclj_b200 import workloads as wl
@@ -400,7 +452,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_of(args, w, extra={"parallelism": f"particles sharded x{world}, map replicated"}),
             "updates_per_s": 1e3 / ms_per_step, "particles_total": n_total,
-            "e2e": e2e, "gpu_launches": (KERNELS_PER_UPDATE if world == 1 else KERNELS_PER_UPDATE_SHARDED) * args.steps,
+            "e2e": e2e, "gpu_launches": int(np.sum(launches)),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
             "wall_s_timed_loop": t_wall,
             "same_share_single_gpu": None if same_share is None else {
@@ -408,7 +460,8 @@ def run_b200(args):
                 "sharded_over_single": same_share / ms_per_step,
                 "note": "each rank's share run as a plain 1-GPU update (no collectives); the ratio is the "
                         "efficiency of the sharded update against the same per-GPU work"},
-            "stage_ms": {"motion": None, "sensor": k_ms, "total_lib_events": float(np.mean(total_ms_lib))},
+            "stage_ms": {"motion": None, "sensor": stage_ms, "sensor_main_kernel": k_ms,
+                         "total_lib_events": float(np.mean(total_ms_lib))},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -75,7 +75,8 @@ typedef struct amclj_params {
   int32_t s9_pr_rot1_variance;
   /* S10 sensor.clj:78-81,142 — 0: base->laser offset ignored (REF and NS default) */
   int32_t s10_apply_laser_offset;
-  int32_t collect_stats; /* count cells visited / probes (small cost) */
+  int32_t collect_stats; /* bit 0: count cells visited / probes (diagnostic kernels); bit 1: time the dominant
+                          * sensor kernel alone (amclj_stats.ms_sensor_main; two more event records per update) */
   /* distance-field placement: 0 auto (maps whose 32 directional planes fit 64 MB: the planes,
    * walked in place for a compact particle cloud and in map-tile order for a spread-out one;
    * larger maps: one byte per cell in L2), 1 isotropic nibbles in shared memory, 2 isotropic bytes
@@ -116,6 +117,9 @@ typedef struct amclj_stats {
   uint64_t table_cells;     /* diagnostic passes only: start cells that got a ray table (0: the walk kernel ran) */
   uint64_t table_particles; /* ... and the particles standing on them */
   uint64_t table_misses;    /* ... and their rays whose end cell was not in the table (walked instead; expected 0) */
+  double ms_sensor_main;    /* the dominant kernel of the last sensor pass alone (sensor_kernel, or rt_lookup_kernel) */
+  int32_t sensor_path;      /* what the last sensor pass ran on: 0 walk in map-tile order, 1 walk in place, 2 ray tables, -1 not known yet */
+  int32_t kernels_launched; /* kernels the last filter update enqueued */
 } amclj_stats;
 
 typedef struct amclj_ctx amclj_ctx;
@@ -177,6 +181,9 @@ int32_t amclj_raycast_debug(amclj_ctx *ctx, int32_t n, float angle_min, float an
                             int32_t *hit_y, int32_t *steps, uint8_t *hit, float *range_m);
 /* Number of beams selected by S6 for an n-beam scan. */
 int32_t amclj_beams_used(const amclj_ctx *ctx, int32_t n);
+/* Entries of one per-start-cell ray table for the staged scan geometry (the end cells a ray of that
+ * length can reach, sensor.clj:130-135), or 0 when the ray-table path is unavailable. */
+int32_t amclj_ray_table_entries(const amclj_ctx *ctx);
 
 /* ---- normalise + resample: roulette-selection pf.clj:156-167 ----------------------- */
 /* Linear weights (w = raw, or exp(raw - max raw) under S7) -> fixed point
