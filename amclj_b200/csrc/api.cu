@@ -184,16 +184,21 @@ int df_mode_of(const amclj_ctx *ctx) {
  * circle of radius r.  The ring keeps every cell whose square of half-side 1.05 does (the 0.05
  * covers the fp32 arithmetic of the end point, ~1e-4 cells); per row the admissible |ex| form one
  * interval.  An end cell outside the ring (never seen) makes the kernel walk that ray instead. */
+void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode);
+
 int stage_ring(amclj_ctx *ctx, double r) {
   RayTables &t = ctx->rt;
+  const bool tables_wanted = ctx->rt_enable && (ctx->p.df_mode == 0 || ctx->p.df_mode == 6);
   t.available = false;
-  if (!ctx->rt_enable || !(ctx->p.df_mode == 0 || ctx->p.df_mode == 6)) return AMCLJ_OK;
   if (t.r_cells == r && t.rows) {
-    t.available = t.n_entries > 0;
+    t.have_ring = t.n_entries > 0;
+    t.available = t.have_ring && tables_wanted;
     return AMCLJ_OK;
   }
   t.r_cells = r;
   t.n_entries = 0;
+  t.have_ring = false;
+  t.recs_mode = -1;
   const double half = 1.05;
   if (!(r + 2.0 * half < 30000.0)) return AMCLJ_OK; /* offsets are stored as 16-bit values */
   const int E = (int)ceil(r + half);
@@ -241,7 +246,8 @@ int stage_ring(amclj_ctx *ctx, double r) {
   t.nrows = (int)rows.size();
   t.E = E;
   t.n_entries = (int)ents.size();
-  t.available = true;
+  t.have_ring = true;
+  t.available = tables_wanted;
   return AMCLJ_OK;
 }
 
@@ -378,6 +384,34 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
   }
   int rrc = stage_ring(ctx, rcells);
   if (rrc) return rrc;
+  /* line set-up records of the walk kernel: one per ring cell, for the field placement it will run on */
+  RayTables &rt = ctx->rt;
+  rt.floor_trick_ok = (double)(ctx->map.W > ctx->map.H ? ctx->map.W : ctx->map.H) + rcells + 4.0 < 4.0e6;
+  if (rt.have_ring && ctx->ring_setup && rt.n_entries <= 8192 && rt.floor_trick_ok) {
+    int walk_mode = (ctx->p.df_mode == 0 && ctx->map.wedge) ? DF_WEDGE8 : mode;
+    /* what the records depend on; rebuilt only when any of it changed */
+    const long long key[6] = {(long long)walk_mode, (long long)p.s3_proper_endpoint, (long long)p.s4_endpoint_termination,
+                              (long long)ctx->map_gen, (long long)d.wide * 1000 + d.dcap, (long long)d.n};
+    if (rt.recs_mode != walk_mode || memcmp(key, rt.recs_key, sizeof(key)) != 0 || rt.recs_r != rcells) {
+      rt.recs_mode = -1;
+      if (2 * rt.n_entries > rt.recs_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        dfree(rt.recs);
+        rt.recs_cap = 0;
+        CK(dalloc(&rt.recs, (size_t)2 * rt.n_entries));
+        rt.recs_cap = 2 * rt.n_entries;
+      }
+      b.staged = true; /* fill_sensor_args reads the staged tables */
+      SensorLaunch a;
+      fill_sensor_args(ctx, a, walk_mode);
+      CK(launch_ring_records(a, walk_mode, rt.ents, rt.n_entries, rt.recs, ctx->stream));
+      memcpy(rt.recs_key, key, sizeof(key));
+      rt.recs_r = rcells;
+      rt.recs_mode = walk_mode;
+    }
+  } else {
+    rt.recs_mode = -1;
+  }
   b.staged = true;
   return AMCLJ_OK;
 }
@@ -423,6 +457,15 @@ void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode) {
   a.k2 = (float)((double)a.inv2s2 * 1.4426950408889634);
   a.laser_x = p.laser_x;
   a.laser_y = p.laser_y;
+  const RayTables &rt = ctx->rt;
+  if (rt.have_ring && rt.recs_mode == mode && rt.recs) {
+    a.ring_rows = rt.rows;
+    a.ring_recs = rt.recs;
+    a.ring_nrows = rt.nrows;
+    a.ring_E = rt.E;
+    a.ring_entries = rt.n_entries;
+    a.ring_ok = rt.floor_trick_ok ? 1 : 0;
+  }
 }
 
 /* enqueue motion + sensor on the ctx stream */
@@ -560,6 +603,10 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
     b.chunks = a.chunks; b.partials = a.partials; b.stats = a.stats;
     a = b;
   }
+  /* the per-ring-cell set-up records pay when neighbouring lanes read neighbouring records (a compact
+   * cloud: C2 on the walk kernel 0.411 -> 0.373 ms); a spread-out cloud scatters the 48 bytes per ray
+   * over the banks (C3: 3.95 -> 4.00 ms), so it keeps computing its set-up */
+  if (hint == 0 || ctx->p.df_mode == 5) a.ring_ok = 0;
   if (ordered || use_rt) {
     if (!ctx->bbox_done) {
       CK(launch_bbox(ctx->x, ctx->y, ctx->n, ctx->bbox, ctx->sm_count, ctx->stream));
@@ -837,6 +884,7 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
   if (const char *e = getenv("AMCLJ_REFILL_GLOBAL")) ctx->refill_global = atoi(e);
   if (const char *e = getenv("AMCLJ_COMPACT_CELLS")) ctx->compact_cells = (float)atof(e);
   if (const char *e = getenv("AMCLJ_RAYTABLE")) ctx->rt_enable = atoi(e) != 0;
+  if (const char *e = getenv("AMCLJ_RING_SETUP")) ctx->ring_setup = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_TIME_MAIN")) ctx->time_main_env = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_RT_THR")) ctx->rt.thr = atoi(e);
   if (const char *e = getenv("AMCLJ_RT_WAVES")) ctx->rt.waves = atoi(e);
@@ -893,7 +941,7 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
     for (int k = 0; k < 7; k++)
       if (ctx->ipc_opened[g][k]) cudaIpcCloseMemHandle(ctx->ipc_opened[g][k]);
   dfree(ctx->stage_out); dfree(ctx->stage_in); dfree(ctx->stage_idx);
-  dfree(ctx->rt.rows); dfree(ctx->rt.ents); dfree(ctx->rt.pstate); dfree(ctx->rt.bins); dfree(ctx->rt.item0); dfree(ctx->rt.slots); dfree(ctx->rt.ctl);
+  dfree(ctx->rt.rows); dfree(ctx->rt.ents); dfree(ctx->rt.recs); dfree(ctx->rt.pstate); dfree(ctx->rt.bins); dfree(ctx->rt.item0); dfree(ctx->rt.slots); dfree(ctx->rt.ctl);
   if (ctx->rt.tables) cudaFree(ctx->rt.tables);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->pin_tab) cudaFreeHost(ctx->pin_tab);
@@ -987,6 +1035,8 @@ int32_t amclj_set_map(amclj_ctx *ctx, const int8_t *cells, int32_t width, int32_
   ctx->beams.staged = false;
   ctx->divs.n = 0;
   *ctx->pin_decision = -1; /* a new map: no hint about the cloud */
+  ctx->map_gen++;
+  ctx->rt.recs_mode = -1;
   ctx->st.map_in_smem = m.fits_smem;
   return AMCLJ_OK;
 }

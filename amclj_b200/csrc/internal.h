@@ -72,6 +72,11 @@ struct SensorLaunch {
   int32_t s1, s3, s4, s7, s10;
   float z_hit, inv2s2, laser_x, laser_y;
   float k2;  // inv2s2 * log2(e): the hit Gaussian is one ex2
+  // ring of end cells around the start cell and one line set-up record per ring cell (walk kernel)
+  const uint4 *ring_rows;
+  const uint4 *ring_recs;
+  int32_t ring_nrows, ring_E, ring_entries;
+  int32_t ring_ok;   // records match this launch (mode, switches, map, geometry) and every end cell quotient stays below 2^22
   uint32_t *rawmax_ord;          // ordered-uint max of raw (may be null)
   unsigned long long *stats;     // rays, cells, probes, hits (may be null)
   // parity probe
@@ -116,7 +121,13 @@ struct RayTables {
   short2 *ents = nullptr;   // entry -> (ex, ey); x = -32768 marks the unused slot of a merged row
   int32_t nrows = 0, E = 0, n_entries = 0, rows_cap = 0, ents_cap = 0;
   double r_cells = -1.0;
-  bool available = false;
+  bool have_ring = false;     // rows / ents describe the staged scan geometry
+  bool available = false;     // ... and the ray-table path may use them
+  uint4 *recs = nullptr;      // [2 * n_entries] line set-up records of the walk kernel (sensor.cu)
+  int32_t recs_cap = 0, recs_mode = -1;
+  long long recs_key[6] = {0, 0, 0, 0, 0, 0};
+  double recs_r = -1.0;
+  bool floor_trick_ok = false; // every end-cell quotient of a start inside the map stays below 2^22   // the field placement the records were built for (-1: none)
   uint32_t *bins = nullptr;   // [RT_BIN_CAP] particles per start cell, then write cursors
   RtSlot *slots = nullptr;    // [RT_BIN_CAP] the dense cells, one table each
   int32_t *item0 = nullptr;   // [RT_BIN_CAP + 1] first work item of each dense cell
@@ -228,6 +239,8 @@ struct amclj_ctx {
   uint32_t *hist = nullptr;           // 256-bin histogram of the radix select
   int32_t force_chunks = 0;
   amclj::RayTables rt;
+  int64_t map_gen = 0;     // bumped by every set_map
+  bool ring_setup = true;  // walk kernel reads its line set-up from per-ring-cell records (AMCLJ_RING_SETUP=0: computes it)
   bool rt_enable = true;   // auto policy may take the ray-table path (AMCLJ_RAYTABLE=0 turns it off)
   void *pinned = nullptr;  // small pinned scratch for scalar readbacks
   void *pin_tab = nullptr; // pinned staging of the beam table
@@ -245,6 +258,8 @@ cudaError_t rt_prepare_device();
 constexpr int WEDGE_BINS = 4;                   /* slope bins per octant */
 constexpr int WEDGE_CLASSES = 8 * WEDGE_BINS;   /* steep x xs x ys x bin */
 cudaError_t build_wedge_fields(amclj_ctx *c, cudaStream_t s);
+cudaError_t launch_ring_records(const SensorLaunch &a, int mode, const short2 *ents, int n_entries, uint4 *recs,
+                                cudaStream_t s);
 int sensor_chunks(const amclj_ctx *c, int64_t n, int nb);
 
 // filter.cu

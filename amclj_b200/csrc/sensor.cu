@@ -48,7 +48,7 @@ constexpr int mode_threads(int mode) {
   return mode == DF_WEDGE8 ? WEDGE_THREADS : (mode == DF_SMEM4 ? kMaxThreads : GLOBAL_THREADS);
 }
 constexpr int mode_ctas(int mode) { return mode == DF_WEDGE8 ? WEDGE_CTAS : (mode == DF_SMEM4 ? 1 : GLOBAL_CTAS); }
-template <int MODE, bool DIAG, bool WIDE, bool TS>
+template <int MODE, bool DIAG, bool WIDE, bool TS, bool RS>
 __global__ void __launch_bounds__(mode_threads(MODE), mode_ctas(MODE))
 sensor_kernel(const SensorLaunch a) {
   extern __shared__ uint4 smem_dyn[];
@@ -104,6 +104,8 @@ sensor_kernel(const SensorLaunch a) {
   tb.dir = reinterpret_cast<const float2 *>(a.beam + 4 * (size_t)a.nb);
   tb.div = a.divtab;
   tb.s_dir = tb.s_mix = tb.s_div = 0;
+  uint32_t s_rows = 0, s_recs = 0;
+  const uint32_t ring_last_row = (uint32_t)a.ring_nrows - 1u;
   if (TS) {
     /* [field | mix float4[nb] | dir float2[nb] | div uint2[ndiv]] */
     uint8_t *base = reinterpret_cast<uint8_t *>(smem_dyn) + (MODE == DF_SMEM4 ? a.df_bytes : 0);
@@ -116,6 +118,14 @@ sensor_kernel(const SensorLaunch a) {
     /* keep the three window addresses in registers: left alone, the compiler rebuilds each of
      * them from SR_CgaCtaId at every use */
     asm volatile("" : "+r"(tb.s_mix), "+r"(tb.s_dir), "+r"(tb.s_div));
+    if (RS) { /* | rows uint4[ring_nrows] | set-up records uint4[2 * ring_entries] (16-byte aligned) */
+      uint4 *srows = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(sdiv + a.ndiv) + 15) & ~(uintptr_t)15);
+      uint4 *srecs = srows + a.ring_nrows;
+      for (int i = threadIdx.x; i < a.ring_nrows; i += blockDim.x) srows[i] = __ldg(a.ring_rows + i);
+      for (int i = threadIdx.x; i < 2 * a.ring_entries; i += blockDim.x) srecs[i] = __ldg(a.ring_recs + i);
+      s_rows = smem_u32(srows); s_recs = smem_u32(srecs);
+      asm volatile("" : "+r"(s_rows), "+r"(s_recs));
+    }
     __syncthreads();
   }
   const ResDiv rdv = make_resdiv(a.res);
@@ -158,6 +168,7 @@ sensor_kernel(const SensorLaunch a) {
     /* padded field: cell (x, y) lives at (y+1)*row + (x+1); entry 0 is a ring cell (d = 0),
      * which makes an out-of-range start an immediate hit (the start cell is tested first) */
     const int idx0 = start_in ? (y0 + 1) * row + (x0 + 1) * idx_scale : 0;
+    const int xoff = 0x4B400000 + x0, yoff = 0x4B400000 + y0 - a.ring_E; /* RS: end cell relative to the start, see below */
     const bool dbg = DIAG && a.dbg_count > 0 && valid && p >= a.dbg_first && p < a.dbg_first + a.dbg_count;
 
     /* the ray in flight; a parked lane (am == 0) turns every update below into a no-op */
@@ -224,9 +235,48 @@ sensor_kernel(const SensorLaunch a) {
             s = fmaf(st, cb, ct * sb);
           }
           /* sensor.clj:99-103 project-pose, map.clj:36-46 world->map */
+          const float ex_w = fmaf(a.R, c, ox), ey_w = fmaf(a.R, s, oy);
+          bool from_table = false;
+          if (RS) {
+            /* Everything sensor.clj:130-139 derives after the two roundings (steep?, the swaps, calc-step,
+             * dx, dy, the miss rule, the reciprocal, the strides and the direction class) depends only on
+             * the end cell RELATIVE to the start cell, and that offset lies on a thin ring around the
+             * circle of the ray's length: one record per ring cell, filled once per scan geometry
+             * (ring_records_kernel below, from this very code), read here with two LDS.128.
+             * floor(q + 0.5) as an FP32 add with round-down against 1.5 * 2^23 (exact below 2^22, which
+             * the host checks for every start inside the map; a start outside hits at step 0 whatever
+             * record it gets, so its garbage offset only has to stay inside the table). */
+            const float qx0 = ex_w * rdv.r, qy0 = ey_w * rdv.r;
+            const float qx = fmaf(fmaf(-qx0, rdv.res, ex_w), rdv.r, qx0);
+            const float qy = fmaf(fmaf(-qy0, rdv.res, ey_w), rdv.r, qy0);
+            const int ex = __float_as_int(__fadd_rd(qx + 0.5f, 12582912.0f)) - xoff;
+            const uint32_t ry = (uint32_t)(__float_as_int(__fadd_rd(qy + 0.5f, 12582912.0f)) - yoff);
+            const uint32_t ryc = min(ry, ring_last_row);
+            uint4 rw;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rw.x), "=r"(rw.y), "=r"(rw.z), "=r"(rw.w) : "r"(s_rows + ryc * 16u));
+            const uint32_t tt = (uint32_t)abs(ex) - rw.y;
+            const bool ok = tt < rw.z && ry <= ring_last_row;
+            from_table = ok || !start_in;
+            if (from_table) {
+              const uint32_t ent = ok ? tt + (ex < 0 ? rw.w : rw.x) : 0u;
+              uint4 r0, r1;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(s_recs + ent * 32u));
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(s_recs + ent * 32u + 16u));
+              dy = (int)r0.x; ndx = (int)r0.y; kmax = (int)r0.z; M = r0.w;
+              sh = WIDE ? (r1.x & 31u) : 0u; stepA = (int)r1.y; stepB = (int)r1.z;
+              idx = (uint32_t)idx0 + (start_in ? r1.w : 0u);
+              k = 0; j = 0; err = 0;
+              if (DIAG) {
+                const bool steep = (r1.x >> 8) & 1u;
+                dg_a0 = steep ? y0 : x0; dg_b0 = steep ? x0 : y0;
+                dg_xs = (r1.x >> 9) & 1u ? -1 : 1; dg_ys = (r1.x >> 10) & 1u ? -1 : 1; dg_steep = steep; dg_probes = 0;
+              }
+            }
+          }
+          if (!from_table) {
           int x1, y1;
-          if (rdv.lim > 0.0f) round_cell2_inrange(fmaf(a.R, c, ox), fmaf(a.R, s, oy), rdv, x1, y1);
-          else round_cell2_fast(fmaf(a.R, c, ox), fmaf(a.R, s, oy), rdv, x1, y1); /* odd resolutions: real divides */
+          if (rdv.lim > 0.0f) round_cell2_inrange(ex_w, ey_w, rdv, x1, y1);
+          else round_cell2_fast(ex_w, ey_w, rdv, x1, y1); /* odd resolutions: real divides */
           int adx = abs(x1 - x0), ady = abs(y1 - y0);
           bool steep = ady > adx; /* sensor.clj:87-91 */
           int a0 = steep ? y0 : x0, b0 = steep ? x0 : y0;
@@ -267,6 +317,7 @@ sensor_kernel(const SensorLaunch a) {
             idx += off;
           }
           if (DIAG) { dg_a0 = a0; dg_b0 = b0; dg_xs = xs; dg_ys = ys; dg_steep = steep; dg_probes = 0; }
+          }
           have_ray = true;
           am = DMASK;
         }
@@ -350,12 +401,60 @@ combine_kernel(const long long *__restrict__ part, int chunks, int64_t n, float 
   if ((threadIdx.x & 31) == 0 && rawmax_ord && v > -INFINITY) atomicMax(rawmax_ord, ord_of_float(v));
 }
 
-static size_t table_bytes(const SensorLaunch &a) { return (size_t)a.nb * 24 + (size_t)a.ndiv * 8; }
+// One set-up record per ring cell (ex, ey) = end cell - start cell: the line parameters the walk
+// starts from, computed by the same expressions as set-up (2) above.
+//   rec[2e]   = {dy, -dx, kmax, M}    rec[2e+1] = {sh | steep << 8 | (xs<0) << 9 | (ys<0) << 10, stepA, stepB, class offset}
+__global__ void __launch_bounds__(256)
+ring_records_kernel(const SensorLaunch a, int mode, const short2 *__restrict__ ents, int n_entries, uint4 *recs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_entries) return;
+  const short2 en = ents[i];
+  if (en.x <= -32767) { /* unused slot / sentinel: never indexed by a valid offset */
+    recs[2 * i] = make_uint4(0u, (uint32_t)-1, 0u, 0u);
+    recs[2 * i + 1] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const bool bytes = mode == DF_GLOBAL8 || mode == DF_WEDGE8;
+  const int idx_scale = bytes ? 1 : 4, row = a.row_nib * idx_scale;
+  const int ex = en.x, ey = en.y;
+  const bool steep = abs(ey) > abs(ex);                       /* sensor.clj:87-91 */
+  const int da = steep ? ey : (a.s3 ? ex : 0), db = steep ? ex : (a.s3 ? ey : 0); /* :137-138 */
+  const int xs = da > 0 ? 1 : -1, ys = db > 0 ? 1 : -1;       /* :108-110, ties -> -1 */
+  int dx = abs(da), dy = abs(db), kmax;
+  if (a.s4) kmax = dx;
+  else if (xs > 0) kmax = dx + 1;
+  else if (dx > 0) kmax = 0;
+  else { kmax = 0x3fffffff; dx = 1; dy = 1; }
+  const uint2 e = a.divtab[min(dx, a.ndiv - 1)];
+  const int stepA = xs * (steep ? row : idx_scale), stepB = ys * (steep ? idx_scale : row);
+  uint32_t off = 0;
+  if (mode == DF_WEDGE8) {
+    const uint32_t P = (uint32_t)a.wedge_plane;
+    off = steep ? 4 * WEDGE_BINS * P : 0;
+    off += xs < 0 ? 2 * WEDGE_BINS * P : 0;
+    off += ys < 0 ? WEDGE_BINS * P : 0;
+    const int dyb = dy * WEDGE_BINS;
+    for (int t = 1; t < WEDGE_BINS; t++) off += (dyb >= t * dx) ? P : 0;
+  }
+  const uint32_t flags = (steep ? 1u : 0u) | (xs < 0 ? 2u : 0u) | (ys < 0 ? 4u : 0u);
+  recs[2 * i] = make_uint4((uint32_t)dy, (uint32_t)(-dx), (uint32_t)kmax, e.x);
+  recs[2 * i + 1] = make_uint4((e.y & 31u) | (flags << 8), (uint32_t)stepA, (uint32_t)stepB, off);
+}
 
-template <int MODE, bool DIAG, bool WIDE, bool TS>
+cudaError_t launch_ring_records(const SensorLaunch &a, int mode, const short2 *ents, int n_entries, uint4 *recs,
+                                cudaStream_t s) {
+  if (n_entries <= 0) return cudaSuccess;
+  ring_records_kernel<<<(n_entries + 255) / 256, 256, 0, s>>>(a, mode, ents, n_entries, recs);
+  return cudaGetLastError();
+}
+
+static size_t table_bytes(const SensorLaunch &a) { return (size_t)a.nb * 24 + (size_t)a.ndiv * 8; }
+static size_t ring_bytes(const SensorLaunch &a) { return 16 + (size_t)a.ring_nrows * 16 + (size_t)a.ring_entries * 32; }
+
+template <int MODE, bool DIAG, bool WIDE, bool TS, bool RS>
 static cudaError_t launch_t(const amclj_ctx *c, const SensorLaunch &a, cudaStream_t s) {
-  auto kern = sensor_kernel<MODE, DIAG, WIDE, TS>;
-  size_t smem = (MODE == DF_SMEM4 ? a.df_bytes : 0) + (TS ? table_bytes(a) : 0);
+  auto kern = sensor_kernel<MODE, DIAG, WIDE, TS, RS>;
+  size_t smem = (MODE == DF_SMEM4 ? a.df_bytes : 0) + (TS ? table_bytes(a) : 0) + (RS ? ring_bytes(a) : 0);
   if (smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -375,19 +474,24 @@ static cudaError_t launch_t(const amclj_ctx *c, const SensorLaunch &a, cudaStrea
   return cudaGetLastError();
 }
 
-template <int MODE, bool TS>
+template <int MODE, bool TS, bool RS>
 static cudaError_t launch_w(const amclj_ctx *c, const SensorLaunch &a, bool diag, bool wide,
                             cudaStream_t s) {
-  if (diag) return wide ? launch_t<MODE, true, true, TS>(c, a, s) : launch_t<MODE, true, false, TS>(c, a, s);
-  return wide ? launch_t<MODE, false, true, TS>(c, a, s) : launch_t<MODE, false, false, TS>(c, a, s);
+  if (diag) return wide ? launch_t<MODE, true, true, TS, RS>(c, a, s) : launch_t<MODE, true, false, TS, RS>(c, a, s);
+  return wide ? launch_t<MODE, false, true, TS, RS>(c, a, s) : launch_t<MODE, false, false, TS, RS>(c, a, s);
 }
 template <int MODE>
 static cudaError_t launch_m(const amclj_ctx *c, const SensorLaunch &a, bool diag, bool wide,
                             cudaStream_t s) {
-  /* tables ride in shared memory behind the field when the SM has room for them */
-  size_t need = (MODE == DF_SMEM4 ? a.df_bytes : 0) + table_bytes(a) + 64;
-  bool ts = need <= (size_t)c->max_smem_optin;
-  return ts ? launch_w<MODE, true>(c, a, diag, wide, s) : launch_w<MODE, false>(c, a, diag, wide, s);
+  /* tables ride in shared memory behind the field when the SM has room for them; so do the ring
+   * rows and set-up records (CTAs per SM share the budget) */
+  const size_t field = MODE == DF_SMEM4 ? a.df_bytes : 0;
+  const size_t per_sm = MODE == DF_SMEM4 ? 1 : (MODE == DF_WEDGE8 ? WEDGE_CTAS : (GLOBAL_CTAS > 2 ? GLOBAL_CTAS : 2));
+  const size_t budget = (size_t)c->max_smem_optin / per_sm;
+  bool ts = field + table_bytes(a) + 64 <= (size_t)c->max_smem_optin;
+  bool rs = ts && a.ring_ok && a.ring_recs && field + table_bytes(a) + ring_bytes(a) + 1024 <= budget;
+  if (rs) return launch_w<MODE, true, true>(c, a, diag, wide, s);
+  return ts ? launch_w<MODE, true, false>(c, a, diag, wide, s) : launch_w<MODE, false, false>(c, a, diag, wide, s);
 }
 
 /* beams of one particle group are split into `chunks` warp tasks when there are too few
