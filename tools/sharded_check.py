@@ -1,6 +1,9 @@
 """torchrun worker: sharded filter update on G GPUs vs the same update on one GPU.
 
-  python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 tools/sharded_check.py [N]
+  python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 tools/sharded_check.py [N] [pull|a2a] [spread|dense]
+
+`dense` shards a pose-tracking cloud (C2's gaussian), which every rank runs on the per-cell ray
+tables (three updates, so that the policy's hint has settled); `spread` (default) is C3's uniform cloud.
 
 Every rank runs its shard through amclj_b200.sharded.ShardedFilter (NCCL all-reduce(max),
 all-gather(totals), all-to-all rebalance); rank 0 also runs all N particles on its own GPU
@@ -27,7 +30,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    w = workloads.c3(n)
+    cloud = sys.argv[3] if len(sys.argv) > 3 else "spread"
+    w = workloads.c2(n) if cloud == "dense" else workloads.c3(n)
+    updates = 3 if cloud == "dense" else 2
     s = w.scan
     lo, cnt = slots_of(rank, world, n)
     ctx = _lib.Context(local, "NS")
@@ -39,7 +44,7 @@ def main():
     with torch.cuda.stream(stream):
         f = ShardedFilter(ctx, rank, world, n, dev, mode=mode)
         f.stage_scan(s)
-        for it in range(2):  # two consecutive updates: the second starts from rebalanced shards
+        for it in range(updates):  # consecutive updates: the later ones start from rebalanced shards
             f.update(w.curr, w.prev, seed=77 + it, u0=w.u0)
         torch.cuda.synchronize()
     x, y, t, wt = ctx.get_particles()
@@ -51,13 +56,13 @@ def main():
         ref = _lib.Context(local, "NS")
         ref.set_map(w.grid)
         ref.set_particles(w.x, w.y, w.theta)
-        for it in range(2):
+        for it in range(updates):
             ref.filter_update(w.curr, w.prev, s.ranges, s.angle_min, s.angle_inc, s.range_max, w.u0, seed=77 + it)
         rx, ry, rt, rw = ref.get_particles()
         full = np.concatenate(got, axis=0)
         ok = (np.array_equal(full[:, 0], rx) and np.array_equal(full[:, 1], ry) and np.array_equal(full[:, 2], rt)
               and np.allclose(full[:, 3], rw))
-        print(f"SHARDED_GPU_{'OK' if ok else 'MISMATCH'} mode={mode} world={world} n={n} "
+        print(f"SHARDED_GPU_{'OK' if ok else 'MISMATCH'} mode={mode} cloud={cloud} world={world} n={n} "
               f"mismatching_slots={(full[:, 0] != rx).sum()}", flush=True)
         ref.close()
     dist.barrier()
