@@ -457,6 +457,8 @@ void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode) {
   a.k2 = (float)((double)a.inv2s2 * 1.4426950408889634);
   a.laser_x = p.laser_x;
   a.laser_y = p.laser_y;
+  a.walk_ctr = ctx->walk_ctr;
+  a.walk_tail_pct = ctx->walk_tail_pct;
   const RayTables &rt = ctx->rt;
   if (rt.have_ring && rt.recs_mode == mode && rt.recs) {
     a.ring_rows = rt.rows;
@@ -607,6 +609,10 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
    * cloud: C2 on the walk kernel 0.411 -> 0.373 ms); a spread-out cloud scatters the 48 bytes per ray
    * over the banks (C3: 3.95 -> 4.00 ms), so it keeps computing its set-up */
   if (hint == 0 || ctx->p.df_mode == 5) a.ring_ok = 0;
+  /* task distribution: a spread-out cloud walked in tile order gains from CTA-contiguous runs drawn
+   * through a shared counter (C3: 3.95 -> 3.82 ms); a compact cloud split into beam chunks does not
+   * (C2 on the walk kernel: 0.372 -> 0.381 ms) and keeps the fixed interleaved shares */
+  if (!(hint == 0 || ctx->p.df_mode == 5)) a.walk_tail_pct = -1;
   if (ordered || use_rt) {
     if (!ctx->bbox_done) {
       CK(launch_bbox(ctx->x, ctx->y, ctx->n, ctx->bbox, ctx->sm_count, ctx->stream));
@@ -885,6 +891,7 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
   if (const char *e = getenv("AMCLJ_COMPACT_CELLS")) ctx->compact_cells = (float)atof(e);
   if (const char *e = getenv("AMCLJ_RAYTABLE")) ctx->rt_enable = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_RING_SETUP")) ctx->ring_setup = atoi(e) != 0;
+  if (const char *e = getenv("AMCLJ_WALK_TAIL_PCT")) ctx->walk_tail_pct = atoi(e) > 100 ? 100 : atoi(e);
   if (const char *e = getenv("AMCLJ_TIME_MAIN")) ctx->time_main_env = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_RT_THR")) ctx->rt.thr = atoi(e);
   if (const char *e = getenv("AMCLJ_RT_WAVES")) ctx->rt.waves = atoi(e);
@@ -908,7 +915,7 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
     ok = cudaMemset(ctx->ctrl, 0, sizeof(uint64_t) * ((size_t)ctx->scan_state_cap + 5)) == cudaSuccess;
   }
   ok = ok && dalloc(&ctx->rawmax, 1) == cudaSuccess && dalloc(&ctx->stats, 12) == cudaSuccess &&
-       dalloc(&ctx->plan, 1) == cudaSuccess && dalloc(&ctx->decision, 1) == cudaSuccess && dalloc(&ctx->totals_all, MAX_WORLD) == cudaSuccess &&
+       dalloc(&ctx->plan, 1) == cudaSuccess && dalloc(&ctx->decision, 1) == cudaSuccess && dalloc(&ctx->walk_ctr, 2) == cudaSuccess && dalloc(&ctx->totals_all, MAX_WORLD) == cudaSuccess &&
        dalloc(&ctx->pose_part, (size_t)pose_blocks() * 4) == cudaSuccess &&
        cudaMallocHost(&ctx->pinned, 4096) == cudaSuccess;
   if (ok) {
@@ -917,6 +924,7 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
     ok = cudaMemset(ctx->decision, 0xff, sizeof(int32_t)) == cudaSuccess;
   }
   if (ok) ok = cudaMemset(ctx->stats, 0, 12 * sizeof(unsigned long long)) == cudaSuccess;
+  if (ok) ok = cudaMemset(ctx->walk_ctr, 0, 2 * sizeof(uint32_t)) == cudaSuccess;
   if (!ok) {
     amclj_destroy(ctx);
     return AMCLJ_ERR_CUDA;
@@ -935,7 +943,7 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
   dfree(ctx->x); dfree(ctx->y); dfree(ctx->th); dfree(ctx->w); dfree(ctx->raw);
   dfree(ctx->x2); dfree(ctx->y2); dfree(ctx->th2); dfree(ctx->w2);
   dfree(ctx->cdf); dfree(ctx->idx); dfree(ctx->normals); dfree(ctx->partials); dfree(ctx->perm); dfree(ctx->tile_counters);
-  dfree(ctx->ctrl); dfree(ctx->rawmax); dfree(ctx->stats);
+  dfree(ctx->ctrl); dfree(ctx->rawmax); dfree(ctx->stats); dfree(ctx->walk_ctr);
   dfree(ctx->pose_part); dfree(ctx->plan); dfree(ctx->hist); dfree(ctx->totals_all); dfree(ctx->decision);
   for (int g = 0; g < MAX_WORLD; g++)
     for (int k = 0; k < 7; k++)

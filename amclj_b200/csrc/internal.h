@@ -66,6 +66,8 @@ struct SensorLaunch {
   float compact_m;       // bounding-box side (metres) up to which the particle set counts as compact
   const int32_t *perm;   // walking order (particle indices sorted by map tile), or null
   int32_t *decision;     // out: 1 when the cloud was compact (host hint for the next update)
+  uint32_t *walk_ctr;        // {next task of the common tail, CTAs finished}: zero between launches
+  int32_t walk_tail_pct;     // share of the tasks drawn dynamically at the end (< 0: fixed interleaved shares)
   const int32_t *skip_flag;  // when set and *skip_flag == 1 the ray-table path took this update: return at once
   float R;            // ray length (S2)
   float miss_value;
@@ -239,6 +241,8 @@ struct amclj_ctx {
   uint32_t *hist = nullptr;           // 256-bin histogram of the radix select
   int32_t force_chunks = 0;
   amclj::RayTables rt;
+  uint32_t *walk_ctr = nullptr;  // device {tail counter, CTAs finished} of the walk kernel
+  int32_t walk_tail_pct = 0;   // spread-out clouds: CTA-contiguous task runs, this share of the tasks as a common tail
   int64_t map_gen = 0;     // bumped by every set_map
   bool ring_setup = true;  // walk kernel reads its line set-up from per-ring-cell records (AMCLJ_RING_SETUP=0: computes it)
   bool rt_enable = true;   // auto policy may take the ray-table path (AMCLJ_RAYTABLE=0 turns it off)

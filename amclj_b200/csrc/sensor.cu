@@ -145,7 +145,40 @@ sensor_kernel(const SensorLaunch a) {
 
   /* task = 32 consecutive particles (in walking order) x one chunk of beams; the warps of a CTA
    * take consecutive tasks, i.e. neighbouring particles */
-  for (int64_t task = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); task < ntasks; task += nwarps) {
+  /* Distribution (a.walk_tail_pct >= 0): every CTA owns a contiguous run of the first tasks (its warps
+   * draw from it through a shared counter, so neighbouring particles still run side by side and no
+   * warp waits for another), and the last walk_tail_pct percent of the tasks are a common tail that
+   * whoever finishes first draws from: with 6-7 tasks per warp a fixed share leaves warps idle for up
+   * to one task in seven (ncu on C3: SM active cycles 5.9M .. 7.3M).  walk_tail_pct < 0: the fixed
+   * interleaved share. */
+  __shared__ int s_next;
+  const bool dyn = a.walk_tail_pct >= 0 && a.walk_ctr != nullptr;
+  const int64_t G = gridDim.x, bid = blockIdx.x;
+  const int64_t nt_static = dyn ? ntasks - ntasks * a.walk_tail_pct / 100 : 0;
+  const int64_t t_lo = nt_static * bid / G, n_own = nt_static * (bid + 1) / G - t_lo;
+  if (dyn) {
+    if (threadIdx.x == 0) s_next = 0;
+    __syncthreads();
+  }
+  for (int64_t it = 0;; it++) {
+    int64_t task;
+    if (dyn) {
+      int kk = 0;
+      if (lane == 0) kk = atomicAdd(&s_next, 1);
+      kk = __shfl_sync(FULL, kk, 0);
+      if (kk < n_own) {
+        task = t_lo + kk;
+      } else {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(a.walk_ctr, 1u);
+        t = __shfl_sync(FULL, t, 0);
+        if ((int64_t)t >= ntasks - nt_static) break;
+        task = nt_static + t;
+      }
+    } else {
+      task = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5) + it * nwarps;
+      if (task >= ntasks) break;
+    }
     const int chunk = (int)(task / ngroups);
     const int64_t slot = (task - (int64_t)chunk * ngroups) * 32 + lane;
     const bool valid = slot < a.n;
@@ -356,6 +389,13 @@ sensor_kernel(const SensorLaunch a) {
         if (a.raw) a.raw[p] = v;
         wmax = fmaxf(wmax, v);
       }
+    }
+  }
+  if (dyn) { /* the last CTA out leaves the tail counter at zero for the next launch */
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(a.walk_ctr + 1, 1u) == gridDim.x - 1) {
+      a.walk_ctr[0] = 0;
+      a.walk_ctr[1] = 0;
     }
   }
   if (a.rawmax_ord && a.chunks == 1) {
