@@ -32,7 +32,7 @@ SYMBOLS = [
     "amclj_get_params", "amclj_set_shard", "amclj_set_map", "amclj_set_particles",
     "amclj_get_particles", "amclj_num_particles", "amclj_init_uniform", "amclj_init_gaussian",
     "amclj_motion_update", "amclj_sensor_update", "amclj_get_raw_weights", "amclj_raycast_debug",
-    "amclj_beams_used", "amclj_ray_table_entries", "amclj_normalize", "amclj_resample", "amclj_get_resample_indices",
+    "amclj_beams_used", "amclj_ray_table_entries", "amclj_ray_ring", "amclj_normalize", "amclj_resample", "amclj_get_resample_indices",
     "amclj_filter_update", "amclj_stage_scan", "amclj_filter_update_async",
     "amclj_filter_update_host", "amclj_pose_estimate", "amclj_get_stats", "amclj_microbench", "amclj_median_weight",
     "amclj_augmented_resample", "amclj_augment_state",
@@ -126,6 +126,7 @@ def lib():
         "amclj_raycast_debug": ([vp, i32, f32, f32, f32, i64, i64, vp, vp, vp, vp, vp], i32),
         "amclj_beams_used": ([vp, i32], i32),
         "amclj_ray_table_entries": ([vp], i32),
+        "amclj_ray_ring": ([f64, i32, vp, vp, C.POINTER(i32)], i32),
         "amclj_normalize": ([vp, i32, C.POINTER(u64), C.POINTER(f32)], i32),
         "amclj_resample": ([vp, i32, f64, vp, vp, i64, u64, vp], i32),
         "amclj_get_resample_indices": ([vp, vp], i32),
@@ -180,6 +181,17 @@ def _d3(v):
 
 def _f32(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def ray_ring(r_cells: float):
+    """Host-only view of the end-cell ring of a ray of r_cells cells: (E, lo[2E+1], cnt[2E+1], entries)."""
+    L = lib()
+    cap = 2 * int(r_cells + 4) + 8
+    lo, cnt = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    e = C.c_int32(0)
+    n = L.amclj_ray_ring(float(r_cells), cap, _vp(lo), _vp(cnt), C.byref(e))
+    rows = 2 * e.value + 1
+    return e.value, lo[:rows], cnt[:rows], int(n)
 
 
 def plan_systematic(totals, n_global, u0):

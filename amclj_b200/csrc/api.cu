@@ -183,27 +183,14 @@ int df_mode_of(const amclj_ctx *ctx) {
  * axis: an offset (ex, ey) is reachable only when the square of half-side 1 around it meets the
  * circle of radius r.  The ring keeps every cell whose square of half-side 1.05 does (the 0.05
  * covers the fp32 arithmetic of the end point, ~1e-4 cells); per row the admissible |ex| form one
- * interval.  An end cell outside the ring (never seen) makes the kernel walk that ray instead. */
-void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode);
-
-int stage_ring(amclj_ctx *ctx, double r) {
-  RayTables &t = ctx->rt;
-  const bool tables_wanted = ctx->rt_enable && (ctx->p.df_mode == 0 || ctx->p.df_mode == 6);
-  t.available = false;
-  if (t.r_cells == r && t.rows) {
-    t.have_ring = t.n_entries > 0;
-    t.available = t.have_ring && tables_wanted;
-    return AMCLJ_OK;
-  }
-  t.r_cells = r;
-  t.n_entries = 0;
-  t.have_ring = false;
-  t.recs_mode = -1;
+ * interval.  An end cell outside the ring (never seen) makes the kernel walk that ray instead.
+ * Returns E (rows are ey = -E .. E), or -1 when the geometry is out of range for the tables. */
+int build_ring(double r, std::vector<uint4> &rows, std::vector<short2> &ents) {
+  rows.clear();
+  ents.clear();
   const double half = 1.05;
-  if (!(r + 2.0 * half < 30000.0)) return AMCLJ_OK; /* offsets are stored as 16-bit values */
+  if (!(r >= 0.0) || !(r + 2.0 * half < 30000.0)) return -1; /* offsets are stored as 16-bit values */
   const int E = (int)ceil(r + half);
-  std::vector<uint4> rows;
-  std::vector<short2> ents;
   rows.reserve((size_t)2 * E + 1);
   uint32_t base = 0;
   for (int ey = -E; ey <= E; ey++) {
@@ -225,10 +212,33 @@ int stage_ring(amclj_ctx *ctx, double r) {
       ents.push_back(make_short2(a == 0 ? (short)-32768 : (short)-a, (short)ey));
     }
     base += 2 * cnt;
-    if (base > (1u << 20)) return AMCLJ_OK; /* a table per cell would not pay */
+    if (base > (1u << 20)) return -1; /* a table per cell would not pay */
   }
-  if (ents.empty()) return AMCLJ_OK;
+  if (ents.empty()) return -1;
   ents.push_back(make_short2((short)-32767, 0)); /* last entry: the NaN the fast path reads for an end cell off the ring */
+  return E;
+}
+
+void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode);
+
+/* stage the ring for this scan geometry (raytable.cu, and the set-up records of sensor.cu) */
+int stage_ring(amclj_ctx *ctx, double r) {
+  RayTables &t = ctx->rt;
+  const bool tables_wanted = ctx->rt_enable && (ctx->p.df_mode == 0 || ctx->p.df_mode == 6);
+  t.available = false;
+  if (t.r_cells == r && t.rows) {
+    t.have_ring = t.n_entries > 0;
+    t.available = t.have_ring && tables_wanted;
+    return AMCLJ_OK;
+  }
+  t.r_cells = r;
+  t.n_entries = 0;
+  t.have_ring = false;
+  t.recs_mode = -1;
+  std::vector<uint4> rows;
+  std::vector<short2> ents;
+  const int E = build_ring(r, rows, ents);
+  if (E < 0) return AMCLJ_OK;
   CK(cudaStreamSynchronize(ctx->stream));
   if ((int)rows.size() > t.rows_cap) {
     dfree(t.rows);
@@ -1168,6 +1178,19 @@ int32_t amclj_get_raw_weights(amclj_ctx *ctx, float *raw) {
   CK(cudaMemcpyAsync(raw, ctx->raw, sizeof(float) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return AMCLJ_OK;
+}
+
+int32_t amclj_ray_ring(double r_cells, int32_t max_rows, int32_t *lo, int32_t *cnt, int32_t *half_rows) {
+  std::vector<uint4> rows;
+  std::vector<short2> ents;
+  const int E = build_ring(r_cells, rows, ents);
+  if (E < 0) return 0;
+  if (half_rows) *half_rows = E;
+  for (int i = 0; i < (int)rows.size() && i < max_rows; i++) {
+    if (lo) lo[i] = (int32_t)rows[i].y;
+    if (cnt) cnt[i] = (int32_t)rows[i].z;
+  }
+  return (int32_t)ents.size();
 }
 
 int32_t amclj_ray_table_entries(const amclj_ctx *ctx) {

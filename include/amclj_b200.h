@@ -184,6 +184,11 @@ int32_t amclj_beams_used(const amclj_ctx *ctx, int32_t n);
 /* Entries of one per-start-cell ray table for the staged scan geometry (the end cells a ray of that
  * length can reach, sensor.clj:130-135), or 0 when the ray-table path is unavailable. */
 int32_t amclj_ray_table_entries(const amclj_ctx *ctx);
+/* The ring itself, host only (no ctx, no device): for a ray of r_cells cells, row i (end-cell offset
+ * ey = i - *half_rows) admits |ex| in [lo[i], lo[i] + cnt[i]).  Returns the entries per table (0: the
+ * geometry is out of range); fills at most max_rows rows.  The CPU tests check it against the
+ * rounding of sensor.clj:134-135 by brute force. */
+int32_t amclj_ray_ring(double r_cells, int32_t max_rows, int32_t *lo, int32_t *cnt, int32_t *half_rows);
 
 /* ---- normalise + resample: roulette-selection pf.clj:156-167 ----------------------- */
 /* Linear weights (w = raw, or exp(raw - max raw) under S7) -> fixed point

@@ -95,3 +95,51 @@ def test_plan_slots_agree_with_sequential_resampler():
 def test_plan_rejects_bad_arguments():
     with pytest.raises(_lib.AmcljError):
         _lib.plan_systematic(np.array([1, 2], np.uint64), 10, 1.0)
+
+
+def _end_cell_offsets(rng, n, r_m, res, span_cells):
+    """(x1 - x0, y1 - y0) exactly as the kernels compute it: fp32 end point (one rounding, as the fma),
+    IEEE fp32 divide by the resolution, floor(q + 0.5) — sensor.clj:99-103, :134-135, map.clj:36-46."""
+    res32 = np.float32(res)
+    ox = (rng.uniform(0, span_cells, n) * res).astype(np.float32)
+    oy = (rng.uniform(0, span_cells, n) * res).astype(np.float32)
+    # a share of the starts sits on the rounding boundary of a cell, where both ends flip most easily
+    k = n // 4
+    ox[:k] = ((np.floor(rng.uniform(0, span_cells, k)) + 0.5) * res).astype(np.float32)
+    oy[:k] = ((np.floor(rng.uniform(0, span_cells, k)) + 0.5) * res).astype(np.float32)
+    a = rng.uniform(-np.pi, np.pi, n)
+    a[: n // 8] = np.round(a[: n // 8] / (np.pi / 4)) * (np.pi / 4)  # axis-aligned and diagonal beams
+    c, s = np.cos(a).astype(np.float32), np.sin(a).astype(np.float32)
+    R = np.float32(r_m)
+    ex_w = (R.astype(np.float64) * c.astype(np.float64) + ox.astype(np.float64)).astype(np.float32)
+    ey_w = (R.astype(np.float64) * s.astype(np.float64) + oy.astype(np.float64)).astype(np.float32)
+
+    def cell(v):
+        return np.floor((v / res32).astype(np.float32) + np.float32(0.5)).astype(np.int64)
+
+    return cell(ex_w) - cell(ox), cell(ey_w) - cell(oy)
+
+
+@pytest.mark.parametrize("r_m,res,span", [(5.6, 0.05, 700), (-1.0, 0.05, 700), (30.0, 0.05, 8192), (0.02, 0.05, 50),
+                                          (0.3, 0.25, 9), (11.0, 1.0, 64), (100.0, 0.005, 300), (2.5, 0.1, 4000)])
+def test_ray_ring_covers_every_end_cell(r_m, res, span):
+    """The ring the ray tables (and the walk kernel's set-up records) are laid out on contains every
+    end-cell offset the rounding of sensor.clj:134-135 can produce (a miss would only cost speed —
+    the kernels walk such a ray — but the claim is that it never happens)."""
+    rng = np.random.Generator(np.random.PCG64(int(abs(r_m) * 1000) + span))
+    r_cells = abs(float(np.float32(r_m))) / float(np.float32(res))
+    E, lo, cnt, n_entries = _lib.ray_ring(r_cells)
+    assert n_entries > 0 and len(lo) == 2 * E + 1
+    ex, ey = _end_cell_offsets(rng, 400_000, r_m, res, span)
+    row = ey + E
+    assert row.min() >= 0 and row.max() <= 2 * E
+    t = np.abs(ex) - lo[row]
+    assert np.all((t >= 0) & (t < cnt[row])), f"{np.count_nonzero((t < 0) | (t >= cnt[row]))} end cells off the ring"
+    # and it is thin: about 2.7 cells per unit of circumference (plus the unused / sentinel slots)
+    assert n_entries <= 2 * np.pi * (r_cells + 2) * 3.2 + 40
+
+
+def test_ray_ring_limits():
+    assert _lib.ray_ring(40_000.0)[3] == 0          # offsets would not fit 16 bits
+    E, lo, cnt, n = _lib.ray_ring(0.0)               # zero-length rays: end = start, +-1 cell of rounding
+    assert E == 2 and n > 0 and cnt[E] >= 2
