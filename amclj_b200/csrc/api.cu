@@ -1109,6 +1109,7 @@ int32_t amclj_init_uniform(amclj_ctx *ctx, int64_t n, int32_t heading_mode, uint
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->n = n;
   ctx->have_raw = ctx->have_cdf = false;
+  *ctx->pin_decision = -1; /* a freshly initialised cloud: forget what the last one looked like */
   return AMCLJ_OK;
 }
 
@@ -1126,6 +1127,7 @@ int32_t amclj_init_gaussian(amclj_ctx *ctx, int64_t n, double x, double y, doubl
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->n = n;
   ctx->have_raw = ctx->have_cdf = false;
+  *ctx->pin_decision = -1; /* a freshly initialised cloud: forget what the last one looked like */
   return AMCLJ_OK;
 }
 
