@@ -177,6 +177,7 @@ struct amclj_ctx {
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [5], [6]: around the dominant sensor kernel
   bool time_main = false, time_main_env = false;  // collect_stats bit 1 (or AMCLJ_TIME_MAIN=1): events around that kernel
   int32_t launches = 0;   // kernels enqueued by the update in progress
+  bool stages_timed = true;  // the last update recorded its inner stage events (ev[1], ev[2])
   std::string err;
   amclj_params p;
   amclj::DeviceMap map;

@@ -655,8 +655,10 @@ rt_lookup_kernel(const __grid_constant__ RtLaunch L) {
 __global__ void __launch_bounds__(256)
 rt_finish_kernel(const RtLaunch L) {
   const SensorLaunch &a = L.s;
-  if (L.ctl->dense != 1 && !L.must_run) return;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  /* the histogram of the next update starts from zero (the scatter left write cursors behind) */
+  for (int64_t b = i; b < RT_BIN_CAP; b += (int64_t)gridDim.x * blockDim.x) L.bins[b] = 0;
+  if (L.ctl->dense != 1 && !L.must_run) return;
   float v = -INFINITY;
   if (i < a.n) {
     v = fixed_to_raw(L.qacc[i]);
@@ -711,7 +713,6 @@ cudaError_t rt_prepare_device() {
 cudaError_t launch_raytable(const amclj_ctx *c, const RtLaunch &L, int mode, bool diag, cudaStream_t s) {
   const SensorLaunch &a = L.s;
   if (a.n <= 0 || a.nb <= 0) return cudaSuccess;
-  cudaMemsetAsync(L.bins, 0, sizeof(uint32_t) * RT_BIN_CAP, s);
   const size_t sort_smem = sizeof(uint32_t) * RT_BIN_CAP; /* a counter per cell of the largest box */
   const unsigned blocks = (unsigned)((a.n + RT_SORT_TILE - 1) / RT_SORT_TILE);
   PlanArgs pa;

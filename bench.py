@@ -280,7 +280,6 @@ def run_b200(args):
                 ev[k][1].record(stream)
                 barrier()
                 st = ctx.stats()
-                sensor_ms.append(st.ms_sensor)
                 total_ms_lib.append(st.ms_total)
                 launches.append(st.kernels_launched)
                 paths.append(st.sensor_path)
@@ -295,9 +294,10 @@ def run_b200(args):
     n_total = w.n * world
     value = n_total * nb / (ms_per_step * 1e-3)
 
-    # ---- the dominant sensor kernel alone: the same K steps again with two more event records
-    # around that launch (collect_stats bit 1; they cost ~3 % of a C2 update, so the headline loop
-    # above runs without them) ----------------------------------------------------------------
+    # ---- stage and dominant-kernel times: the same K steps again with event records at the stage
+    # boundaries and around the dominant sensor kernel (collect_stats bit 1; an event between two
+    # kernels keeps the second from being staged behind the first, ~2.5 us each, so the headline
+    # loop above runs without them) -------------------------------------------------------------
     ctx.set_params(_lib.params("NS", collect_stats=2, df_mode=args.df_mode))
     if filt:
         filt.stage_scan(s)
@@ -310,7 +310,9 @@ def run_b200(args):
             barrier()
             one_step(args.warmup + k)
             barrier()
-            main_ms.append(ctx.stats().ms_sensor_main)
+            st2 = ctx.stats()
+            main_ms.append(st2.ms_sensor_main)
+            sensor_ms.append(st2.ms_sensor)
     ctx.set_params(_lib.params("NS", df_mode=args.df_mode))
     if filt:
         filt.stage_scan(s)
