@@ -143,3 +143,28 @@ def test_ray_ring_limits():
     assert _lib.ray_ring(40_000.0)[3] == 0          # offsets would not fit 16 bits
     E, lo, cnt, n = _lib.ray_ring(0.0)               # zero-length rays: end = start, +-1 cell of rounding
     assert E == 2 and n > 0 and cnt[E] >= 2
+
+
+def test_struct_layouts_match_the_c_header(tmp_path):
+    """The ctypes mirrors of amclj_params / amclj_stats against what a C compiler makes of
+    include/amclj_b200.h (sizeof and every field offset): the header is what a JNA / cgo binding reads."""
+    import subprocess
+
+    def fields(struct):
+        return [n for n, _ in struct._fields_]
+
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "amclj_b200.h"', "int main(void) {",
+             '  printf("params %zu\\n", sizeof(amclj_params));', '  printf("stats %zu\\n", sizeof(amclj_stats));']
+    for cname, struct in (("amclj_params", _lib.Params), ("amclj_stats", _lib.Stats)):
+        for f in fields(struct):
+            lines.append(f'  printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    assert int(out["params"]) == C.sizeof(_lib.Params) and int(out["stats"]) == C.sizeof(_lib.Stats)
+    for cname, struct in (("amclj_params", _lib.Params), ("amclj_stats", _lib.Stats)):
+        for f in fields(struct):
+            assert int(out[f"{cname}.{f}"]) == getattr(struct, f).offset, f"{cname}.{f}"
