@@ -120,6 +120,21 @@ def mcl_step(control, scan, grid, cloud: ParticleCloud, u0=None, seed=None):
     return pose_estimate(cloud)
 
 
+def amcl_step(control, scan, grid, cloud: ParticleCloud, alpha_slow=0.01, alpha_fast=0.1, seed=None):
+    """One iteration of amcl* (pf.clj:243-279): motion -> sensor -> augmented selection (median
+    weight, w-slow / w-fast, random injection over free space, roulette-step otherwise) ->
+    estimate.  The w-slow / w-fast atoms live in the ctx (``ctx.augment_state``).  As in the
+    reference the selection works on linear weights (S7 = 0, i.e. the REF preset's sum of cubes)."""
+    if grid is not cloud._map:
+        cloud.ctx.set_map(grid)
+        cloud._map = grid
+    curr, prev = control
+    cloud.ctx.motion_update(curr, prev, None, _seed(cloud, seed))
+    cloud.ctx.sensor_update(scan.ranges, scan.angle_min, scan.angle_inc, scan.range_max)
+    cloud.ctx.augmented_resample(alpha_slow, alpha_fast, _seed(cloud, seed))
+    return pose_estimate(cloud)
+
+
 def likelihood_field_range_finder_model(scan, pose, grid, cloud: ParticleCloud):
     """sensor.clj:165-173 for ONE pose (x, y, theta): returns its weight."""
     if grid is not cloud._map:
