@@ -23,14 +23,14 @@ OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM, ERR_NODEVICE = 0, -1, -2, -3, -
 PRESET_REF, PRESET_NS = 0, 1
 RESAMPLE_ROULETTE, RESAMPLE_SYSTEMATIC, RESAMPLE_TOURNAMENT = 0, 1, 2
 BUF_X, BUF_Y, BUF_THETA, BUF_W, BUF_RAW, BUF_RAW_MAX, BUF_TOTAL, BUF_STAGE_OUT, BUF_STAGE_IN, BUF_CDF, BUF_TOTALS_ALL = range(11)
-IPC_BYTES = 7 * 64
+IPC_BYTES = 8 * 64
 
 # every symbol include/amclj_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "amclj_abi_version", "amclj_params_default", "amclj_create", "amclj_destroy",
     "amclj_last_error", "amclj_set_stream", "amclj_synchronize", "amclj_set_params",
     "amclj_get_params", "amclj_set_shard", "amclj_set_map", "amclj_set_particles",
-    "amclj_get_particles", "amclj_num_particles", "amclj_init_uniform", "amclj_init_gaussian",
+    "amclj_get_particles", "amclj_num_particles", "amclj_set_poses_quat", "amclj_get_poses_quat", "amclj_init_uniform", "amclj_init_gaussian",
     "amclj_motion_update", "amclj_sensor_update", "amclj_get_raw_weights", "amclj_raycast_debug",
     "amclj_beams_used", "amclj_ray_table_entries", "amclj_ray_ring", "amclj_normalize", "amclj_resample", "amclj_get_resample_indices",
     "amclj_filter_update", "amclj_stage_scan", "amclj_filter_update_async",
@@ -39,7 +39,11 @@ SYMBOLS = [
     "amclj_shard_motion_sensor_async", "amclj_shard_cdf_async", "amclj_shard_generate_async",
     "amclj_shard_get_stage_idx", "amclj_shard_adopt_async", "amclj_plan_systematic",
     "amclj_device_ptr", "amclj_reserve_stage", "amclj_shard_export", "amclj_shard_import",
-    "amclj_shard_attach_local", "amclj_shard_pull_async",
+    "amclj_shard_attach_local", "amclj_shard_pull_async", "amclj_shard_update_async", "amclj_shard_update_host",
+    "amclj_create_multi", "amclj_destroy_multi", "amclj_multi_size", "amclj_multi_ctx", "amclj_mlast_error",
+    "amclj_mset_params", "amclj_mset_map", "amclj_mset_particles", "amclj_mget_particles", "amclj_mnum_particles",
+    "amclj_minit_uniform", "amclj_mstage_scan", "amclj_mfilter_update_async", "amclj_mfilter_update_host",
+    "amclj_msynchronize", "amclj_mpose_estimate",
 ]
 
 
@@ -69,6 +73,7 @@ class Stats(C.Structure):
         ("beams_used", C.c_int32), ("map_in_smem", C.c_int32), ("oob_probes", C.c_uint64),
         ("table_cells", C.c_uint64), ("table_particles", C.c_uint64), ("table_misses", C.c_uint64),
         ("ms_sensor_main", C.c_double), ("sensor_path", C.c_int32), ("kernels_launched", C.c_int32),
+        ("zero_weight_updates", C.c_uint64), ("ms_table_fill", C.c_double), ("table_bytes", C.c_uint64),
     ]
 
 
@@ -118,6 +123,8 @@ def lib():
         "amclj_set_particles": ([vp, vp, vp, vp, vp, i64], i32),
         "amclj_get_particles": ([vp, vp, vp, vp, vp], i32),
         "amclj_num_particles": ([vp], i64),
+        "amclj_set_poses_quat": ([vp, vp, vp, i64], i32),
+        "amclj_get_poses_quat": ([vp, vp, vp], i32),
         "amclj_init_uniform": ([vp, i64, i32, u64], i32),
         "amclj_init_gaussian": ([vp, i64, f64, f64, f64, f64, f64, u64], i32),
         "amclj_motion_update": ([vp, d3, d3, vp, u64], i32),
@@ -153,6 +160,24 @@ def lib():
         "amclj_shard_import": ([vp, i32, vp, i64, i64], i32),
         "amclj_shard_attach_local": ([vp, i32, vp], i32),
         "amclj_shard_pull_async": ([vp, f64], i32),
+        "amclj_shard_update_async": ([vp, d3, d3, u64, f64], i32),
+        "amclj_shard_update_host": ([vp, vp, vp, vp, vp, i64, d3, d3, u64, vp, i32, f32, f32, f32, f64], i32),
+        "amclj_create_multi": ([vp, i32, C.POINTER(vp)], i32),
+        "amclj_destroy_multi": ([vp], i32),
+        "amclj_multi_size": ([vp], i32),
+        "amclj_multi_ctx": ([vp, i32], vp),
+        "amclj_mlast_error": ([vp], C.c_char_p),
+        "amclj_mset_params": ([vp, PP], i32),
+        "amclj_mset_map": ([vp, vp, i32, i32, f32], i32),
+        "amclj_mset_particles": ([vp, vp, vp, vp, vp, i64], i32),
+        "amclj_mget_particles": ([vp, vp, vp, vp, vp], i32),
+        "amclj_mnum_particles": ([vp], i64),
+        "amclj_minit_uniform": ([vp, i64, i32, u64], i32),
+        "amclj_mstage_scan": ([vp, vp, i32, f32, f32, f32], i32),
+        "amclj_mfilter_update_async": ([vp, d3, d3, u64, f64], i32),
+        "amclj_mfilter_update_host": ([vp, vp, vp, vp, vp, i64, d3, d3, u64, vp, i32, f32, f32, f32, f64], i32),
+        "amclj_msynchronize": ([vp], i32),
+        "amclj_mpose_estimate": ([vp, d3], i32),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -282,6 +307,17 @@ class Context:
         x, y, t, w = out if out is not None else (np.empty(n, np.float32) for _ in range(4))
         self._ck(self._L.amclj_get_particles(self._h, _vp(x), _vp(y), _vp(t), _vp(w)))
         return x, y, t, w
+
+    def set_poses_quat(self, poses7, w=None):
+        """PoseArray rows (x, y, z, qx, qy, qz, qw) in double; theta = quat/to-heading inside the library."""
+        poses7 = np.ascontiguousarray(poses7, np.float64).reshape(-1, 7)
+        w = _f32(w)
+        self._ck(self._L.amclj_set_poses_quat(self._h, _vp(poses7), _vp(w), len(poses7)))
+
+    def get_poses_quat(self):
+        poses7, w = np.empty((self.n, 7), np.float64), np.empty(self.n, np.float32)
+        self._ck(self._L.amclj_get_poses_quat(self._h, _vp(poses7), _vp(w)))
+        return poses7, w
 
     def init_uniform(self, n, heading_mode=1, seed=1):
         self._ck(self._L.amclj_init_uniform(self._h, int(n), int(heading_mode), int(seed)))
@@ -443,6 +479,18 @@ class Context:
     def shard_pull_async(self, u0):
         self._ck(self._L.amclj_shard_pull_async(self._h, float(u0)))
 
+    def shard_update_async(self, curr, prev, seed, u0):
+        """The whole sharded update in one call: exchanges through peer-memory mailboxes, no collective library."""
+        self._ck(self._L.amclj_shard_update_async(self._h, _d3(curr), _d3(prev), int(seed), float(u0)))
+
+    def shard_update_host(self, x, y, theta, w, curr, prev, ranges, angle_min, angle_inc, range_max, u0, seed=0):
+        ranges = _f32(ranges)
+        for a in (x, y, theta, w):
+            assert a.dtype == np.float32 and a.flags.c_contiguous
+        self._ck(self._L.amclj_shard_update_host(self._h, _vp(x), _vp(y), _vp(theta), _vp(w), len(x), _d3(curr),
+                                                 _d3(prev), int(seed), _vp(ranges), len(ranges), angle_min, angle_inc,
+                                                 range_max, float(u0)))
+
     def reserve_stage(self, rows):
         self._ck(self._L.amclj_reserve_stage(self._h, int(rows)))
 
@@ -456,6 +504,109 @@ class Context:
         import torch
         ptr, nbytes = self.device_ptr(which)
         return torch.as_tensor(_DevArray(ptr, tuple(shape), typestr), device=f"cuda:{self.device}")
+
+
+class _RankView(Context):
+    """A rank's ``amclj_ctx`` inside a MultiContext (borrowed: never destroyed from here)."""
+
+    def __init__(self, handle, device):
+        self._L = lib()
+        self._h = handle
+        self.device = device
+
+    def close(self):
+        self._h = None
+
+
+class MultiContext:
+    """``amclj_mctx``: one process, one caller thread, several GPUs."""
+
+    def __init__(self, devices, preset: str | None = None):
+        self._L = lib()
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self._L.amclj_create_multi(devs, len(devices), C.byref(h))
+        if rc:
+            raise AmcljError(rc, "amclj_create_multi failed (no usable CUDA device? there is no CPU fallback)")
+        self._h = h
+        self.devices = list(devices)
+        if preset is not None:
+            self.set_params(params(preset))
+
+    def _ck(self, rc):
+        if rc:
+            raise AmcljError(rc, self._L.amclj_mlast_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.amclj_destroy_multi(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def world(self):
+        return int(self._L.amclj_multi_size(self._h))
+
+    def rank(self, r) -> Context:
+        return _RankView(C.c_void_p(self._L.amclj_multi_ctx(self._h, int(r))), self.devices[r])
+
+    def set_params(self, p):
+        self._ck(self._L.amclj_mset_params(self._h, C.byref(p)))
+
+    def set_map(self, grid):
+        cells = np.ascontiguousarray(grid.data, dtype=np.int8)
+        self._ck(self._L.amclj_mset_map(self._h, _vp(cells), int(grid.info.width), int(grid.info.height),
+                                        float(np.float32(grid.info.resolution))))
+
+    def set_particles(self, x, y, theta, w=None):
+        x, y, theta, w = _f32(x), _f32(y), _f32(theta), _f32(w)
+        self._ck(self._L.amclj_mset_particles(self._h, _vp(x), _vp(y), _vp(theta), _vp(w), len(x)))
+
+    @property
+    def n(self):
+        return int(self._L.amclj_mnum_particles(self._h))
+
+    def get_particles(self):
+        x, y, t, w = (np.empty(self.n, np.float32) for _ in range(4))
+        self._ck(self._L.amclj_mget_particles(self._h, _vp(x), _vp(y), _vp(t), _vp(w)))
+        return x, y, t, w
+
+    def init_uniform(self, n, heading_mode=1, seed=1):
+        self._ck(self._L.amclj_minit_uniform(self._h, int(n), int(heading_mode), int(seed)))
+
+    def stage_scan(self, ranges, angle_min, angle_inc, range_max):
+        ranges = _f32(ranges)
+        self._ck(self._L.amclj_mstage_scan(self._h, _vp(ranges), len(ranges), angle_min, angle_inc, range_max))
+
+    def filter_update_async(self, curr, prev, seed, u0):
+        self._ck(self._L.amclj_mfilter_update_async(self._h, _d3(curr), _d3(prev), int(seed), float(u0)))
+
+    def filter_update_host(self, x, y, theta, w, curr, prev, ranges, angle_min, angle_inc, range_max, u0, seed=0):
+        ranges = _f32(ranges)
+        for a in (x, y, theta, w):
+            assert a.dtype == np.float32 and a.flags.c_contiguous
+        self._ck(self._L.amclj_mfilter_update_host(self._h, _vp(x), _vp(y), _vp(theta), _vp(w), len(x), _d3(curr),
+                                                   _d3(prev), int(seed), _vp(ranges), len(ranges), angle_min, angle_inc,
+                                                   range_max, float(u0)))
+
+    def synchronize(self):
+        self._ck(self._L.amclj_msynchronize(self._h))
+
+    def pose_estimate(self):
+        out = (C.c_double * 4)()
+        self._ck(self._L.amclj_mpose_estimate(self._h, C.cast(out, C.POINTER(C.c_double))))
+        return np.array(list(out))
 
 
 class _DevArray:

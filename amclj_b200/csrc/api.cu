@@ -166,6 +166,9 @@ void make_control(const amclj_params &p, const double curr[3], const double prev
   m.sd2 = (float)sqrt(a1 * rot2 * rot2 + a2 * trans * trans);
 }
 
+/* df_mode 0 and 8 pick the field placement per update; 8 leaves the persistent ray tables out */
+bool auto_mode(const amclj_ctx *ctx) { return ctx->p.df_mode == 0 || ctx->p.df_mode == 8; }
+
 int df_mode_of(const amclj_ctx *ctx) {
   switch (ctx->p.df_mode) {
     case 1: return ctx->map.fits_smem ? DF_SMEM4 : -1;
@@ -174,6 +177,7 @@ int df_mode_of(const amclj_ctx *ctx) {
     case 4: return ctx->map.wedge ? DF_WEDGE8 : -1;
     case 5: return ctx->map.wedge ? DF_WEDGE8 : -1; /* directional planes, particles walked in tile order */
     case 6: return ctx->map.wedge ? DF_WEDGE8 : (ctx->map.df8 ? DF_GLOBAL8 : DF_GLOBAL4); /* ray tables, filled over these */
+    case 7: return ctx->map.wedge ? DF_WEDGE8 : (ctx->map.df8 ? DF_GLOBAL8 : DF_GLOBAL4); /* persistent ray tables */
     default: return ctx->map.fits_smem ? DF_SMEM4 : (ctx->map.df8 ? DF_GLOBAL8 : DF_GLOBAL4);
   }
 }
@@ -224,7 +228,7 @@ void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode);
 /* stage the ring for this scan geometry (raytable.cu, and the set-up records of sensor.cu) */
 int stage_ring(amclj_ctx *ctx, double r) {
   RayTables &t = ctx->rt;
-  const bool tables_wanted = ctx->rt_enable && (ctx->p.df_mode == 0 || ctx->p.df_mode == 6);
+  const bool tables_wanted = ctx->rt_enable && (auto_mode(ctx) || ctx->p.df_mode == 6 || ctx->p.df_mode == 7);
   t.available = false;
   if (t.r_cells == r && t.rows) {
     t.have_ring = t.n_entries > 0;
@@ -310,6 +314,171 @@ int ensure_rt_scratch(amclj_ctx *ctx, int64_t n, bool diag, int thr, int *max_sl
   return AMCLJ_OK;
 }
 
+
+/* ---- persistent map-wide ray tables (ptable.cu) -------------------------------------------- */
+void pt_free(amclj_ctx *ctx) {
+  PersistentTables &t = ctx->pt;
+  dfree(t.slot_of_cell); dfree(t.cell_of_slot); dfree(t.bin_count); dfree(t.bin_start); dfree(t.cursor);
+  if (t.tables) cudaFree(t.tables);
+  t.tables = nullptr;
+  t.tables_bytes = 0;
+  t.n_slots = 0;
+  t.built = false;
+  t.key_map_gen = -1;
+}
+
+/* slot maps of a new map: one table slot per free cell (map.clj:48-57: free = cell 0) */
+int pt_set_map(amclj_ctx *ctx, const int8_t *cells, int W, int H) {
+  pt_free(ctx);
+  PersistentTables &t = ctx->pt;
+  const size_t ncell = (size_t)W * H;
+  if (!t.enable || ncell > (1u << 24)) return AMCLJ_OK; /* larger maps: no table per cell would fit anyway */
+  std::vector<int32_t> soc(ncell);
+  std::vector<int2> cos;
+  for (size_t i = 0; i < ncell; i++)
+    if (cells[i] == 0) {
+      soc[i] = (int32_t)cos.size();
+      cos.push_back(make_int2((int)(i % W), (int)(i / W)));
+    }
+  const int32_t n_slots = (int32_t)cos.size();
+  if (n_slots == 0) return AMCLJ_OK;
+  for (size_t i = 0; i < ncell; i++)
+    if (cells[i] != 0) soc[i] = n_slots; /* the zero table */
+  CK(dalloc(&t.slot_of_cell, ncell));
+  CK(dalloc(&t.cell_of_slot, (size_t)n_slots));
+  CK(dalloc(&t.bin_count, (size_t)n_slots + 2));
+  CK(dalloc(&t.bin_start, (size_t)n_slots + 2));
+  CK(dalloc(&t.cursor, (size_t)n_slots + 2));
+  CK(cudaMemcpyAsync(t.slot_of_cell, soc.data(), sizeof(int32_t) * ncell, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(t.cell_of_slot, cos.data(), sizeof(int2) * (size_t)n_slots, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(t.bin_count, 0, sizeof(uint32_t) * ((size_t)n_slots + 2), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  t.n_slots = n_slots;
+  return AMCLJ_OK;
+}
+
+int pt_fill_mode(const amclj_ctx *ctx) {
+  return ctx->map.wedge ? DF_WEDGE8 : (ctx->map.df8 ? DF_GLOBAL8 : DF_GLOBAL4);
+}
+
+void fill_pt_args(const amclj_ctx *ctx, PtLaunch &L) {
+  const PersistentTables &t = ctx->pt;
+  const RayTables &r = ctx->rt;
+  memset(&L, 0, sizeof(L));
+  fill_sensor_args(ctx, L.s, pt_fill_mode(ctx));
+  L.rows = r.rows; L.ents = r.ents; L.nrows = r.nrows; L.E = r.E; L.n_entries = r.n_entries;
+  L.stride = t.stride;
+  L.n_slots = t.n_slots;
+  L.slot_of_cell = t.slot_of_cell; L.cell_of_slot = t.cell_of_slot; L.tables = t.tables;
+  L.bin_count = t.bin_count; L.bin_start = t.bin_start; L.cursor = t.cursor;
+  L.pkey = t.pkey;
+  L.perm = ctx->perm;
+  L.pstate = r.pstate;
+  L.qacc = ctx->partials;
+  L.warps = t.warps;
+}
+
+/* Called at the end of stage_scan_impl: are the persistent tables usable for the staged scan, and do
+ * they have to be (re)filled?  They depend on the map, the ray length in cells, S3 / S4, the miss value
+ * and the resolution — not on the scan's ranges, the beam count or the particles. */
+int pt_prepare(amclj_ctx *ctx, double rcells) {
+  PersistentTables &t = ctx->pt;
+  const RayTables &r = ctx->rt;
+  const amclj_params &p = ctx->p;
+  t.built = false;
+  const bool wanted = t.enable && (p.df_mode == 0 || p.df_mode == 7) && t.n_slots > 0 && r.have_ring && r.floor_trick_ok &&
+                      ctx->map.res > 1.0e-6f && ctx->map.res < 1.0e6f;
+  if (!wanted) return AMCLJ_OK;
+  const int32_t stride = (r.n_entries + 3) & ~3;
+  const size_t bytes = ((size_t)t.n_slots + 1) * (size_t)stride * sizeof(float);
+  if (bytes > t.budget) return AMCLJ_OK;
+  PtLaunch probe;
+  memset(&probe, 0, sizeof(probe));
+  probe.s.nb = ctx->beams.nb; probe.nrows = r.nrows; probe.stride = stride;
+  int warps = 0;
+  const int wmax = ctx->pt.warps > 0 && ctx->pt.warps <= 16 ? ctx->pt.warps : 16;
+  for (int w = wmax; w >= 2; w--)
+    if (pt_lookup_smem(probe, w) + 1024 <= (size_t)ctx->max_smem_optin) { warps = w; break; }
+  if (warps < 2) return AMCLJ_OK; /* a table does not fit the shared memory twice over: the other paths take it */
+  const float R = p.s2_use_scan_range_max ? ctx->beams.range_max : p.max_range;
+  uint32_t Rb, resb;
+  memcpy(&Rb, &R, 4);
+  memcpy(&resb, &ctx->map.res, 4);
+  const bool same = t.tables && t.key_map_gen == ctx->map_gen && t.key_r == rcells && t.key_s3 == p.s3_proper_endpoint &&
+                    t.key_s4 == p.s4_endpoint_termination && t.key_entries == r.n_entries && t.key_R_bits == Rb &&
+                    t.key_res_bits == resb && t.fill_mode == pt_fill_mode(ctx);
+  t.stride = stride;
+  if (!same) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (bytes > t.tables_bytes) {
+      if (t.tables) cudaFree(t.tables);
+      t.tables = nullptr;
+      t.tables_bytes = 0;
+      CK(cudaMalloc(reinterpret_cast<void **>(&t.tables), bytes));
+      t.tables_bytes = bytes;
+    }
+    PtLaunch L;
+    fill_pt_args(ctx, L);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, ctx->stream));
+    CK(launch_pt_fill(ctx, L, pt_fill_mode(ctx), ctx->stream));
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    t.ms_fill = ms;
+    t.key_map_gen = ctx->map_gen; t.key_r = rcells; t.key_s3 = p.s3_proper_endpoint; t.key_s4 = p.s4_endpoint_termination;
+    t.key_entries = r.n_entries; t.key_R_bits = Rb; t.key_res_bits = resb; t.fill_mode = pt_fill_mode(ctx);
+  }
+  t.warps = warps;
+  t.built = true;
+  return AMCLJ_OK;
+}
+
+/* scratch of the persistent-table update for this particle count */
+int ensure_pt_scratch(amclj_ctx *ctx, int64_t n) {
+  PersistentTables &t = ctx->pt;
+  RayTables &r = ctx->rt;
+  if (n > t.pkey_cap || n > r.pstate_cap || n > ctx->partials_cap) CK(cudaStreamSynchronize(ctx->stream));
+  if (n > t.pkey_cap) {
+    dfree(t.pkey);
+    t.pkey_cap = 0;
+    CK(dalloc(&t.pkey, (size_t)n));
+    t.pkey_cap = n;
+  }
+  if (n > r.pstate_cap) {
+    dfree(r.pstate);
+    r.pstate_cap = 0;
+    CK(dalloc(&r.pstate, (size_t)n));
+    r.pstate_cap = n;
+  }
+  if (n > ctx->partials_cap) {
+    dfree(ctx->partials);
+    ctx->partials_cap = 0;
+    CK(dalloc(&ctx->partials, (size_t)n));
+    ctx->partials_cap = n;
+  }
+  return AMCLJ_OK;
+}
+
+/* the persistent-table sensor pass over the particles of `base`; results land in base.raw */
+int enqueue_ptable(amclj_ctx *ctx, const SensorLaunch &base, bool dbg) {
+  int rc = ensure_pt_scratch(ctx, base.n);
+  if (rc) return rc;
+  PtLaunch L;
+  fill_pt_args(ctx, L);
+  L.s.x = base.x; L.s.y = base.y; L.s.th = base.th; L.s.raw = base.raw; L.s.n = base.n;
+  L.s.rawmax_ord = base.rawmax_ord; L.s.stats = base.stats;
+  L.s.dbg_first = base.dbg_first; L.s.dbg_count = base.dbg_count; L.s.dbg_range = base.dbg_range;
+  CK(launch_pt_update(ctx, L, pt_fill_mode(ctx), dbg, ctx->stream));
+  ctx->launches += 5; /* histogram, scan, scatter, look-up, finish */
+  return AMCLJ_OK;
+}
+
 int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min, float angle_inc,
                     float range_max) {
   NEED(n > 0 && n <= (1 << 20), AMCLJ_ERR_INVALID, "scan: n = %d out of range", n);
@@ -348,6 +517,16 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
     float pz4 = o < range_max ? p.z_rand / range_max : 0.0f;   /* sensor.clj:160-161 */
     mix[4 * j + 2] = pz3 + pz4;
     mix[4 * j + 3] = 0.0f;
+    if (p.s7_log_weights && !(o <= range_max && o >= -3.0e38f)) {
+      /* Log-weights only (the north-star aggregation; no reference counterpart): a return beyond
+       * rangeMax, an inf or a NaN — common in ROS LaserScans — has probability 0 under every term
+       * of sensor.clj:151-161, and log 0 would wipe out every particle alike.  Such a beam is left
+       * out: z = +inf makes pz1 = pz2 = 0 and the constant term 1 makes the beam's factor exactly 1.
+       * The reference's sum of cubes (S7 off) just adds 0 for it and keeps doing so here. */
+      mix[4 * j] = INFINITY;
+      mix[4 * j + 1] = 0.0f;
+      mix[4 * j + 2] = 1.0f;
+    }
   }
   BeamTable &b = ctx->beams;
   if (nb > b.cap) {
@@ -369,7 +548,7 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
   int mode = df_mode_of(ctx);
   NEED(mode >= 0, AMCLJ_ERR_INVALID, "scan: df_mode %d unavailable for this map", ctx->p.df_mode);
   /* the directional planes (also when the auto policy may pick them) and the byte field jump up to 255 */
-  int dcap = (mode == DF_GLOBAL8 || mode == DF_WEDGE8 || (ctx->p.df_mode == 0 && ctx->map.wedge)) ? 255 : 15;
+  int dcap = (mode == DF_GLOBAL8 || mode == DF_WEDGE8 || ((auto_mode(ctx) || ctx->p.df_mode == 7) && ctx->map.wedge)) ? 255 : 15;
   uint64_t Dmax = 2ull * (uint64_t)(ndiv - 1);
   int wide = (uint64_t)(dcap + 1) * Dmax * Dmax > (1ull << 32);
   DivTable &d = ctx->divs;
@@ -399,7 +578,7 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
   RayTables &rt = ctx->rt;
   rt.floor_trick_ok = (double)(ctx->map.W > ctx->map.H ? ctx->map.W : ctx->map.H) + rcells + 4.0 < 4.0e6;
   if (rt.have_ring && ctx->ring_setup && rt.n_entries <= 8192 && rt.floor_trick_ok) {
-    int walk_mode = (ctx->p.df_mode == 0 && ctx->map.wedge) ? DF_WEDGE8 : mode;
+    int walk_mode = (auto_mode(ctx) && ctx->map.wedge) ? DF_WEDGE8 : mode;
     /* what the records depend on; rebuilt only when any of it changed */
     const long long key[6] = {(long long)walk_mode, (long long)p.s3_proper_endpoint, (long long)p.s4_endpoint_termination,
                               (long long)ctx->map_gen, (long long)d.wide * 1000 + d.dcap, (long long)d.n};
@@ -424,7 +603,7 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
     rt.recs_mode = -1;
   }
   b.staged = true;
-  return AMCLJ_OK;
+  return pt_prepare(ctx, rcells);
 }
 
 void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode) {
@@ -496,7 +675,7 @@ int enqueue_motion(amclj_ctx *ctx, const double curr[3], const double prev[3], b
   m.seed = seed;
   m.bbox = nullptr;
   if (ctx->ctrl_fresh && !m.is_static &&
-      ((ctx->p.df_mode == 0 && (ctx->map.wedge || ctx->order_large_maps || ctx->rt_enable)) || ctx->p.df_mode == 6)) {
+      ((auto_mode(ctx) && (ctx->map.wedge || ctx->order_large_maps || ctx->rt_enable)) || ctx->p.df_mode == 6)) {
     m.bbox = ctx->bbox; /* the moved cloud's bounding box comes for free */
     ctx->bbox_done = true;
   }
@@ -587,22 +766,46 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
     CK(cudaMemsetAsync(ctx->stats, 0, 7 * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->stats + 8, 0, 4 * sizeof(unsigned long long), ctx->stream));
   }
+  /* Persistent map-wide ray tables (ptable.cu): when the staged scan has them (df_mode 0 on a map small
+   * enough for one table per free cell, or df_mode 7), every cloud runs on them — no policy, nothing the
+   * host has to read back.  Diagnostic passes (cell / probe counters) keep the walking paths, which visit
+   * the cells the counters count. */
+  NEED(ctx->p.df_mode != 7 || ctx->pt.built, AMCLJ_ERR_INVALID,
+       "sensor: df_mode 7 (persistent ray tables) unavailable for this map / rays of %.0f cells", ctx->rt.r_cells);
+  if (ctx->pt.built && (ctx->p.df_mode == 7 || !diag)) {
+    int prc = enqueue_ptable(ctx, a, false);
+    if (prc) return prc;
+    if (decode_max) {
+      CK(launch_decode_max(ctx->rawmax_ord, ctx->rawmax, ctx->stream));
+      ctx->launches += 1;
+    }
+    ctx->bbox_done = false;
+    ctx->max_in_ord = !decode_max;
+    ctx->last_diag = diag;
+    ctx->have_raw = true;
+    ctx->have_cdf = false;
+    ctx->st.map_in_smem = 0;
+    ctx->st.beams_used = ctx->beams.nb;
+    ctx->st.n_particles = ctx->n;
+    *ctx->pin_decision = 3;
+    return AMCLJ_OK;
+  }
   /* df_mode 0 on a map that has the directional planes: they are used for every cloud.  A compact
    * cloud is local as it is; a spread-out one is walked in map-tile order so that each CTA's probes
    * share an L1-sized neighbourhood.  A 5 us bounding-box kernel leaves the decision on the device
    * (the tile-order kernels return at once for a compact cloud, and the sensor kernel ignores the
    * permutation); either way the results are identical. */
-  bool directional = ctx->p.df_mode == 0 && ctx->map.wedge != nullptr;
+  bool directional = auto_mode(ctx) && ctx->map.wedge != nullptr;
   /* large maps (byte field through L2) get the tile-order walk too: it is what keeps a CTA's
    * probes in L1 */
-  bool ordered = directional || (ctx->p.df_mode == 0 && mode == DF_GLOBAL8 && ctx->order_large_maps);
+  bool ordered = directional || (auto_mode(ctx) && mode == DF_GLOBAL8 && ctx->order_large_maps);
   /* dense clouds (pose tracking: thousands of particles per start cell) go through per-cell ray
    * tables (raytable.cu).  Whether the cloud is dense is decided on the device, every update; the
    * verdict of the previous update, left in pinned host memory, only picks which kernels are
    * launched at all: 0 spread out -> walk kernel only; 1 compact / -1 unknown -> both, the device flag
    * picks one; 2 dense -> ray tables only (they take any cloud, a sparse one slowly). */
   const bool rt_forced = ctx->p.df_mode == 6;
-  const bool rt_auto = ctx->p.df_mode == 0 && ctx->rt_enable && ctx->rt.available && !ctx->p.s10_apply_laser_offset;
+  const bool rt_auto = auto_mode(ctx) && ctx->rt_enable && ctx->rt.available && !ctx->p.s10_apply_laser_offset;
   NEED(!rt_forced || ctx->rt.available, AMCLJ_ERR_INVALID, "sensor: df_mode 6 (ray tables) unavailable for rays of %.0f cells",
        ctx->rt.r_cells);
   const int hint = *ctx->pin_decision;
@@ -716,6 +919,7 @@ int enqueue_systematic(amclj_ctx *ctx, double u0) {
   g.ow = ctx->w2;
   g.oidx = ctx->idx;
   g.wout = 1.0f / (float)ctx->n;
+  g.zero_flag = ctx->stats + 12;
   CK(launch_systematic(g, ctx->stream));
   ctx->launches += 1;
   swap_particles(ctx);
@@ -839,6 +1043,26 @@ int upload_normals(amclj_ctx *ctx, const float *normals) {
   return AMCLJ_OK;
 }
 
+
+/* after a synchronisation: did an update since the last check find every weight zero?  (the device
+ * kept the particles as they were; the caller hears about it) */
+int check_zero_total(amclj_ctx *ctx, const char *who) {
+  unsigned long long *h = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(ctx->pinned) + 1024);
+  CK(cudaMemcpyAsync(h, ctx->stats + 12, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (h[1] != ctx->mbox_errors_seen) {
+    ctx->mbox_errors_seen = h[1];
+    return fail(ctx, AMCLJ_ERR_STATE, "%s: a rank never published its share of the exchange (peers not all updating?)", who);
+  }
+  const uint64_t seen = *h;
+  const bool fresh = seen != ctx->zero_seen;
+  ctx->zero_seen = seen;
+  ctx->st.zero_weight_updates = seen;
+  if (fresh)
+    return fail(ctx, AMCLJ_ERR_STATE, "%s: all weights are zero (a zero-probability scan?): particles kept, not resampled", who);
+  return AMCLJ_OK;
+}
+
 void stamp(amclj_ctx *ctx, int k) {
   cudaEventRecord(ctx->ev[k], ctx->stream);
   if (k == 0) {
@@ -912,6 +1136,9 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
   if (const char *e = getenv("AMCLJ_RT_WAVES")) ctx->rt.waves = atoi(e);
   if (const char *e = getenv("AMCLJ_RT_TAIL_PCT")) ctx->rt.tail_pct = atoi(e) < 0 ? 0 : (atoi(e) > 100 ? 100 : atoi(e));
   if (const char *e = getenv("AMCLJ_RT_BUDGET_MB")) ctx->rt.budget = (size_t)atoll(e) << 20;
+  if (const char *e = getenv("AMCLJ_PTABLE")) ctx->pt.enable = atoi(e) != 0;
+  if (const char *e = getenv("AMCLJ_PT_BUDGET_MB")) ctx->pt.budget = (size_t)atoll(e) << 20;
+  if (const char *e = getenv("AMCLJ_PT_WARPS")) ctx->pt.warps = atoi(e);
   memset(&ctx->st, 0, sizeof(ctx->st));
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ctx->stream = ctx->own_stream;
@@ -929,8 +1156,8 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
     ctx->scan_state = ctx->ctrl + 5;
     ok = cudaMemset(ctx->ctrl, 0, sizeof(uint64_t) * ((size_t)ctx->scan_state_cap + 5)) == cudaSuccess;
   }
-  ok = ok && dalloc(&ctx->rawmax, 1) == cudaSuccess && dalloc(&ctx->stats, 12) == cudaSuccess &&
-       dalloc(&ctx->plan, 1) == cudaSuccess && dalloc(&ctx->decision, 1) == cudaSuccess && dalloc(&ctx->walk_ctr, 2) == cudaSuccess && dalloc(&ctx->totals_all, MAX_WORLD) == cudaSuccess &&
+  ok = ok && dalloc(&ctx->rawmax, 1) == cudaSuccess && dalloc(&ctx->stats, 16) == cudaSuccess &&
+       dalloc(&ctx->plan, 1) == cudaSuccess && dalloc(&ctx->decision, 1) == cudaSuccess && dalloc(&ctx->walk_ctr, 2) == cudaSuccess && dalloc(&ctx->totals_all, MAX_WORLD) == cudaSuccess && dalloc(&ctx->mbox, (size_t)MBOX_WORDS) == cudaSuccess &&
        dalloc(&ctx->pose_part, (size_t)pose_blocks() * 4) == cudaSuccess &&
        cudaMallocHost(&ctx->pinned, 4096) == cudaSuccess;
   if (ok) {
@@ -938,13 +1165,15 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
     *ctx->pin_decision = -1;
     ok = cudaMemset(ctx->decision, 0xff, sizeof(int32_t)) == cudaSuccess;
   }
-  if (ok) ok = cudaMemset(ctx->stats, 0, 12 * sizeof(unsigned long long)) == cudaSuccess;
+  if (ok) ok = cudaMemset(ctx->stats, 0, 16 * sizeof(unsigned long long)) == cudaSuccess;
   if (ok) ok = cudaMemset(ctx->walk_ctr, 0, 2 * sizeof(uint32_t)) == cudaSuccess;
+  if (ok) ok = cudaMemset(ctx->mbox, 0, sizeof(unsigned long long) * MBOX_WORDS) == cudaSuccess;
   if (!ok) {
     amclj_destroy(ctx);
     return AMCLJ_ERR_CUDA;
   }
   for (int i = 0; i < 7; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
+  cudaDeviceSynchronize(); /* the clears above ran on the legacy stream: done before anything uses ctx->stream */
   *out = ctx;
   return AMCLJ_OK;
 }
@@ -959,13 +1188,15 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
   dfree(ctx->x2); dfree(ctx->y2); dfree(ctx->th2); dfree(ctx->w2);
   dfree(ctx->cdf); dfree(ctx->idx); dfree(ctx->normals); dfree(ctx->partials); dfree(ctx->perm); dfree(ctx->tile_counters);
   dfree(ctx->ctrl); dfree(ctx->rawmax); dfree(ctx->stats); dfree(ctx->walk_ctr);
-  dfree(ctx->pose_part); dfree(ctx->plan); dfree(ctx->hist); dfree(ctx->totals_all); dfree(ctx->decision);
+  dfree(ctx->pose_part); dfree(ctx->plan); dfree(ctx->hist); dfree(ctx->totals_all); dfree(ctx->decision); dfree(ctx->mbox);
   for (int g = 0; g < MAX_WORLD; g++)
-    for (int k = 0; k < 7; k++)
+    for (int k = 0; k < AMCLJ_IPC_BUFFERS; k++)
       if (ctx->ipc_opened[g][k]) cudaIpcCloseMemHandle(ctx->ipc_opened[g][k]);
   dfree(ctx->stage_out); dfree(ctx->stage_in); dfree(ctx->stage_idx);
   dfree(ctx->rt.rows); dfree(ctx->rt.ents); dfree(ctx->rt.recs); dfree(ctx->rt.pstate); dfree(ctx->rt.bins); dfree(ctx->rt.item0); dfree(ctx->rt.slots); dfree(ctx->rt.ctl);
   if (ctx->rt.tables) cudaFree(ctx->rt.tables);
+  pt_free(ctx);
+  dfree(ctx->pt.pkey);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->pin_tab) cudaFreeHost(ctx->pin_tab);
   for (int i = 0; i < 7; i++)
@@ -993,7 +1224,7 @@ int32_t amclj_synchronize(amclj_ctx *ctx) {
 int32_t amclj_set_params(amclj_ctx *ctx, const amclj_params *p) {
   ENTER();
   NEED(p, AMCLJ_ERR_INVALID, "set_params: null");
-  NEED(p->df_mode >= 0 && p->df_mode <= 6, AMCLJ_ERR_INVALID, "set_params: df_mode %d", p->df_mode);
+  NEED(p->df_mode >= 0 && p->df_mode <= 8, AMCLJ_ERR_INVALID, "set_params: df_mode %d", p->df_mode);
   if ((p->df_mode == 4 || p->df_mode == 5) && ctx->map.cells && !ctx->map.wedge) { /* directional fields are built on demand */
     NEED((size_t)ctx->map.pitch8 * (ctx->map.H + 2) * WEDGE_CLASSES <= (8ull << 30), AMCLJ_ERR_INVALID,
          "set_params: map too large for directional fields");
@@ -1051,7 +1282,7 @@ int32_t amclj_set_map(amclj_ctx *ctx, const int8_t *cells, int32_t width, int32_
   if (ctx->p.df_mode == 4 || ctx->p.df_mode == 5) {
     NEED(m.bytes8 * WEDGE_CLASSES <= (8ull << 30), AMCLJ_ERR_INVALID, "set_map: map too large for directional fields");
     CK(build_wedge_fields(ctx, ctx->stream));
-  } else if ((ctx->p.df_mode == 0 || ctx->p.df_mode == 6) && m.bytes8 * WEDGE_CLASSES <= ctx->wedge_budget &&
+  } else if ((auto_mode(ctx) || ctx->p.df_mode == 6 || ctx->p.df_mode == 7) && m.bytes8 * WEDGE_CLASSES <= ctx->wedge_budget &&
              m.bytes8 * WEDGE_CLASSES < (1ull << 32)) {
     CK(build_wedge_fields(ctx, ctx->stream)); /* auto: both field sets, chosen per update */
   }
@@ -1059,6 +1290,10 @@ int32_t amclj_set_map(amclj_ctx *ctx, const int8_t *cells, int32_t width, int32_
   ctx->divs.n = 0;
   *ctx->pin_decision = -1; /* a new map: no hint about the cloud */
   ctx->map_gen++;
+  {
+    int prc = pt_set_map(ctx, cells, width, height);
+    if (prc) return prc;
+  }
   ctx->rt.recs_mode = -1;
   ctx->st.map_in_smem = m.fits_smem;
   return AMCLJ_OK;
@@ -1099,6 +1334,45 @@ int32_t amclj_get_particles(amclj_ctx *ctx, float *x, float *y, float *theta, fl
 }
 
 int64_t amclj_num_particles(const amclj_ctx *ctx) { return ctx ? ctx->n : 0; }
+
+/* quaternions.clj:82-97 to-heading, in double as on the JVM */
+static double to_heading(double qx, double qy, double qz, double qw) {
+  const double test = qx * qy + qz * qw;
+  if (test > 0.4999) return 2.0 * atan2(qx, qw);   /* singularity at the north pole */
+  if (test < -0.499) return -2.0 * atan2(qx, qw);  /* ... and at the south pole (the reference's own constant) */
+  return atan2(2.0 * qz * qw - 2.0 * qx * qy, 1.0 - 2.0 * qz * qz - 2.0 * qy * qy);
+}
+
+int32_t amclj_set_poses_quat(amclj_ctx *ctx, const double *poses7, const float *w, int64_t n) {
+  ENTER();
+  NEED(poses7 && n > 0 && n <= (1ll << 31) - 1, AMCLJ_ERR_INVALID, "set_poses_quat: bad arguments");
+  std::vector<float> x((size_t)n), y((size_t)n), th((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    const double *p = poses7 + 7 * i;
+    x[(size_t)i] = (float)p[0];
+    y[(size_t)i] = (float)p[1];
+    th[(size_t)i] = (float)to_heading(p[3], p[4], p[5], p[6]);
+  }
+  return amclj_set_particles(ctx, x.data(), y.data(), th.data(), w, n);
+}
+
+int32_t amclj_get_poses_quat(amclj_ctx *ctx, double *poses7, float *w) {
+  ENTER();
+  NEED(poses7, AMCLJ_ERR_INVALID, "get_poses_quat: null");
+  NEED(ctx->n > 0, AMCLJ_ERR_STATE, "get_poses_quat: no particles");
+  const size_t n = (size_t)ctx->n;
+  std::vector<float> x(n), y(n), th(n);
+  int rc = amclj_get_particles(ctx, x.data(), y.data(), th.data(), w);
+  if (rc) return rc;
+  for (size_t i = 0; i < n; i++) {
+    double *p = poses7 + 7 * i;
+    const double h = (double)th[i];
+    p[0] = (double)x[i]; p[1] = (double)y[i]; p[2] = 0.0;
+    /* quaternions.clj:57-62 from-heading = rotate (0 0 0 1) by the heading (:19-36, pitch = bank = 0) */
+    p[3] = 0.0; p[4] = 0.0; p[5] = sin(h / 2.0); p[6] = cos(h / 2.0);
+  }
+  return AMCLJ_OK;
+}
 
 int32_t amclj_init_uniform(amclj_ctx *ctx, int64_t n, int32_t heading_mode, uint64_t seed) {
   ENTER();
@@ -1250,7 +1524,18 @@ int32_t amclj_raycast_debug(amclj_ctx *ctx, int32_t n, float angle_min, float an
     ctx->last_diag = true;
     ctx->st.beams_used = ctx->beams.nb;
     cudaMemsetAsync(ctx->stats, 0, 12 * sizeof(unsigned long long), ctx->stream);
-    if (ctx->p.df_mode == 6) { /* parity probe through the ray tables: every occupied cell gets a table */
+    if (ctx->p.df_mode == 7) { /* parity probe through the persistent tables' production look-up (ranges only) */
+      if (!ctx->pt.built) {
+        status = fail(ctx, AMCLJ_ERR_INVALID, "raycast_debug: df_mode 7 unavailable for this map / rays of %.0f cells", ctx->rt.r_cells);
+      } else {
+        if (d_hx) cudaMemsetAsync(d_hx, 0xff, rays * 4, ctx->stream);
+        if (d_hy) cudaMemsetAsync(d_hy, 0xff, rays * 4, ctx->stream);
+        if (d_st) cudaMemsetAsync(d_st, 0xff, rays * 4, ctx->stream);
+        if (d_hit) cudaMemsetAsync(d_hit, 0xff, rays, ctx->stream);
+        ctx->st.map_in_smem = 0;
+        status = enqueue_ptable(ctx, a, true);
+      }
+    } else if (ctx->p.df_mode == 6) { /* parity probe through the ray tables: every occupied cell gets a table */
       if (!ctx->rt.available) {
         status = fail(ctx, AMCLJ_ERR_INVALID, "raycast_debug: df_mode 6 unavailable for rays of %.0f cells", ctx->rt.r_cells);
       } else {
@@ -1378,9 +1663,9 @@ int32_t amclj_filter_update(amclj_ctx *ctx, const double curr[3], const double p
     ctx->normals_staged = normals != nullptr;
     rc = amclj_filter_update_async(ctx, curr, prev, seed, u0);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
+    rc = check_zero_total(ctx, "filter_update");
     collect_times(ctx);
-    return AMCLJ_OK;
+    return rc;
   }
   /* roulette / tournament need the host in the loop (pf.clj:156-167 has an unbounded
    * attempt count) */
@@ -1448,9 +1733,9 @@ int32_t amclj_filter_update_host(amclj_ctx *ctx, float *x, float *y, float *thet
   CK(cudaMemcpyAsync(y, ctx->y, b, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(theta, ctx->th, b, cudaMemcpyDeviceToHost, ctx->stream));
   if (w) CK(cudaMemcpyAsync(w, ctx->w, b, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  rc = check_zero_total(ctx, "filter_update_host");
   collect_times(ctx);
-  return AMCLJ_OK;
+  return rc;
 }
 
 int32_t amclj_pose_estimate(amclj_ctx *ctx, double out[4]) {
@@ -1476,8 +1761,11 @@ int32_t amclj_get_stats(amclj_ctx *ctx, amclj_stats *out) {
   NEED(out, AMCLJ_ERR_INVALID, "get_stats: null");
   CK(cudaStreamSynchronize(ctx->stream));
   collect_times(ctx);
-  unsigned long long h[12] = {0};
+  unsigned long long h[16] = {0};
   CK(cudaMemcpy(h, ctx->stats, sizeof(h), cudaMemcpyDeviceToHost));
+  ctx->st.zero_weight_updates = h[12];
+  ctx->st.ms_table_fill = ctx->pt.ms_fill;
+  ctx->st.table_bytes = ctx->pt.tables_bytes;
   ctx->st.oob_probes = h[6];
   if (h[8] && ctx->last_diag) ctx->st.map_in_smem = (int)h[8] - 1 == DF_SMEM4; /* the placement that actually ran */
   ctx->st.rays = h[0];
@@ -1672,8 +1960,11 @@ int32_t amclj_shard_export(amclj_ctx *ctx, uint8_t *handles) {
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->flip = 0;
   ctx->frozen = true;
-  void *bufs[7] = {ctx->x, ctx->y, ctx->th, ctx->x2, ctx->y2, ctx->th2, ctx->cdf};
-  for (int k = 0; k < 7; k++) {
+  ctx->gen = 0;
+  CK(cudaMemsetAsync(ctx->mbox, 0, sizeof(unsigned long long) * MBOX_WORDS, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  void *bufs[AMCLJ_IPC_BUFFERS] = {ctx->x, ctx->y, ctx->th, ctx->x2, ctx->y2, ctx->th2, ctx->cdf, ctx->mbox};
+  for (int k = 0; k < AMCLJ_IPC_BUFFERS; k++) {
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, bufs[k]));
     memcpy(handles + (size_t)k * AMCLJ_IPC_HANDLE_BYTES, &h, sizeof(h));
@@ -1685,8 +1976,8 @@ int32_t amclj_shard_import(amclj_ctx *ctx, int32_t rank, const uint8_t *handles,
                            int64_t peer_global_offset) {
   ENTER();
   NEED(handles && rank >= 0 && rank < MAX_WORLD && n_peer > 0, AMCLJ_ERR_INVALID, "shard_import: bad arguments");
-  void *p[7];
-  for (int k = 0; k < 7; k++) {
+  void *p[AMCLJ_IPC_BUFFERS];
+  for (int k = 0; k < AMCLJ_IPC_BUFFERS; k++) {
     cudaIpcMemHandle_t h;
     memcpy(&h, handles + (size_t)k * AMCLJ_IPC_HANDLE_BYTES, sizeof(h));
     if (ctx->ipc_opened[rank][k]) cudaIpcCloseMemHandle(ctx->ipc_opened[rank][k]);
@@ -1697,6 +1988,7 @@ int32_t amclj_shard_import(amclj_ctx *ctx, int32_t rank, const uint8_t *handles,
   PeerView b = {(float *)p[3], (float *)p[4], (float *)p[5], (uint64_t *)p[6], n_peer, peer_global_offset};
   ctx->peers[0][rank] = a;
   ctx->peers[1][rank] = b;
+  ctx->peer_mbox[rank] = reinterpret_cast<unsigned long long *>(p[7]);
   ctx->peer_set[rank] = true;
   return AMCLJ_OK;
 }
@@ -1707,16 +1999,137 @@ int32_t amclj_shard_attach_local(amclj_ctx *ctx, int32_t rank, amclj_ctx *peer) 
   if (peer == ctx) {
     ctx->flip = 0;
     ctx->frozen = true;
+    ctx->gen = 0;
+    CK(cudaMemsetAsync(ctx->mbox, 0, sizeof(unsigned long long) * MBOX_WORDS, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  } else if (peer->device != ctx->device) { /* one process, several GPUs: plain peer access */
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, ctx->device, peer->device));
+    NEED(can, AMCLJ_ERR_INVALID, "shard_attach_local: device %d cannot access device %d", ctx->device, peer->device);
+    cudaError_t pe = cudaDeviceEnablePeerAccess(peer->device, 0);
+    if (pe == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+    else CK(pe);
   }
   NEED(peer->flip == 0, AMCLJ_ERR_STATE, "shard_attach_local: attach before the first pull");
   peer->frozen = true;
   local_views(peer, &ctx->peers[0][rank], &ctx->peers[1][rank]);
+  ctx->peer_mbox[rank] = peer->mbox;
   ctx->peer_set[rank] = true;
   return AMCLJ_OK;
 }
 
+/* ---- the whole sharded update behind ONE call per rank: exchanges through the mailboxes ------- */
+static void mailbox_args(amclj_ctx *ctx, MailboxArgs &a) {
+  memset(&a, 0, sizeof(a));
+  a.mbox = ctx->mbox;
+  for (int g = 0; g < ctx->world; g++) a.peer_mbox[g] = ctx->peer_mbox[g];
+  a.rank = ctx->rank;
+  a.world = ctx->world;
+  a.gen = ctx->gen;
+  a.rawmax_ord = ctx->rawmax_ord;
+  a.rawmax = ctx->rawmax;
+  a.total = ctx->total;
+  a.totals_all = reinterpret_cast<unsigned long long *>(ctx->totals_all);
+  a.error_flag = ctx->stats + 13; /* [13]: mailbox waits that timed out */
+}
+
+/* phase A: motion + sensor, publish the local max */
+static int shard_phase_a(amclj_ctx *ctx, const double curr[3], const double prev[3], uint64_t seed) {
+  NEED(curr && prev, AMCLJ_ERR_INVALID, "shard_update: null control");
+  NEED(ctx->n > 0, AMCLJ_ERR_STATE, "shard_update: no particles");
+  NEED(ctx->beams.staged, AMCLJ_ERR_STATE, "shard_update: no scan staged");
+  NEED(ctx->world >= 1 && ctx->world <= MAX_WORLD, AMCLJ_ERR_INVALID, "shard_update: world %d", ctx->world);
+  for (int g = 0; g < ctx->world; g++)
+    NEED(ctx->peer_set[g] && ctx->peer_mbox[g], AMCLJ_ERR_STATE, "shard_update: rank %d not connected", g);
+  ctx->gen++;
+  stamp(ctx, 0);
+  CK(reset_ctrl(ctx, true));
+  ctx->ctrl_fresh = true;
+  ctx->bbox_done = false;
+  ctx->time_main = ctx->time_main_env || (ctx->p.collect_stats & 2) != 0;
+  ctx->stages_timed = ctx->time_main;
+  int rc = enqueue_motion(ctx, curr, prev, ctx->normals_staged, seed);
+  ctx->normals_staged = false;
+  if (rc) return rc;
+  if (ctx->stages_timed) stamp(ctx, 1);
+  rc = enqueue_sensor(ctx, false);
+  if (rc) return rc;
+  if (ctx->stages_timed) stamp(ctx, 2);
+  MailboxArgs m;
+  mailbox_args(ctx, m);
+  CK(launch_mailbox(m, 0, ctx->stream));
+  ctx->launches += 1;
+  return AMCLJ_OK;
+}
+
+/* phase B: wait for every rank's max, CDF against the global max, publish the local total */
+static int shard_phase_b(amclj_ctx *ctx) {
+  MailboxArgs m;
+  mailbox_args(ctx, m);
+  CK(launch_mailbox(m, 1, ctx->stream));
+  ctx->max_in_ord = false; /* AMCLJ_BUF_RAW_MAX now holds the global max */
+  int rc = enqueue_cdf(ctx, true, true);
+  if (rc) return rc;
+  CK(launch_mailbox(m, 2, ctx->stream));
+  ctx->launches += 2;
+  return AMCLJ_OK;
+}
+
+static int enqueue_pull(amclj_ctx *ctx, double u0);
+
+/* phase C: wait for every rank's total, then pull this rank's slots over peer memory */
+static int shard_phase_c(amclj_ctx *ctx, double u0) {
+  MailboxArgs m;
+  mailbox_args(ctx, m);
+  CK(launch_mailbox(m, 3, ctx->stream));
+  ctx->launches += 1;
+  return enqueue_pull(ctx, u0);
+}
+
+int32_t amclj_shard_update_async(amclj_ctx *ctx, const double curr[3], const double prev[3], uint64_t seed,
+                                 double u0) {
+  ENTER();
+  NEED(u0 >= 0.0 && u0 < 1.0, AMCLJ_ERR_INVALID, "shard_update: u0 must be in [0,1)");
+  int rc = shard_phase_a(ctx, curr, prev, seed);
+  if (rc) return rc;
+  rc = shard_phase_b(ctx);
+  if (rc) return rc;
+  return shard_phase_c(ctx, u0);
+}
+
+int32_t amclj_shard_update_host(amclj_ctx *ctx, float *x, float *y, float *theta, float *w, int64_t n,
+                                const double curr[3], const double prev[3], uint64_t seed, const float *ranges,
+                                int32_t n_ranges, float angle_min, float angle_increment, float range_max,
+                                double u0) {
+  ENTER();
+  NEED(x && y && theta && n > 0 && n == ctx->n, AMCLJ_ERR_INVALID,
+       "shard_update_host: the shard holds %lld particles (buffers are fixed once connected)", (long long)ctx->n);
+  NEED(curr && prev && ranges, AMCLJ_ERR_INVALID, "shard_update_host: null argument");
+  NEED(u0 >= 0.0 && u0 < 1.0, AMCLJ_ERR_INVALID, "shard_update: u0 must be in [0,1)");
+  const size_t b = sizeof(float) * (size_t)n;
+  CK(cudaMemcpyAsync(ctx->x, x, b, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->y, y, b, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->th, theta, b, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->have_raw = ctx->have_cdf = false;
+  int rc = stage_scan_impl(ctx, ranges, n_ranges, angle_min, angle_increment, range_max);
+  if (rc) return rc;
+  rc = amclj_shard_update_async(ctx, curr, prev, seed, u0);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(x, ctx->x, b, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(y, ctx->y, b, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(theta, ctx->th, b, cudaMemcpyDeviceToHost, ctx->stream));
+  if (w) CK(cudaMemcpyAsync(w, ctx->w, b, cudaMemcpyDeviceToHost, ctx->stream));
+  rc = check_zero_total(ctx, "shard_update_host");
+  collect_times(ctx);
+  return rc;
+}
+
 int32_t amclj_shard_pull_async(amclj_ctx *ctx, double u0) {
   ENTER();
+  return enqueue_pull(ctx, u0);
+}
+
+static int enqueue_pull(amclj_ctx *ctx, double u0) {
   NEED(ctx->have_cdf, AMCLJ_ERR_STATE, "shard_pull: no CDF");
   NEED(u0 >= 0.0 && u0 < 1.0, AMCLJ_ERR_INVALID, "shard_pull: u0 must be in [0,1)");
   NEED(ctx->world <= MAX_WORLD, AMCLJ_ERR_INVALID, "shard_pull: world > %d", MAX_WORLD);
@@ -1738,7 +2151,7 @@ int32_t amclj_shard_pull_async(amclj_ctx *ctx, double u0) {
   a.ow = ctx->w2;
   a.oidx64 = ctx->stage_idx && ctx->stage_cap >= ctx->n ? ctx->stage_idx : nullptr;
   a.wout = 1.0f / (float)ctx->n_global;
-  a.zero_flag = ctx->stats + 5;
+  a.zero_flag = ctx->stats + 12; /* [12]: updates whose total was zero (never cleared) */
   CK(launch_pull(a, ctx->stream));
   ctx->launches += 1;
   swap_particles(ctx);
@@ -1824,6 +2237,256 @@ int32_t amclj_reserve_stage(amclj_ctx *ctx, int64_t rows) {
   NEED(rows >= 0, AMCLJ_ERR_INVALID, "reserve_stage: bad rows");
   CK(cudaStreamSynchronize(ctx->stream));
   return ensure_stage(ctx, rows);
+}
+
+
+/* ---- one process, several GPUs: SURVEY 8b `amclj_create(const int* devices, int n_devices, ...)` ----
+ * The reference has ONE caller thread making three calls per update (pf.clj:229-233, :297); a JVM host
+ * cannot spawn a process per GPU.  An amclj_mctx owns one amclj_ctx per device, shards the particles in
+ * contiguous blocks, replicates map and scan, and runs the sharded update of amclj_shard_update_async on
+ * every device from the caller's thread: the kernels exchange {max, total} through peer-memory mailboxes
+ * and pull their resampled slots over NVLink, so the host only enqueues.  The work is enqueued phase by
+ * phase over all ranks (every publish before any wait), which keeps it deadlock-free even when several
+ * ranks share one device (the emulated shards of the tests). */
+struct amclj_mctx {
+  int32_t n = 0;
+  amclj_ctx *ctx[MAX_WORLD] = {};
+  int64_t n_global = 0;
+  bool connected = false;
+  std::string err;
+};
+
+static int mfail(amclj_mctx *m, int rank, int rc) {
+  if (rc && m) m->err = std::string("rank ") + std::to_string(rank) + ": " + amclj_last_error(m->ctx[rank]);
+  return rc;
+}
+#define MEACH(call)                                  \
+  do {                                               \
+    for (int r_ = 0; r_ < m->n; r_++) {              \
+      amclj_ctx *c = m->ctx[r_];                     \
+      int rc_ = (call);                              \
+      if (rc_) return mfail(m, r_, rc_);             \
+    }                                                \
+  } while (0)
+
+static void mslots(const amclj_mctx *m, int rank, int64_t n_global, int64_t *lo, int64_t *cnt) {
+  const int64_t q = n_global / m->n, rem = n_global % m->n;
+  *lo = rank * q + (rank < rem ? rank : rem);
+  *cnt = q + (rank < rem ? 1 : 0);
+}
+
+static int mconnect(amclj_mctx *m) {
+  for (int r = 0; r < m->n; r++) { /* own rank first: it resets the mailbox and the buffer alternation */
+    int rc = amclj_shard_attach_local(m->ctx[r], r, m->ctx[r]);
+    if (rc) return mfail(m, r, rc);
+  }
+  for (int r = 0; r < m->n; r++)
+    for (int g = 0; g < m->n; g++) {
+      if (g == r) continue;
+      int rc = amclj_shard_attach_local(m->ctx[r], g, m->ctx[g]);
+      if (rc) return mfail(m, r, rc);
+    }
+  m->connected = true;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_create_multi(const int32_t *devices, int32_t n_devices, amclj_mctx **out) {
+  if (!out) return AMCLJ_ERR_INVALID;
+  *out = nullptr;
+  if (!devices || n_devices < 1 || n_devices > MAX_WORLD) return AMCLJ_ERR_INVALID;
+  amclj_mctx *m = new amclj_mctx();
+  for (int r = 0; r < n_devices; r++) {
+    int rc = amclj_create(devices[r], &m->ctx[r]);
+    if (rc) {
+      for (int k = 0; k < r; k++) amclj_destroy(m->ctx[k]);
+      delete m;
+      return rc;
+    }
+    m->n = r + 1;
+  }
+  *out = m;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_destroy_multi(amclj_mctx *m) {
+  if (!m) return AMCLJ_OK;
+  for (int r = 0; r < m->n; r++) { /* nobody may still be reading a peer's buffers */
+    cudaSetDevice(m->ctx[r]->device);
+    cudaStreamSynchronize(m->ctx[r]->stream);
+  }
+  for (int r = 0; r < m->n; r++) amclj_destroy(m->ctx[r]);
+  delete m;
+  return AMCLJ_OK;
+}
+
+int32_t amclj_multi_size(const amclj_mctx *m) { return m ? m->n : 0; }
+amclj_ctx *amclj_multi_ctx(amclj_mctx *m, int32_t rank) { return (m && rank >= 0 && rank < m->n) ? m->ctx[rank] : nullptr; }
+const char *amclj_mlast_error(const amclj_mctx *m) { return m ? m->err.c_str() : "null mctx"; }
+
+int32_t amclj_mset_params(amclj_mctx *m, const amclj_params *p) {
+  if (!m) return AMCLJ_ERR_INVALID;
+  MEACH(amclj_set_params(c, p));
+  return AMCLJ_OK;
+}
+
+int32_t amclj_mset_map(amclj_mctx *m, const int8_t *cells, int32_t width, int32_t height, float resolution) {
+  if (!m) return AMCLJ_ERR_INVALID;
+  MEACH(amclj_set_map(c, cells, width, height, resolution));
+  return AMCLJ_OK;
+}
+
+int32_t amclj_mset_particles(amclj_mctx *m, const float *x, const float *y, const float *theta, const float *w,
+                             int64_t n_global) {
+  if (!m || !x || !y || !theta || n_global < m->n) return AMCLJ_ERR_INVALID;
+  const bool same_split = m->connected && m->n_global == n_global;
+  for (int r = 0; r < m->n; r++) {
+    int64_t lo, cnt;
+    mslots(m, r, n_global, &lo, &cnt);
+    amclj_ctx *c = m->ctx[r];
+    if (!same_split) c->frozen = false; /* a new split: the buffers may be reallocated, peers are re-attached below */
+    int rc = amclj_set_shard(c, r, m->n, lo, n_global);
+    if (!rc) rc = amclj_set_particles(c, x + lo, y + lo, theta + lo, w ? w + lo : nullptr, cnt);
+    if (rc) return mfail(m, r, rc);
+  }
+  m->n_global = n_global;
+  return same_split ? AMCLJ_OK : mconnect(m);
+}
+
+int32_t amclj_minit_uniform(amclj_mctx *m, int64_t n_global, int32_t heading_mode, uint64_t seed) {
+  if (!m || n_global < m->n) return AMCLJ_ERR_INVALID;
+  const bool same_split = m->connected && m->n_global == n_global;
+  for (int r = 0; r < m->n; r++) {
+    int64_t lo, cnt;
+    mslots(m, r, n_global, &lo, &cnt);
+    amclj_ctx *c = m->ctx[r];
+    if (!same_split) c->frozen = false;
+    int rc = amclj_set_shard(c, r, m->n, lo, n_global);
+    if (!rc) rc = amclj_init_uniform(c, cnt, heading_mode, seed); /* Philox keyed by the global particle id */
+    if (rc) return mfail(m, r, rc);
+  }
+  m->n_global = n_global;
+  return same_split ? AMCLJ_OK : mconnect(m);
+}
+
+int32_t amclj_mget_particles(amclj_mctx *m, float *x, float *y, float *theta, float *w) {
+  if (!m || m->n_global <= 0) return AMCLJ_ERR_INVALID;
+  for (int r = 0; r < m->n; r++) {
+    int64_t lo, cnt;
+    mslots(m, r, m->n_global, &lo, &cnt);
+    int rc = amclj_get_particles(m->ctx[r], x ? x + lo : nullptr, y ? y + lo : nullptr, theta ? theta + lo : nullptr,
+                                 w ? w + lo : nullptr);
+    if (rc) return mfail(m, r, rc);
+  }
+  return AMCLJ_OK;
+}
+
+int64_t amclj_mnum_particles(const amclj_mctx *m) { return m ? m->n_global : 0; }
+
+int32_t amclj_mstage_scan(amclj_mctx *m, const float *ranges, int32_t n, float angle_min, float angle_increment,
+                          float range_max) {
+  if (!m) return AMCLJ_ERR_INVALID;
+  MEACH(amclj_stage_scan(c, ranges, n, angle_min, angle_increment, range_max));
+  return AMCLJ_OK;
+}
+
+static int mphases(amclj_mctx *m, const double curr[3], const double prev[3], uint64_t seed, double u0) {
+  if (!m->connected) {
+    m->err = "mfilter_update: no particles yet (amclj_mset_particles / amclj_minit_uniform)";
+    return AMCLJ_ERR_STATE;
+  }
+  if (!(u0 >= 0.0 && u0 < 1.0)) {
+    m->err = "mfilter_update: u0 must be in [0,1)";
+    return AMCLJ_ERR_INVALID;
+  }
+  for (int r = 0; r < m->n; r++) {
+    if (cudaSetDevice(m->ctx[r]->device) != cudaSuccess) return AMCLJ_ERR_CUDA;
+    int rc = shard_phase_a(m->ctx[r], curr, prev, seed);
+    if (rc) return mfail(m, r, rc);
+  }
+  for (int r = 0; r < m->n; r++) {
+    if (cudaSetDevice(m->ctx[r]->device) != cudaSuccess) return AMCLJ_ERR_CUDA;
+    int rc = shard_phase_b(m->ctx[r]);
+    if (rc) return mfail(m, r, rc);
+  }
+  for (int r = 0; r < m->n; r++) {
+    if (cudaSetDevice(m->ctx[r]->device) != cudaSuccess) return AMCLJ_ERR_CUDA;
+    int rc = shard_phase_c(m->ctx[r], u0);
+    if (rc) return mfail(m, r, rc);
+  }
+  return AMCLJ_OK;
+}
+
+int32_t amclj_mfilter_update_async(amclj_mctx *m, const double curr[3], const double prev[3], uint64_t seed,
+                                   double u0) {
+  if (!m) return AMCLJ_ERR_INVALID;
+  return mphases(m, curr, prev, seed, u0);
+}
+
+int32_t amclj_msynchronize(amclj_mctx *m) {
+  if (!m) return AMCLJ_ERR_INVALID;
+  MEACH(amclj_synchronize(c));
+  return AMCLJ_OK;
+}
+
+int32_t amclj_mfilter_update_host(amclj_mctx *m, float *x, float *y, float *theta, float *w, int64_t n_global,
+                                  const double curr[3], const double prev[3], uint64_t seed, const float *ranges,
+                                  int32_t n_ranges, float angle_min, float angle_increment, float range_max,
+                                  double u0) {
+  if (!m || !x || !y || !theta || !ranges || !curr || !prev) return AMCLJ_ERR_INVALID;
+  if (!m->connected || n_global != m->n_global) { /* first call, or a different particle count: (re)shard */
+    int rc = amclj_mset_particles(m, x, y, theta, nullptr, n_global);
+    if (rc) return rc;
+  } else {
+    for (int r = 0; r < m->n; r++) {
+      int64_t lo, cnt;
+      mslots(m, r, n_global, &lo, &cnt);
+      amclj_ctx *ctx = m->ctx[r];
+      if (cudaSetDevice(ctx->device) != cudaSuccess) return AMCLJ_ERR_CUDA;
+      const size_t b = sizeof(float) * (size_t)cnt;
+      cudaError_t e = cudaMemcpyAsync(ctx->x, x + lo, b, cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->y, y + lo, b, cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->th, theta + lo, b, cudaMemcpyHostToDevice, ctx->stream);
+      if (e != cudaSuccess) return mfail(m, r, fail(ctx, AMCLJ_ERR_CUDA, "mfilter_update_host: %s", cudaGetErrorString(e)));
+      ctx->have_raw = ctx->have_cdf = false;
+    }
+  }
+  MEACH(amclj_stage_scan(c, ranges, n_ranges, angle_min, angle_increment, range_max));
+  int rc = mphases(m, curr, prev, seed, u0);
+  if (rc) return rc;
+  for (int r = 0; r < m->n; r++) {
+    int64_t lo, cnt;
+    mslots(m, r, n_global, &lo, &cnt);
+    amclj_ctx *ctx = m->ctx[r];
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return AMCLJ_ERR_CUDA;
+    const size_t b = sizeof(float) * (size_t)cnt;
+    cudaError_t e = cudaMemcpyAsync(x + lo, ctx->x, b, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(y + lo, ctx->y, b, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(theta + lo, ctx->th, b, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && w) e = cudaMemcpyAsync(w + lo, ctx->w, b, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess) return mfail(m, r, fail(ctx, AMCLJ_ERR_CUDA, "mfilter_update_host: %s", cudaGetErrorString(e)));
+  }
+  for (int r = 0; r < m->n; r++) {
+    amclj_ctx *ctx = m->ctx[r];
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return AMCLJ_ERR_CUDA;
+    rc = check_zero_total(ctx, "mfilter_update_host");
+    collect_times(ctx);
+    if (rc) return mfail(m, r, rc);
+  }
+  return AMCLJ_OK;
+}
+
+int32_t amclj_mpose_estimate(amclj_mctx *m, double out[4]) {
+  if (!m || !out || m->n_global <= 0) return AMCLJ_ERR_INVALID;
+  double s[4] = {0, 0, 0, 0};
+  for (int r = 0; r < m->n; r++) {
+    double part[4];
+    int rc = amclj_pose_estimate(m->ctx[r], part); /* local sums on a shard */
+    if (rc) return mfail(m, r, rc);
+    const double scale = m->n > 1 ? 1.0 : (double)m->ctx[r]->n;
+    for (int k = 0; k < 4; k++) s[k] += part[k] * scale;
+  }
+  for (int k = 0; k < 4; k++) out[k] = s[k] / (double)m->n_global;
+  return AMCLJ_OK;
 }
 
 }  // extern "C"

@@ -41,6 +41,17 @@ AMCLJ_HD void sincos_det(float a, float &sn, float &cs) {
   cs = co;
 }
 
+// Heading kept in (-pi, pi] (as quat/to-heading returns it, quaternions.clj:82-97): an unbounded fp32
+// angle would lose resolution with uptime (ulp 1e-3 rad at |theta| ~ 1e4) and drag the ray end cells
+// with it.  Values already inside the interval pass through untouched; IEEE ops only.
+AMCLJ_HD float wrap_heading(float t) {
+  if (fabsf(t) <= 3.14159274f) return t;
+  float k = rintf(t * 0.159154937f);
+  k = fminf(fmaxf(k, -1.0e9f), 1.0e9f);
+  float r = fmaf(k, -6.28318548f, t);
+  return fmaf(k, 1.74845553e-07f, r); /* 2 pi = 6.28318548 - 1.74845553e-07 */
+}
+
 // Deterministic exp for x <= 0 (used to turn log-weights into linear ones before the
 // fixed-point conversion): Cody-Waite by ln2, Cephes degree-5 polynomial, exact 2^n scale.
 // Anything below -87 (and NaN) flushes to 0.

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) motion_kernel(const MotionLaunch a) {
     float nx = fmaf(tr, cs, a.x[i]), ny = fmaf(tr, sn, a.y[i]); /* motion.clj:39-44 */
     a.x[i] = nx;
     a.y[i] = ny;
-    a.th[i] = th + (r1 + r2);      /* quat/rotate by rot1* + rot2* */
+    a.th[i] = wrap_heading(th + (r1 + r2)); /* quat/rotate by rot1* + rot2*; the next to-heading is in (-pi, pi] */
     m0 = ord_of_float_m(nx); m1 = ord_of_float_m(-nx); m2 = ord_of_float_m(ny); m3 = ord_of_float_m(-ny);
   }
   if (a.bbox) { /* bounding box of the moved cloud, for the sensor stage's walking-order decision */
@@ -478,14 +478,23 @@ __global__ void __launch_bounds__(256) systematic_gather_kernel(const GatherArgs
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= a.count) return;
   const SysPlan plan = s_plan;
-  uint64_t U = sys_threshold(plan, (uint64_t)(a.m_lo + k));
-  uint64_t key = U - a.cdf_offset; /* caller guarantees U >= cdf_offset */
-  int64_t lo = 0, hi = a.n_local;
-  while (lo < hi) { /* first i with cdf[i] > key */
-    int64_t mid = (lo + hi) >> 1;
-    if (__ldg(a.cdf + mid) > key) hi = mid; else lo = mid + 1;
+  int64_t i;
+  if (plan.total == 0) {
+    /* every weight is zero (e.g. a zero-probability beam under log-weights): there is no CDF to draw
+     * from.  Keep the particle that sits in the slot, exactly as pull_kernel does, and count the
+     * event so that the synchronising callers can report it (AMCLJ_ERR_STATE). */
+    if (k == 0 && a.zero_flag) atomicAdd(a.zero_flag, 1ull);
+    i = a.m_lo + k < a.n_local ? a.m_lo + k : a.n_local - 1;
+  } else {
+    uint64_t U = sys_threshold(plan, (uint64_t)(a.m_lo + k));
+    uint64_t key = U - a.cdf_offset; /* caller guarantees U >= cdf_offset */
+    int64_t lo = 0, hi = a.n_local;
+    while (lo < hi) { /* first i with cdf[i] > key */
+      int64_t mid = (lo + hi) >> 1;
+      if (__ldg(a.cdf + mid) > key) hi = mid; else lo = mid + 1;
+    }
+    i = lo < a.n_local ? lo : a.n_local - 1;
   }
-  int64_t i = lo < a.n_local ? lo : a.n_local - 1;
   float px = __ldg(a.x + i), py = __ldg(a.y + i), pt = __ldg(a.th + i);
   if (a.ox) { a.ox[k] = px; a.oy[k] = py; a.oth[k] = pt; a.ow[k] = a.wout; }
   if (a.orow) a.orow[k] = make_float4(px, py, pt, a.wout);
@@ -929,7 +938,7 @@ __global__ void __launch_bounds__(256) pull_kernel(const PullArgs a) {
     p.b = T % p.n;
     p.r = __umul64hi(a.u0_bits, T);
     s_plan = p;
-    if (T == 0 && blockIdx.x == 0) *a.zero_flag = 1ull;
+    if (T == 0 && blockIdx.x == 0) atomicAdd(a.zero_flag, 1ull);
   }
   __syncthreads();
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -958,6 +967,76 @@ __global__ void __launch_bounds__(256) pull_kernel(const PullArgs a) {
   a.oth[k] = a.peer[g].th[i];
   a.ow[k] = a.wout;
   if (a.oidx64) a.oidx64[k] = a.peer[g].gid0 + i;
+}
+
+// ======================================================================================
+// The two exchanges of a sharded update, done by the kernels themselves over peer
+// memory instead of by a collective library: every rank owns a mailbox with one slot per rank;
+// a rank PUBLISHES by storing into its slot of every rank's mailbox (plain stores over NVLink, or
+// into its own memory), tagged with the update's generation, and WAITS by polling its own
+// mailbox — local memory — until every slot carries this generation.  12 bytes per rank and
+// update; no host round trip, nothing for the host framework to schedule.
+//   max:    one 64-bit word {generation : 32 | ordered-uint of the rank's largest raw weight : 32}
+//   totals: the 64-bit fixed-point total, then (after a system-scope fence) its generation word;
+//           the reader takes them in the opposite order.  The publishing kernel runs after the
+//           scan in stream order, so a peer that has seen the generation may read that rank's CDF.
+// ======================================================================================
+__device__ __forceinline__ void st_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void publish_max_kernel(const MailboxArgs a) {
+  const int g = threadIdx.x;
+  if (g >= a.world) return;
+  const unsigned long long word = ((unsigned long long)a.gen << 32) | (unsigned long long)(*a.rawmax_ord);
+  st_sys_u64(a.peer_mbox[g] + MBOX_MAX + a.rank, word);
+}
+
+__global__ void wait_max_kernel(const MailboxArgs a) {
+  const int g = threadIdx.x;
+  uint32_t ord = 0;
+  if (g < a.world) {
+    unsigned long long w;
+    long long spins = 0;
+    do { w = ld_sys_u64(a.mbox + MBOX_MAX + g); } while ((uint32_t)(w >> 32) != a.gen && ++spins < MBOX_SPIN_LIMIT);
+    if ((uint32_t)(w >> 32) != a.gen && a.error_flag) atomicAdd(a.error_flag, 1ull); /* a rank never published: fail loudly */
+    ord = (uint32_t)w;
+  }
+  ord = __reduce_max_sync(0xffffffffu, ord);
+  if (g == 0) *a.rawmax = ord == 0 ? -INFINITY : float_of_ord(ord); /* the global max, as decode_max_kernel leaves the local one */
+}
+
+__global__ void publish_total_kernel(const MailboxArgs a) {
+  const int g = threadIdx.x;
+  if (g >= a.world) return;
+  st_sys_u64(a.peer_mbox[g] + MBOX_TOTAL + a.rank, (unsigned long long)*a.total);
+  __threadfence_system();
+  st_sys_u64(a.peer_mbox[g] + MBOX_TOTAL_GEN + a.rank, (unsigned long long)a.gen);
+}
+
+__global__ void wait_total_kernel(const MailboxArgs a) {
+  const int g = threadIdx.x;
+  if (g >= a.world) return;
+  long long spins = 0;
+  while ((uint32_t)ld_sys_u64(a.mbox + MBOX_TOTAL_GEN + g) != a.gen && ++spins < MBOX_SPIN_LIMIT) {}
+  if (spins >= MBOX_SPIN_LIMIT && a.error_flag) atomicAdd(a.error_flag, 1ull);
+  __threadfence_system();
+  a.totals_all[g] = ld_sys_u64(a.mbox + MBOX_TOTAL + g);
+}
+
+cudaError_t launch_mailbox(const MailboxArgs &a, int what, cudaStream_t s) {
+  switch (what) {
+    case 0: publish_max_kernel<<<1, 32, 0, s>>>(a); break;
+    case 1: wait_max_kernel<<<1, 32, 0, s>>>(a); break;
+    case 2: publish_total_kernel<<<1, 32, 0, s>>>(a); break;
+    default: wait_total_kernel<<<1, 32, 0, s>>>(a); break;
+  }
+  return cudaGetLastError();
 }
 
 cudaError_t launch_pull(const PullArgs &a, cudaStream_t s) {

@@ -161,6 +161,57 @@ struct RtLaunch {
   int32_t must_run;  // 1: the walk kernel is not launched for this update, so this path takes every particle
 };
 
+// ---------------------------------------------------------------------------------------
+// persistent map-wide ray tables (ptable.cu).  The map is static and a ray's range is a pure
+// function of (start cell, end cell) (sensor.clj:130-139 rounds both ends before anything else
+// looks at them), so ONE table per free cell of the map, filled once per (map, ray length,
+// S3/S4, resolution), serves every later update of every cloud, spread out or dense: per update
+// the particles are counting-sorted by start cell and every (particle, 30-beam segment) looks its
+// ranges up in the cell's table, which the warp stages into shared memory with the bulk-copy
+// engine.  A particle standing on a non-free or out-of-range cell sees range 0 on every beam
+// (extract-line tests the start cell first): those share one all-zero table.
+// ---------------------------------------------------------------------------------------
+struct PersistentTables {
+  int32_t n_slots = 0;             // free cells of the map = tables
+  int32_t *slot_of_cell = nullptr; // [H][W] -> table slot, or n_slots (the zero table)
+  int2 *cell_of_slot = nullptr;    // [n_slots]
+  float *tables = nullptr;         // [n_slots + 1][stride]; the last one is all zeros
+  size_t tables_bytes = 0;
+  int32_t stride = 0;              // floats per table: n_entries rounded up to 4 (16-byte bulk copies)
+  uint32_t *bin_count = nullptr;   // [n_slots + 2] particles per slot (zeroed by the scan)
+  uint32_t *bin_start = nullptr;   // [n_slots + 2] exclusive prefix; [n_slots + 1] = n
+  uint32_t *cursor = nullptr;      // [n_slots + 2] write cursors of the scatter
+  int32_t *pkey = nullptr;         // [pkey_cap] slot of every particle
+  int64_t pkey_cap = 0;
+  bool enable = true;              // AMCLJ_PTABLE=0 turns the path off
+  bool built = false;
+  size_t budget = 4ull << 30;      // AMCLJ_PT_BUDGET_MB
+  int32_t warps = 0;               // look-up warps per CTA (0: as many as the shared memory takes, at most 16)
+  // what the tables were built for
+  int64_t key_map_gen = -1;
+  double key_r = -1.0;
+  int32_t key_s3 = -1, key_s4 = -1, key_entries = -1;
+  uint32_t key_R_bits = 0, key_res_bits = 0;
+  int32_t fill_mode = -1;
+  double ms_fill = 0.0;            // what the one-time fill took
+};
+struct PtLaunch {
+  SensorLaunch s;
+  const uint4 *rows;
+  const short2 *ents;
+  int32_t nrows, E, n_entries, stride;
+  int32_t n_slots;
+  const int32_t *slot_of_cell;
+  const int2 *cell_of_slot;
+  float *tables;
+  uint32_t *bin_count, *bin_start, *cursor;
+  int32_t *pkey;
+  int32_t *perm;
+  float4 *pstate;
+  long long *qacc;
+  int32_t warps;   // look-up warps per CTA
+};
+
 constexpr int MAX_WORLD = 16;
 struct PeerView {   /* one rank's shard as seen from this GPU (own memory or NVLink peer memory) */
   const float *x, *y, *th;
@@ -222,13 +273,18 @@ struct amclj_ctx {
   // peer-memory resampling: both particle buffer sets of every rank (A = current at export)
   amclj::PeerView peers[2][amclj::MAX_WORLD];
   bool peer_set[amclj::MAX_WORLD] = {};
-  void *ipc_opened[amclj::MAX_WORLD][7] = {};
+  void *ipc_opened[amclj::MAX_WORLD][8] = {};
+  unsigned long long *mbox = nullptr;                        /* this rank's mailbox (device memory, zeroed) */
+  unsigned long long *peer_mbox[amclj::MAX_WORLD] = {};      /* every rank's mailbox as seen from here */
+  uint32_t gen = 0;                                          /* sharded updates so far (the mailbox tag) */
   int flip = 0;            // swaps since export, mod 2
   bool frozen = false;     // buffers exported: no reallocation
   uint64_t *totals_all = nullptr;  // [MAX_WORLD] all-gathered totals
   float4 *stage_out = nullptr, *stage_in = nullptr;
   int64_t stage_cap = 0;
   int64_t *stage_idx = nullptr;
+  uint64_t zero_seen = 0;  /* zero-total updates already reported (device counter: stats[12]) */
+  uint64_t mbox_errors_seen = 0;  /* mailbox time-outs already reported (stats[13]) */
   bool have_raw = false, have_cdf = false, cdf_from_raw = false, normals_staged = false;
   float last_wmax = 0.f;
   uint64_t last_total = 0;
@@ -242,6 +298,7 @@ struct amclj_ctx {
   uint32_t *hist = nullptr;           // 256-bin histogram of the radix select
   int32_t force_chunks = 0;
   amclj::RayTables rt;
+  amclj::PersistentTables pt;
   uint32_t *walk_ctr = nullptr;  // device {tail counter, CTAs finished} of the walk kernel
   int32_t walk_tail_pct = 0;   // spread-out clouds: CTA-contiguous task runs, this share of the tasks as a common tail
   int64_t map_gen = 0;     // bumped by every set_map
@@ -257,6 +314,10 @@ namespace amclj {
 cudaError_t launch_sensor(const amclj_ctx *c, const SensorLaunch &a, int mode, bool diag,
                           cudaStream_t s);
 enum { DF_SMEM4 = 0, DF_GLOBAL8 = 1, DF_GLOBAL4 = 2, DF_WEDGE8 = 3 };
+// ptable.cu
+cudaError_t launch_pt_fill(const amclj_ctx *c, const PtLaunch &L, int mode, cudaStream_t s);
+cudaError_t launch_pt_update(const amclj_ctx *c, const PtLaunch &L, int mode, bool dbg, cudaStream_t s);
+size_t pt_lookup_smem(const PtLaunch &L, int warps);
 // raytable.cu
 cudaError_t launch_raytable(const amclj_ctx *c, const RtLaunch &L, int mode, bool diag, cudaStream_t s);
 cudaError_t rt_prepare_device();
@@ -284,6 +345,7 @@ struct GatherArgs {
   int64_t *oidx64;
   int64_t gid0;
   float wout;
+  unsigned long long *zero_flag; /* counts updates whose fixed-point total was zero (may be null) */
 };
 struct PullArgs {
   PeerView peer[MAX_WORLD];
@@ -297,6 +359,23 @@ struct PullArgs {
   unsigned long long *zero_flag;
 };
 cudaError_t launch_pull(const PullArgs &a, cudaStream_t s);
+/* mailbox exchange of a sharded update (filter.cu): word offsets inside a rank's mailbox */
+constexpr int MBOX_MAX = 0, MBOX_TOTAL = MAX_WORLD, MBOX_TOTAL_GEN = 2 * MAX_WORLD, MBOX_WORDS = 3 * MAX_WORLD;
+struct MailboxArgs {
+  unsigned long long *mbox;                 /* this rank's mailbox (its own memory) */
+  unsigned long long *peer_mbox[MAX_WORLD]; /* every rank's mailbox as seen from this GPU */
+  int32_t rank, world;
+  uint32_t gen;
+  const uint32_t *rawmax_ord;   /* local max (ordered uint) */
+  float *rawmax;                /* out: the global max */
+  const uint64_t *total;        /* local fixed-point total */
+  unsigned long long *totals_all; /* out: every rank's total */
+  unsigned long long *error_flag; /* counts waits that gave up (a rank that never published) */
+};
+/* polls before a wait gives up (a few seconds): a mis-wired exchange must not hang the GPU */
+constexpr long long MBOX_SPIN_LIMIT = 1ll << 24;
+/* what: 0 publish max, 1 wait for every max, 2 publish total, 3 wait for every total */
+cudaError_t launch_mailbox(const MailboxArgs &a, int what, cudaStream_t s);
 
 struct RouletteArgs {
   const uint64_t *cdf;

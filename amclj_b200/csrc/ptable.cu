@@ -1,0 +1,434 @@
+// ptable.cu — K2c: the laser measurement model on PERSISTENT, map-wide ray tables.
+//
+// Replaces the same reference code as sensor.cu (pf.clj:148-154 -> sensor.clj:165-173 -> :141-162
+// -> :130-139 map-range -> :112-128 extract-line), with the same results bit for bit.
+//
+// map-range rounds both ends of a ray to integer cells before anything else looks at them
+// (sensor.clj:134-135, map.clj:36-46): the range of a ray is a pure function of (start cell, end
+// cell), and the map does not change between updates.  So the tables of raytable.cu need not be
+// rebuilt every update for the cells a dense cloud happens to stand on: ONE table per free cell
+// of the map (lgfloor: 78,513 cells x 1,923 end cells of a 5.6 m ray = 604 MB of float ranges,
+// filled once in a few milliseconds by walking 151 M rays with sensor.cu's own distance-field
+// walk) serves every later update of every cloud.  Per update:
+//   1. pt_hist_kernel / pt_scan_kernel / pt_scatter_kernel: counting sort of the particles by the
+//      table slot of their start cell (warp-aggregated atomics, so a tracking cloud that piles
+//      thousands of particles on one cell does not serialise), leaving next to the permutation what
+//      every look-up of a particle starts from (ray origin, sine and cosine of the heading);
+//   2. pt_lookup_kernel: every warp owns a contiguous run of the sorted particles and walks through
+//      the cells of that run: the cell's table comes into the warp's own shared-memory buffer by one
+//      bulk copy (cp.async.bulk + mbarrier, the next cell's copy in flight while this one is used),
+//      and the (particle, 30-beam segment) pairs of the cell are spread over the lanes: rotate the
+//      beam by the heading, round the end point exactly as sensor.cu does, ring index, one LDS,
+//      beam mixture.  Each table is read from HBM once per update;
+//   3. pt_finish_kernel: fixed-point accumulators -> raw weights and their maximum.
+// Segment sums are rounded once to 32.32 fixed point and added as integers exactly as in
+// sensor.cu / raytable.cu, so the three paths agree bit for bit and which one ran can never be
+// seen in a result.  An end cell off the ring reads the table's NaN entry and the segment is
+// redone by walking (never seen; the table is an accelerator, never an approximation).
+#include "internal.h"
+#include "raycast.cuh"
+#include "sensor_common.cuh"
+
+namespace amclj {
+
+constexpr int PT_SORT_THREADS = 256;
+
+/* ray origin (S10: the laser, sensor.clj:78-81) and heading sine / cosine of particle i */
+__device__ __forceinline__ float4 pt_origin(const SensorLaunch &a, int64_t i) {
+  float ox = __ldg(a.x + i), oy = __ldg(a.y + i), st, ct;
+  sincos_det(__ldg(a.th + i), st, ct);
+  if (a.s10) {
+    float nx = ox + fmaf(a.laser_x, ct, -(a.laser_y * st));
+    float ny = oy + fmaf(a.laser_x, st, a.laser_y * ct);
+    ox = nx; oy = ny;
+  }
+  return make_float4(ox, oy, st, ct);
+}
+
+// ---- one-time fill: one ray per (free cell, ring entry) ----------------------------------------
+template <int MODE, bool WIDE>
+__global__ void __launch_bounds__(256)
+pt_fill_kernel(const __grid_constant__ PtLaunch L) {
+  const SensorLaunch &a = L.s;
+  const int64_t total = (int64_t)L.n_slots * L.stride;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float nanv = __int_as_float(0x7fc00000);
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
+    const int slot = (int)(w / L.stride), e = (int)(w - (int64_t)slot * L.stride);
+    float v = nanv; /* padding, the unused slot of a merged row, and the sentinel behind the ring */
+    if (e < L.n_entries) {
+      const short2 en = __ldg(L.ents + e);
+      if (en.x > -32767) {
+        const int2 c = __ldg(L.cell_of_slot + slot);
+        RayOut o;
+        v = cast_ray<MODE, WIDE, false>(a, a.df, c.x, c.y, c.x + en.x, c.y + en.y, o);
+      }
+    }
+    L.tables[w] = v;
+  }
+}
+
+// ---- per update: counting sort by table slot ---------------------------------------------------
+__global__ void __launch_bounds__(PT_SORT_THREADS)
+pt_hist_kernel(const __grid_constant__ PtLaunch L) {
+  const SensorLaunch &a = L.s;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int key = -1 - lane; /* lanes past the end: a key nobody shares */
+  if (i < a.n) {
+    L.qacc[i] = 0; /* the weight accumulators of this update */
+    const ResDiv rdv = make_resdiv(a.res);
+    const float4 o = pt_origin(a, i);
+    int x0, y0;
+    round_cell2_fast(o.x, o.y, rdv, x0, y0);
+    const bool in = (uint32_t)x0 < (uint32_t)a.W && (uint32_t)y0 < (uint32_t)a.H;
+    key = in ? __ldg(L.slot_of_cell + (size_t)y0 * a.W + x0) : L.n_slots;
+    L.pkey[i] = key;
+  }
+  const uint32_t peers = __match_any_sync(FULL, key);
+  if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(L.bin_count + key, (uint32_t)__popc(peers));
+}
+
+// exclusive scan of the bin counts (one CTA; n_slots + 1 bins), which also re-zeroes them
+__global__ void __launch_bounds__(1024)
+pt_scan_kernel(uint32_t *bin_count, uint32_t *bin_start, uint32_t *cursor, int nbins) {
+  __shared__ uint32_t warp_tot[32];
+  const int per = (nbins + 1023) / 1024, lo = min((int)threadIdx.x * per, nbins), hi = min(lo + per, nbins);
+  uint32_t sum = 0;
+  for (int b = lo; b < hi; b++) sum += bin_count[b];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(FULL, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = warp_tot[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(FULL, wi, o);
+      if (lane >= o) wi += t;
+    }
+    warp_tot[lane] = wi - w;
+  }
+  __syncthreads();
+  uint32_t run = warp_tot[wid] + inc - sum;
+  for (int b = lo; b < hi; b++) {
+    const uint32_t c = bin_count[b];
+    bin_start[b] = run;
+    cursor[b] = run;
+    bin_count[b] = 0;
+    run += c;
+  }
+  if (threadIdx.x == 1023) bin_start[nbins] = run; /* = n */
+}
+
+__global__ void __launch_bounds__(PT_SORT_THREADS)
+pt_scatter_kernel(const __grid_constant__ PtLaunch L) {
+  const SensorLaunch &a = L.s;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int key = i < a.n ? L.pkey[i] : -1 - lane;
+  const uint32_t peers = __match_any_sync(FULL, key);
+  const int leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if (key >= 0 && lane == leader) base = atomicAdd(L.cursor + key, (uint32_t)__popc(peers));
+  base = __shfl_sync(FULL, base, leader);
+  if (key < 0) return;
+  const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+  L.perm[pos] = (int32_t)i;
+  L.pstate[pos] = pt_origin(a, i);
+}
+
+// ---- the look-up -------------------------------------------------------------------------------
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// One 30-beam segment of one particle, every range from the staged table of its start cell:
+// the arithmetic of raytable.cu's table_segment (and of sensor.cu's set-up) with the table in
+// shared memory.  DBG: also leave every range in the parity probe's buffer.
+template <bool S7, bool DBG>
+__device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunch &L, const ResDiv &rdv, uint32_t s_tab,
+                                            uint32_t s_mix, uint32_t s_dir, uint32_t s_rows, float ox, float oy, float st,
+                                            float ct, int xoff, int yoff, int jb0, int jb1, float *dbg_row) {
+  float acc = 0.0f, prod = 1.0f;
+  int pexp = 0;
+  const uint32_t last_row = (uint32_t)L.nrows - 1u, nan_entry = (uint32_t)L.n_entries - 1u;
+  /* S1 off = rotation by zero: fma(1, cb, -(0 * sb)) and fma(0, cb, 1 * sb) give back (cb, sb) */
+  const float rc = a.s1 ? ct : 1.0f, rs = a.s1 ? st : 0.0f;
+#pragma unroll 2
+  for (int jb = jb0; jb < jb1; jb++) {
+    const float2 bd = lds_f2(s_dir + (uint32_t)jb * 8u);
+    const float c = fmaf(rc, bd.x, -(rs * bd.y)), s = fmaf(rs, bd.x, rc * bd.y); /* S1: angle addition */
+    /* sensor.clj:130-135 / map.clj:36-46: end point of the beam to its cell, as round_cell2_inrange */
+    const float ex_w = fmaf(a.R, c, ox), ey_w = fmaf(a.R, s, oy);
+    const float qx0 = ex_w * rdv.r, qy0 = ey_w * rdv.r;
+    const float qx = fmaf(fmaf(-qx0, rdv.res, ex_w), rdv.r, qx0);
+    const float qy = fmaf(fmaf(-qy0, rdv.res, ey_w), rdv.r, qy0);
+    /* floor(q + 0.5) on the FP32 pipe (exact for |q| < 2^22: the start is a cell of the map) */
+    const int ex = __float_as_int(__fadd_rd(qx + 0.5f, 12582912.0f)) - xoff;
+    const uint32_t ry = (uint32_t)(__float_as_int(__fadd_rd(qy + 0.5f, 12582912.0f)) - yoff);
+    const uint32_t ryc = min(ry, last_row);
+    const uint4 rw = lds_u4(s_rows + ryc * 16u); /* {first entry, lo, cnt, first entry of the negative arc} */
+    const uint32_t tt = (uint32_t)abs(ex) - rw.y;
+    const bool ok = tt < rw.z && ry <= last_row;
+    const uint32_t ent = ok ? tt + (ex < 0 ? rw.w : rw.x) : nan_entry;
+    const float rng = lds_f1(s_tab + ent * 4u);
+    if (DBG && dbg_row) dbg_row[jb] = rng;
+    /* sensor.clj:149-162 beam mixture, exactly as in sensor.cu */
+    const float4 mx = lds_f4(s_mix + (uint32_t)jb * 16u);
+    const float z = mx.x - rng;
+    const float pz1 = hit_gauss(z, a.k2, a.z_hit);
+    const float pz2 = z < 0.0f ? mx.y : 0.0f;
+    const float sum = (pz1 + pz2) + mx.z;
+    if (S7) logprod_mul(acc, prod, pexp, sum);
+    else acc += (sum * sum) * sum;
+  }
+  return S7 ? logprod_close(acc, prod, pexp) : acc;
+}
+
+/* a segment whose table look-up came back NaN (an end cell off the ring, a NaN pose): walk its rays */
+template <int MODE, bool WIDE>
+__device__ __noinline__ float pt_segment_walk(const SensorLaunch &a, float ox, float oy, float st, float ct, int jb0, int jb1,
+                                              float *dbg_row) {
+  const ResDiv rdv = make_resdiv(a.res);
+  const float4 *mixt = reinterpret_cast<const float4 *>(a.beam);
+  const float2 *dirt = reinterpret_cast<const float2 *>(a.beam + 4 * (size_t)a.nb);
+  int x0, y0;
+  round_cell2_fast(ox, oy, rdv, x0, y0);
+  float acc = 0.0f, prod = 1.0f;
+  int pexp = 0;
+  for (int jb = jb0; jb < jb1; jb++) {
+    const float2 bd = __ldg(dirt + jb);
+    float c = bd.x, s = bd.y;
+    if (a.s1) {
+      c = fmaf(ct, bd.x, -(st * bd.y));
+      s = fmaf(st, bd.x, ct * bd.y);
+    }
+    const float ex_w = fmaf(a.R, c, ox), ey_w = fmaf(a.R, s, oy);
+    RayOut o;
+    const float rng = cast_ray_slow<MODE, WIDE, false>(a, x0, y0, ex_w, ey_w, o);
+    if (dbg_row) dbg_row[jb] = rng;
+    const float4 mx = __ldg(mixt + jb);
+    const float z = mx.x - rng;
+    const float pz1 = hit_gauss(z, a.k2, a.z_hit);
+    const float pz2 = z < 0.0f ? mx.y : 0.0f;
+    const float sum = (pz1 + pz2) + mx.z;
+    if (a.s7) logprod_mul(acc, prod, pexp, sum);
+    else acc += (sum * sum) * sum;
+  }
+  return a.s7 ? logprod_close(acc, prod, pexp) : acc;
+}
+
+constexpr int PT_MAX_WARPS = 16;
+
+template <int MODE, bool WIDE, bool DBG>
+__global__ void __launch_bounds__(PT_MAX_WARPS * 32, 1)
+pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
+  const SensorLaunch &a = L.s;
+  extern __shared__ uint4 smem_dyn[];
+  __shared__ uint64_t bars[PT_MAX_WARPS][2];
+  const int nb = a.nb, nseg = (nb + SEG - 1) / SEG;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  /* [mix float4[nb] | rows uint4[nrows] | dir float2[nb] | pad to 16 | per warp: 2 tables of stride floats] */
+  float4 *smix = reinterpret_cast<float4 *>(smem_dyn);
+  uint4 *srows = reinterpret_cast<uint4 *>(smix + nb);
+  float2 *sdir = reinterpret_cast<float2 *>(srows + L.nrows);
+  float *stab = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(sdir + nb) + 15) & ~(uintptr_t)15) +
+                (size_t)wid * 2 * L.stride;
+  {
+    const float4 *mixt = reinterpret_cast<const float4 *>(a.beam);
+    const float2 *dirt = reinterpret_cast<const float2 *>(a.beam + 4 * (size_t)nb);
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) { smix[i] = __ldg(mixt + i); sdir[i] = __ldg(dirt + i); }
+    for (int i = threadIdx.x; i < L.nrows; i += blockDim.x) srows[i] = __ldg(L.rows + i);
+  }
+  uint32_t s_mix = smem_u32(smix), s_dir = smem_u32(sdir), s_rows = smem_u32(srows);
+  asm volatile("" : "+r"(s_mix), "+r"(s_dir), "+r"(s_rows));
+  const uint32_t s_tab0 = smem_u32(stab), tab_bytes = (uint32_t)L.stride * 4u;
+  const uint32_t bar0 = smem_u32(&bars[wid][0]);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  /* this warp's run of the sorted particles */
+  const int64_t n = a.n, Wt = (int64_t)gridDim.x * wpb, g = (int64_t)blockIdx.x * wpb + wid;
+  const uint32_t q_lo = (uint32_t)(n * g / Wt), q_hi = (uint32_t)(n * (g + 1) / Wt);
+  if (q_lo >= q_hi) return;
+  const int nbins = L.n_slots + 1;
+  const uint32_t *start = L.bin_start;
+  int s; /* the slot holding position q_lo: the last one with start[s] <= q_lo */
+  {
+    int lo_s = 0, hi_s = nbins;
+    while (hi_s - lo_s > 1) {
+      const int mid = (lo_s + hi_s) >> 1;
+      if (__ldg(start + mid) <= q_lo) lo_s = mid; else hi_s = mid;
+    }
+    s = lo_s;
+  }
+  uint32_t q = q_lo;
+  const ResDiv rdv = make_resdiv(a.res);
+
+  /* the next cell of the run: slot, first position, particles */
+  auto next_cell = [&](int &slot, uint32_t &p0, int &cnt) -> bool {
+    if (q >= q_hi) return false;
+    for (;;) { /* advance s to the slot holding q: the first s' >= s with start[s' + 1] > q */
+      const int t = s + 1 + lane;
+      const uint32_t v = t <= nbins ? __ldg(start + t) : 0xffffffffu;
+      const uint32_t m = __ballot_sync(FULL, v > q);
+      if (m) { s += __ffs(m) - 1; break; }
+      s += 32;
+    }
+    const uint32_t end = min(__ldg(start + s + 1), q_hi);
+    slot = s; p0 = q; cnt = (int)(end - q);
+    q = end;
+    return true;
+  };
+  auto issue = [&](int slot, int buf) { /* lane 0: bulk copy of the slot's table into buffer buf */
+    if (lane == 0) {
+      const uint32_t bar = bar0 + 8u * (uint32_t)buf, dst = s_tab0 + (uint32_t)buf * tab_bytes;
+      const float *src = L.tables + (size_t)slot * L.stride;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* the buffer's last readers are done (syncwarp) */
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tab_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(src), "r"(tab_bytes), "r"(bar)
+                   : "memory");
+    }
+  };
+
+  int c_slot = 0, n_slot = 0, c_cnt = 0, n_cnt = 0;
+  uint32_t c_p0 = 0, n_p0 = 0;
+  bool have = next_cell(c_slot, c_p0, c_cnt);
+  if (have) issue(c_slot, 0);
+  for (int it = 0; have; it++) {
+    const bool have_n = next_cell(n_slot, n_p0, n_cnt);
+    if (have_n) issue(n_slot, (it + 1) & 1);
+    { /* wait for this cell's table */
+      const uint32_t bar = bar0 + 8u * (uint32_t)(it & 1), parity = (uint32_t)(it >> 1) & 1u;
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+      }
+    }
+    const uint32_t s_tab = s_tab0 + (uint32_t)(it & 1) * tab_bytes;
+    int2 cc = make_int2(0, 0);
+    if (c_slot < L.n_slots) cc = __ldg(L.cell_of_slot + c_slot);
+    const int xoff = 0x4B400000 + cc.x, yoff = 0x4B400000 + cc.y - L.E;
+    const int ntask = c_cnt * nseg; /* (segment, particle) pairs, particle fastest: a warp shares its beams */
+    for (int t = lane; t < ntask; t += 32) {
+      const int sgm = t / c_cnt, j = t - sgm * c_cnt;
+      const uint32_t pos = c_p0 + (uint32_t)j;
+      const int64_t p = (int64_t)__ldg(L.perm + pos);
+      const float4 ps = __ldg(L.pstate + pos);
+      const int jb0 = sgm * SEG, jb1 = min(jb0 + SEG, nb);
+      float *dbg_row = nullptr;
+      if (DBG && a.dbg_range && p >= a.dbg_first && p < a.dbg_first + a.dbg_count)
+        dbg_row = a.dbg_range + (p - a.dbg_first) * nb;
+      float v = a.s7 ? pt_segment<true, DBG>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, xoff, yoff, jb0, jb1, dbg_row)
+                     : pt_segment<false, DBG>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, xoff, yoff, jb0, jb1, dbg_row);
+      if (v != v) {
+        v = pt_segment_walk<MODE, WIDE>(a, ps.x, ps.y, ps.z, ps.w, jb0, jb1, dbg_row);
+        if (a.stats) atomicAdd(a.stats + 11, 1ull); /* table_misses: expected 0 */
+      }
+      /* close the segment: one rounding to fixed point; segments add as integers */
+      atomicAdd(reinterpret_cast<unsigned long long *>(L.qacc) + p,
+                (unsigned long long)__float2ll_rn(fmaxf(v, FIX_FLOOR) * FIX_SCALE));
+    }
+    __syncwarp();
+    c_slot = n_slot; c_p0 = n_p0; c_cnt = n_cnt;
+    have = have_n;
+  }
+}
+
+// raw[p] = the fixed-point sum of the particle's segments as a float, plus the max for the normaliser
+__global__ void __launch_bounds__(256)
+pt_finish_kernel(const long long *__restrict__ qacc, int64_t n, float *__restrict__ raw, uint32_t *rawmax_ord) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float v = -INFINITY;
+  if (i < n) {
+    v = fixed_to_raw(__ldg(qacc + i));
+    if (raw) raw[i] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+  if ((threadIdx.x & 31) == 0 && rawmax_ord && v > -INFINITY) atomicMax(rawmax_ord, ord_of_float(v));
+}
+
+size_t pt_lookup_smem(const PtLaunch &L, int warps) {
+  return (size_t)L.s.nb * 24 + (size_t)L.nrows * 16 + 16 + (size_t)warps * 2 * L.stride * 4;
+}
+
+template <int MODE, bool WIDE>
+static cudaError_t launch_pt_fill_t(const amclj_ctx *c, const PtLaunch &L, cudaStream_t s) {
+  pt_fill_kernel<MODE, WIDE><<<(unsigned)(c->sm_count * 16), 256, 0, s>>>(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pt_fill(const amclj_ctx *c, const PtLaunch &L, int mode, cudaStream_t s) {
+  const bool wide = L.s.div_wide != 0;
+  /* the zero table: every beam of a particle on a non-free cell hits at step 0 (range 0) */
+  cudaError_t e = cudaMemsetAsync(L.tables + (size_t)L.n_slots * L.stride, 0, sizeof(float) * (size_t)L.stride, s);
+  if (e != cudaSuccess || L.n_slots == 0) return e;
+  switch (mode) {
+    case DF_WEDGE8: return wide ? launch_pt_fill_t<DF_WEDGE8, true>(c, L, s) : launch_pt_fill_t<DF_WEDGE8, false>(c, L, s);
+    case DF_GLOBAL8: return wide ? launch_pt_fill_t<DF_GLOBAL8, true>(c, L, s) : launch_pt_fill_t<DF_GLOBAL8, false>(c, L, s);
+    default: return wide ? launch_pt_fill_t<DF_GLOBAL4, true>(c, L, s) : launch_pt_fill_t<DF_GLOBAL4, false>(c, L, s);
+  }
+}
+
+template <int MODE, bool WIDE, bool DBG>
+static cudaError_t launch_pt_lookup_t(const amclj_ctx *c, const PtLaunch &L, cudaStream_t s) {
+  auto kern = pt_lookup_kernel<MODE, WIDE, DBG>;
+  const size_t smem = pt_lookup_smem(L, L.warps);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  /* persistent: one CTA per SM; fewer when there are not enough particles to give every warp a few */
+  int64_t ctas = c->sm_count;
+  const int64_t want = (L.s.n + (int64_t)L.warps * 4 - 1) / ((int64_t)L.warps * 4);
+  if (ctas > want) ctas = want < 1 ? 1 : want;
+  if (c->time_main) cudaEventRecord(c->ev[5], s);
+  kern<<<(unsigned)ctas, L.warps * 32, smem, s>>>(L);
+  if (c->time_main) cudaEventRecord(c->ev[6], s);
+  return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t launch_pt_lookup_m(const amclj_ctx *c, const PtLaunch &L, bool wide, bool dbg, cudaStream_t s) {
+  if (dbg) return wide ? launch_pt_lookup_t<MODE, true, true>(c, L, s) : launch_pt_lookup_t<MODE, false, true>(c, L, s);
+  return wide ? launch_pt_lookup_t<MODE, true, false>(c, L, s) : launch_pt_lookup_t<MODE, false, false>(c, L, s);
+}
+
+cudaError_t launch_pt_update(const amclj_ctx *c, const PtLaunch &L, int mode, bool dbg, cudaStream_t s) {
+  const SensorLaunch &a = L.s;
+  if (a.n <= 0 || a.nb <= 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((a.n + PT_SORT_THREADS - 1) / PT_SORT_THREADS);
+  pt_hist_kernel<<<blocks, PT_SORT_THREADS, 0, s>>>(L);
+  pt_scan_kernel<<<1, 1024, 0, s>>>(L.bin_count, L.bin_start, L.cursor, L.n_slots + 1);
+  pt_scatter_kernel<<<blocks, PT_SORT_THREADS, 0, s>>>(L);
+  const bool wide = a.div_wide != 0;
+  cudaError_t e;
+  switch (mode) {
+    case DF_WEDGE8: e = launch_pt_lookup_m<DF_WEDGE8>(c, L, wide, dbg, s); break;
+    case DF_GLOBAL8: e = launch_pt_lookup_m<DF_GLOBAL8>(c, L, wide, dbg, s); break;
+    default: e = launch_pt_lookup_m<DF_GLOBAL4>(c, L, wide, dbg, s); break;
+  }
+  if (e != cudaSuccess) return e;
+  pt_finish_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(L.qacc, a.n, a.raw, a.rawmax_ord);
+  return cudaGetLastError();
+}
+
+}  // namespace amclj

@@ -30,9 +30,14 @@ class ParticleCloud:
 
     # -- PoseArray <-> SoA -----------------------------------------------------------------
     def set_poses(self, x, y, theta=None, orientation=None, weight=None):
+        """``orientation`` = (qx, qy, qz, qw) arrays as in geometry_msgs/Pose: converted by the library
+        (amclj_set_poses_quat = quat/to-heading, quaternions.clj:82-97)."""
         if theta is None:
-            theta = quaternions.to_heading(*orientation)
-        self.ctx.set_particles(x, y, theta, weight)
+            qx, qy, qz, qw = (np.asarray(v, np.float64) for v in orientation)
+            rows = np.stack([np.asarray(x, np.float64), np.asarray(y, np.float64), np.zeros(len(qx)), qx, qy, qz, qw], 1)
+            self.ctx.set_poses_quat(rows, weight)
+        else:
+            self.ctx.set_particles(x, y, theta, weight)
         return self
 
     def poses(self):
@@ -40,7 +45,9 @@ class ParticleCloud:
         return self.ctx.get_particles()
 
     def orientations(self):
-        return quaternions.from_heading(self.ctx.get_particles()[2])
+        """(qx, qy, qz, qw) of every particle: quat/from-heading inside the library (amclj_get_poses_quat)."""
+        rows, _ = self.ctx.get_poses_quat()
+        return rows[:, 3], rows[:, 4], rows[:, 5], rows[:, 6]
 
     def __len__(self):
         return self.ctx.n

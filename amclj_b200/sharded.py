@@ -16,6 +16,12 @@ One update needs exactly three exchanges:
      "a2a": each rank generates the offspring of its CDF interval and an NCCL all-to-all moves
          the rows to the ranks that own the slots (slot m lives on rank m / (N/G)).
 
+     "mailbox" (default on GPUs): exchanges 1 and 2 are done by the library's own kernels as well —
+         every rank stores its {max, total} into every peer's mailbox over NVLink and polls its
+         own (12 bytes per rank and update) — so an update is ONE library call per rank
+         (amclj_shard_update_async): no NCCL, no Python between the kernels, nothing but the
+         one-time exchange of CUDA IPC handles goes through torch.distributed.
+
 The resulting global index list is identical to the single-GPU one (integer CDF).  The
 reference has no counterpart (single-threaded Clojure, pf.clj:222-240); this is the
 data-parallel form of pf.clj:229-233.
@@ -88,6 +94,9 @@ class CudaShard:
     def pull(self, u0):
         self.ctx.shard_pull_async(u0)
 
+    def update_mailbox(self, curr, prev, seed, u0):
+        self.ctx.shard_update_async(curr, prev, seed, u0)
+
 
 def slots_of(rank, world, n_global):
     """Output slots owned by ``rank``: n_global / world each, the remainder to the low ranks."""
@@ -102,10 +111,17 @@ class ShardedFilter:
         self.rank, self.world, self.n_global, self.group = rank, world, int(n_global), group
         self.backend = backend if backend is not None else CudaShard(ctx, device)
         self.ctx = ctx
-        self.stream = stream
+        # The NCCL collectives run on torch's current stream and read / write library buffers in place,
+        # so the library's kernels must be ordered on that very stream: bind the ctx to it here and run
+        # every update under it (the race-freedom argument of pull mode needs collectives and kernels on
+        # ONE stream as well).
+        self.stream = None
+        if backend is None:
+            self.stream = stream if stream is not None else torch.cuda.current_stream(device)
+            ctx.set_stream(self.stream.cuda_stream)
         self.slot0, self.n_slots = slots_of(rank, world, self.n_global)
         self.backend.set_shard(rank, world, self.slot0, self.n_global)
-        self.mode = mode or ("pull" if backend is None and world <= 16 else "a2a")
+        self.mode = mode or ("mailbox" if backend is None and world <= 16 else "a2a")
         self.connected = False
         if self.mode == "a2a":
             self.backend.reserve(max(self.n_slots, 1))
@@ -113,7 +129,7 @@ class ShardedFilter:
 
     def connect(self):
         """Pull mode: map the peers' buffers (call once, after the particles are in place)."""
-        if self.mode == "pull" and not self.connected:
+        if self.mode in ("pull", "mailbox") and not self.connected:
             self.backend.connect_peers(self.rank, self.world, self.n_global, self.group)
             self.connected = True
 
@@ -124,7 +140,17 @@ class ShardedFilter:
         self.backend.set_shard(self.rank, self.world, self.slot0, self.n_global)
 
     def update(self, curr, prev, seed, u0):
+        if self.stream is not None:
+            with torch.cuda.stream(self.stream):
+                return self._update(curr, prev, seed, u0)
+        return self._update(curr, prev, seed, u0)
+
+    def _update(self, curr, prev, seed, u0):
         b = self.backend
+        if self.mode == "mailbox":
+            self.connect()
+            b.update_mailbox(curr, prev, seed, u0)  # one library call: the kernels do the exchanges
+            return None
         b.motion_sensor(curr, prev, seed)
         mx = b.raw_max()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AMCLJ_ABI_VERSION 1
+#define AMCLJ_ABI_VERSION 2
 
 #define AMCLJ_OK 0
 #define AMCLJ_ERR_INVALID (-1)  /* bad argument */
@@ -83,7 +83,11 @@ typedef struct amclj_params {
    * in global memory, 3 isotropic nibbles in global memory,
    * 4 directional byte fields (32 direction classes) through L1/L2, 5 the same with the particles
    * walked in map-tile order (spread-out clouds), 6 per-start-cell ray tables for every occupied cell
-   * (mode 0 takes them by itself when most particles share their start cell with many others) */
+   * (mode 8 takes them by itself when most particles share their start cell with many others),
+   * 7 persistent map-wide ray tables: one table per FREE CELL OF THE MAP, filled once per (map, ray length,
+   * S3/S4) and looked up by every later update of any cloud; mode 0 uses them whenever the map is small
+   * enough (lgfloor: 604 MB) and falls back to the policy of mode 8 otherwise,
+   * 8 the auto policy without the persistent tables (walk kernel / per-update tables picked per update) */
   int32_t df_mode;
   float max_range;    /* sensor.clj:12  (-1.0) */
   float z_hit;        /* sensor.clj:14 */
@@ -118,8 +122,13 @@ typedef struct amclj_stats {
   uint64_t table_particles; /* ... and the particles standing on them */
   uint64_t table_misses;    /* ... and their rays whose end cell was not in the table (walked instead; expected 0) */
   double ms_sensor_main;    /* the dominant kernel of the last sensor pass alone (sensor_kernel, or rt_lookup_kernel) */
-  int32_t sensor_path;      /* what the last sensor pass ran on: 0 walk in map-tile order, 1 walk in place, 2 ray tables, -1 not known yet */
+  int32_t sensor_path;      /* what the last sensor pass ran on: 0 walk in map-tile order, 1 walk in place, 2 per-update ray tables,
+                             * 3 persistent map-wide ray tables, -1 not known yet */
   int32_t kernels_launched; /* kernels the last filter update enqueued */
+  uint64_t zero_weight_updates; /* updates so far whose weights were all zero: the resampler kept the particles
+                                 * as they were (synchronous calls return AMCLJ_ERR_STATE for such an update) */
+  double ms_table_fill;     /* what the last one-time fill of the persistent ray tables took (0: none yet) */
+  uint64_t table_bytes;     /* device memory held by the persistent ray tables */
 } amclj_stats;
 
 typedef struct amclj_ctx amclj_ctx;
@@ -154,6 +163,14 @@ int32_t amclj_set_particles(amclj_ctx *ctx, const float *x, const float *y,
                             const float *theta, const float *w, int64_t n);
 int32_t amclj_get_particles(amclj_ctx *ctx, float *x, float *y, float *theta, float *w);
 int64_t amclj_num_particles(const amclj_ctx *ctx);
+/* The same two calls for the reference's own record shape: poses7 = [n][7] doubles, one
+ * geometry_msgs/Pose per row as (position.x, position.y, position.z, orientation.x, .y, .z, .w)
+ * (geometry_msgs.clj:9,30,54).  set: theta = quat/to-heading(orientation), quaternions.clj:82-97 — pole
+ * guards at 0.4999 / -0.499 included, no normalisation of q, position.z dropped as the filter never
+ * reads it.  get: orientation = quat/from-heading(theta), quaternions.clj:57-62 = (0, 0, sin(theta/2),
+ * cos(theta/2)), position.z = 0.  Both in double on the host, as on the JVM.  w (float[n]) may be NULL. */
+int32_t amclj_set_poses_quat(amclj_ctx *ctx, const double *poses7, const float *w, int64_t n);
+int32_t amclj_get_poses_quat(amclj_ctx *ctx, double *poses7, float *w);
 /* map.clj:71-84 uniform-initialization / map.clj:108-111 gaussian-initialization, on device
  * (in-kernel Philox).  heading_mode 0: N(0,1) rad (REF, map.clj:67-68); 1: U(-pi,pi). */
 int32_t amclj_init_uniform(amclj_ctx *ctx, int64_t n, int32_t heading_mode, uint64_t seed);
@@ -280,12 +297,26 @@ int32_t amclj_shard_adopt_async(amclj_ctx *ctx, int64_t count);
  *           stage 2; fills this rank's slots [global_offset, global_offset + n) and swaps them in.
  * Every rank must call pull the same number of times (the buffer sets alternate in lock step). */
 #define AMCLJ_IPC_HANDLE_BYTES 64
-#define AMCLJ_IPC_BUFFERS 7
+#define AMCLJ_IPC_BUFFERS 8
 int32_t amclj_shard_export(amclj_ctx *ctx, uint8_t *handles);
 int32_t amclj_shard_import(amclj_ctx *ctx, int32_t rank, const uint8_t *handles, int64_t n_peer,
                            int64_t peer_global_offset);
 int32_t amclj_shard_attach_local(amclj_ctx *ctx, int32_t rank, amclj_ctx *peer);
 int32_t amclj_shard_pull_async(amclj_ctx *ctx, double u0);
+/* The whole sharded update behind ONE call per rank, without a collective library and without a host
+ * round trip: motion + sensor, then the ranks exchange {largest raw weight, fixed-point total} through
+ * peer-memory mailboxes written and polled by small kernels (12 bytes per rank and update), then pull.
+ * Needs export / import (or attach_local) of every rank, the scan staged, and the same call made the same
+ * number of times on every rank (the mailbox entries carry the update's generation).  Replaces
+ * shard_motion_sensor_async + all-reduce + shard_cdf_async + all-gather + shard_pull_async. */
+int32_t amclj_shard_update_async(amclj_ctx *ctx, const double curr[3], const double prev[3], uint64_t seed,
+                                 double u0);
+/* The same for a host-resident shard: upload x, y, theta of this rank's n particles, stage the scan, update,
+ * download the rank's resampled slots (in place).  n must equal the connected shard size. */
+int32_t amclj_shard_update_host(amclj_ctx *ctx, float *x, float *y, float *theta, float *w, int64_t n,
+                                const double curr[3], const double prev[3], uint64_t seed, const float *ranges,
+                                int32_t n_ranges, float angle_min, float angle_increment, float range_max,
+                                double u0);
 /* Host-only planning (no GPU needed): for per-rank totals T_g, systematic offset
  * r = floor(u0 * T), and slots split evenly (n_global / world per rank, remainder to the
  * low ranks) computes m_lo[g], m_cnt[g] and the world x world send matrix (row = source). */
@@ -310,6 +341,39 @@ int32_t amclj_plan_systematic(const uint64_t *totals, int32_t world, int64_t n_g
 int32_t amclj_device_ptr(amclj_ctx *ctx, int32_t which, void **ptr, int64_t *bytes);
 /* Make sure the staging buffers hold at least `rows` float4 rows. */
 int32_t amclj_reserve_stage(amclj_ctx *ctx, int64_t rows);
+
+/* ---- one process, several GPUs (`amclj_create(const int* devices, int n_devices, ...)`) ------
+ * One caller thread, as in the reference (pf.clj:297): an amclj_mctx owns one amclj_ctx per listed device
+ * (a device may be listed more than once: emulated shards), splits the particles into contiguous blocks
+ * (n_global / n each, the remainder to the low ranks), replicates map and scan, and runs
+ * amclj_shard_update_async on every device.  Results are identical to one amclj_ctx holding all particles.
+ * Per-rank calls that have no m-variant (amclj_get_stats, amclj_set_stream, ...) go through amclj_multi_ctx. */
+typedef struct amclj_mctx amclj_mctx;
+int32_t amclj_create_multi(const int32_t *devices, int32_t n_devices, amclj_mctx **out);
+int32_t amclj_destroy_multi(amclj_mctx *m);
+int32_t amclj_multi_size(const amclj_mctx *m);
+amclj_ctx *amclj_multi_ctx(amclj_mctx *m, int32_t rank);
+const char *amclj_mlast_error(const amclj_mctx *m);
+int32_t amclj_mset_params(amclj_mctx *m, const amclj_params *p);
+int32_t amclj_mset_map(amclj_mctx *m, const int8_t *cells, int32_t width, int32_t height, float resolution);
+/* x, y, theta, w: host arrays of ALL n_global particles (w may be NULL). */
+int32_t amclj_mset_particles(amclj_mctx *m, const float *x, const float *y, const float *theta, const float *w,
+                             int64_t n_global);
+int32_t amclj_mget_particles(amclj_mctx *m, float *x, float *y, float *theta, float *w);
+int64_t amclj_mnum_particles(const amclj_mctx *m);
+int32_t amclj_minit_uniform(amclj_mctx *m, int64_t n_global, int32_t heading_mode, uint64_t seed);
+int32_t amclj_mstage_scan(amclj_mctx *m, const float *ranges, int32_t n, float angle_min, float angle_increment,
+                          float range_max);
+/* One mcl* iteration's hot path (pf.clj:229-233) over all devices, enqueue only / with host buffers. */
+int32_t amclj_mfilter_update_async(amclj_mctx *m, const double curr[3], const double prev[3], uint64_t seed,
+                                   double u0);
+int32_t amclj_mfilter_update_host(amclj_mctx *m, float *x, float *y, float *theta, float *w, int64_t n_global,
+                                  const double curr[3], const double prev[3], uint64_t seed, const float *ranges,
+                                  int32_t n_ranges, float angle_min, float angle_increment, float range_max,
+                                  double u0);
+int32_t amclj_msynchronize(amclj_mctx *m);
+/* pose-estimate pf.clj:67-84 over all shards: {mean x, mean y, mean qz, mean qw}. */
+int32_t amclj_mpose_estimate(amclj_mctx *m, double out[4]);
 
 #ifdef __cplusplus
 }

@@ -330,6 +330,9 @@ ORACLE_API void amclj_oracle_sensor_f64(const amclj_params *p, const int8_t *cel
       double pz3 = obs == rmax ? 1.0 * zmax : 0.0;
       double pz4 = obs < rmax ? zrand * (1.0 / rmax) : 0.0;
       double s = pz1 + pz2 + pz3 + pz4;
+      /* north-star log-weights only (no reference counterpart): a return beyond rangeMax, inf or
+       * NaN has probability 0 under every term above; such a beam is left out (factor 1) */
+      if (p->s7_log_weights && !(obs <= rmax && obs >= -3.0e38)) s = 1.0;
       acc += p->s7_log_weights ? log(s) : pow(s, 3.0);
       t_rays++;
       t_cells += (uint64_t)ray.cells;
@@ -383,6 +386,7 @@ ORACLE_API void amclj_oracle_sensor_f32(const amclj_params *p, const int8_t *cel
       float pz3 = obs == range_max ? zmax : 0.0f;
       float pz4 = obs < range_max ? zrand / range_max : 0.0f;
       float s = pz1 + pz2 + pz3 + pz4;
+      if (p->s7_log_weights && !(obs <= range_max && obs >= -3.0e38f)) s = 1.0f; /* beam left out, as above */
       acc += p->s7_log_weights ? (double)logf(s) : (double)(s * s * s);
       size_t o = (size_t)ip * (size_t)nb + (size_t)j;
       if (hit_x) hit_x[o] = ray.hit_x;
@@ -457,6 +461,16 @@ ORACLE_API void amclj_oracle_motion_f64(const amclj_params *p, const double curr
   }
 }
 
+/* fp32 contract: the stored heading stays in (-pi, pi], as quat/to-heading (quaternions.clj:82-97)
+ * returns it every update; values already inside pass through untouched */
+static inline float wrap_heading_f32(float t) {
+  if (fabsf(t) <= 3.14159274f) return t;
+  float k = rintf(t * 0.159154937f);
+  k = fminf(fmaxf(k, -1.0e9f), 1.0e9f);
+  float r = fmaf(k, -6.28318548f, t);
+  return fmaf(k, 1.74845553e-07f, r);
+}
+
 ORACLE_API void amclj_oracle_motion_f32(const amclj_params *p, const double curr[3],
                                         const double prev[3], const float *normals, float *x,
                                         float *y, float *theta, int64_t np) {
@@ -474,7 +488,7 @@ ORACLE_API void amclj_oracle_motion_f32(const amclj_params *p, const double curr
     amclj_oracle_sincosf(theta[i] + r1, &sn, &cs);
     x[i] = fmaf(tr, cs, x[i]);
     y[i] = fmaf(tr, sn, y[i]);
-    theta[i] = theta[i] + (r1 + r2);
+    theta[i] = wrap_heading_f32(theta[i] + (r1 + r2));
   }
 }
 

@@ -27,7 +27,7 @@ def test_header_symbols_exported():
     L = C.CDLL(str(_lib.LIB_PATH))
     for name in declared:
         assert hasattr(L, name), name
-    assert _lib.lib().amclj_abi_version() == 1
+    assert _lib.lib().amclj_abi_version() == 2
 
 
 def test_params_struct_layout_matches_oracle_mirror():

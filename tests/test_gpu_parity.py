@@ -175,7 +175,29 @@ def test_motion_injected_normals(ctx, lg, curr, prev):
     dx, dy, dt = oracle.motion_f64(po, curr, prev, nrm, w.x, w.y, w.theta)
     np.testing.assert_allclose(x, dx, rtol=RTOL)
     np.testing.assert_allclose(y, dy, rtol=RTOL)
+    # the stored heading is kept in (-pi, pi] (what quat/to-heading returns); the double restatement adds up
+    dt = dt - 2 * math.pi * np.round(dt / (2 * math.pi))
     np.testing.assert_allclose(t, dt, rtol=RTOL, atol=1e-6)
+
+
+def test_motion_heading_stays_wrapped(ctx):
+    """theta must not grow without bound over many updates (fp32 resolution, ray end cells)."""
+    n = 4096
+    rng = np.random.Generator(np.random.PCG64(17))
+    x, y = rng.uniform(5, 25, n).astype(np.float32), rng.uniform(5, 25, n).astype(np.float32)
+    th = rng.uniform(-math.pi, math.pi, n).astype(np.float32)
+    pl, po = _pair("NS")
+    ctx.set_params(pl)
+    ctx.set_particles(x, y, th)
+    rx, ry, rt = x.copy(), y.copy(), th.copy()
+    for k in range(40):  # a robot turning on the spot: +0.9 rad per update
+        nrm = rng.standard_normal((n, 3)).astype(np.float32)
+        curr, prev = (1.0, 1.0, 0.9 * (k + 1)), (1.0, 1.0, 0.9 * k)
+        ctx.motion_update(curr, prev, nrm)
+        rx, ry, rt = oracle.motion_f32(po, curr, prev, nrm, rx, ry, rt)
+    gx, gy, gt, _ = ctx.get_particles()
+    assert np.array_equal(gx, rx) and np.array_equal(gy, ry) and np.array_equal(gt, rt)
+    assert np.abs(gt).max() <= np.float32(math.pi) + 1e-6
 
 
 def test_motion_philox_normals(ctx):
@@ -267,6 +289,21 @@ def test_roulette_philox_bit_exact(ctx, n):
     idx = ctx.resample(_lib.RESAMPLE_ROULETTE, 0.0, seed=6)
     q, total = oracle.fixed_weights(w, oracle.wmax(w))
     ref, _ = oracle.roulette_philox(q, total, 6)
+    assert np.array_equal(idx, ref)
+
+
+def test_roulette_philox_bit_exact_c2_size(ctx):
+    """pf.clj:156-167 at C2's particle count: N = 100,000 means about N^2 = 1e10 attempts
+    (every attempt is accepted with probability 1/N whatever the weights); the GPU compacts them in
+    attempt order, the oracle walks the same Philox stream on every host core."""
+    n = 100_000
+    w = _weights(n, 15)
+    z = np.zeros(n, np.float32)
+    ctx.set_particles(z, z, z, w)
+    idx = ctx.resample(_lib.RESAMPLE_ROULETTE, 0.0, seed=16)
+    q, total = oracle.fixed_weights(w, oracle.wmax(w))
+    ref, attempts = oracle.roulette_philox(q, total, 16)
+    assert attempts > 5e9
     assert np.array_equal(idx, ref)
 
 

@@ -148,3 +148,57 @@ def test_sharded_pull_equals_single(world, n):
     for c in shards:
         c.close()
     ref.close()
+
+
+@pytest.mark.parametrize("world,n", [(1, 30_000), (2, 200_000), (3, 100_003), (8, 400_000)])
+def test_multi_context_equals_single(world, n):
+    """amclj_create_multi (one process, one caller thread; the shards emulated on GPU 0): the kernels
+    exchange {max, total} through the peer-memory mailboxes and pull their slots; three updates and the
+    host-buffer call give the particle list of ONE ctx holding everything, bit for bit."""
+    g = maps.lgfloor()
+    w = workloads.c3(n)
+    s = w.scan
+    with _lib.Context(0, "NS") as ref, _lib.MultiContext([0] * world, "NS") as m:
+        ref.set_map(g)
+        m.set_map(g)
+        ref.set_particles(w.x, w.y, w.theta)
+        m.set_particles(w.x, w.y, w.theta)
+        m.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max)
+        for it in range(3):
+            curr, prev = (0.2 * (it + 1), 0.0, 0.1 * (it + 1)), (0.2 * it, 0.0, 0.1 * it)
+            ref.filter_update(curr, prev, s.ranges, s.angle_min, s.angle_inc, s.range_max, 0.1 + 0.3 * it, seed=40 + it)
+            m.filter_update_async(curr, prev, 40 + it, 0.1 + 0.3 * it)
+            m.synchronize()
+            for a, b in zip(m.get_particles()[:3], ref.get_particles()[:3]):
+                assert np.array_equal(a, b)
+        np.testing.assert_allclose(m.pose_estimate(), ref.pose_estimate(), rtol=1e-9)
+        # host-buffer entry point
+        bufs = [a.copy() for a in ref.get_particles()]
+        mine = [a.copy() for a in bufs]
+        ref.filter_update_host(*bufs, (0.9, 0.1, 0.4), (0.6, 0.0, 0.3), s.ranges, s.angle_min, s.angle_inc, s.range_max, 0.77, seed=5)
+        m.filter_update_host(*mine, (0.9, 0.1, 0.4), (0.6, 0.0, 0.3), s.ranges, s.angle_min, s.angle_inc, s.range_max, 0.77, seed=5)
+        for a, b in zip(mine[:3], bufs[:3]):
+            assert np.array_equal(a, b)
+        assert m.rank(0).stats().sensor_path == 3
+
+
+def test_multi_context_skewed_weights():
+    """Nearly all weight on the last shard: most slots are pulled from a peer."""
+    g = maps.lgfloor()
+    n, world = 120_000, 4
+    x, y, th = workloads.uniform_particles(g, n, seed=61)
+    gx, gy, gt = workloads.gaussian_particles(n // 4)
+    x[-len(gx):], y[-len(gx):], th[-len(gx):] = gx, gy, gt  # the last shard sits on the true pose
+    s = workloads.c2(10).scan
+    with _lib.Context(0, "NS") as ref, _lib.MultiContext([0] * world, "NS") as m:
+        for q in (ref, m):
+            q.set_map(g)
+            q.set_particles(x, y, th)
+        m.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max)
+        ref.filter_update((0, 0, 0), (0, 0, 0), s.ranges, s.angle_min, s.angle_inc, s.range_max, 0.5, seed=1)
+        m.filter_update_async((0, 0, 0), (0, 0, 0), 1, 0.5)
+        m.synchronize()
+        for a, b in zip(m.get_particles()[:3], ref.get_particles()[:3]):
+            assert np.array_equal(a, b)
+        idx = ref.resample_indices()
+        assert (idx >= n - len(gx)).mean() > 0.9  # the test does what it says

@@ -43,6 +43,22 @@ class OracleShard:
         self._in = torch.empty(rows, 4, dtype=torch.float32); return self._in
     def adopt(self, rows): self.rows = self._in.numpy().copy()
 
+class OraclePullShard(OracleShard):
+    """Pull mode: peer memory is stood in for by an all-gather of every rank's CDF increments and rows
+    (what the kernel would read through NVLink pointers); the collectives and their order are the real ones."""
+    def connect_peers(self, rank, world, n_global, group=None): self.rank, self.world = rank, world
+    def totals_all(self, world):
+        self._tot = torch.zeros(world, dtype=torch.int64); return self._tot
+    def pull(self, u0):
+        qs, rows = [None] * self.world, [None] * self.world
+        dist.all_gather_object(qs, self.q); dist.all_gather_object(rows, self.rows)
+        q, allrows = np.concatenate(qs), np.concatenate(rows)
+        total = int(self._tot.numpy().view(np.uint64).sum(dtype=np.uint64))
+        assert total == int(q.sum(dtype=np.uint64))
+        lo, cnt = slots_of(self.rank, self.world, self.n_global)
+        idx = oracle.systematic(q, total, 0, oracle.systematic_offset(u0, total), self.n_global, lo, cnt)
+        self.rows = allrows[idx].copy(); self.rows[:, 3] = 1.0 / self.n_global
+
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 n = int(os.environ["AMCLJ_N"])
@@ -53,8 +69,9 @@ raw = (np.log(rng.random(n) ** 8 + 1e-30)).astype(np.float32)
 if os.environ.get("AMCLJ_SKEW") == "1":
     raw[: n // 2] -= 60.0                      # nearly all weight on the last rank
 lo, cnt = slots_of(rank, world, n)
-be = OracleShard(rows[lo:lo + cnt], raw[lo:lo + cnt])
-f = ShardedFilter(None, rank, world, n, None, backend=be)
+mode = os.environ.get("AMCLJ_MODE", "a2a")
+be = (OraclePullShard if mode == "pull" else OracleShard)(rows[lo:lo + cnt], raw[lo:lo + cnt])
+f = ShardedFilter(None, rank, world, n, None, backend=be, mode=mode)
 u0 = 0.4142135
 f.update((0, 0, 0), (0, 0, 0), 1, u0)
 got = [None] * world
@@ -69,9 +86,9 @@ dist.destroy_process_group()
 '''
 
 
-def _run(n, skew, port):
-    env = dict(os.environ, AMCLJ_ROOT=str(ROOT), AMCLJ_N=str(n), AMCLJ_SKEW="1" if skew else "0")
-    script = ROOT / "tests" / "_sharded_worker.py"
+def _run(n, skew, port, mode="a2a"):
+    env = dict(os.environ, AMCLJ_ROOT=str(ROOT), AMCLJ_N=str(n), AMCLJ_SKEW="1" if skew else "0", AMCLJ_MODE=mode)
+    script = ROOT / "tests" / f"_sharded_worker_{port}.py"
     script.write_text(WORKER)
     try:
         p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
@@ -89,3 +106,10 @@ def test_sharded_update_world2_balanced():
 
 def test_sharded_update_world2_skewed():
     _run(4000, True, 29732)
+
+
+def test_sharded_update_world2_pull_choreography():
+    """the pull choreography (max all-reduce, totals all-gather, then every rank fills its own
+    slots from whichever rank holds them) on CPU, balanced and skewed."""
+    _run(5001, False, 29733, mode="pull")
+    _run(4000, True, 29734, mode="pull")

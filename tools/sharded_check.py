@@ -1,12 +1,13 @@
 """torchrun worker: sharded filter update on G GPUs vs the same update on one GPU.
 
-  python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 tools/sharded_check.py [N] [pull|a2a] [spread|dense]
+  python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 tools/sharded_check.py [N] [mailbox|pull|a2a] [spread|dense]
 
 `dense` shards a pose-tracking cloud (C2's gaussian), which every rank runs on the per-cell ray
 tables (three updates, so that the policy's hint has settled); `spread` (default) is C3's uniform cloud.
 
-Every rank runs its shard through amclj_b200.sharded.ShardedFilter (NCCL all-reduce(max),
-all-gather(totals), all-to-all rebalance); rank 0 also runs all N particles on its own GPU
+Every rank runs its shard through amclj_b200.sharded.ShardedFilter (mailbox: one library call per
+update, exchanges inside the kernels; pull / a2a: NCCL all-reduce(max), all-gather(totals), then peer pull
+or all-to-all rebalance); rank 0 also runs all N particles on its own GPU
 through amclj_filter_update and compares: identical particle lists (same source index for
 every output slot) and identical motion-sampled poses (Philox keyed by global particle id).
 """
@@ -25,7 +26,7 @@ from amclj_b200.sharded import ShardedFilter, slots_of  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
-    mode = sys.argv[2] if len(sys.argv) > 2 else "pull"
+    mode = sys.argv[2] if len(sys.argv) > 2 else "mailbox"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
