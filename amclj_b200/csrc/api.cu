@@ -143,6 +143,19 @@ int ensure_stage(amclj_ctx *ctx, int64_t rows) {
   return AMCLJ_OK;
 }
 
+/* The Clojure `def` constants are double literals (motion.clj:12-15: 0.002, 0.02) while amclj_params
+ * carries floats: widen a parameter to the double its shortest round-tripping decimal names
+ * (0.002f -> 0.002), i.e. back to the reference's literal. */
+double decimal_exact(float f) {
+  if (!(f == f) || f == 0.0f || f - f != 0.0f) return (double)f;
+  char buf[40];
+  for (int prec = 1; prec <= 9; prec++) {
+    snprintf(buf, sizeof buf, "%.*g", prec, (double)f);
+    if (strtof(buf, nullptr) == f) return strtod(buf, nullptr);
+  }
+  return (double)f;
+}
+
 /* motion.clj:68-79 + :24-34: the control is launch-uniform; doubles as on the JVM. */
 void make_control(const amclj_params &p, const double curr[3], const double prev[3],
                   MotionLaunch &m) {
@@ -154,7 +167,7 @@ void make_control(const amclj_params &p, const double curr[3], const double prev
   double rot1 = atan2(yn - y, xn - x) - t;
   double trans = hypot(x - xn, y - yn);
   double rot2 = tn - t - rot1;
-  double a1 = p.alpha1, a2 = p.alpha2, a3 = p.alpha3, a4 = p.alpha4;
+  double a1 = decimal_exact(p.alpha1), a2 = decimal_exact(p.alpha2), a3 = decimal_exact(p.alpha3), a4 = decimal_exact(p.alpha4);
   double v1 = p.s9_pr_rot1_variance ? a1 * rot1 * rot1 + a2 * trans * trans
                                     : a1 * rot1 * rot1 + a2 * rot2 * rot2; /* motion.clj:35 */
   m.trans_zero = trans == 0.0; /* motion.clj:36 */

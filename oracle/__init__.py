@@ -4,7 +4,9 @@ TEST INFRASTRUCTURE ONLY — see the header of amclj_oracle.c.  The product pack
 ``amclj_b200`` never imports this module; it is used by tests/, by
 ``__graft_entry__.smoke()`` and by ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
 legs, as the checker and as the timed CPU stand-in for the (un-runnable) Clojure reference.
-PARITY UNPINNED by the reference's own tests (it has none on this path).
+Pinned to the reference's own source text: tests/golden/clj_eval.py evaluates the reference's .clj files
+and tests/test_reference_text.py holds the oracle to the vectors that produced (the reference ships no
+golden vectors of its own on this path and cannot run here: no JVM).
 """
 from __future__ import annotations
 

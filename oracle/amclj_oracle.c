@@ -5,13 +5,18 @@
  * call this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * `--impl reference` legs use it, as the checker and as the timed CPU stand-in.
  *
- * PARITY UNPINNED BY THE REFERENCE: jvia/amclj ships no golden vectors or known-answer
- * tests for this path (test/amclj/pf_test.clj pins only add-pose; one fact references an
- * undefined symbol) and it cannot run here (no JVM/Clojure/Leiningen in this image), so
- * this file is a line-by-line restatement of the cited Clojure, pinned by (i) hand-derived
- * known answers on tiny maps, (ii) an independent literal Python transliteration
- * (tests/golden/make_golden.py) and (iii) the survey-time cross-check value on the
- * reference's own dev fixture (sensor.clj:26-74).
+ * HOW IT IS PINNED.  jvia/amclj ships no golden vectors or known-answer tests for this path
+ * (test/amclj/pf_test.clj pins only add-pose; one fact references an undefined symbol) and it
+ * cannot run here (Clojure on the JVM; no JVM in this image), so there is no oracle/_ref.  The
+ * pin is the reference's own SOURCE TEXT instead: tests/golden/clj_eval.py evaluates
+ * src/amclj/{quaternions,map,motion,sensor,pf}.clj verbatim (the hot path uses a small subset of
+ * Clojure), tests/golden/make_golden_from_reference.py runs the reference's functions on its own
+ * dev fixtures (sensor.clj:26-74, core.clj:56-63, launch/lgfloor.*) and on seeded random inputs
+ * with the noise streams injected, and tests/test_reference_text.py holds this file to those
+ * vectors: 7,740 rays cell for cell, weights, motion, quaternions, resamplers to 1e-12.
+ * Further witnesses: hand-derived known answers on tiny maps (tests/test_oracle_kat.py) and an
+ * independent Python transliteration that also covers the north-star switches, which have no
+ * reference text (tests/golden/make_golden.py).
  *
  * Citations are file:line in the reference repository (jvia/amclj).
  *
@@ -65,6 +70,21 @@ typedef struct oracle_map {
  * x == width fall through into incanter's sel (exception / unpinned wrap).  Contract here:
  * x < 0 or x >= W or y < 0 or y >= H => blocked.
  * ---------------------------------------------------------------------------------- */
+/* The Clojure `def` constants (sensor.clj:11-21, motion.clj:12-16) are double literals — 0.95, 0.002 —
+ * while amclj_params carries them as float (the ABI).  The double restatement widens a parameter to the
+ * double its shortest round-tripping decimal names (0.95f -> 0.95), i.e. back to the reference's own
+ * literal, not to 0.949999988...; message fields (ranges, angles, resolution) are float32 on the wire and
+ * stay float-widened. */
+static double decimal_exact(float f) {
+  if (!(f == f) || f == 0.0f || f - f != 0.0f) return (double)f;
+  char buf[40];
+  for (int prec = 1; prec <= 9; prec++) {
+    snprintf(buf, sizeof buf, "%.*g", prec, (double)f);
+    if (strtof(buf, NULL) == f) return strtod(buf, NULL);
+  }
+  return (double)f;
+}
+
 static inline int blocked(const oracle_map *m, int64_t x, int64_t y) {
   if (x < 0 || x >= m->W || y < 0 || y >= m->H) return 1;
   return m->cells[(size_t)y * (size_t)m->W + (size_t)x] != 0;
@@ -204,10 +224,10 @@ ORACLE_API void amclj_oracle_map_range_f64(const amclj_params *p, const int8_t *
   oracle_map m = {cells, W, H, res};
   double rres = (double)res;
   double dir = p->s1_use_heading ? theta + obs_bearing : obs_bearing; /* sensor.clj:131,133 */
-  double R = p->s2_use_scan_range_max ? scan_range_max : (double)p->max_range;
+  double R = p->s2_use_scan_range_max ? scan_range_max : decimal_exact(p->max_range);
   if (p->s10_apply_laser_offset) {
     double c = cos(theta), s = sin(theta);
-    double lx = p->laser_x, ly = p->laser_y;
+    double lx = decimal_exact(p->laser_x), ly = decimal_exact(p->laser_y);
     double nx = ox + (lx * c - ly * s), ny = oy + (lx * s + ly * c);
     ox = nx;
     oy = ny;
@@ -307,9 +327,10 @@ ORACLE_API void amclj_oracle_sensor_f64(const amclj_params *p, const int8_t *cel
                                         int32_t threads) {
   int32_t step = amclj_oracle_beam_step(n, p->s6_max_beams);
   double rmax = (double)range_max;
-  double zhit = p->z_hit, zshort = p->z_short, zmax = p->z_max, zrand = p->z_rand;
-  double lam = p->lambda_short;
-  double sig = p->s5_use_sigma_hit ? (double)p->sigma_hit : zhit; /* sensor.clj:151-153 */
+  double zhit = decimal_exact(p->z_hit), zshort = decimal_exact(p->z_short), zmax = decimal_exact(p->z_max),
+         zrand = decimal_exact(p->z_rand);
+  double lam = decimal_exact(p->lambda_short);
+  double sig = p->s5_use_sigma_hit ? decimal_exact(p->sigma_hit) : zhit; /* sensor.clj:151-153 */
   uint64_t t_rays = 0, t_cells = 0, t_hits = 0;
 #ifdef _OPENMP
   if (threads <= 0) threads = omp_get_max_threads();
@@ -432,7 +453,8 @@ ORACLE_API void amclj_oracle_control(const amclj_params *p, const double curr[3]
   double rot1 = atan2(yn - y, xn - x) - t;
   double trans = hypot(x - xn, y - yn);
   double rot2 = tn - t - rot1;
-  double a1 = p->alpha1, a2 = p->alpha2, a3 = p->alpha3, a4 = p->alpha4;
+  double a1 = decimal_exact(p->alpha1), a2 = decimal_exact(p->alpha2), a3 = decimal_exact(p->alpha3),
+         a4 = decimal_exact(p->alpha4);
   c->rot1 = rot1;
   c->trans = trans;
   c->rot2 = rot2;

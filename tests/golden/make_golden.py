@@ -32,11 +32,11 @@ f32 = lambda v: float(np.float32(v))  # a ROS float32 field, widened to double
 # sensor.clj:11-21
 MAX_RANGE = -1.0
 MAX_BEAMS = 30
-Z_HIT, Z_SHORT, Z_MAX, Z_RAND = f32(0.95), f32(0.1), f32(0.05), f32(0.05)
-SIGMA_HIT, LAMBDA_SHORT = f32(0.2), f32(0.1)
+Z_HIT, Z_SHORT, Z_MAX, Z_RAND = 0.95, 0.1, 0.05, 0.05
+SIGMA_HIT, LAMBDA_SHORT = 0.2, 0.1
 # motion.clj:12-15
-ALPHA1, ALPHA2, ALPHA3, ALPHA4 = f32(0.002), f32(0.002), f32(0.02), f32(0.02)
-# (the constants are carried as float32 in amclj_params, hence the f32())
+ALPHA1, ALPHA2, ALPHA3, ALPHA4 = 0.002, 0.002, 0.02, 0.02
+# (the Clojure double literals themselves: the oracle widens amclj_params' floats back to them, decimal_exact)
 
 
 def java_round(v):  # Math/round

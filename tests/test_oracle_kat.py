@@ -149,27 +149,28 @@ def test_beam_subsampling():
 
 
 def test_weight_formulas_by_hand():
-    # one beam, known range: NS log p and REF p^3
+    # one beam, known range: NS log p and REF p^3, with the Clojure constants as the double literals they are
+    # (sensor.clj:14-19: 0.95, 0.1, 0.05, 0.2; the oracle widens amclj_params' floats back to them)
     g = tiny(["........#."] * 3)
     ranges = np.array([6.5], np.float32)
     ns = oracle.params("ns")
     raw, _ = oracle.sensor_f64(ns, g, ranges, 0.0, 0.1, 20.0, [1.0], [1.0], [0.0])
     z = 6.5 - 7.0
-    p = (float(np.float32(0.95)) * math.exp(-z * z / (2 * float(np.float32(0.2)) ** 2))
-         + float(np.float32(0.1)) * float(np.float32(0.1)) * math.exp(-float(np.float32(0.1)) * 6.5)
-         + float(np.float32(0.05)) / 20.0)
+    p = (0.95 * math.exp(-z * z / (2 * 0.2 ** 2))
+         + 0.1 * 0.1 * math.exp(-0.1 * 6.5)
+         + 0.05 / 20.0)
     assert raw[0] == pytest.approx(math.log(p), rel=1e-13)
     ref = oracle.params("ref", s1_use_heading=1, s2_use_scan_range_max=1, s3_proper_endpoint=1,
                         s4_endpoint_termination=1)
     raw, _ = oracle.sensor_f64(ref, g, ranges, 0.0, 0.1, 20.0, [1.0], [1.0], [0.0])
-    p = (float(np.float32(0.95)) * math.exp(-z * z / (2 * float(np.float32(0.95)) ** 2))
-         + float(np.float32(0.1)) * float(np.float32(0.1)) * math.exp(-float(np.float32(0.1)) * 6.5)
-         + float(np.float32(0.05)) / 20.0)
+    p = (0.95 * math.exp(-z * z / (2 * 0.95 ** 2))
+         + 0.1 * 0.1 * math.exp(-0.1 * 6.5)
+         + 0.05 / 20.0)
     assert raw[0] == pytest.approx(p ** 3, rel=1e-13)
     # obs == rangeMax: pz3 replaces pz4
     raw, _ = oracle.sensor_f64(ns, g, np.array([20.0], np.float32), 0.0, 0.1, 20.0, [1.0], [1.0], [0.0])
     z = 20.0 - 7.0
-    p = float(np.float32(0.95)) * math.exp(-z * z / (2 * float(np.float32(0.2)) ** 2)) + float(np.float32(0.05))
+    p = 0.95 * math.exp(-z * z / (2 * 0.2 ** 2)) + 0.05
     assert raw[0] == pytest.approx(math.log(p), rel=1e-13)
 
 
