@@ -168,3 +168,22 @@ def test_struct_layouts_match_the_c_header(tmp_path):
     for cname, struct in (("amclj_params", _lib.Params), ("amclj_stats", _lib.Stats)):
         for f in fields(struct):
             assert int(out[f"{cname}.{f}"]) == getattr(struct, f).offset, f"{cname}.{f}"
+
+
+def test_clojure_shim_reads_and_names_only_exported_symbols():
+    """shim/src/amclj/gpu.clj cannot be executed here (no JVM), but it must at least be well-formed Clojure
+    (read with the evaluator's reader) and every entry point it names must be one the library exports."""
+    import re
+    import sys
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    import clj_eval
+    text = (ROOT / "shim" / "src" / "amclj" / "gpu.clj").read_text()
+    forms = clj_eval.read_all(text)
+    assert len(forms) > 20 and forms[0][0] == "ns"
+    named = set(re.findall(r'"(amclj_[a-z_0-9]+)"', text)) - {"amclj_b200"}  # the library's own name
+    assert len(named) >= 15
+    L = _lib.lib()
+    missing = [s for s in named if not hasattr(L, s)]
+    assert not missing, missing
+    patch = (ROOT / "shim" / "pf.clj.patch").read_text()
+    assert "apply-motion-model" in patch and "roulette-selection" in patch
