@@ -389,6 +389,7 @@ void fill_pt_args(const amclj_ctx *ctx, PtLaunch &L) {
   L.pstate = r.pstate;
   L.qacc = ctx->partials;
   L.warps = t.warps;
+  L.fuse_finish = (t.fuse_finish && (ctx->beams.nb + 29) / 30 <= 15) ? 1 : 0;
 }
 
 /* Called at the end of stage_scan_impl: are the persistent tables usable for the staged scan, and do
@@ -488,7 +489,7 @@ int enqueue_ptable(amclj_ctx *ctx, const SensorLaunch &base, bool dbg) {
   L.s.rawmax_ord = base.rawmax_ord; L.s.stats = base.stats;
   L.s.dbg_first = base.dbg_first; L.s.dbg_count = base.dbg_count; L.s.dbg_range = base.dbg_range;
   CK(launch_pt_update(ctx, L, pt_fill_mode(ctx), dbg, ctx->stream));
-  ctx->launches += 5; /* histogram, scan, scatter, look-up, finish */
+  ctx->launches += L.fuse_finish ? 4 : 5; /* histogram, scan, scatter, look-up (, finish) */
   return AMCLJ_OK;
 }
 
@@ -1152,10 +1153,12 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
   if (const char *e = getenv("AMCLJ_PTABLE")) ctx->pt.enable = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_PT_BUDGET_MB")) ctx->pt.budget = (size_t)atoll(e) << 20;
   if (const char *e = getenv("AMCLJ_PT_WARPS")) ctx->pt.warps = atoi(e);
+  if (const char *e = getenv("AMCLJ_PT_FUSE")) ctx->pt.fuse_finish = atoi(e) != 0;
   memset(&ctx->st, 0, sizeof(ctx->st));
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ctx->stream = ctx->own_stream;
   for (int i = 0; ok && i < 7; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+  for (int i = 0; ok && i < 2; i++) ok = cudaEventCreateWithFlags(&ctx->ev_pub[i], cudaEventDisableTiming) == cudaSuccess;
   /* control block: [0..1] particle bounding box (4 ordered-uint maxima) | [2] ordered-uint max
    * weight | [3] fixed-point total | [4] tile counter | [5..] tile descriptors of the scan (2^20
    * tiles = 2^31 particles; also serves the roulette compaction) */
@@ -1214,6 +1217,8 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
   if (ctx->pin_tab) cudaFreeHost(ctx->pin_tab);
   for (int i = 0; i < 7; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 2; i++)
+    if (ctx->ev_pub[i]) cudaEventDestroy(ctx->ev_pub[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return AMCLJ_OK;
@@ -2071,6 +2076,7 @@ static int shard_phase_a(amclj_ctx *ctx, const double curr[3], const double prev
   MailboxArgs m;
   mailbox_args(ctx, m);
   CK(launch_mailbox(m, 0, ctx->stream));
+  CK(cudaEventRecord(ctx->ev_pub[0], ctx->stream));
   ctx->launches += 1;
   return AMCLJ_OK;
 }
@@ -2084,6 +2090,7 @@ static int shard_phase_b(amclj_ctx *ctx) {
   int rc = enqueue_cdf(ctx, true, true);
   if (rc) return rc;
   CK(launch_mailbox(m, 2, ctx->stream));
+  CK(cudaEventRecord(ctx->ev_pub[1], ctx->stream));
   ctx->launches += 2;
   return AMCLJ_OK;
 }
@@ -2266,6 +2273,7 @@ struct amclj_mctx {
   amclj_ctx *ctx[MAX_WORLD] = {};
   int64_t n_global = 0;
   bool connected = false;
+  bool shared_device = false; /* two ranks on one GPU (emulated shards) */
   std::string err;
 };
 
@@ -2316,6 +2324,7 @@ int32_t amclj_create_multi(const int32_t *devices, int32_t n_devices, amclj_mctx
       return rc;
     }
     m->n = r + 1;
+    for (int k = 0; k < r; k++) m->shared_device = m->shared_device || devices[k] == devices[r];
   }
   *out = m;
   return AMCLJ_OK;
@@ -2416,14 +2425,26 @@ static int mphases(amclj_mctx *m, const double curr[3], const double prev[3], ui
     int rc = shard_phase_a(m->ctx[r], curr, prev, seed);
     if (rc) return mfail(m, r, rc);
   }
+  /* Kernels that wait on one another must never share a GPU (nothing guarantees that they run at the same
+   * time): when two ranks do share one — the emulated shards of the tests — every wait is ordered behind the
+   * publishes it waits for by stream events, so that it finds its mailbox full and never spins.  On distinct
+   * GPUs the mailbox alone carries the dependency and the host adds nothing. */
+  auto after_publishes = [&](int r, int which) -> int {
+    if (!m->shared_device) return AMCLJ_OK;
+    for (int g = 0; g < m->n; g++)
+      if (g != r && cudaStreamWaitEvent(m->ctx[r]->stream, m->ctx[g]->ev_pub[which], 0) != cudaSuccess) return AMCLJ_ERR_CUDA;
+    return AMCLJ_OK;
+  };
   for (int r = 0; r < m->n; r++) {
     if (cudaSetDevice(m->ctx[r]->device) != cudaSuccess) return AMCLJ_ERR_CUDA;
-    int rc = shard_phase_b(m->ctx[r]);
+    int rc = after_publishes(r, 0);
+    if (!rc) rc = shard_phase_b(m->ctx[r]);
     if (rc) return mfail(m, r, rc);
   }
   for (int r = 0; r < m->n; r++) {
     if (cudaSetDevice(m->ctx[r]->device) != cudaSuccess) return AMCLJ_ERR_CUDA;
-    int rc = shard_phase_c(m->ctx[r], u0);
+    int rc = after_publishes(r, 1);
+    if (!rc) rc = shard_phase_c(m->ctx[r], u0);
     if (rc) return mfail(m, r, rc);
   }
   return AMCLJ_OK;

@@ -187,6 +187,7 @@ struct PersistentTables {
   bool built = false;
   size_t budget = 4ull << 30;      // AMCLJ_PT_BUDGET_MB
   int32_t warps = 0;               // look-up warps per CTA (0: as many as the shared memory takes, at most 16)
+  bool fuse_finish = true;         // AMCLJ_PT_FUSE=0: separate finish kernel
   // what the tables were built for
   int64_t key_map_gen = -1;
   double key_r = -1.0;
@@ -210,6 +211,7 @@ struct PtLaunch {
   float4 *pstate;
   long long *qacc;
   int32_t warps;   // look-up warps per CTA
+  int32_t fuse_finish;  // 1: the look-up kernel finishes a particle when its last segment lands (<= 15 segments)
 };
 
 constexpr int MAX_WORLD = 16;
@@ -277,6 +279,7 @@ struct amclj_ctx {
   unsigned long long *mbox = nullptr;                        /* this rank's mailbox (device memory, zeroed) */
   unsigned long long *peer_mbox[amclj::MAX_WORLD] = {};      /* every rank's mailbox as seen from here */
   uint32_t gen = 0;                                          /* sharded updates so far (the mailbox tag) */
+  cudaEvent_t ev_pub[2] = {nullptr, nullptr};                /* recorded after this rank published its max / its total */
   int flip = 0;            // swaps since export, mod 2
   bool frozen = false;     // buffers exported: no reallocation
   uint64_t *totals_all = nullptr;  // [MAX_WORLD] all-gathered totals

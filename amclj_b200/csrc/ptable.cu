@@ -306,6 +306,7 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
 
   int c_slot = 0, n_slot = 0, c_cnt = 0, n_cnt = 0;
   uint32_t c_p0 = 0, n_p0 = 0;
+  float wmax = -INFINITY;
   bool have = next_cell(c_slot, c_p0, c_cnt);
   if (have) issue(c_slot, 0);
   for (int it = 0; have; it++) {
@@ -345,12 +346,33 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
         if (a.stats) atomicAdd(a.stats + 11, 1ull); /* table_misses: expected 0 */
       }
       /* close the segment: one rounding to fixed point; segments add as integers */
-      atomicAdd(reinterpret_cast<unsigned long long *>(L.qacc) + p,
-                (unsigned long long)__float2ll_rn(fmaxf(v, FIX_FLOOR) * FIX_SCALE));
+      const long long fx = __float2ll_rn(fmaxf(v, FIX_FLOOR) * FIX_SCALE);
+      if (!L.fuse_finish) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(L.qacc) + p, (unsigned long long)fx);
+      } else {
+        /* the accumulator's top 4 bits count the segments added so far; the low 60 bits hold the sum of the
+         * segments, each biased by 2^53 so that it is positive (|segment| < 2^52 by the floor) and the field
+         * can never carry into the count (15 x 2^54 < 2^60).  Whoever adds the particle's last segment has its
+         * complete sum and finishes it here — raw weight and running maximum — instead of a kernel of its own */
+        constexpr long long BIAS = 1ll << 53;
+        const unsigned long long add = (unsigned long long)(fx + BIAS) + (1ull << 60);
+        const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(L.qacc) + p, add);
+        if ((int)(old >> 60) == nseg - 1) {
+          const long long q = (long long)((old + add) & 0x0fffffffffffffffull) - (long long)nseg * BIAS;
+          const float r = fixed_to_raw(q);
+          if (a.raw) a.raw[p] = r;
+          wmax = fmaxf(wmax, r);
+        }
+      }
     }
     __syncwarp();
     c_slot = n_slot; c_p0 = n_p0; c_cnt = n_cnt;
     have = have_n;
+  }
+  if (L.fuse_finish && a.rawmax_ord) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(FULL, wmax, o));
+    if (lane == 0 && wmax > -INFINITY) atomicMax(a.rawmax_ord, ord_of_float(wmax));
   }
 }
 
@@ -427,7 +449,7 @@ cudaError_t launch_pt_update(const amclj_ctx *c, const PtLaunch &L, int mode, bo
     default: e = launch_pt_lookup_m<DF_GLOBAL4>(c, L, wide, dbg, s); break;
   }
   if (e != cudaSuccess) return e;
-  pt_finish_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(L.qacc, a.n, a.raw, a.rawmax_ord);
+  if (!L.fuse_finish) pt_finish_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(L.qacc, a.n, a.raw, a.rawmax_ord);
   return cudaGetLastError();
 }
 
