@@ -331,7 +331,7 @@ int ensure_rt_scratch(amclj_ctx *ctx, int64_t n, bool diag, int thr, int *max_sl
 /* ---- persistent map-wide ray tables (ptable.cu) -------------------------------------------- */
 void pt_free(amclj_ctx *ctx) {
   PersistentTables &t = ctx->pt;
-  dfree(t.slot_of_cell); dfree(t.cell_of_slot); dfree(t.bin_count); dfree(t.bin_start); dfree(t.cursor);
+  dfree(t.slot_of_cell); dfree(t.cell_of_slot); dfree(t.bin_count); dfree(t.bin_start); dfree(t.cursor); dfree(t.scan_state);
   if (t.tables) cudaFree(t.tables);
   t.tables = nullptr;
   t.tables_bytes = 0;
@@ -362,6 +362,9 @@ int pt_set_map(amclj_ctx *ctx, const int8_t *cells, int W, int H) {
   CK(dalloc(&t.bin_count, (size_t)n_slots + 2));
   CK(dalloc(&t.bin_start, (size_t)n_slots + 2));
   CK(dalloc(&t.cursor, (size_t)n_slots + 2));
+  t.scan_words = (n_slots + 1 + 2047) / 2048 + 2;
+  CK(dalloc(&t.scan_state, (size_t)t.scan_words));
+  CK(cudaMemsetAsync(t.scan_state, 0, sizeof(unsigned long long) * (size_t)t.scan_words, ctx->stream));
   CK(cudaMemcpyAsync(t.slot_of_cell, soc.data(), sizeof(int32_t) * ncell, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(t.cell_of_slot, cos.data(), sizeof(int2) * (size_t)n_slots, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(t.bin_count, 0, sizeof(uint32_t) * ((size_t)n_slots + 2), ctx->stream));
@@ -389,6 +392,12 @@ void fill_pt_args(const amclj_ctx *ctx, PtLaunch &L) {
   L.pstate = r.pstate;
   L.qacc = ctx->partials;
   L.warps = t.warps;
+  L.nbuf = t.nbuf_used;
+  L.scan_state = t.scan_state;
+  L.scan_words = t.scan_words;
+  L.tail_pct = t.tail_pct;
+  L.tail_ctr = reinterpret_cast<uint32_t *>(t.scan_state) + 1;
+  L.rows32 = (t.rows32 && r.n_entries < 8192 && r.E < 255) ? 1 : 0;
   L.fuse_finish = (t.fuse_finish && (ctx->beams.nb + 29) / 30 <= 15) ? 1 : 0;
 }
 
@@ -409,11 +418,17 @@ int pt_prepare(amclj_ctx *ctx, double rcells) {
   PtLaunch probe;
   memset(&probe, 0, sizeof(probe));
   probe.s.nb = ctx->beams.nb; probe.nrows = r.nrows; probe.stride = stride;
-  int warps = 0;
-  const int wmax = ctx->pt.warps > 0 && ctx->pt.warps <= 16 ? ctx->pt.warps : 16;
-  for (int w = wmax; w >= 2; w--)
-    if (pt_lookup_smem(probe, w) + 1024 <= (size_t)ctx->max_smem_optin) { warps = w; break; }
-  if (warps < 2) return AMCLJ_OK; /* a table does not fit the shared memory twice over: the other paths take it */
+  /* warps per CTA and table buffers per warp: as many warps as the shared memory takes (they hide one
+   * another's latencies: 8 -> 14 warps took the look-up from 1.86 to 1.40 ms); with one buffer per warp
+   * more of them fit */
+  int warps = 0, nbuf = 0;
+  const int wcap = t.warps_req > 0 && t.warps_req <= pt_max_warps() ? t.warps_req : pt_max_warps();
+  for (int nb_try = (t.nbuf == 2 ? 2 : 1); nb_try <= (t.nbuf == 1 ? 1 : 2) && !warps; nb_try++) {
+    probe.nbuf = nb_try;
+    for (int w = wcap; w >= 4; w--)
+      if (pt_lookup_smem(probe, w) + 1024 <= (size_t)ctx->max_smem_optin) { warps = w; nbuf = nb_try; break; }
+  }
+  if (warps < 4) return AMCLJ_OK; /* the tables do not fit the shared memory: the other paths take it */
   const float R = p.s2_use_scan_range_max ? ctx->beams.range_max : p.max_range;
   uint32_t Rb, resb;
   memcpy(&Rb, &R, 4);
@@ -449,6 +464,7 @@ int pt_prepare(amclj_ctx *ctx, double rcells) {
     t.key_entries = r.n_entries; t.key_R_bits = Rb; t.key_res_bits = resb; t.fill_mode = pt_fill_mode(ctx);
   }
   t.warps = warps;
+  t.nbuf_used = nbuf;
   t.built = true;
   return AMCLJ_OK;
 }
@@ -1152,7 +1168,10 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
   if (const char *e = getenv("AMCLJ_RT_BUDGET_MB")) ctx->rt.budget = (size_t)atoll(e) << 20;
   if (const char *e = getenv("AMCLJ_PTABLE")) ctx->pt.enable = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_PT_BUDGET_MB")) ctx->pt.budget = (size_t)atoll(e) << 20;
-  if (const char *e = getenv("AMCLJ_PT_WARPS")) ctx->pt.warps = atoi(e);
+  if (const char *e = getenv("AMCLJ_PT_WARPS")) ctx->pt.warps_req = atoi(e);
+  if (const char *e = getenv("AMCLJ_PT_NBUF")) ctx->pt.nbuf = atoi(e);
+  if (const char *e = getenv("AMCLJ_PT_TAIL_PCT")) ctx->pt.tail_pct = atoi(e) < 0 ? 0 : (atoi(e) > 100 ? 100 : atoi(e));
+  if (const char *e = getenv("AMCLJ_PT_ROWS32")) ctx->pt.rows32 = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_PT_FUSE")) ctx->pt.fuse_finish = atoi(e) != 0;
   memset(&ctx->st, 0, sizeof(ctx->st));
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;

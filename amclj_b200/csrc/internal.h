@@ -187,7 +187,14 @@ struct PersistentTables {
   bool built = false;
   size_t budget = 4ull << 30;      // AMCLJ_PT_BUDGET_MB
   int32_t warps = 0;               // look-up warps per CTA (0: as many as the shared memory takes, at most 16)
-  bool fuse_finish = true;         // AMCLJ_PT_FUSE=0: separate finish kernel
+  bool fuse_finish = false;        // AMCLJ_PT_FUSE=1: the look-up kernel finishes the particles itself (measured slower:
+                                   // an atomic that returns its old value stalls the warp, a plain reduction does not)
+  int32_t nbuf = 0;                // table buffers per warp requested (0: one, so that more warps fit; AMCLJ_PT_NBUF)
+  int32_t nbuf_used = 1, warps_req = 0;
+  int32_t tail_pct = 0;            // AMCLJ_PT_TAIL_PCT
+  int32_t rows32 = 1;              // AMCLJ_PT_ROWS32
+  unsigned long long *scan_state = nullptr;  // bin scan ticket + tile descriptors
+  int32_t scan_words = 0;
   // what the tables were built for
   int64_t key_map_gen = -1;
   double key_r = -1.0;
@@ -212,6 +219,12 @@ struct PtLaunch {
   long long *qacc;
   int32_t warps;   // look-up warps per CTA
   int32_t fuse_finish;  // 1: the look-up kernel finishes a particle when its last segment lands (<= 15 segments)
+  int32_t nbuf;         // table buffers per look-up warp: 2 (next table in flight) or 1
+  unsigned long long *scan_state;  // bin scan: {ticket | tail counter, descriptor per tile}
+  int32_t scan_words;
+  int32_t tail_pct;     // share of the sorted particles handed out in chunks at the end of the look-up
+  uint32_t *tail_ctr;   // next chunk of that tail (zeroed by the histogram)
+  int32_t rows32;       // 1: ring rows packed into one word in shared memory (base < 8192, lo < 256, cnt < 2048)
 };
 
 constexpr int MAX_WORLD = 16;
@@ -321,6 +334,7 @@ enum { DF_SMEM4 = 0, DF_GLOBAL8 = 1, DF_GLOBAL4 = 2, DF_WEDGE8 = 3 };
 cudaError_t launch_pt_fill(const amclj_ctx *c, const PtLaunch &L, int mode, cudaStream_t s);
 cudaError_t launch_pt_update(const amclj_ctx *c, const PtLaunch &L, int mode, bool dbg, cudaStream_t s);
 size_t pt_lookup_smem(const PtLaunch &L, int warps);
+int pt_max_warps();
 // raytable.cu
 cudaError_t launch_raytable(const amclj_ctx *c, const RtLaunch &L, int mode, bool diag, cudaStream_t s);
 cudaError_t rt_prepare_device();

@@ -87,43 +87,96 @@ pt_hist_kernel(const __grid_constant__ PtLaunch L) {
   }
   const uint32_t peers = __match_any_sync(FULL, key);
   if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(L.bin_count + key, (uint32_t)__popc(peers));
+  if (blockIdx.x == 0) /* the bin scan's ticket and tile descriptors start from zero */
+    for (int t = threadIdx.x; t < L.scan_words; t += blockDim.x) L.scan_state[t] = 0ull;
 }
 
-// exclusive scan of the bin counts (one CTA; n_slots + 1 bins), which also re-zeroes them
-__global__ void __launch_bounds__(1024)
-pt_scan_kernel(uint32_t *bin_count, uint32_t *bin_start, uint32_t *cursor, int nbins) {
-  __shared__ uint32_t warp_tot[32];
-  const int per = (nbins + 1023) / 1024, lo = min((int)threadIdx.x * per, nbins), hi = min(lo + per, nbins);
-  uint32_t sum = 0;
-  for (int b = lo; b < hi; b++) sum += bin_count[b];
+// Exclusive scan of the bin counts (n_slots + 1 bins; lgfloor: 78,514), which also re-zeroes them: single
+// pass, decoupled look-back over tiles of 2048 bins (the same scheme as filter.cu's weight scan; one CTA
+// walking all bins took 150 us).  scan_state = {ticket, pad, descriptor per tile}, zeroed by the histogram.
+constexpr int PT_SCAN_THREADS = 256, PT_SCAN_ITEMS = 8, PT_SCAN_TILE = PT_SCAN_THREADS * PT_SCAN_ITEMS;
+constexpr unsigned long long PT_AGG = 1ull << 62, PT_PREFIX = 2ull << 62, PT_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long pt_ld_volatile(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(PT_SCAN_THREADS)
+pt_scan_kernel(uint32_t *bin_count, uint32_t *bin_start, uint32_t *cursor, int nbins, unsigned long long *scan_state) {
+  __shared__ uint32_t warp_tot[PT_SCAN_THREADS / 32];
+  __shared__ uint32_t s_excl, s_tile;
+  if (threadIdx.x == 0) s_tile = atomicAdd(reinterpret_cast<uint32_t *>(scan_state), 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  unsigned long long *desc = scan_state + 1;
+  const int base = (int)tile * PT_SCAN_TILE + (int)threadIdx.x * PT_SCAN_ITEMS;
+  uint32_t c[PT_SCAN_ITEMS];
+  if (base + PT_SCAN_ITEMS <= nbins) { /* base is a multiple of 8: two 128-bit loads */
+    const uint4 u = *reinterpret_cast<const uint4 *>(bin_count + base), v = *reinterpret_cast<const uint4 *>(bin_count + base + 4);
+    c[0] = u.x; c[1] = u.y; c[2] = u.z; c[3] = u.w; c[4] = v.x; c[5] = v.y; c[6] = v.z; c[7] = v.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < PT_SCAN_ITEMS; k++) c[k] = base + k < nbins ? bin_count[base + k] : 0u;
+  }
+  uint32_t run = 0;
+#pragma unroll
+  for (int k = 0; k < PT_SCAN_ITEMS; k++) { const uint32_t t = c[k]; c[k] = run; run += t; } /* exclusive inside the thread */
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t inc = sum;
+  uint32_t inc = run;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(FULL, inc, o);
+    const uint32_t t = __shfl_up_sync(FULL, inc, o);
     if (lane >= o) inc += t;
   }
   if (lane == 31) warp_tot[wid] = inc;
   __syncthreads();
-  if (wid == 0) {
-    uint32_t w = warp_tot[lane], wi = w;
+  uint32_t woff = 0, tile_total = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(FULL, wi, o);
-      if (lane >= o) wi += t;
+  for (int k = 0; k < PT_SCAN_THREADS / 32; k++) {
+    const uint32_t ws = warp_tot[k];
+    if (k < wid) woff += ws;
+    tile_total += ws;
+  }
+  if (wid == 0) {
+    unsigned long long excl = 0;
+    if (tile == 0) {
+      if (lane == 0) atomicExch(&desc[0], PT_PREFIX | tile_total);
+    } else {
+      if (lane == 0) atomicExch(&desc[tile], PT_AGG | tile_total);
+      int look = (int)tile - 1;
+      for (;;) {
+        const int t = look - lane;
+        unsigned long long sv;
+        do {
+          sv = t >= 0 ? pt_ld_volatile(&desc[t]) : PT_PREFIX;
+        } while (__any_sync(FULL, (sv >> 62) == 0));
+        const uint32_t is_prefix = __ballot_sync(FULL, (sv >> 62) == 2);
+        const int first = is_prefix ? __ffs(is_prefix) - 1 : 32;
+        unsigned long long contrib = lane <= first ? (sv & PT_MASK) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(FULL, contrib, o);
+        excl += contrib;
+        if (is_prefix) break;
+        look -= 32;
+      }
+      if (lane == 0) atomicExch(&desc[tile], PT_PREFIX | (excl + tile_total));
     }
-    warp_tot[lane] = wi - w;
+    if (lane == 0) {
+      s_excl = (uint32_t)excl;
+      if ((int)(tile + 1) * PT_SCAN_TILE >= nbins) bin_start[nbins] = (uint32_t)excl + tile_total; /* = n */
+    }
   }
   __syncthreads();
-  uint32_t run = warp_tot[wid] + inc - sum;
-  for (int b = lo; b < hi; b++) {
-    const uint32_t c = bin_count[b];
-    bin_start[b] = run;
-    cursor[b] = run;
-    bin_count[b] = 0;
-    run += c;
-  }
-  if (threadIdx.x == 1023) bin_start[nbins] = run; /* = n */
+  const uint32_t off = s_excl + woff + inc - run;
+#pragma unroll
+  for (int k = 0; k < PT_SCAN_ITEMS; k++)
+    if (base + k < nbins) {
+      bin_start[base + k] = off + c[k];
+      cursor[base + k] = off + c[k];
+      bin_count[base + k] = 0;
+    }
 }
 
 __global__ void __launch_bounds__(PT_SORT_THREADS)
@@ -153,7 +206,13 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
 // One 30-beam segment of one particle, every range from the staged table of its start cell:
 // the arithmetic of raytable.cu's table_segment (and of sensor.cu's set-up) with the table in
 // shared memory.  DBG: also leave every range in the parity probe's buffer.
-template <bool S7, bool DBG>
+__device__ __forceinline__ uint32_t lds_u1(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+template <bool S7, bool DBG, bool R32>
 __device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunch &L, const ResDiv &rdv, uint32_t s_tab,
                                             uint32_t s_mix, uint32_t s_dir, uint32_t s_rows, float ox, float oy, float st,
                                             float ct, int xoff, int yoff, int jb0, int jb1, float *dbg_row) {
@@ -175,10 +234,17 @@ __device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunc
     const int ex = __float_as_int(__fadd_rd(qx + 0.5f, 12582912.0f)) - xoff;
     const uint32_t ry = (uint32_t)(__float_as_int(__fadd_rd(qy + 0.5f, 12582912.0f)) - yoff);
     const uint32_t ryc = min(ry, last_row);
-    const uint4 rw = lds_u4(s_rows + ryc * 16u); /* {first entry, lo, cnt, first entry of the negative arc} */
-    const uint32_t tt = (uint32_t)abs(ex) - rw.y;
-    const bool ok = tt < rw.z && ry <= last_row;
-    const uint32_t ent = ok ? tt + (ex < 0 ? rw.w : rw.x) : nan_entry;
+    uint32_t r_base, r_lo, r_cnt; /* the row's first entry, first |ex|, entries per arc (the negative arc follows the positive) */
+    if (R32) { /* one word per row: a random 4-byte read meets ~3.5-way bank conflicts, a 16-byte one ~8 wavefronts */
+      const uint32_t rw = lds_u1(s_rows + ryc * 4u);
+      r_base = rw & 0x1fffu; r_lo = (rw >> 13) & 0xffu; r_cnt = rw >> 21;
+    } else {
+      const uint4 rw = lds_u4(s_rows + ryc * 16u);
+      r_base = rw.x; r_lo = rw.y; r_cnt = rw.z;
+    }
+    const uint32_t tt = (uint32_t)abs(ex) - r_lo;
+    const bool ok = tt < r_cnt && ry <= last_row;
+    const uint32_t ent = ok ? r_base + tt + (ex < 0 ? r_cnt : 0u) : nan_entry;
     const float rng = lds_f1(s_tab + ent * 4u);
     if (DBG && dbg_row) dbg_row[jb] = rng;
     /* sensor.clj:149-162 beam mixture, exactly as in sensor.cu */
@@ -226,7 +292,8 @@ __device__ __noinline__ float pt_segment_walk(const SensorLaunch &a, float ox, f
   return a.s7 ? logprod_close(acc, prod, pexp) : acc;
 }
 
-constexpr int PT_MAX_WARPS = 16;
+constexpr int PT_MAX_WARPS = 24;
+constexpr int PT_TAIL_CHUNK = 64; /* sorted particles per unit of the common tail */
 
 template <int MODE, bool WIDE, bool DBG>
 __global__ void __launch_bounds__(PT_MAX_WARPS * 32, 1)
@@ -241,12 +308,20 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
   uint4 *srows = reinterpret_cast<uint4 *>(smix + nb);
   float2 *sdir = reinterpret_cast<float2 *>(srows + L.nrows);
   float *stab = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(sdir + nb) + 15) & ~(uintptr_t)15) +
-                (size_t)wid * 2 * L.stride;
+                (size_t)wid * L.nbuf * L.stride;
   {
     const float4 *mixt = reinterpret_cast<const float4 *>(a.beam);
     const float2 *dirt = reinterpret_cast<const float2 *>(a.beam + 4 * (size_t)nb);
     for (int i = threadIdx.x; i < nb; i += blockDim.x) { smix[i] = __ldg(mixt + i); sdir[i] = __ldg(dirt + i); }
-    for (int i = threadIdx.x; i < L.nrows; i += blockDim.x) srows[i] = __ldg(L.rows + i);
+    if (L.rows32) {
+      uint32_t *srows32 = reinterpret_cast<uint32_t *>(srows);
+      for (int i = threadIdx.x; i < L.nrows; i += blockDim.x) {
+        const uint4 rw = __ldg(L.rows + i);
+        srows32[i] = rw.x | (rw.y << 13) | (rw.z << 21);
+      }
+    } else {
+      for (int i = threadIdx.x; i < L.nrows; i += blockDim.x) srows[i] = __ldg(L.rows + i);
+    }
   }
   uint32_t s_mix = smem_u32(smix), s_dir = smem_u32(sdir), s_rows = smem_u32(srows);
   asm volatile("" : "+r"(s_mix), "+r"(s_dir), "+r"(s_rows));
@@ -259,12 +334,27 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
   }
   __syncthreads();
 
-  /* this warp's run of the sorted particles */
+  /* this warp's runs of the sorted particles: a contiguous share of the first (100 - tail_pct) percent, then
+   * chunks of the rest drawn from a common counter by whoever finishes first */
   const int64_t n = a.n, Wt = (int64_t)gridDim.x * wpb, g = (int64_t)blockIdx.x * wpb + wid;
-  const uint32_t q_lo = (uint32_t)(n * g / Wt), q_hi = (uint32_t)(n * (g + 1) / Wt);
-  if (q_lo >= q_hi) return;
+  const int64_t n_static = n - n * L.tail_pct / 100;
   const int nbins = L.n_slots + 1;
   const uint32_t *start = L.bin_start;
+  const ResDiv rdv = make_resdiv(a.res);
+  float wmax = -INFINITY;
+  int it = 0; /* tables staged so far by this warp (mbarrier phase) */
+  uint32_t q_lo = (uint32_t)(n_static * g / Wt), q_hi = (uint32_t)(n_static * (g + 1) / Wt);
+  for (bool own = true;; own = false) {
+  if (!own) { /* next chunk of the common tail */
+    uint32_t c = 0;
+    if (lane == 0) c = atomicAdd(L.tail_ctr, 1u);
+    c = __shfl_sync(FULL, c, 0);
+    const int64_t lo64 = n_static + (int64_t)c * PT_TAIL_CHUNK;
+    if (lo64 >= n) break;
+    q_lo = (uint32_t)lo64;
+    q_hi = (uint32_t)min(lo64 + PT_TAIL_CHUNK, n);
+  }
+  if (q_lo >= q_hi) continue;
   int s; /* the slot holding position q_lo: the last one with start[s] <= q_lo */
   {
     int lo_s = 0, hi_s = nbins;
@@ -275,7 +365,6 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
     s = lo_s;
   }
   uint32_t q = q_lo;
-  const ResDiv rdv = make_resdiv(a.res);
 
   /* the next cell of the run: slot, first position, particles */
   auto next_cell = [&](int &slot, uint32_t &p0, int &cnt) -> bool {
@@ -306,14 +395,20 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
 
   int c_slot = 0, n_slot = 0, c_cnt = 0, n_cnt = 0;
   uint32_t c_p0 = 0, n_p0 = 0;
-  float wmax = -INFINITY;
+  /* nbuf = 2: the next cell's table is in flight while this one is used; nbuf = 1: one buffer per warp (more
+   * warps fit the SM and cover the copy's latency for one another) */
+  const bool dbl = L.nbuf == 2;
   bool have = next_cell(c_slot, c_p0, c_cnt);
-  if (have) issue(c_slot, 0);
-  for (int it = 0; have; it++) {
-    const bool have_n = next_cell(n_slot, n_p0, n_cnt);
-    if (have_n) issue(n_slot, (it + 1) & 1);
+  if (have) issue(c_slot, dbl ? (it & 1) : 0);
+  for (; have; it++) {
+    bool have_n = false;
+    if (dbl) {
+      have_n = next_cell(n_slot, n_p0, n_cnt);
+      if (have_n) issue(n_slot, (it + 1) & 1);
+    }
+    const int buf = dbl ? (it & 1) : 0;
     { /* wait for this cell's table */
-      const uint32_t bar = bar0 + 8u * (uint32_t)(it & 1), parity = (uint32_t)(it >> 1) & 1u;
+      const uint32_t bar = bar0 + 8u * (uint32_t)buf, parity = (uint32_t)(dbl ? (it >> 1) : it) & 1u;
       uint32_t done = 0;
       while (!done) {
         asm volatile(
@@ -325,7 +420,7 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
             : "memory");
       }
     }
-    const uint32_t s_tab = s_tab0 + (uint32_t)(it & 1) * tab_bytes;
+    const uint32_t s_tab = s_tab0 + (uint32_t)buf * tab_bytes;
     int2 cc = make_int2(0, 0);
     if (c_slot < L.n_slots) cc = __ldg(L.cell_of_slot + c_slot);
     const int xoff = 0x4B400000 + cc.x, yoff = 0x4B400000 + cc.y - L.E;
@@ -339,8 +434,13 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
       float *dbg_row = nullptr;
       if (DBG && a.dbg_range && p >= a.dbg_first && p < a.dbg_first + a.dbg_count)
         dbg_row = a.dbg_range + (p - a.dbg_first) * nb;
-      float v = a.s7 ? pt_segment<true, DBG>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, xoff, yoff, jb0, jb1, dbg_row)
-                     : pt_segment<false, DBG>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, xoff, yoff, jb0, jb1, dbg_row);
+      float v;
+      if (L.rows32)
+        v = a.s7 ? pt_segment<true, DBG, true>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, xoff, yoff, jb0, jb1, dbg_row)
+                 : pt_segment<false, DBG, true>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, xoff, yoff, jb0, jb1, dbg_row);
+      else
+        v = a.s7 ? pt_segment<true, DBG, false>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, xoff, yoff, jb0, jb1, dbg_row)
+                 : pt_segment<false, DBG, false>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, xoff, yoff, jb0, jb1, dbg_row);
       if (v != v) {
         v = pt_segment_walk<MODE, WIDE>(a, ps.x, ps.y, ps.z, ps.w, jb0, jb1, dbg_row);
         if (a.stats) atomicAdd(a.stats + 11, 1ull); /* table_misses: expected 0 */
@@ -366,9 +466,14 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
       }
     }
     __syncwarp();
+    if (!dbl) {
+      have_n = next_cell(n_slot, n_p0, n_cnt);
+      if (have_n) issue(n_slot, 0);
+    }
     c_slot = n_slot; c_p0 = n_p0; c_cnt = n_cnt;
     have = have_n;
   }
+  } /* ranges */
   if (L.fuse_finish && a.rawmax_ord) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(FULL, wmax, o));
@@ -391,8 +496,9 @@ pt_finish_kernel(const long long *__restrict__ qacc, int64_t n, float *__restric
 }
 
 size_t pt_lookup_smem(const PtLaunch &L, int warps) {
-  return (size_t)L.s.nb * 24 + (size_t)L.nrows * 16 + 16 + (size_t)warps * 2 * L.stride * 4;
+  return (size_t)L.s.nb * 24 + (size_t)L.nrows * 16 + 16 + (size_t)warps * L.nbuf * L.stride * 4;
 }
+int pt_max_warps() { return PT_MAX_WARPS; }
 
 template <int MODE, bool WIDE>
 static cudaError_t launch_pt_fill_t(const amclj_ctx *c, const PtLaunch &L, cudaStream_t s) {
@@ -439,7 +545,8 @@ cudaError_t launch_pt_update(const amclj_ctx *c, const PtLaunch &L, int mode, bo
   if (a.n <= 0 || a.nb <= 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((a.n + PT_SORT_THREADS - 1) / PT_SORT_THREADS);
   pt_hist_kernel<<<blocks, PT_SORT_THREADS, 0, s>>>(L);
-  pt_scan_kernel<<<1, 1024, 0, s>>>(L.bin_count, L.bin_start, L.cursor, L.n_slots + 1);
+  pt_scan_kernel<<<(unsigned)((L.n_slots + 1 + PT_SCAN_TILE - 1) / PT_SCAN_TILE), PT_SCAN_THREADS, 0, s>>>(L.bin_count, L.bin_start, L.cursor,
+                                                                                                                L.n_slots + 1, L.scan_state);
   pt_scatter_kernel<<<blocks, PT_SORT_THREADS, 0, s>>>(L);
   const bool wide = a.div_wide != 0;
   cudaError_t e;

@@ -226,7 +226,8 @@ def test_gpu_ref_mode_against_the_reference_text(ref, lgfloor):
             raw = c.raw_weights()
             want = np.array([k["weight"] for k in cases])
             close = np.isclose(raw, want, rtol=1e-5)
-            assert close.mean() >= 0.98, (sname, close.mean())  # the rest: a start/end cell moved by fp32 rounding at a .5 boundary
+            # the rest: a start/end cell moved by fp32 rounding at a .5 boundary (one pose sits on such a boundary on purpose)
+            assert (~close).sum() <= max(2, 0.02 * len(close)), (sname, int((~close).sum()), len(close))
             # rays: the walk kernel's diagnostic pass against the cells the reference's text visited
             c.set_params(_lib.params("REF", df_mode=4))
             dbg = c.raycast_debug(len(r), amin, ainc, rmax)
