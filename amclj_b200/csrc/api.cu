@@ -504,8 +504,10 @@ int enqueue_ptable(amclj_ctx *ctx, const SensorLaunch &base, bool dbg) {
   L.s.x = base.x; L.s.y = base.y; L.s.th = base.th; L.s.raw = base.raw; L.s.n = base.n;
   L.s.rawmax_ord = base.rawmax_ord; L.s.stats = base.stats;
   L.s.dbg_first = base.dbg_first; L.s.dbg_count = base.dbg_count; L.s.dbg_range = base.dbg_range;
-  CK(launch_pt_update(ctx, L, pt_fill_mode(ctx), dbg, ctx->stream));
-  ctx->launches += L.fuse_finish ? 4 : 5; /* histogram, scan, scatter, look-up (, finish) */
+  const bool hist_done = ctx->pt.hist_done && !dbg && base.x == ctx->x && base.n == ctx->n;
+  ctx->pt.hist_done = false;
+  CK(launch_pt_update(ctx, L, pt_fill_mode(ctx), dbg, hist_done, ctx->stream));
+  ctx->launches += (L.fuse_finish ? 4 : 5) - (hist_done ? 1 : 0); /* histogram, scan, scatter, look-up (, finish) */
   return AMCLJ_OK;
 }
 
@@ -708,6 +710,22 @@ int enqueue_motion(amclj_ctx *ctx, const double curr[3], const double prev[3], b
       ((auto_mode(ctx) && (ctx->map.wedge || ctx->order_large_maps || ctx->rt_enable)) || ctx->p.df_mode == 6)) {
     m.bbox = ctx->bbox; /* the moved cloud's bounding box comes for free */
     ctx->bbox_done = true;
+  }
+  /* the persistent-table sort's histogram pass rides along when the sensor pass of this update will run on
+   * the tables (same rounding of the same moved pose: ptable.cu pt_hist_kernel) */
+  ctx->pt.hist_done = false;
+  if (ctx->pt.fuse_motion && ctx->pt.built && ctx->ctrl_fresh && !m.is_static && ctx->beams.staged &&
+      (ctx->p.df_mode == 7 || (ctx->p.df_mode == 0 && !(ctx->p.collect_stats & 1)))) {
+    int rc = ensure_pt_scratch(ctx, ctx->n);
+    if (rc) return rc;
+    const PersistentTables &t = ctx->pt;
+    m.hist_slot_of_cell = t.slot_of_cell;
+    m.hist_W = ctx->map.W; m.hist_H = ctx->map.H; m.hist_n_slots = t.n_slots;
+    m.hist_s10 = ctx->p.s10_apply_laser_offset;
+    m.hist_res = ctx->map.res; m.hist_laser_x = ctx->p.laser_x; m.hist_laser_y = ctx->p.laser_y;
+    m.hist_bin_count = t.bin_count; m.hist_pkey = t.pkey; m.hist_qacc = ctx->partials;
+    m.hist_scan_state = t.scan_state; m.hist_scan_words = t.scan_words;
+    ctx->pt.hist_done = true;
   }
   CK(launch_motion(m, ctx->stream));
   ctx->launches += 1;
@@ -1170,6 +1188,7 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
   if (const char *e = getenv("AMCLJ_PT_BUDGET_MB")) ctx->pt.budget = (size_t)atoll(e) << 20;
   if (const char *e = getenv("AMCLJ_PT_WARPS")) ctx->pt.warps_req = atoi(e);
   if (const char *e = getenv("AMCLJ_PT_NBUF")) ctx->pt.nbuf = atoi(e);
+  if (const char *e = getenv("AMCLJ_PT_FUSE_MOTION")) ctx->pt.fuse_motion = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_PT_TAIL_PCT")) ctx->pt.tail_pct = atoi(e) < 0 ? 0 : (atoi(e) > 100 ? 100 : atoi(e));
   if (const char *e = getenv("AMCLJ_PT_ROWS32")) ctx->pt.rows32 = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_PT_FUSE")) ctx->pt.fuse_finish = atoi(e) != 0;

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include "internal.h"
+#include "sensor_common.cuh"
 
 namespace amclj {
 
@@ -35,30 +36,95 @@ __device__ __forceinline__ void philox_normals3(uint64_t seed, uint64_t gid, uin
   n3 = rb * cosf(b);
 }
 
-__global__ void __launch_bounds__(256) motion_kernel(const MotionLaunch a) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = i < a.n;
-  uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-  if (valid) {
-    float n1, n2, n3;
-    if (a.normals) {
-      n1 = __ldg(a.normals + 3 * i);
-      n2 = __ldg(a.normals + 3 * i + 1);
-      n3 = __ldg(a.normals + 3 * i + 2);
-    } else {
-      philox_normals3(a.seed, (uint64_t)(a.gid0 + i), TAG_MOTION, n1, n2, n3);
+/* one particle: motion.clj:24-45 with the launch-uniform control; returns its table slot when the sort's first
+ * pass rides along (else -1) */
+__device__ __forceinline__ int motion_one(const MotionLaunch &a, int64_t i, float &x, float &y, float &th, float n1,
+                                          float n2, float n3) {
+  float r1 = fmaf(-n1, a.sd1, a.rot1);                          /* motion.clj:35 */
+  float tr = a.trans_zero ? 0.0f : fmaf(-n2, a.sdt, a.trans);   /* motion.clj:36-37 */
+  float r2 = fmaf(-n3, a.sd2, a.rot2);                          /* motion.clj:38 */
+  float sn, cs;
+  sincos_det(th + r1, sn, cs);
+  const float nx = fmaf(tr, cs, x), ny = fmaf(tr, sn, y);     /* motion.clj:39-44 */
+  const float nth = wrap_heading(th + (r1 + r2)); /* quat/rotate by rot1* + rot2*; the next to-heading is in (-pi, pi] */
+  x = nx; y = ny; th = nth;
+  int hkey = -1;
+  if (a.hist_slot_of_cell) { /* first pass of the persistent-table sort (ptable.cu pt_hist_kernel), same arithmetic */
+    float ox = nx, oy = ny;
+    if (a.hist_s10) {
+      float st, ct;
+      sincos_det(nth, st, ct);
+      ox = nx + fmaf(a.hist_laser_x, ct, -(a.hist_laser_y * st));
+      oy = ny + fmaf(a.hist_laser_x, st, a.hist_laser_y * ct);
     }
-    float th = a.th[i];
-    float r1 = fmaf(-n1, a.sd1, a.rot1);                          /* motion.clj:35 */
-    float tr = a.trans_zero ? 0.0f : fmaf(-n2, a.sdt, a.trans);   /* motion.clj:36-37 */
-    float r2 = fmaf(-n3, a.sd2, a.rot2);                          /* motion.clj:38 */
-    float sn, cs;
-    sincos_det(th + r1, sn, cs);
-    float nx = fmaf(tr, cs, a.x[i]), ny = fmaf(tr, sn, a.y[i]); /* motion.clj:39-44 */
-    a.x[i] = nx;
-    a.y[i] = ny;
-    a.th[i] = wrap_heading(th + (r1 + r2)); /* quat/rotate by rot1* + rot2*; the next to-heading is in (-pi, pi] */
-    m0 = ord_of_float_m(nx); m1 = ord_of_float_m(-nx); m2 = ord_of_float_m(ny); m3 = ord_of_float_m(-ny);
+    const ResDiv rdv = make_resdiv(a.hist_res);
+    int x0, y0;
+    round_cell2_fast(ox, oy, rdv, x0, y0);
+    const bool in = (uint32_t)x0 < (uint32_t)a.hist_W && (uint32_t)y0 < (uint32_t)a.hist_H;
+    hkey = in ? __ldg(a.hist_slot_of_cell + (size_t)y0 * a.hist_W + x0) : a.hist_n_slots;
+    a.hist_pkey[i] = hkey;
+    a.hist_qacc[i] = 0;
+  }
+  return hkey;
+}
+
+// Every thread moves FOUR consecutive particles: x, y, theta (and the injected normals) stream through
+// 128-bit coalesced loads and stores; the last, partial group of a set whose size is not a multiple of four
+// goes element by element.
+__global__ void __launch_bounds__(256) motion_kernel(const MotionLaunch a) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, i0 = g * 4;
+  const int lane = threadIdx.x & 31;
+  uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+  float px[4], py[4], pt[4], nz[12];
+  const int cnt = i0 < a.n ? (int)min((int64_t)4, a.n - i0) : 0;
+  const bool vec = cnt == 4 && a.vec_ok;
+  if (vec) {
+    const float4 vx = *reinterpret_cast<const float4 *>(a.x + i0), vy = *reinterpret_cast<const float4 *>(a.y + i0),
+                 vt = *reinterpret_cast<const float4 *>(a.th + i0);
+    px[0] = vx.x; px[1] = vx.y; px[2] = vx.z; px[3] = vx.w;
+    py[0] = vy.x; py[1] = vy.y; py[2] = vy.z; py[3] = vy.w;
+    pt[0] = vt.x; pt[1] = vt.y; pt[2] = vt.z; pt[3] = vt.w;
+    if (a.normals) {
+      const float4 *nn = reinterpret_cast<const float4 *>(a.normals + 3 * i0); /* 48 bytes per group: 16-byte aligned */
+      const float4 na = __ldg(nn), nb = __ldg(nn + 1), nc = __ldg(nn + 2);
+      nz[0] = na.x; nz[1] = na.y; nz[2] = na.z; nz[3] = na.w; nz[4] = nb.x; nz[5] = nb.y;
+      nz[6] = nb.z; nz[7] = nb.w; nz[8] = nc.x; nz[9] = nc.y; nz[10] = nc.z; nz[11] = nc.w;
+    }
+  } else {
+    for (int u = 0; u < cnt; u++) {
+      px[u] = a.x[i0 + u]; py[u] = a.y[i0 + u]; pt[u] = a.th[i0 + u];
+      if (a.normals)
+        for (int k = 0; k < 3; k++) nz[3 * u + k] = __ldg(a.normals + 3 * (i0 + u) + k);
+    }
+  }
+  int hkey[4] = {-1, -1, -1, -1};
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    if (u < cnt) {
+      float n1, n2, n3;
+      if (a.normals) { n1 = nz[3 * u]; n2 = nz[3 * u + 1]; n3 = nz[3 * u + 2]; }
+      else philox_normals3(a.seed, (uint64_t)(a.gid0 + i0 + u), TAG_MOTION, n1, n2, n3);
+      hkey[u] = motion_one(a, i0 + u, px[u], py[u], pt[u], n1, n2, n3);
+      m0 = max(m0, ord_of_float_m(px[u])); m1 = max(m1, ord_of_float_m(-px[u]));
+      m2 = max(m2, ord_of_float_m(py[u])); m3 = max(m3, ord_of_float_m(-py[u]));
+    }
+  }
+  if (vec) {
+    *reinterpret_cast<float4 *>(a.x + i0) = make_float4(px[0], px[1], px[2], px[3]);
+    *reinterpret_cast<float4 *>(a.y + i0) = make_float4(py[0], py[1], py[2], py[3]);
+    *reinterpret_cast<float4 *>(a.th + i0) = make_float4(pt[0], pt[1], pt[2], pt[3]);
+  } else {
+    for (int u = 0; u < cnt; u++) { a.x[i0 + u] = px[u]; a.y[i0 + u] = py[u]; a.th[i0 + u] = pt[u]; }
+  }
+  if (a.hist_slot_of_cell) { /* histogram with one atomic per distinct cell per warp and round */
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int key = u < cnt ? hkey[u] : -1 - lane;
+      const uint32_t peers = __match_any_sync(0xffffffffu, key);
+      if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(a.hist_bin_count + key, (uint32_t)__popc(peers));
+    }
+    if (blockIdx.x == 0)
+      for (int t = threadIdx.x; t < a.hist_scan_words; t += blockDim.x) a.hist_scan_state[t] = 0ull;
   }
   if (a.bbox) { /* bounding box of the moved cloud, for the sensor stage's walking-order decision */
     m0 = __reduce_max_sync(0xffffffffu, m0);
@@ -79,9 +145,13 @@ __global__ void __launch_bounds__(256) motion_kernel(const MotionLaunch a) {
   }
 }
 
-cudaError_t launch_motion(const MotionLaunch &a, cudaStream_t s) {
-  if (a.n <= 0 || a.is_static) return cudaSuccess; /* motion.clj:26-27 */
-  motion_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a);
+cudaError_t launch_motion(const MotionLaunch &a_in, cudaStream_t s) {
+  if (a_in.n <= 0 || a_in.is_static) return cudaSuccess; /* motion.clj:26-27 */
+  MotionLaunch a = a_in;
+  auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  a.vec_ok = al16(a.x) && al16(a.y) && al16(a.th) && (!a.normals || al16(a.normals));
+  const int64_t groups = (a.n + 3) / 4;
+  motion_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -162,10 +232,6 @@ cudaError_t build_distance_fields(amclj_ctx *c, bool want8, cudaStream_t s) {
 // summation order, so the contract here is integer: q_i = floor(w_i / w_max * 2^32)
 // elementwise, then an exact u64 inclusive scan (single pass, decoupled look-back).
 // ======================================================================================
-__device__ __forceinline__ uint32_t ord_of_float(float f) {
-  uint32_t b = __float_as_uint(f);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
 __device__ __forceinline__ float float_of_ord(uint32_t o) {
   return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
@@ -476,8 +542,23 @@ __global__ void __launch_bounds__(256) systematic_gather_kernel(const GatherArgs
   }
   __syncthreads();
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= a.count) return;
   const SysPlan plan = s_plan;
+  /* The thresholds of a CTA's slots are monotone, so their sources lie between the source of its first slot
+   * and the source of its last: two threads search the whole CDF (~21 dependent loads for a million entries),
+   * the others only that window (a few hundred entries the CTA shares in L1). */
+  __shared__ int64_t s_win[2];
+  if (plan.total != 0 && (threadIdx.x == 0 || threadIdx.x == blockDim.x - 1)) {
+    const int64_t kk = min(k, a.count - 1);
+    const uint64_t key = sys_threshold(plan, (uint64_t)(a.m_lo + kk)) - a.cdf_offset;
+    int64_t lo = 0, hi = a.n_local;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (__ldg(a.cdf + mid) > key) hi = mid; else lo = mid + 1;
+    }
+    s_win[threadIdx.x == 0 ? 0 : 1] = lo;
+  }
+  __syncthreads();
+  if (k >= a.count) return;
   int64_t i;
   if (plan.total == 0) {
     /* every weight is zero (e.g. a zero-probability beam under log-weights): there is no CDF to draw
@@ -488,7 +569,7 @@ __global__ void __launch_bounds__(256) systematic_gather_kernel(const GatherArgs
   } else {
     uint64_t U = sys_threshold(plan, (uint64_t)(a.m_lo + k));
     uint64_t key = U - a.cdf_offset; /* caller guarantees U >= cdf_offset */
-    int64_t lo = 0, hi = a.n_local;
+    int64_t lo = s_win[0], hi = min(s_win[1] + 1, a.n_local);
     while (lo < hi) { /* first i with cdf[i] > key */
       int64_t mid = (lo + hi) >> 1;
       if (__ldg(a.cdf + mid) > key) hi = mid; else lo = mid + 1;
@@ -942,8 +1023,28 @@ __global__ void __launch_bounds__(256) pull_kernel(const PullArgs a) {
   }
   __syncthreads();
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= a.count) return;
   const SysPlan plan = s_plan;
+  /* as in the single-GPU gather: when the CTA's first and last slot draw from the same rank, the sources of
+   * all its slots lie between theirs, and only two threads search that rank's whole CDF */
+  __shared__ int64_t s_win[2];
+  __shared__ int s_wing[2];
+  if (plan.total != 0 && (threadIdx.x == 0 || threadIdx.x == blockDim.x - 1)) {
+    const int64_t kk = min(k, a.count - 1);
+    const uint64_t U = sys_threshold(plan, (uint64_t)(a.slot0 + kk));
+    int gg = 0;
+    for (; gg + 1 < a.world && U >= s_off[gg + 1]; gg++) {}
+    const uint64_t key = U - s_off[gg];
+    const uint64_t *cdf = a.peer[gg].cdf;
+    int64_t lo = 0, hi = a.peer[gg].n;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (cdf[mid] > key) hi = mid; else lo = mid + 1;
+    }
+    s_win[threadIdx.x == 0 ? 0 : 1] = lo;
+    s_wing[threadIdx.x == 0 ? 0 : 1] = gg;
+  }
+  __syncthreads();
+  if (k >= a.count) return;
   const int64_t m = a.slot0 + k;
   int g = 0;
   int64_t i = 0;
@@ -956,6 +1057,7 @@ __global__ void __launch_bounds__(256) pull_kernel(const PullArgs a) {
     const uint64_t key = U - s_off[g];
     const uint64_t *cdf = a.peer[g].cdf;
     int64_t lo = 0, hi = a.peer[g].n;
+    if (s_wing[0] == s_wing[1] && s_wing[0] == g) { lo = s_win[0]; hi = min(s_win[1] + 1, a.peer[g].n); }
     while (lo < hi) { /* first i with cdf[i] > key */
       int64_t mid = (lo + hi) >> 1;
       if (cdf[mid] > key) hi = mid; else lo = mid + 1;

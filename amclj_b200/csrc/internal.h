@@ -95,8 +95,19 @@ struct MotionLaunch {
   const float *normals;  // [n][3] or null -> Philox
   uint64_t seed;
   int32_t is_static, trans_zero;
+  int32_t vec_ok;  // set by launch_motion: every array is 16-byte aligned (128-bit loads and stores)
   uint32_t *bbox;  // when set: accumulate the bounding box of the moved cloud (4 ordered-uint maxima)
   float rot1, trans, rot2, sd1, sdt, sd2;
+  /* optional: the first pass of the persistent-table sort fused in (ptable.cu's pt_hist_kernel): table slot of
+   * the moved particle's start cell, histogram, cleared accumulator.  hist_slot_of_cell == null: off */
+  const int32_t *hist_slot_of_cell;
+  int32_t hist_W, hist_H, hist_n_slots, hist_s10;
+  float hist_res, hist_laser_x, hist_laser_y;
+  uint32_t *hist_bin_count;
+  int32_t *hist_pkey;
+  long long *hist_qacc;
+  unsigned long long *hist_scan_state;
+  int32_t hist_scan_words;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -192,6 +203,8 @@ struct PersistentTables {
   int32_t nbuf = 0;                // table buffers per warp requested (0: one, so that more warps fit; AMCLJ_PT_NBUF)
   int32_t nbuf_used = 1, warps_req = 0;
   int32_t tail_pct = 0;            // AMCLJ_PT_TAIL_PCT
+  bool fuse_motion = false;        // AMCLJ_PT_FUSE_MOTION=1: the motion kernel takes the sort's histogram pass along
+  bool hist_done = false;          // ... and did so for the update in progress
   int32_t rows32 = 1;              // AMCLJ_PT_ROWS32
   unsigned long long *scan_state = nullptr;  // bin scan ticket + tile descriptors
   int32_t scan_words = 0;
@@ -332,7 +345,7 @@ cudaError_t launch_sensor(const amclj_ctx *c, const SensorLaunch &a, int mode, b
 enum { DF_SMEM4 = 0, DF_GLOBAL8 = 1, DF_GLOBAL4 = 2, DF_WEDGE8 = 3 };
 // ptable.cu
 cudaError_t launch_pt_fill(const amclj_ctx *c, const PtLaunch &L, int mode, cudaStream_t s);
-cudaError_t launch_pt_update(const amclj_ctx *c, const PtLaunch &L, int mode, bool dbg, cudaStream_t s);
+cudaError_t launch_pt_update(const amclj_ctx *c, const PtLaunch &L, int mode, bool dbg, bool hist_done, cudaStream_t s);
 size_t pt_lookup_smem(const PtLaunch &L, int warps);
 int pt_max_warps();
 // raytable.cu

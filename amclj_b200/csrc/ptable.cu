@@ -540,11 +540,11 @@ static cudaError_t launch_pt_lookup_m(const amclj_ctx *c, const PtLaunch &L, boo
   return wide ? launch_pt_lookup_t<MODE, true, false>(c, L, s) : launch_pt_lookup_t<MODE, false, false>(c, L, s);
 }
 
-cudaError_t launch_pt_update(const amclj_ctx *c, const PtLaunch &L, int mode, bool dbg, cudaStream_t s) {
+cudaError_t launch_pt_update(const amclj_ctx *c, const PtLaunch &L, int mode, bool dbg, bool hist_done, cudaStream_t s) {
   const SensorLaunch &a = L.s;
   if (a.n <= 0 || a.nb <= 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((a.n + PT_SORT_THREADS - 1) / PT_SORT_THREADS);
-  pt_hist_kernel<<<blocks, PT_SORT_THREADS, 0, s>>>(L);
+  if (!hist_done) pt_hist_kernel<<<blocks, PT_SORT_THREADS, 0, s>>>(L); /* else: the motion kernel took this pass along */
   pt_scan_kernel<<<(unsigned)((L.n_slots + 1 + PT_SCAN_TILE - 1) / PT_SCAN_TILE), PT_SCAN_THREADS, 0, s>>>(L.bin_count, L.bin_start, L.cursor,
                                                                                                                 L.n_slots + 1, L.scan_state);
   pt_scatter_kernel<<<blocks, PT_SORT_THREADS, 0, s>>>(L);
