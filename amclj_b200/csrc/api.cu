@@ -397,7 +397,7 @@ void fill_pt_args(const amclj_ctx *ctx, PtLaunch &L) {
   L.scan_words = t.scan_words;
   L.tail_pct = t.tail_pct;
   L.tail_ctr = reinterpret_cast<uint32_t *>(t.scan_state) + 1;
-  L.rows32 = (t.rows32 && r.n_entries < 8192 && r.E < 255) ? 1 : 0;
+  L.rows32 = (t.rows32 && r.n_entries < 65536 && r.E < 250) ? 1 : 0; /* base : 16 | lo : 8 | cnt : 8 (cnt <= ~sqrt(8 r) + 4) */
   L.fuse_finish = (t.fuse_finish && (ctx->beams.nb + 29) / 30 <= 15) ? 1 : 0;
 }
 
@@ -410,6 +410,7 @@ int pt_prepare(amclj_ctx *ctx, double rcells) {
   const amclj_params &p = ctx->p;
   t.built = false;
   const bool wanted = t.enable && (p.df_mode == 0 || p.df_mode == 7) && t.n_slots > 0 && r.have_ring && r.floor_trick_ok &&
+                      ctx->beams.cr.K != 0.0f &&
                       ctx->map.res > 1.0e-6f && ctx->map.res < 1.0e6f;
   if (!wanted) return AMCLJ_OK;
   const int32_t stride = (r.n_entries + 3) & ~3;
@@ -525,23 +526,27 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
   int nb = beams_used(n, p.s6_max_beams);
   /* host staging in pinned memory, guarded by an event, so the upload needs no synchronisation */
   size_t tab_bytes = sizeof(float) * (size_t)nb * 6;
-  if (tab_bytes > ctx->pin_tab_bytes) {
+  const size_t dbl_off = (tab_bytes + 15) & ~(size_t)15, dbl_bytes = sizeof(double) * (size_t)nb * 2;
+  if (dbl_off + dbl_bytes > ctx->pin_tab_bytes) {
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->pin_tab) cudaFreeHost(ctx->pin_tab);
     ctx->pin_tab = nullptr;
-    CK(cudaMallocHost(&ctx->pin_tab, tab_bytes));
-    ctx->pin_tab_bytes = tab_bytes;
+    CK(cudaMallocHost(&ctx->pin_tab, dbl_off + dbl_bytes));
+    ctx->pin_tab_bytes = dbl_off + dbl_bytes;
   }
   CK(cudaEventSynchronize(ctx->ev[4])); /* the previous upload from this buffer has finished */
   /* float4 (obs, e2, p34, 0) first so that it stays 16-byte aligned for any beam count | float2 (cb, sb) */
   float *mix = reinterpret_cast<float *>(ctx->pin_tab), *dir = mix + 4 * (size_t)nb;
+  double *dird = reinterpret_cast<double *>(reinterpret_cast<char *>(ctx->pin_tab) + dbl_off); /* near-tie refinement */
   float zshort = p.z_short, lam = p.lambda_short;
   int j = 0;
   for (int i = 0; i < n; i += step, j++) {
     /* sensor.clj:93-97 bearing: float32 message fields, double arithmetic */
     double a = (double)angle_min + (double)i * (double)angle_inc;
-    dir[2 * j] = (float)cos(a);
-    dir[2 * j + 1] = (float)sin(a);
+    dird[2 * j] = cos(a);
+    dird[2 * j + 1] = sin(a);
+    dir[2 * j] = (float)dird[2 * j];
+    dir[2 * j + 1] = (float)dird[2 * j + 1];
     float o = ranges ? ranges[i] : 0.0f;
     mix[4 * j] = o;
     mix[4 * j + 1] = zshort * lam * expf(-lam * o);            /* sensor.clj:154-157 */
@@ -562,11 +567,16 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
   }
   BeamTable &b = ctx->beams;
   if (nb > b.cap) {
+    CK(cudaStreamSynchronize(ctx->stream));
     dfree(b.dev);
+    dfree(b.dev_d);
     CK(dalloc(&b.dev, (size_t)nb * 6));
+    CK(dalloc(&b.dev_d, (size_t)nb * 2));
     b.cap = nb;
   }
   CK(cudaMemcpyAsync(b.dev, ctx->pin_tab, tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(b.dev_d, dird, dbl_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  b.cr = make_cell_refine(ctx->map.W, ctx->map.H, rcells, ctx->exact_cells && ctx->map.res > 1.0e-6f && ctx->map.res < 1.0e6f);
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   b.nb = nb;
   b.n_scan = n;
@@ -660,6 +670,8 @@ void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode) {
     a.df_bytes = m.bytes4;
   }
   a.beam = ctx->beams.dev;
+  a.beam_d = ctx->beams.dev_d;
+  a.cr = ctx->beams.cr;
   a.nb = ctx->beams.nb;
   a.divtab = ctx->divs.dev;
   a.ndiv = ctx->divs.n;
@@ -1177,6 +1189,7 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
   if (const char *e = getenv("AMCLJ_REFILL_GLOBAL")) ctx->refill_global = atoi(e);
   if (const char *e = getenv("AMCLJ_COMPACT_CELLS")) ctx->compact_cells = (float)atof(e);
   if (const char *e = getenv("AMCLJ_RAYTABLE")) ctx->rt_enable = atoi(e) != 0;
+  if (const char *e = getenv("AMCLJ_EXACT_CELLS")) ctx->exact_cells = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_RING_SETUP")) ctx->ring_setup = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_WALK_TAIL_PCT")) ctx->walk_tail_pct = atoi(e) > 100 ? 100 : atoi(e);
   if (const char *e = getenv("AMCLJ_TIME_MAIN")) ctx->time_main_env = atoi(e) != 0;
@@ -1237,7 +1250,7 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   dfree(ctx->map.cells); dfree(ctx->map.df4); dfree(ctx->map.df8); dfree(ctx->map.wedge);
-  dfree(ctx->beams.dev); dfree(ctx->divs.dev);
+  dfree(ctx->beams.dev); dfree(ctx->beams.dev_d); dfree(ctx->divs.dev);
   dfree(ctx->x); dfree(ctx->y); dfree(ctx->th); dfree(ctx->w); dfree(ctx->raw);
   dfree(ctx->x2); dfree(ctx->y2); dfree(ctx->th2); dfree(ctx->w2);
   dfree(ctx->cdf); dfree(ctx->idx); dfree(ctx->normals); dfree(ctx->partials); dfree(ctx->perm); dfree(ctx->tile_counters);

@@ -9,6 +9,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define AMCLJ_HD __host__ __device__ __forceinline__
@@ -77,6 +78,75 @@ AMCLJ_HD float exp_det(float x) {
 AMCLJ_HD int32_t round_cell(float v, float res) {
   float t = floorf(v / res + 0.5f);
   t = fminf(fmaxf(t, -1.0e9f), 1.0e9f); /* NaN -> -1e9 */
+  return (int32_t)t;
+}
+
+// Deterministic double-precision sincos for |a| up to a few pi (headings are kept in (-pi, pi]): Cody-Waite
+// reduction by pi/2 with fdlibm's split of pi/2, fdlibm's kernel polynomials, explicit fma — host and device
+// agree bit for bit, and with the C library to ~1e-16.  Used by the near-tie refinement of end cells only.
+AMCLJ_HD void sincos_det_d(double a, double &sn, double &cs) {
+  double j = rint(a * 6.36619772367581382433e-01);
+  j = fmin(fmax(j, -1.0e6), 1.0e6);
+  double r = fma(-j, 1.57079632673412561417e+00, a);
+  r = fma(-j, 6.07710050650619224932e-11, r);
+  const int q = ((int)j) & 3;
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  const double s = fma(ps * z, r, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  const double c = fma(pc * z, z, fma(-0.5, z, 1.0));
+  double so = (q & 1) ? c : s, co = (q & 1) ? s : c;
+  if (q & 2) so = -so;
+  if ((q + 1) & 2) co = -co;
+  sn = so;
+  cs = co;
+}
+
+// Near-tie refinement of END cells.  An end point is rounded to its cell in float arithmetic; where the
+// quotient lies within two units of 2^-fb of a .5 boundary the float result could differ from what the
+// reference computes in double from the same float32 inputs, and the cell is recomputed in double
+// (end_cells_exact in sensor_common.cuh).  The test costs one AND: q + K is formed with
+// K = 1.5 * 2^(23-fb) + 0.5 + 2^(1-fb), which leaves round((q + 0.5) * 2^fb) + 2 in the low mantissa bits:
+// cell = bits >> fb (minus a constant), near a boundary <=> (bits & (2^fb - 4)) == 0.  fb is the largest
+// that keeps every quotient of the map inside the mantissa window; maxq = cells the farthest end point can
+// be from the origin.
+struct CellRefine {
+  float K;        /* 0: no refinement (odd geometry) */
+  int32_t fb;
+  int32_t coff;   /* bits(1.5 * 2^(23-fb)) >> fb */
+  uint32_t mask;  /* 2^fb - 4 */
+};
+inline CellRefine make_cell_refine(int W, int H, double rcells, bool enabled) {
+  CellRefine c = {0.0f, 0, 0, 0u};
+  const double maxq = (double)(W > H ? W : H) + ceil(rcells) + 6.0;
+  int fb = 12;
+  while (fb > 4 && maxq >= ldexp(1.0, 22 - fb) - 2.0) fb--;
+  if (maxq >= ldexp(1.0, 22 - fb) - 2.0) return c; /* rays of > 260,000 cells: plain float rounding (K == 0) */
+  const float big = (float)ldexp(1.5, 23 - fb);
+  c.K = big + 0.5f + (float)ldexp(1.0, 1 - fb);
+  c.fb = fb;
+  uint32_t bits;
+  memcpy(&bits, &big, 4);
+  c.coff = (int32_t)(bits >> fb);
+  /* disabled (AMCLJ_EXACT_CELLS=0, timing experiments): a mask bit that is always set, i.e. never "near" */
+  c.mask = enabled ? (1u << fb) - 4u : 0x40000000u;
+  return c;
+}
+
+// The START cell of a particle's rays (map.clj:36-46 on the pose itself): once per particle, so it is taken
+// the way the JVM takes it from the same float32 inputs — a double divide — and no particle starts its 360
+// rays from a cell that differs from the reference's because v / res was rounded to float first.
+AMCLJ_HD int32_t round_cell_start(float v, float res) {
+  double t = floor((double)v / (double)res + 0.5);
+  t = fmin(fmax(t, -1.0e9), 1.0e9); /* NaN -> -1e9 */
   return (int32_t)t;
 }
 

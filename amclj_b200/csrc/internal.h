@@ -31,6 +31,8 @@ struct DeviceMap {
 
 struct BeamTable {       // float4 mix[nb] = (obs, e2, p34, 0) then float2 dir[nb] = (cb, sb)
   float *dev = nullptr;
+  double *dev_d = nullptr;   // double2 (cos, sin) per beam (near-tie refinement)
+  amclj::CellRefine cr = {0.0f, 0, 0, 0u};
   int32_t nb = 0, cap = 0;
   int32_t n_scan = 0;
   float angle_min = 0, angle_inc = 0, range_max = 0;
@@ -74,6 +76,8 @@ struct SensorLaunch {
   int32_t s1, s3, s4, s7, s10;
   float z_hit, inv2s2, laser_x, laser_y;
   float k2;  // inv2s2 * log2(e): the hit Gaussian is one ex2
+  CellRefine cr;          // near-tie refinement of end cells (contract.h); cr.K == 0: off
+  const double *beam_d;   // double2 (cos, sin) per beam, for the refinement's double path
   // ring of end cells around the start cell and one line set-up record per ring cell (walk kernel)
   const uint4 *ring_rows;
   const uint4 *ring_recs;
@@ -202,7 +206,7 @@ struct PersistentTables {
                                    // an atomic that returns its old value stalls the warp, a plain reduction does not)
   int32_t nbuf = 0;                // table buffers per warp requested (0: one, so that more warps fit; AMCLJ_PT_NBUF)
   int32_t nbuf_used = 1, warps_req = 0;
-  int32_t tail_pct = 0;            // AMCLJ_PT_TAIL_PCT
+  int32_t tail_pct = 15;           // AMCLJ_PT_TAIL_PCT (measured: 0 -> 1.046, 15 -> 0.994, 30 -> 1.014 ms on the C4 share)
   bool fuse_motion = false;        // AMCLJ_PT_FUSE_MOTION=1: the motion kernel takes the sort's histogram pass along
   bool hist_done = false;          // ... and did so for the update in progress
   int32_t rows32 = 1;              // AMCLJ_PT_ROWS32
@@ -333,6 +337,7 @@ struct amclj_ctx {
   int64_t map_gen = 0;     // bumped by every set_map
   bool ring_setup = true;  // walk kernel reads its line set-up from per-ring-cell records (AMCLJ_RING_SETUP=0: computes it)
   bool rt_enable = true;   // auto policy may take the ray-table path (AMCLJ_RAYTABLE=0 turns it off)
+  bool exact_cells = true; // near-tie refinement of end cells (AMCLJ_EXACT_CELLS=0: plain float rounding)
   void *pinned = nullptr;  // small pinned scratch for scalar readbacks
   void *pin_tab = nullptr; // pinned staging of the beam table
   size_t pin_tab_bytes = 0;

@@ -80,7 +80,8 @@ pt_hist_kernel(const __grid_constant__ PtLaunch L) {
     const ResDiv rdv = make_resdiv(a.res);
     const float4 o = pt_origin(a, i);
     int x0, y0;
-    round_cell2_fast(o.x, o.y, rdv, x0, y0);
+    (void)rdv;
+    x0 = round_cell_start(o.x, a.res); y0 = round_cell_start(o.y, a.res);
     const bool in = (uint32_t)x0 < (uint32_t)a.W && (uint32_t)y0 < (uint32_t)a.H;
     key = in ? __ldg(L.slot_of_cell + (size_t)y0 * a.W + x0) : L.n_slots;
     L.pkey[i] = key;
@@ -215,42 +216,53 @@ __device__ __forceinline__ uint32_t lds_u1(uint32_t addr) {
 template <bool S7, bool DBG, bool R32>
 __device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunch &L, const ResDiv &rdv, uint32_t s_tab,
                                             uint32_t s_mix, uint32_t s_dir, uint32_t s_rows, float ox, float oy, float st,
-                                            float ct, int xoff, int yoff, int jb0, int jb1, float *dbg_row) {
+                                            float ct, float th, int xoff, int yoff, int jb0, int jb1,
+                                            float *dbg_row) {
   float acc = 0.0f, prod = 1.0f;
   int pexp = 0;
   const uint32_t last_row = (uint32_t)L.nrows - 1u, nan_entry = (uint32_t)L.n_entries - 1u;
   /* S1 off = rotation by zero: fma(1, cb, -(0 * sb)) and fma(0, cb, 1 * sb) give back (cb, sb) */
-  const float rc = a.s1 ? ct : 1.0f, rs = a.s1 ? st : 0.0f;
+  float rc = a.s1 ? ct : 1.0f, rs = a.s1 ? st : 0.0f;
+  /* kept in registers: left alone, the compiler re-derives the rotation and re-loads the launch constants
+   * from the parameter bank for every beam (a dozen instructions of the ~75 per ray) */
+  float Rr = a.R, k2 = a.k2, zh = a.z_hit;
+  ResDiv rd = rdv;
+  CellRefine cr = a.cr;
+  asm volatile("" : "+f"(rc), "+f"(rs), "+f"(Rr), "+f"(k2), "+f"(zh), "+f"(rd.res), "+f"(rd.r), "+f"(cr.K), "+r"(cr.fb), "+r"(cr.coff),
+               "+r"(cr.mask));
 #pragma unroll 2
   for (int jb = jb0; jb < jb1; jb++) {
     const float2 bd = lds_f2(s_dir + (uint32_t)jb * 8u);
     const float c = fmaf(rc, bd.x, -(rs * bd.y)), s = fmaf(rs, bd.x, rc * bd.y); /* S1: angle addition */
     /* sensor.clj:130-135 / map.clj:36-46: end point of the beam to its cell, as round_cell2_inrange */
-    const float ex_w = fmaf(a.R, c, ox), ey_w = fmaf(a.R, s, oy);
-    const float qx0 = ex_w * rdv.r, qy0 = ey_w * rdv.r;
-    const float qx = fmaf(fmaf(-qx0, rdv.res, ex_w), rdv.r, qx0);
-    const float qy = fmaf(fmaf(-qy0, rdv.res, ey_w), rdv.r, qy0);
-    /* floor(q + 0.5) on the FP32 pipe (exact for |q| < 2^22: the start is a cell of the map) */
-    const int ex = __float_as_int(__fadd_rd(qx + 0.5f, 12582912.0f)) - xoff;
-    const uint32_t ry = (uint32_t)(__float_as_int(__fadd_rd(qy + 0.5f, 12582912.0f)) - yoff);
-    const uint32_t ryc = min(ry, last_row);
+    const float ex_w = fmaf(Rr, c, ox), ey_w = fmaf(Rr, s, oy);
+    /* the cell of the end point (contract.h): float arithmetic, and the reference's own double computation where
+     * the quotient lies within two units of 2^-fb of a .5 boundary (0.2 % of the rays) */
+    int x1, y1;
+    if (end_cells_fast(ex_w, ey_w, rd, cr, x1, y1)) {
+      const int2 e = end_cells_exact(a, ox, oy, th, jb);
+      x1 = e.x; y1 = e.y;
+    }
+    const int ex = x1 - xoff;
+    const uint32_t ry = (uint32_t)(y1 - yoff);
+    const uint32_t ryc = min(ry, R32 ? last_row + 1u : last_row);
     uint32_t r_base, r_lo, r_cnt; /* the row's first entry, first |ex|, entries per arc (the negative arc follows the positive) */
     if (R32) { /* one word per row: a random 4-byte read meets ~3.5-way bank conflicts, a 16-byte one ~8 wavefronts */
-      const uint32_t rw = lds_u1(s_rows + ryc * 4u);
-      r_base = rw & 0x1fffu; r_lo = (rw >> 13) & 0xffu; r_cnt = rw >> 21;
+      const uint32_t rw = lds_u1(s_rows + ryc * 4u); /* base : 16 | lo : 8 | cnt : 8; the row behind the last is empty */
+      r_base = rw & 0xffffu; r_lo = __byte_perm(rw, 0u, 0x4442); r_cnt = rw >> 24;
     } else {
       const uint4 rw = lds_u4(s_rows + ryc * 16u);
       r_base = rw.x; r_lo = rw.y; r_cnt = rw.z;
     }
     const uint32_t tt = (uint32_t)abs(ex) - r_lo;
-    const bool ok = tt < r_cnt && ry <= last_row;
+    const bool ok = R32 ? tt < r_cnt : (tt < r_cnt && ry <= last_row);
     const uint32_t ent = ok ? r_base + tt + (ex < 0 ? r_cnt : 0u) : nan_entry;
     const float rng = lds_f1(s_tab + ent * 4u);
     if (DBG && dbg_row) dbg_row[jb] = rng;
     /* sensor.clj:149-162 beam mixture, exactly as in sensor.cu */
     const float4 mx = lds_f4(s_mix + (uint32_t)jb * 16u);
     const float z = mx.x - rng;
-    const float pz1 = hit_gauss(z, a.k2, a.z_hit);
+    const float pz1 = hit_gauss(z, k2, zh);
     const float pz2 = z < 0.0f ? mx.y : 0.0f;
     const float sum = (pz1 + pz2) + mx.z;
     if (S7) logprod_mul(acc, prod, pexp, sum);
@@ -261,13 +273,13 @@ __device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunc
 
 /* a segment whose table look-up came back NaN (an end cell off the ring, a NaN pose): walk its rays */
 template <int MODE, bool WIDE>
-__device__ __noinline__ float pt_segment_walk(const SensorLaunch &a, float ox, float oy, float st, float ct, int jb0, int jb1,
-                                              float *dbg_row) {
+__device__ __noinline__ float pt_segment_walk(const SensorLaunch &a, float ox, float oy, float st, float ct, float th,
+                                              int jb0, int jb1, float *dbg_row) {
   const ResDiv rdv = make_resdiv(a.res);
   const float4 *mixt = reinterpret_cast<const float4 *>(a.beam);
   const float2 *dirt = reinterpret_cast<const float2 *>(a.beam + 4 * (size_t)a.nb);
   int x0, y0;
-  round_cell2_fast(ox, oy, rdv, x0, y0);
+  x0 = round_cell_start(ox, a.res); y0 = round_cell_start(oy, a.res);
   float acc = 0.0f, prod = 1.0f;
   int pexp = 0;
   for (int jb = jb0; jb < jb1; jb++) {
@@ -279,7 +291,7 @@ __device__ __noinline__ float pt_segment_walk(const SensorLaunch &a, float ox, f
     }
     const float ex_w = fmaf(a.R, c, ox), ey_w = fmaf(a.R, s, oy);
     RayOut o;
-    const float rng = cast_ray_slow<MODE, WIDE, false>(a, x0, y0, ex_w, ey_w, o);
+    const float rng = cast_ray_slow<MODE, WIDE, false>(a, x0, y0, ex_w, ey_w, ox, oy, th, jb, o);
     if (dbg_row) dbg_row[jb] = rng;
     const float4 mx = __ldg(mixt + jb);
     const float z = mx.x - rng;
@@ -317,8 +329,9 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
       uint32_t *srows32 = reinterpret_cast<uint32_t *>(srows);
       for (int i = threadIdx.x; i < L.nrows; i += blockDim.x) {
         const uint4 rw = __ldg(L.rows + i);
-        srows32[i] = rw.x | (rw.y << 13) | (rw.z << 21);
+        srows32[i] = rw.x | (rw.y << 16) | (rw.z << 24);
       }
+      if (threadIdx.x == 0) srows32[L.nrows] = 0u; /* the sentinel row: no end cell, i.e. the NaN entry */
     } else {
       for (int i = threadIdx.x; i < L.nrows; i += blockDim.x) srows[i] = __ldg(L.rows + i);
     }
@@ -423,7 +436,7 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
     const uint32_t s_tab = s_tab0 + (uint32_t)buf * tab_bytes;
     int2 cc = make_int2(0, 0);
     if (c_slot < L.n_slots) cc = __ldg(L.cell_of_slot + c_slot);
-    const int xoff = 0x4B400000 + cc.x, yoff = 0x4B400000 + cc.y - L.E;
+    const int xoff = cc.x, yoff = cc.y - L.E; /* end cell relative to the start cell; ring rows start at -E */
     const int ntask = c_cnt * nseg; /* (segment, particle) pairs, particle fastest: a warp shares its beams */
     for (int t = lane; t < ntask; t += 32) {
       const int sgm = t / c_cnt, j = t - sgm * c_cnt;
@@ -436,13 +449,13 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
         dbg_row = a.dbg_range + (p - a.dbg_first) * nb;
       float v;
       if (L.rows32)
-        v = a.s7 ? pt_segment<true, DBG, true>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, xoff, yoff, jb0, jb1, dbg_row)
-                 : pt_segment<false, DBG, true>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, xoff, yoff, jb0, jb1, dbg_row);
+        v = a.s7 ? pt_segment<true, DBG, true>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, __ldg(a.th + p), xoff, yoff, jb0, jb1, dbg_row)
+                 : pt_segment<false, DBG, true>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, __ldg(a.th + p), xoff, yoff, jb0, jb1, dbg_row);
       else
-        v = a.s7 ? pt_segment<true, DBG, false>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, xoff, yoff, jb0, jb1, dbg_row)
-                 : pt_segment<false, DBG, false>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, xoff, yoff, jb0, jb1, dbg_row);
+        v = a.s7 ? pt_segment<true, DBG, false>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, __ldg(a.th + p), xoff, yoff, jb0, jb1, dbg_row)
+                 : pt_segment<false, DBG, false>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, __ldg(a.th + p), xoff, yoff, jb0, jb1, dbg_row);
       if (v != v) {
-        v = pt_segment_walk<MODE, WIDE>(a, ps.x, ps.y, ps.z, ps.w, jb0, jb1, dbg_row);
+        v = pt_segment_walk<MODE, WIDE>(a, ps.x, ps.y, ps.z, ps.w, __ldg(a.th + p), jb0, jb1, dbg_row);
         if (a.stats) atomicAdd(a.stats + 11, 1ull); /* table_misses: expected 0 */
       }
       /* close the segment: one rounding to fixed point; segments add as integers */

@@ -94,12 +94,12 @@ __device__ __forceinline__ float cast_ray(const SensorLaunch &a, const uint8_t *
 
 /* the rare paths of the look-up kernel, kept out of line so that its beam loop stays small */
 template <int MODE, bool WIDE, bool DIAG>
-__device__ __noinline__ float cast_ray_slow(const SensorLaunch &a, int x0, int y0, float ex_w, float ey_w, RayOut &out) {
-  /* the end point again, with the full range handling of sensor.cu (huge / NaN coordinates) */
+__device__ __noinline__ float cast_ray_slow(const SensorLaunch &a, int x0, int y0, float ex_w, float ey_w, float ox, float oy,
+                                            float th, int jb, RayOut &out) {
+  /* the end point again, with the full range handling of sensor.cu (huge / NaN coordinates) and the refinement */
   const ResDiv rdv = make_resdiv(a.res);
   int x1, y1;
-  if (rdv.lim > 0.0f) round_cell2_inrange(ex_w, ey_w, rdv, x1, y1);
-  else round_cell2_fast(ex_w, ey_w, rdv, x1, y1);
+  end_cell(a, rdv, ex_w, ey_w, ox, oy, th, jb, x1, y1);
   return cast_ray<MODE, WIDE, DIAG>(a, a.df, x0, y0, x1, y1, out);
 }
 

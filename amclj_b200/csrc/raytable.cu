@@ -46,8 +46,8 @@ __device__ __forceinline__ bool cell_box(const uint32_t *bbox, float res, int &c
   float ymax = ord_to_float(bbox[2]), ymin = -ord_to_float(bbox[3]);
   if (!(fabsf(xmax) < 1.0e30f && fabsf(xmin) < 1.0e30f && fabsf(ymax) < 1.0e30f && fabsf(ymin) < 1.0e30f))
     return false; /* empty box, NaN or infinite coordinates */
-  long long xa = round_cell(xmin, res), xb = round_cell(xmax, res);
-  long long ya = round_cell(ymin, res), yb = round_cell(ymax, res);
+  long long xa = round_cell_start(xmin, res), xb = round_cell_start(xmax, res);
+  long long ya = round_cell_start(ymin, res), yb = round_cell_start(ymax, res);
   long long w = xb - xa + 1, h = yb - ya + 1;
   if (w <= 0 || h <= 0 || w > RT_BIN_CAP || h > RT_BIN_CAP || w * h > RT_BIN_CAP) return false;
   cx0 = (int)xa; cy0 = (int)ya; bw = (int)w; bh = (int)h;
@@ -55,7 +55,7 @@ __device__ __forceinline__ bool cell_box(const uint32_t *bbox, float res, int &c
 }
 
 __device__ __forceinline__ int bin_of(float px, float py, float res, int cx0, int cy0, int bw, int bh) {
-  int cx = min(max(round_cell(px, res) - cx0, 0), bw - 1), cy = min(max(round_cell(py, res) - cy0, 0), bh - 1);
+  int cx = min(max(round_cell_start(px, res) - cx0, 0), bw - 1), cy = min(max(round_cell_start(py, res) - cy0, 0), bh - 1);
   return cy * bw + cx;
 }
 
@@ -286,11 +286,11 @@ template <bool S7, bool TS>
 __device__ __forceinline__ float table_segment(const SensorLaunch &a, const RtLaunch &L, const ResDiv &rdv,
                                                const float *__restrict__ table, uint32_t s_mix, uint32_t s_dir,
                                                uint32_t s_rows, const float4 *mixt, const float2 *dirt, float ox, float oy,
-                                               float st, float ct, int x0, int y0, int jb0, int jb1) {
+                                               float st, float ct, float th, int x0, int y0, int jb0, int jb1) {
   float acc = 0.0f, prod = 1.0f;
   int pexp = 0;
   const uint32_t last_row = (uint32_t)L.nrows - 1u, nan_entry = (uint32_t)L.n_entries - 1u;
-  const int xoff = 0x4B400000 + x0, yoff = 0x4B400000 + y0 - L.E;
+  const int xoff = x0, yoff = y0 - L.E;
   /* S1 off = rotation by zero: fma(1, cb, -(0 * sb)) and fma(0, cb, 1 * sb) give back (cb, sb) */
   const float rc = a.s1 ? ct : 1.0f, rs = a.s1 ? st : 0.0f;
 #pragma unroll 2
@@ -301,13 +301,13 @@ __device__ __forceinline__ float table_segment(const SensorLaunch &a, const RtLa
      * round_cell2_inrange; a start inside a table cell keeps the quotient far from the int32 range,
      * so the clamps (and their NaN duty) are not needed */
     const float ex_w = fmaf(a.R, c, ox), ey_w = fmaf(a.R, s, oy);
-    const float qx0 = ex_w * rdv.r, qy0 = ey_w * rdv.r;
-    const float qx = fmaf(fmaf(-qx0, rdv.res, ex_w), rdv.r, qx0);
-    const float qy = fmaf(fmaf(-qy0, rdv.res, ey_w), rdv.r, qy0);
-    /* floor(q + 0.5) on the FP32 pipe: adding 1.5 * 2^23 with round-down leaves the integer in
-     * the mantissa (exact for |q| < 2^22; the caller keeps table cells inside 2^21) */
-    const int ex = __float_as_int(__fadd_rd(qx + 0.5f, 12582912.0f)) - xoff;
-    const uint32_t ry = (uint32_t)(__float_as_int(__fadd_rd(qy + 0.5f, 12582912.0f)) - yoff);
+    int x1, y1; /* float arithmetic, the reference's double computation next to a .5 boundary (contract.h) */
+    if (end_cells_fast(ex_w, ey_w, rdv, a.cr, x1, y1)) {
+      const int2 e = end_cells_exact(a, ox, oy, th, jb);
+      x1 = e.x; y1 = e.y;
+    }
+    const int ex = x1 - xoff;
+    const uint32_t ry = (uint32_t)(y1 - yoff);
     /* ring entry of the end cell; off the ring: the NaN entry, which poisons the segment */
     const uint32_t ryc = min(ry, last_row);
     const uint4 rw = TS ? lds_u4(s_rows + ryc * 16u) : __ldg(L.rows + ryc);
@@ -431,16 +431,16 @@ rt_lookup_kernel(const __grid_constant__ RtLaunch L) {
       }
     }
     int x0, y0;
-    round_cell2_fast(ox, oy, rdv, x0, y0);
+    x0 = round_cell_start(ox, a.res); y0 = round_cell_start(oy, a.res);
     /* the table belongs to cell (cx, cy): a particle that is not there walks (the sort and this
      * kernel round the same coordinates the same way, so this fires only with S10) */
-    const bool use_table = table != nullptr && x0 == cx && y0 == cy && fast_round && abs(x0) < (1 << 21) && abs(y0) < (1 << 21);
+    const bool use_table = table != nullptr && x0 == cx && y0 == cy && fast_round && a.cr.K != 0.0f && abs(x0) < (1 << 21) && abs(y0) < (1 << 21);
     const int jb0 = sgm * SEG, jb1 = min(jb0 + SEG, nb);
     float v = 0.0f;
     bool general = DIAG || !use_table;
     if (!general) {
-      v = a.s7 ? table_segment<true, TS>(a, L, rdv, table, s_mix, s_dir, s_rows, mixt, dirt, ox, oy, st, ct, x0, y0, jb0, jb1)
-               : table_segment<false, TS>(a, L, rdv, table, s_mix, s_dir, s_rows, mixt, dirt, ox, oy, st, ct, x0, y0, jb0, jb1);
+      v = a.s7 ? table_segment<true, TS>(a, L, rdv, table, s_mix, s_dir, s_rows, mixt, dirt, ox, oy, st, ct, __ldg(a.th + p), x0, y0, jb0, jb1)
+               : table_segment<false, TS>(a, L, rdv, table, s_mix, s_dir, s_rows, mixt, dirt, ox, oy, st, ct, __ldg(a.th + p), x0, y0, jb0, jb1);
       general = v != v;
     }
     if (general) { /* sparse cells, diagnostics, and the segments the fast path gave back */
@@ -458,10 +458,9 @@ rt_lookup_kernel(const __grid_constant__ RtLaunch L) {
         bool ok = false;
         uint32_t ent = 0;
         if (use_table) {
-          const float qx0 = ex_w * rdv.r, qy0 = ey_w * rdv.r;
-          const float qx = fmaf(fmaf(-qx0, rdv.res, ex_w), rdv.r, qx0);
-          const float qy = fmaf(fmaf(-qy0, rdv.res, ey_w), rdv.r, qy0);
-          const int ex = __float2int_rd(qx + 0.5f) - x0, ey = __float2int_rd(qy + 0.5f) - y0;
+          int x1, y1;
+          end_cell(a, rdv, ex_w, ey_w, ox, oy, __ldg(a.th + p), jb, x1, y1);
+          const int ex = x1 - x0, ey = y1 - y0;
           const uint32_t ry = (uint32_t)(ey + L.E);
           if (ry < nrows) {
             const uint4 rw = TS ? lds_u4(s_rows + ry * 16u) : __ldg(L.rows + ry);
@@ -484,7 +483,7 @@ rt_lookup_kernel(const __grid_constant__ RtLaunch L) {
             rng = __ldg(table + ent);
           }
         } else {
-          rng = cast_ray_slow<MODE, WIDE, DIAG>(a, x0, y0, ex_w, ey_w, o);
+          rng = cast_ray_slow<MODE, WIDE, DIAG>(a, x0, y0, ex_w, ey_w, ox, oy, __ldg(a.th + p), jb, o);
           if (DIAG && use_table) n_miss++; /* an end cell outside the ring: never seen */
         }
         const float4 mx = TS ? lds_f4(s_mix + (uint32_t)jb * 16u) : __ldg(mixt + jb);

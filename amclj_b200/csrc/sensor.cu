@@ -196,12 +196,12 @@ sensor_kernel(const SensorLaunch a) {
       ox = nx; oy = ny;
     }
     int x0, y0;
-    round_cell2_fast(ox, oy, rdv, x0, y0);
+    x0 = round_cell_start(ox, a.res); y0 = round_cell_start(oy, a.res); /* once per task: the reference's own double divide */
     const bool start_in = (uint32_t)x0 < (uint32_t)a.W && (uint32_t)y0 < (uint32_t)a.H;
     /* padded field: cell (x, y) lives at (y+1)*row + (x+1); entry 0 is a ring cell (d = 0),
      * which makes an out-of-range start an immediate hit (the start cell is tested first) */
     const int idx0 = start_in ? (y0 + 1) * row + (x0 + 1) * idx_scale : 0;
-    const int xoff = 0x4B400000 + x0, yoff = 0x4B400000 + y0 - a.ring_E; /* RS: end cell relative to the start, see below */
+    const int xoff = x0, yoff = y0 - a.ring_E; /* RS: end cell relative to the start, see below */
     const bool dbg = DIAG && a.dbg_count > 0 && valid && p >= a.dbg_first && p < a.dbg_first + a.dbg_count;
 
     /* the ray in flight; a parked lane (am == 0) turns every update below into a no-op */
@@ -269,6 +269,10 @@ sensor_kernel(const SensorLaunch a) {
           }
           /* sensor.clj:99-103 project-pose, map.clj:36-46 world->map */
           const float ex_w = fmaf(a.R, c, ox), ey_w = fmaf(a.R, s, oy);
+          /* the cell of the end point (contract.h: float arithmetic, the reference's double computation next to a
+           * .5 boundary) — once, for the record look-up and for the computed set-up alike */
+          int x1, y1;
+          end_cell(a, rdv, ex_w, ey_w, ox, oy, th, jb, x1, y1);
           bool from_table = false;
           if (RS) {
             /* Everything sensor.clj:130-139 derives after the two roundings (steep?, the swaps, calc-step,
@@ -279,11 +283,8 @@ sensor_kernel(const SensorLaunch a) {
              * floor(q + 0.5) as an FP32 add with round-down against 1.5 * 2^23 (exact below 2^22, which
              * the host checks for every start inside the map; a start outside hits at step 0 whatever
              * record it gets, so its garbage offset only has to stay inside the table). */
-            const float qx0 = ex_w * rdv.r, qy0 = ey_w * rdv.r;
-            const float qx = fmaf(fmaf(-qx0, rdv.res, ex_w), rdv.r, qx0);
-            const float qy = fmaf(fmaf(-qy0, rdv.res, ey_w), rdv.r, qy0);
-            const int ex = __float_as_int(__fadd_rd(qx + 0.5f, 12582912.0f)) - xoff;
-            const uint32_t ry = (uint32_t)(__float_as_int(__fadd_rd(qy + 0.5f, 12582912.0f)) - yoff);
+            const int ex = x1 - xoff;
+            const uint32_t ry = (uint32_t)(y1 - yoff);
             const uint32_t ryc = min(ry, ring_last_row);
             uint4 rw;
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rw.x), "=r"(rw.y), "=r"(rw.z), "=r"(rw.w) : "r"(s_rows + ryc * 16u));
@@ -307,9 +308,6 @@ sensor_kernel(const SensorLaunch a) {
             }
           }
           if (!from_table) {
-          int x1, y1;
-          if (rdv.lim > 0.0f) round_cell2_inrange(ex_w, ey_w, rdv, x1, y1);
-          else round_cell2_fast(ex_w, ey_w, rdv, x1, y1); /* odd resolutions: real divides */
           int adx = abs(x1 - x0), ady = abs(y1 - y0);
           bool steep = ady > adx; /* sensor.clj:87-91 */
           int a0 = steep ? y0 : x0, b0 = steep ? x0 : y0;

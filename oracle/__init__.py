@@ -150,7 +150,9 @@ def lib():
                                           f32p, i32p]
     L.amclj_oracle_map_range_f32.argtypes = [PP, i8p, C.c_int32, C.c_int32, C.c_float,
                                              C.c_float, C.c_float, C.c_float, C.c_float,
-                                             C.c_float, C.c_float, C.c_float, C.POINTER(Ray)]
+                                             C.c_float, C.c_float, C.c_float, C.c_float, C.c_double, C.c_double,
+                                             C.POINTER(Ray)]
+    L.amclj_oracle_sincos_f64.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.amclj_oracle_sensor_f64.argtypes = [PP, i8p, C.c_int32, C.c_int32, C.c_float, f32p,
                                           C.c_int32, C.c_float, C.c_float, C.c_float, f64p,
                                           f64p, f64p, C.c_int64, f64p, C.POINTER(SensorStats),
@@ -222,6 +224,12 @@ def map_range_f64(p, grid, ox, oy, theta, obs_bearing, scan_range_max) -> Ray:
     lib().amclj_oracle_map_range_f64(C.byref(p), cells, W, H, res, ox, oy, theta, obs_bearing,
                                      scan_range_max, C.byref(r))
     return r
+
+
+def sincos_f64(a):
+    s, c = C.c_double(), C.c_double()
+    lib().amclj_oracle_sincos_f64(float(a), C.byref(s), C.byref(c))
+    return s.value, c.value
 
 
 def sincosf(a):

@@ -285,10 +285,65 @@ ORACLE_API void amclj_oracle_beam_table(int32_t n, float angle_min, float angle_
   }
 }
 
+/* fp32 contract, END cells: float arithmetic, except next to a .5 boundary, where the float quotient could
+ * round the other way than the double computation of the reference — there the cell is taken in double
+ * (end point by the angle-addition identity on double sines and cosines, double divide).
+ * "Next to" is decided on the bits of q + K, K = 1.5 * 2^(23-fb) + 0.5 + 2^(1-fb): the low fb mantissa bits
+ * then hold round((q + 0.5) * 2^fb) + 2, and the quotient is near a boundary when that value mod 2^fb is
+ * below 4.  fb = the most fraction bits that keep every quotient of the map inside the mantissa window. */
+static void sincos_det_f64(double a, double *sn, double *cs) {
+  double j = rint(a * 6.36619772367581382433e-01);
+  j = fmin(fmax(j, -1.0e6), 1.0e6);
+  double r = fma(-j, 1.57079632673412561417e+00, a);
+  r = fma(-j, 6.07710050650619224932e-11, r);
+  int q = ((int)j) & 3;
+  double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  double s = fma(ps * z, r, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  double c = fma(pc * z, z, fma(-0.5, z, 1.0));
+  double so = (q & 1) ? c : s, co = (q & 1) ? s : c;
+  if (q & 2) so = -so;
+  if ((q + 1) & 2) co = -co;
+  *sn = so;
+  *cs = co;
+}
+
+ORACLE_API void amclj_oracle_sincos_f64(double a, double *sn, double *cs) { sincos_det_f64(a, sn, cs); }
+
+static int refine_fraction_bits(int32_t W, int32_t H, double rcells) {
+  double maxq = (double)(W > H ? W : H) + ceil(rcells) + 6.0;
+  int fb = 12;
+  while (fb > 4 && maxq >= ldexp(1.0, 22 - fb) - 2.0) fb--;
+  if (maxq >= ldexp(1.0, 22 - fb) - 2.0) return 0; /* rays too long for the mantissa window: plain float rounding */
+  return fb;
+}
+
+/* cell of one coordinate from its float quotient; *near = the double computation must decide */
+static int32_t cell_from_quotient(float q, int fb, int *near) {
+  float big = (float)ldexp(1.5, 23 - fb);
+  float K = big + 0.5f + (float)ldexp(1.0, 1 - fb);
+  float t = q + K;
+  uint32_t bits, bbig;
+  memcpy(&bits, &t, 4);
+  memcpy(&bbig, &big, 4);
+  if ((bits & ((1u << fb) - 4u)) == 0u) *near = 1;
+  return (int32_t)((int32_t)bits >> fb) - (int32_t)(bbig >> fb);
+}
+
 ORACLE_API void amclj_oracle_map_range_f32(const amclj_params *p, const int8_t *cells,
                                            int32_t W, int32_t H, float res, float ox, float oy,
                                            float ct, float st, float cb, float sb,
-                                           float scan_range_max, oracle_ray *out) {
+                                           float scan_range_max, float theta, double cbd, double sbd,
+                                           oracle_ray *out) {
   oracle_map m = {cells, W, H, res};
   float c = cb, s = sb;
   if (p->s1_use_heading) {
@@ -302,9 +357,37 @@ ORACLE_API void amclj_oracle_map_range_f32(const amclj_params *p, const int8_t *
     ox = nx;
     oy = ny;
   }
-  int32_t x0 = round_cell_f32(ox, res), y0 = round_cell_f32(oy, res);
+  /* contract: the START cell is taken once per particle with the JVM's own double divide on the float32
+   * inputs (Math/round((double)x / (double)res), map.clj:36-46); end cells stay in float arithmetic */
+  int32_t x0 = (int32_t)round_cell_f64((double)ox, (double)res), y0 = (int32_t)round_cell_f64((double)oy, (double)res);
   float ex = fmaf(R, c, ox), ey = fmaf(R, s, oy);
-  int32_t x1 = round_cell_f32(ex, res), y1 = round_cell_f32(ey, res);
+  int32_t x1, y1;
+  if (res > 1.0e-6f && res < 1.0e6f && fabsf(ex) < 1.0e18f && fabsf(ey) < 1.0e18f) {
+    int near = 0;
+    int fb = refine_fraction_bits(W, H, fabs((double)R) / (double)res);
+    if (fb == 0) {
+      x1 = round_cell_f32(ex, res);
+      y1 = round_cell_f32(ey, res);
+    } else {
+      x1 = cell_from_quotient(ex / res, fb, &near);
+      y1 = cell_from_quotient(ey / res, fb, &near);
+    }
+    if (near) { /* the reference's own computation from the same float32 inputs */
+      double cd = cbd, sd = sbd;
+      if (p->s1_use_heading) {
+        double std_, ctd;
+        sincos_det_f64((double)theta, &std_, &ctd);
+        cd = fma(ctd, cbd, -(std_ * sbd));
+        sd = fma(std_, cbd, ctd * sbd);
+      }
+      double exd = fma((double)R, cd, (double)ox), eyd = fma((double)R, sd, (double)oy);
+      x1 = (int32_t)round_cell_f64(exd, (double)res);
+      y1 = (int32_t)round_cell_f64(eyd, (double)res);
+    }
+  } else { /* odd geometry: plain float rounding */
+    x1 = round_cell_f32(ex, res);
+    y1 = round_cell_f32(ey, res);
+  }
   map_range_cells(p, &m, x0, y0, x1, y1, (double)R, out);
   if (out->hit) { /* contract: sqrtf of the exact integer d^2, times res, in float */
     int64_t ddx = (int64_t)out->hit_x - x0, ddy = (int64_t)out->hit_y - y0;
@@ -398,8 +481,9 @@ ORACLE_API void amclj_oracle_sensor_f32(const amclj_params *p, const int8_t *cel
     for (int32_t j = 0; j < nb; j++) {
       float obs = ranges[bi[j]];
       oracle_ray ray;
+      double abeam = (double)angle_min + (double)bi[j] * (double)angle_inc; /* sensor.clj:93-97 */
       amclj_oracle_map_range_f32(p, cells, W, H, res, x[ip], y[ip], ct, st, cb[j], sb[j],
-                                 range_max, &ray);
+                                 range_max, theta[ip], cos(abeam), sin(abeam), &ray);
       float rng = (float)ray.range;
       float z = obs - rng;
       float pz1 = zhit * expf(-(z * z) * inv2s2);

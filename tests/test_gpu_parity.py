@@ -139,7 +139,9 @@ def test_sensor_weights_c1(ctx, lg, preset):
     ref64, _ = oracle.sensor_f64(po, lg, w.scan.ranges, w.scan.angle_min, w.scan.angle_inc,
                                  w.scan.range_max, w.x, w.y, w.theta)
     close = np.isclose(raw, ref64, rtol=RTOL)
-    assert close.mean() > 0.97
+    # start cells are taken in double and end cells are re-taken in double next to a .5 boundary (contract.h), so
+    # the fp32 path casts the rays the double path casts: every weight agrees, not "the bulk"
+    assert close.mean() >= 0.999
 
 
 def test_sensor_weights_c2_sample(ctx, lg):

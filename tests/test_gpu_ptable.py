@@ -210,7 +210,7 @@ def _bench_size_parity(lg, n, seed):
         np.testing.assert_allclose(raw[sel], ref, rtol=RTOL)
         ref64, _ = oracle.sensor_f64(po, lg, scan.ranges, scan.angle_min, scan.angle_inc, scan.range_max,
                                      x[sel], y[sel], th[sel])
-        assert np.isclose(raw[sel], ref64, rtol=RTOL).mean() > 0.995
+        assert np.isclose(raw[sel], ref64, rtol=RTOL).mean() >= 0.9995  # near-tie refinement: the double path's rays
         first = n // 2
         _ranges_vs_oracle(c, lg, x, y, th, scan, "NS", first=first, count=64)
         # and the same window through the walk kernel's diagnostic pass: hit flag, cell, steps
