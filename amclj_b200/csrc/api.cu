@@ -576,7 +576,8 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
   }
   CK(cudaMemcpyAsync(b.dev, ctx->pin_tab, tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(b.dev_d, dird, dbl_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  b.cr = make_cell_refine(ctx->map.W, ctx->map.H, rcells, ctx->exact_cells && ctx->map.res > 1.0e-6f && ctx->map.res < 1.0e6f);
+  b.cr = make_cell_refine(ctx->map.W, ctx->map.H, rcells, ctx->map.res,
+                          ctx->exact_cells && ctx->map.res > 1.0e-6f && ctx->map.res < 1.0e6f);
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   b.nb = nb;
   b.n_scan = n;

@@ -123,9 +123,10 @@ struct CellRefine {
   int32_t fb;
   int32_t coff;   /* bits(1.5 * 2^(23-fb)) >> fb */
   uint32_t mask;  /* 2^fb - 4 */
+  float vmax;     /* coordinates (metres) below this keep their quotient inside the mantissa window */
 };
-inline CellRefine make_cell_refine(int W, int H, double rcells, bool enabled) {
-  CellRefine c = {0.0f, 0, 0, 0u};
+inline CellRefine make_cell_refine(int W, int H, double rcells, float res, bool enabled) {
+  CellRefine c = {0.0f, 0, 0, 0u, 0.0f};
   const double maxq = (double)(W > H ? W : H) + ceil(rcells) + 6.0;
   int fb = 12;
   while (fb > 4 && maxq >= ldexp(1.0, 22 - fb) - 2.0) fb--;
@@ -138,6 +139,7 @@ inline CellRefine make_cell_refine(int W, int H, double rcells, bool enabled) {
   c.coff = (int32_t)(bits >> fb);
   /* disabled (AMCLJ_EXACT_CELLS=0, timing experiments): a mask bit that is always set, i.e. never "near" */
   c.mask = enabled ? (1u << fb) - 4u : 0x40000000u;
+  c.vmax = (float)((double)res * (ldexp(1.0, 22 - fb) - 4.0));
   return c;
 }
 

@@ -32,7 +32,7 @@ struct DeviceMap {
 struct BeamTable {       // float4 mix[nb] = (obs, e2, p34, 0) then float2 dir[nb] = (cb, sb)
   float *dev = nullptr;
   double *dev_d = nullptr;   // double2 (cos, sin) per beam (near-tie refinement)
-  amclj::CellRefine cr = {0.0f, 0, 0, 0u};
+  amclj::CellRefine cr = {0.0f, 0, 0, 0u, 0.0f};
   int32_t nb = 0, cap = 0;
   int32_t n_scan = 0;
   float angle_min = 0, angle_inc = 0, range_max = 0;

@@ -362,9 +362,11 @@ ORACLE_API void amclj_oracle_map_range_f32(const amclj_params *p, const int8_t *
   int32_t x0 = (int32_t)round_cell_f64((double)ox, (double)res), y0 = (int32_t)round_cell_f64((double)oy, (double)res);
   float ex = fmaf(R, c, ox), ey = fmaf(R, s, oy);
   int32_t x1, y1;
-  if (res > 1.0e-6f && res < 1.0e6f && fabsf(ex) < 1.0e18f && fabsf(ey) < 1.0e18f) {
+  int fb = (res > 1.0e-6f && res < 1.0e6f) ? refine_fraction_bits(W, H, fabs((double)R) / (double)res) : 0;
+  /* the window test: coordinates whose quotient fits the mantissa trick (NaN, inf and far-away starts do not) */
+  float vmax = fb ? (float)((double)res * (ldexp(1.0, 22 - fb) - 4.0)) : 0.0f;
+  if (fb && fabsf(ex) < vmax && fabsf(ey) < vmax) { /* NaN fails both */
     int near = 0;
-    int fb = refine_fraction_bits(W, H, fabs((double)R) / (double)res);
     if (fb == 0) {
       x1 = round_cell_f32(ex, res);
       y1 = round_cell_f32(ey, res);
