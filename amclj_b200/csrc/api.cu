@@ -388,6 +388,8 @@ void fill_pt_args(const amclj_ctx *ctx, PtLaunch &L) {
   L.slot_of_cell = t.slot_of_cell; L.cell_of_slot = t.cell_of_slot; L.tables = t.tables;
   L.bin_count = t.bin_count; L.bin_start = t.bin_start; L.cursor = t.cursor;
   L.pkey = t.pkey;
+  L.pstate_d = t.pstate_d;
+  L.rinv_d = 1.0 / (double)ctx->map.res;
   L.perm = ctx->perm;
   L.pstate = r.pstate;
   L.qacc = ctx->partials;
@@ -477,8 +479,10 @@ int ensure_pt_scratch(amclj_ctx *ctx, int64_t n) {
   if (n > t.pkey_cap || n > r.pstate_cap || n > ctx->partials_cap) CK(cudaStreamSynchronize(ctx->stream));
   if (n > t.pkey_cap) {
     dfree(t.pkey);
+    dfree(t.pstate_d);
     t.pkey_cap = 0;
     CK(dalloc(&t.pkey, (size_t)n));
+    CK(dalloc(&t.pstate_d, (size_t)n));
     t.pkey_cap = n;
   }
   if (n > r.pstate_cap) {
@@ -673,6 +677,7 @@ void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode) {
   a.beam = ctx->beams.dev;
   a.beam_d = ctx->beams.dev_d;
   a.cr = ctx->beams.cr;
+  a.rinv_d = 1.0 / (double)ctx->map.res;
   a.nb = ctx->beams.nb;
   a.divtab = ctx->divs.dev;
   a.ndiv = ctx->divs.n;
@@ -1265,6 +1270,7 @@ int32_t amclj_destroy(amclj_ctx *ctx) {
   if (ctx->rt.tables) cudaFree(ctx->rt.tables);
   pt_free(ctx);
   dfree(ctx->pt.pkey);
+  dfree(ctx->pt.pstate_d);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->pin_tab) cudaFreeHost(ctx->pin_tab);
   for (int i = 0; i < 7; i++)

@@ -78,6 +78,7 @@ struct SensorLaunch {
   float k2;  // inv2s2 * log2(e): the hit Gaussian is one ex2
   CellRefine cr;          // near-tie refinement of end cells (contract.h); cr.K == 0: off
   const double *beam_d;   // double2 (cos, sin) per beam, for the refinement's double path
+  double rinv_d;          // 1 / resolution in double (host)
   // ring of end cells around the start cell and one line set-up record per ring cell (walk kernel)
   const uint4 *ring_rows;
   const uint4 *ring_recs;
@@ -197,6 +198,7 @@ struct PersistentTables {
   uint32_t *bin_start = nullptr;   // [n_slots + 2] exclusive prefix; [n_slots + 1] = n
   uint32_t *cursor = nullptr;      // [n_slots + 2] write cursors of the scatter
   int32_t *pkey = nullptr;         // [pkey_cap] slot of every particle
+  double2 *pstate_d = nullptr;     // [pkey_cap] heading sine / cosine in double, sorted order
   int64_t pkey_cap = 0;
   bool enable = true;              // AMCLJ_PTABLE=0 turns the path off
   bool built = false;
@@ -233,6 +235,8 @@ struct PtLaunch {
   int32_t *pkey;
   int32_t *perm;
   float4 *pstate;
+  double2 *pstate_d;   // [n] (sin, cos) of the heading in double, sorted order: read only on the near-tie path
+  double rinv_d;       // 1 / resolution in double
   long long *qacc;
   int32_t warps;   // look-up warps per CTA
   int32_t fuse_finish;  // 1: the look-up kernel finishes a particle when its last segment lands (<= 15 segments)

@@ -195,6 +195,10 @@ pt_scatter_kernel(const __grid_constant__ PtLaunch L) {
   const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
   L.perm[pos] = (int32_t)i;
   L.pstate[pos] = pt_origin(a, i);
+  /* for the near-tie end cells of the look-up (contract.h): the heading's sine and cosine in double, once per particle */
+  double st_d = 0.0, ct_d = 1.0; /* S1 off: rotation by zero */
+  if (a.s1) sincos_det_d((double)__ldg(a.th + i), st_d, ct_d);
+  L.pstate_d[pos] = make_double2(st_d, ct_d);
 }
 
 // ---- the look-up -------------------------------------------------------------------------------
@@ -213,36 +217,65 @@ __device__ __forceinline__ uint32_t lds_u1(uint32_t addr) {
   return v;
 }
 
+/* exact end cells (contract.h) of those of the beams jb, jb + 1 whose float quotient lies next to a .5 boundary
+ * (which & 1, which & 2); out of line and once per PAIR of beams, so that the hot loop below stays two
+ * straight-line halves.  The end point lies on the map's window (the particle stands on a cell of the map), so
+ * the quotient needs no clamping here. */
+static __device__ __noinline__ int4 pt_exact_pair(const SensorLaunch &a, double rinv_d, float ox, float oy,
+                                                  const double2 *psd, int jb, int which, int4 cells) {
+  const double2 hd = __ldg(psd); /* (sin, cos) of the heading; S1 off: (0, 1), which gives back (cb, sb) */
+  const double Rd = (double)a.R, res = (double)a.res, oxd = (double)ox, oyd = (double)oy;
+#pragma unroll
+  for (int u = 0; u < 2; u++) {
+    if (!(which & (1 << u))) continue;
+    const double cbd = __ldg(a.beam_d + 2 * (jb + u)), sbd = __ldg(a.beam_d + 2 * (jb + u) + 1);
+    const double cd = fma(hd.y, cbd, -(hd.x * sbd)), sd = fma(hd.x, cbd, hd.y * sbd);
+    const double vx = fma(Rd, cd, oxd), vy = fma(Rd, sd, oyd);
+    const double tx = fma(vx, rinv_d, 0.5), ty = fma(vy, rinv_d, 0.5);
+    double fx = floor(tx), fy = floor(ty);
+    /* the product is within 4e-13 of the quotient: only a value that close to an integer needs the real divide */
+    if (fmin(fmin(tx - fx, (fx + 1.0) - tx), fmin(ty - fy, (fy + 1.0) - ty)) < 1.0e-7) {
+      fx = floor(vx / res + 0.5);
+      fy = floor(vy / res + 0.5);
+    }
+    if (u == 0) { cells.x = (int)fx; cells.y = (int)fy; } else { cells.z = (int)fx; cells.w = (int)fy; }
+  }
+  return cells;
+}
+
+// One 30-beam segment of one particle, every range from the staged table of its start cell.  Beams go in
+// pairs: [end cells of both, float arithmetic] -> [one test: is either next to a .5 boundary? then both are
+// re-taken in double, out of line] -> [ring index, table entry, beam mixture of both].  Each half is
+// straight-line, so the compiler pairs the two beams' instructions as it did before the refinement.
 template <bool S7, bool DBG, bool R32>
 __device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunch &L, const ResDiv &rdv, uint32_t s_tab,
                                             uint32_t s_mix, uint32_t s_dir, uint32_t s_rows, float ox, float oy, float st,
-                                            float ct, float th, int xoff, int yoff, int jb0, int jb1,
+                                            float ct, const double2 *psd, int xoff, int yoff, int jb0, int jb1,
                                             float *dbg_row) {
   float acc = 0.0f, prod = 1.0f;
   int pexp = 0;
   const uint32_t last_row = (uint32_t)L.nrows - 1u, nan_entry = (uint32_t)L.n_entries - 1u;
   /* S1 off = rotation by zero: fma(1, cb, -(0 * sb)) and fma(0, cb, 1 * sb) give back (cb, sb) */
   float rc = a.s1 ? ct : 1.0f, rs = a.s1 ? st : 0.0f;
-  /* kept in registers: left alone, the compiler re-derives the rotation and re-loads the launch constants
-   * from the parameter bank for every beam (a dozen instructions of the ~75 per ray) */
-  float Rr = a.R, k2 = a.k2, zh = a.z_hit;
-  ResDiv rd = rdv;
-  CellRefine cr = a.cr;
-  asm volatile("" : "+f"(rc), "+f"(rs), "+f"(Rr), "+f"(k2), "+f"(zh), "+f"(rd.res), "+f"(rd.r), "+f"(cr.K), "+r"(cr.fb), "+r"(cr.coff),
-               "+r"(cr.mask));
-#pragma unroll 2
-  for (int jb = jb0; jb < jb1; jb++) {
+  asm volatile("" : "+f"(rc), "+f"(rs)); /* kept in registers: left alone, the selection is redone for every pair of beams */
+  const CellRefine cr = a.cr;
+
+  /* first half: sensor.clj:130-135 / map.clj:36-46, the cell of the beam's end point in float arithmetic
+   * (contract.h); returns the low mantissa bits the near-tie test looks at */
+  auto cells = [&](int jb, int &x1, int &y1) -> uint32_t {
     const float2 bd = lds_f2(s_dir + (uint32_t)jb * 8u);
     const float c = fmaf(rc, bd.x, -(rs * bd.y)), s = fmaf(rs, bd.x, rc * bd.y); /* S1: angle addition */
-    /* sensor.clj:130-135 / map.clj:36-46: end point of the beam to its cell, as round_cell2_inrange */
-    const float ex_w = fmaf(Rr, c, ox), ey_w = fmaf(Rr, s, oy);
-    /* the cell of the end point (contract.h): float arithmetic, and the reference's own double computation where
-     * the quotient lies within two units of 2^-fb of a .5 boundary (0.2 % of the rays) */
-    int x1, y1;
-    if (end_cells_fast(ex_w, ey_w, rd, cr, x1, y1)) {
-      const int2 e = end_cells_exact(a, ox, oy, th, jb);
-      x1 = e.x; y1 = e.y;
-    }
+    const float ex_w = fmaf(a.R, c, ox), ey_w = fmaf(a.R, s, oy);
+    const float qx0 = ex_w * rdv.r, qy0 = ey_w * rdv.r;
+    const float qx = fmaf(fmaf(-qx0, rdv.res, ex_w), rdv.r, qx0);
+    const float qy = fmaf(fmaf(-qy0, rdv.res, ey_w), rdv.r, qy0);
+    const int ux = __float_as_int(qx + cr.K), uy = __float_as_int(qy + cr.K);
+    x1 = (ux >> cr.fb) - cr.coff;
+    y1 = (uy >> cr.fb) - cr.coff;
+    return min((uint32_t)ux & cr.mask, (uint32_t)uy & cr.mask); /* 0: next to a .5 boundary */
+  };
+  /* second half: ring entry of the end cell, range from the table, sensor.clj:149-162 beam mixture */
+  auto score = [&](int jb, int x1, int y1) {
     const int ex = x1 - xoff;
     const uint32_t ry = (uint32_t)(y1 - yoff);
     const uint32_t ryc = min(ry, R32 ? last_row + 1u : last_row);
@@ -259,14 +292,33 @@ __device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunc
     const uint32_t ent = ok ? r_base + tt + (ex < 0 ? r_cnt : 0u) : nan_entry;
     const float rng = lds_f1(s_tab + ent * 4u);
     if (DBG && dbg_row) dbg_row[jb] = rng;
-    /* sensor.clj:149-162 beam mixture, exactly as in sensor.cu */
     const float4 mx = lds_f4(s_mix + (uint32_t)jb * 16u);
     const float z = mx.x - rng;
-    const float pz1 = hit_gauss(z, k2, zh);
+    const float pz1 = hit_gauss(z, a.k2, a.z_hit);
     const float pz2 = z < 0.0f ? mx.y : 0.0f;
     const float sum = (pz1 + pz2) + mx.z;
     if (S7) logprod_mul(acc, prod, pexp, sum);
     else acc += (sum * sum) * sum;
+  };
+
+  int jb = jb0;
+  for (; jb + 1 < jb1; jb += 2) {
+    int xa, ya, xb, yb;
+    const uint32_t na = cells(jb, xa, ya), nb = cells(jb + 1, xb, yb);
+    if (min(na, nb) == 0u) { /* 0.4 % of the pairs */
+      const int4 e = pt_exact_pair(a, L.rinv_d, ox, oy, psd, jb, (na == 0u ? 1 : 0) | (nb == 0u ? 2 : 0), make_int4(xa, ya, xb, yb));
+      xa = e.x; ya = e.y; xb = e.z; yb = e.w;
+    }
+    score(jb, xa, ya);
+    score(jb + 1, xb, yb);
+  }
+  if (jb < jb1) { /* a last segment with an odd number of beams */
+    int xa, ya;
+    if (cells(jb, xa, ya) == 0u) {
+      const int4 e = pt_exact_pair(a, L.rinv_d, ox, oy, psd, jb, 1, make_int4(xa, ya, 0, 0));
+      xa = e.x; ya = e.y;
+    }
+    score(jb, xa, ya);
   }
   return S7 ? logprod_close(acc, prod, pexp) : acc;
 }
@@ -351,6 +403,9 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
    * chunks of the rest drawn from a common counter by whoever finishes first */
   const int64_t n = a.n, Wt = (int64_t)gridDim.x * wpb, g = (int64_t)blockIdx.x * wpb + wid;
   const int64_t n_static = n - n * L.tail_pct / 100;
+  /* a unit of the tail: a quarter of a warp's own share, 8 .. 64 sorted particles (a dense cloud of 100k
+   * particles gives every warp ~28: units of 64 would be the longest thing in the kernel) */
+  const int64_t chunk = max((int64_t)8, min((int64_t)PT_TAIL_CHUNK, n / (Wt * 4)));
   const int nbins = L.n_slots + 1;
   const uint32_t *start = L.bin_start;
   const ResDiv rdv = make_resdiv(a.res);
@@ -362,10 +417,10 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
     uint32_t c = 0;
     if (lane == 0) c = atomicAdd(L.tail_ctr, 1u);
     c = __shfl_sync(FULL, c, 0);
-    const int64_t lo64 = n_static + (int64_t)c * PT_TAIL_CHUNK;
+    const int64_t lo64 = n_static + (int64_t)c * chunk;
     if (lo64 >= n) break;
     q_lo = (uint32_t)lo64;
-    q_hi = (uint32_t)min(lo64 + PT_TAIL_CHUNK, n);
+    q_hi = (uint32_t)min(lo64 + chunk, n);
   }
   if (q_lo >= q_hi) continue;
   int s; /* the slot holding position q_lo: the last one with start[s] <= q_lo */
@@ -449,11 +504,11 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
         dbg_row = a.dbg_range + (p - a.dbg_first) * nb;
       float v;
       if (L.rows32)
-        v = a.s7 ? pt_segment<true, DBG, true>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, __ldg(a.th + p), xoff, yoff, jb0, jb1, dbg_row)
-                 : pt_segment<false, DBG, true>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, __ldg(a.th + p), xoff, yoff, jb0, jb1, dbg_row);
+        v = a.s7 ? pt_segment<true, DBG, true>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + pos, xoff, yoff, jb0, jb1, dbg_row)
+                 : pt_segment<false, DBG, true>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + pos, xoff, yoff, jb0, jb1, dbg_row);
       else
-        v = a.s7 ? pt_segment<true, DBG, false>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, __ldg(a.th + p), xoff, yoff, jb0, jb1, dbg_row)
-                 : pt_segment<false, DBG, false>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, __ldg(a.th + p), xoff, yoff, jb0, jb1, dbg_row);
+        v = a.s7 ? pt_segment<true, DBG, false>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + pos, xoff, yoff, jb0, jb1, dbg_row)
+                 : pt_segment<false, DBG, false>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + pos, xoff, yoff, jb0, jb1, dbg_row);
       if (v != v) {
         v = pt_segment_walk<MODE, WIDE>(a, ps.x, ps.y, ps.z, ps.w, __ldg(a.th + p), jb0, jb1, dbg_row);
         if (a.stats) atomicAdd(a.stats + 11, 1ull); /* table_misses: expected 0 */
