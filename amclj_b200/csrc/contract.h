@@ -130,7 +130,9 @@ inline CellRefine make_cell_refine(int W, int H, double rcells, float res, bool 
   const double maxq = (double)(W > H ? W : H) + ceil(rcells) + 6.0;
   int fb = 12;
   while (fb > 4 && maxq >= ldexp(1.0, 22 - fb) - 2.0) fb--;
-  if (maxq >= ldexp(1.0, 22 - fb) - 2.0) return c; /* rays of > 260,000 cells: plain float rounding (K == 0) */
+  /* below 10 fraction bits (map + ray beyond ~4,000 cells per axis) a quotient is "near" a boundary so often that
+   * the refinement costs the walk kernel 14 % (C5): such maps keep the plain float rounding (K == 0) */
+  if (fb < 10) return c;
   const float big = (float)ldexp(1.5, 23 - fb);
   c.K = big + 0.5f + (float)ldexp(1.0, 1 - fb);
   c.fb = fb;

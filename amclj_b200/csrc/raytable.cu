@@ -302,9 +302,17 @@ __device__ __forceinline__ float table_segment(const SensorLaunch &a, const RtLa
      * so the clamps (and their NaN duty) are not needed */
     const float ex_w = fmaf(a.R, c, ox), ey_w = fmaf(a.R, s, oy);
     int x1, y1; /* float arithmetic, the reference's double computation next to a .5 boundary (contract.h) */
-    if (end_cells_fast(ex_w, ey_w, rdv, a.cr, x1, y1)) {
-      const int2 e = end_cells_exact(a, ox, oy, th, jb);
-      x1 = e.x; y1 = e.y;
+    if (a.cr.K != 0.0f) {
+      if (end_cells_fast(ex_w, ey_w, rdv, a.cr, x1, y1)) {
+        const int2 e = end_cells_exact(a, ox, oy, th, jb);
+        x1 = e.x; y1 = e.y;
+      }
+    } else { /* large maps: plain float rounding, floor(q + 0.5) as an add with round-down against 1.5 * 2^23 */
+      const float qx0 = ex_w * rdv.r, qy0 = ey_w * rdv.r;
+      const float qx = fmaf(fmaf(-qx0, rdv.res, ex_w), rdv.r, qx0);
+      const float qy = fmaf(fmaf(-qy0, rdv.res, ey_w), rdv.r, qy0);
+      x1 = __float_as_int(__fadd_rd(qx + 0.5f, 12582912.0f)) - 0x4B400000;
+      y1 = __float_as_int(__fadd_rd(qy + 0.5f, 12582912.0f)) - 0x4B400000;
     }
     const int ex = x1 - xoff;
     const uint32_t ry = (uint32_t)(y1 - yoff);
@@ -434,7 +442,7 @@ rt_lookup_kernel(const __grid_constant__ RtLaunch L) {
     x0 = round_cell_start(ox, a.res); y0 = round_cell_start(oy, a.res);
     /* the table belongs to cell (cx, cy): a particle that is not there walks (the sort and this
      * kernel round the same coordinates the same way, so this fires only with S10) */
-    const bool use_table = table != nullptr && x0 == cx && y0 == cy && fast_round && a.cr.K != 0.0f && abs(x0) < (1 << 21) && abs(y0) < (1 << 21);
+    const bool use_table = table != nullptr && x0 == cx && y0 == cy && fast_round && abs(x0) < (1 << 21) && abs(y0) < (1 << 21);
     const int jb0 = sgm * SEG, jb1 = min(jb0 + SEG, nb);
     float v = 0.0f;
     bool general = DIAG || !use_table;

@@ -323,7 +323,7 @@ static int refine_fraction_bits(int32_t W, int32_t H, double rcells) {
   double maxq = (double)(W > H ? W : H) + ceil(rcells) + 6.0;
   int fb = 12;
   while (fb > 4 && maxq >= ldexp(1.0, 22 - fb) - 2.0) fb--;
-  if (maxq >= ldexp(1.0, 22 - fb) - 2.0) return 0; /* rays too long for the mantissa window: plain float rounding */
+  if (fb < 10) return 0; /* map + ray beyond ~4,000 cells per axis: plain float rounding (the contract's own limit) */
   return fb;
 }
 
