@@ -482,7 +482,7 @@ int ensure_pt_scratch(amclj_ctx *ctx, int64_t n) {
     dfree(t.pstate_d);
     t.pkey_cap = 0;
     CK(dalloc(&t.pkey, (size_t)n));
-    CK(dalloc(&t.pstate_d, (size_t)n));
+    CK(dalloc(&t.pstate_d, 2 * (size_t)n)); /* {(sin, cos), ray origin} per particle */
     t.pkey_cap = n;
   }
   if (n > r.pstate_cap) {
@@ -580,8 +580,7 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
   }
   CK(cudaMemcpyAsync(b.dev, ctx->pin_tab, tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(b.dev_d, dird, dbl_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  b.cr = make_cell_refine(ctx->map.W, ctx->map.H, rcells, ctx->map.res,
-                          ctx->exact_cells && ctx->map.res > 1.0e-6f && ctx->map.res < 1.0e6f);
+  b.cr = make_cell_refine(R, ctx->map.res, ctx->exact_cells);
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   b.nb = nb;
   b.n_scan = n;
@@ -698,7 +697,7 @@ void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode) {
   a.laser_x = p.laser_x;
   a.laser_y = p.laser_y;
   a.walk_ctr = ctx->walk_ctr;
-  a.walk_tail_pct = ctx->walk_tail_pct;
+  a.walk_tail_pct = (mode == DF_GLOBAL8 || mode == DF_GLOBAL4) ? ctx->walk_tail_pct_global : ctx->walk_tail_pct;
   const RayTables &rt = ctx->rt;
   if (rt.have_ring && rt.recs_mode == mode && rt.recs) {
     a.ring_rows = rt.rows;
@@ -909,7 +908,8 @@ int enqueue_sensor(amclj_ctx *ctx, bool decode_max) {
      * kernels are not even launched (a wrong guess costs speed for one update, never a result) */
     if (hint != 1) {
       CK(launch_tile_order(ctx->x, ctx->y, ctx->th, ctx->n, ctx->map.res, ctx->map.W, ctx->map.H,
-                           ctx->tile_counters, ctx->perm, ctx->bbox, a.compact_m, ctx->stream));
+                           ctx->tile_counters, ctx->perm, ctx->bbox, a.compact_m,
+                           ctx->tile_shift > 0 ? ctx->tile_shift : tile_order_shift(ctx->n, ctx->map.free_cells), ctx->stream));
       ctx->launches += 3;
       a.perm = ctx->perm;
     }
@@ -1197,7 +1197,9 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
   if (const char *e = getenv("AMCLJ_RAYTABLE")) ctx->rt_enable = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_EXACT_CELLS")) ctx->exact_cells = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_RING_SETUP")) ctx->ring_setup = atoi(e) != 0;
-  if (const char *e = getenv("AMCLJ_WALK_TAIL_PCT")) ctx->walk_tail_pct = atoi(e) > 100 ? 100 : atoi(e);
+  if (const char *e = getenv("AMCLJ_TILE_SHIFT")) ctx->tile_shift = atoi(e);
+  if (const char *e = getenv("AMCLJ_WALK_CARVEOUT")) ctx->walk_carveout = atoi(e);
+  if (const char *e = getenv("AMCLJ_WALK_TAIL_PCT")) ctx->walk_tail_pct = ctx->walk_tail_pct_global = atoi(e) > 100 ? 100 : atoi(e);
   if (const char *e = getenv("AMCLJ_TIME_MAIN")) ctx->time_main_env = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_RT_THR")) ctx->rt.thr = atoi(e);
   if (const char *e = getenv("AMCLJ_RT_WAVES")) ctx->rt.waves = atoi(e);
@@ -1344,6 +1346,8 @@ int32_t amclj_set_map(amclj_ctx *ctx, const int8_t *cells, int32_t width, int32_
   m.H = height;
   m.res = resolution;
   size_t ncell = (size_t)width * height;
+  m.free_cells = 0;
+  for (size_t i = 0; i < ncell; i++) m.free_cells += cells[i] == 0;
   CK(dalloc(&m.cells, ncell));
   CK(cudaMemcpyAsync(m.cells, cells, ncell, cudaMemcpyHostToDevice, ctx->stream));
   m.row_bytes4 = ((width + 2 + 1) / 2 + 15) / 16 * 16;

@@ -110,29 +110,36 @@ AMCLJ_HD void sincos_det_d(double a, double &sn, double &cs) {
   cs = co;
 }
 
-// Near-tie refinement of END cells.  An end point is rounded to its cell in float arithmetic; where the
-// quotient lies within two units of 2^-fb of a .5 boundary the float result could differ from what the
-// reference computes in double from the same float32 inputs, and the cell is recomputed in double
-// (end_cells_exact in sensor_common.cuh).  The test costs one AND: q + K is formed with
-// K = 1.5 * 2^(23-fb) + 0.5 + 2^(1-fb), which leaves round((q + 0.5) * 2^fb) + 2 in the low mantissa bits:
-// cell = bits >> fb (minus a constant), near a boundary <=> (bits & (2^fb - 4)) == 0.  fb is the largest
-// that keeps every quotient of the map inside the mantissa window; maxq = cells the farthest end point can
-// be from the origin.
+// END cells (sensor.clj:134-135 + map.clj:36-46), relative to the start cell, with a near-tie refinement.
+// The reference rounds (x + R cos(..)) / res in double.  Here the start cell x0 and the particle's offset
+// inside it, f = x / res - x0 in [-0.5, 0.5), are taken ONCE per particle in double (start_cell_frac); per ray
+// the end cell's offset from the start cell is round(f + rc * c) with rc = R / res (cells), one float FMA:
+//     u = fma(rc, c, fK),   fK = float(f + K),   K = 1.5 * 2^(23-fb) + 0.5 + 2^(1-fb)
+// which leaves round((f + rc c + 0.5) * 2^fb) + 2 in the low mantissa bits of u: offset = (bits >> fb) - coff,
+// and "within two units of 2^-fb of a .5 boundary" <=> (bits & (2^fb - 4)) == 0.  Only there could the float
+// result differ from the reference's double computation; those rays (about 1 in 2,000 at fb = 14) are
+// recomputed in double from the same float32 inputs (end_cells_exact in sensor_common.cuh).  Error budget, in
+// units of 2^-fb: rounding of fK 0.5, rounding of u 0.5, and (error of the direction c + rounding of rc) times
+// the ray length, where |err c| <= 2.5e-7 (float angle addition of sincos_det, measured max error 9.3e-8, and
+// of the float beam table, 3e-8; one product and one FMA rounding) and rc carries 6e-8 relative: 3.1e-7 per
+// cell of ray.  A cell can only come out wrong unflagged when the sum reaches 2; fb is the largest that keeps
+// the last term below 0.9 and the offset inside the mantissa window: lgfloor's 112-cell rays get fb = 14,
+// C5's 600-cell rays fb = 12.  No division per ray, and no dependence on the size of the map: a ray's geometry
+// is relative to its start cell.
 struct CellRefine {
-  float K;        /* 0: no refinement (odd geometry) */
+  float K;        /* 0: no refinement (rays of 4,000 cells or more, non-finite geometry): plain float rounding */
   int32_t fb;
   int32_t coff;   /* bits(1.5 * 2^(23-fb)) >> fb */
   uint32_t mask;  /* 2^fb - 4 */
-  float vmax;     /* coordinates (metres) below this keep their quotient inside the mantissa window */
+  float rc;       /* ray length in cells, R / res (signed: REF casts rays of -1 m) */
 };
-inline CellRefine make_cell_refine(int W, int H, double rcells, float res, bool enabled) {
+inline CellRefine make_cell_refine(float R, float res, bool enabled) {
   CellRefine c = {0.0f, 0, 0, 0u, 0.0f};
-  const double maxq = (double)(W > H ? W : H) + ceil(rcells) + 6.0;
-  int fb = 12;
-  while (fb > 4 && maxq >= ldexp(1.0, 22 - fb) - 2.0) fb--;
-  /* below 10 fraction bits (map + ray beyond ~4,000 cells per axis) a quotient is "near" a boundary so often that
-   * the refinement costs the walk kernel 14 % (C5): such maps keep the plain float rounding (K == 0) */
-  if (fb < 10) return c;
+  const double rcd = (double)R / (double)res, ar = fabs(rcd);
+  if (!(ar < 4000.0) || !(res > 1.0e-6f && res < 1.0e6f)) return c; /* NaN fails too */
+  int fb = 14;
+  while (fb >= 8 && (ar + 3.0 >= ldexp(1.0, 22 - fb) || 3.1e-7 * (ar + 1.0) * ldexp(1.0, fb) > 0.9)) fb--;
+  if (fb < 8) return c;
   const float big = (float)ldexp(1.5, 23 - fb);
   c.K = big + 0.5f + (float)ldexp(1.0, 1 - fb);
   c.fb = fb;
@@ -141,7 +148,7 @@ inline CellRefine make_cell_refine(int W, int H, double rcells, float res, bool 
   c.coff = (int32_t)(bits >> fb);
   /* disabled (AMCLJ_EXACT_CELLS=0, timing experiments): a mask bit that is always set, i.e. never "near" */
   c.mask = enabled ? (1u << fb) - 4u : 0x40000000u;
-  c.vmax = (float)((double)res * (ldexp(1.0, 22 - fb) - 4.0));
+  c.rc = (float)rcd;
   return c;
 }
 
@@ -151,6 +158,16 @@ inline CellRefine make_cell_refine(int W, int H, double rcells, float res, bool 
 AMCLJ_HD int32_t round_cell_start(float v, float res) {
   double t = floor((double)v / (double)res + 0.5);
   t = fmin(fmax(t, -1.0e9), 1.0e9); /* NaN -> -1e9 */
+  return (int32_t)t;
+}
+// ... together with fK = float((v / res - cell) + K) for the end cells of its rays (CellRefine above); the cell
+// is round_cell_start's.  Meaningful for a start on the map only (a far-away or NaN start has no use for it:
+// its rays end at step 0).
+AMCLJ_HD int32_t start_cell_frac(float v, float res, float K, float &fK) {
+  const double q = (double)v / (double)res;
+  double t = floor(q + 0.5);
+  t = fmin(fmax(t, -1.0e9), 1.0e9); /* NaN -> -1e9 */
+  fK = (float)((q - t) + (double)K);
   return (int32_t)t;
 }
 

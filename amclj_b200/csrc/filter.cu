@@ -303,20 +303,26 @@ cudaError_t launch_bbox(const float *x, const float *y, int64_t n, uint32_t *bbo
   return cudaGetLastError();
 }
 
-// Walking order for spread-out clouds: a counting sort of the particle indices by 8x8-cell map
-// tile (row-major tiles).  The order inside a tile is whatever the atomics give — it only decides
+// Walking order for spread-out clouds: a counting sort of the particle indices by square map tile
+// (row-major tiles) and heading sector.  The order inside a tile is whatever the atomics give — it only decides
 // which lanes walk together, never a result.  Skipped (the kernels return) for a compact cloud.
-#ifndef AMCLJ_TILE_SHIFT
-#define AMCLJ_TILE_SHIFT 3
-#endif
-constexpr int TILE_SHIFT = AMCLJ_TILE_SHIFT;
+// Tile side: 8 cells (shift 3) on a densely covered map; on a sparsely covered one (C5: one particle per
+// 16 cells) the side doubles until a tile holds ~128 particles, so that the 32 lanes of a warp still share
+// their heading sector and the tile counters stay few (tile_order_shift).
+constexpr int TILE_SHIFT_MIN = 3, TILE_SHIFT_MAX = 8;
+int tile_order_shift(int64_t n, int64_t free_cells) {
+  int s = TILE_SHIFT_MIN;
+  while (s < TILE_SHIFT_MAX && (n << (2 * s)) < 128ll * free_cells) s++;
+  return s;
+}
 #ifndef AMCLJ_HEADING_BINS
 #define AMCLJ_HEADING_BINS 8
 #endif
 constexpr int HEADING_BINS = AMCLJ_HEADING_BINS; /* power of two: secondary key, heading sector */
-int tile_count(int W, int H) { return ((W >> TILE_SHIFT) + 1) * ((H >> TILE_SHIFT) + 1) * HEADING_BINS; }
+static int tile_count_at(int W, int H, int shift) { return ((W >> shift) + 1) * ((H >> shift) + 1) * HEADING_BINS; }
+int tile_count(int W, int H) { return tile_count_at(W, H, TILE_SHIFT_MIN); } /* the most there can be */
 
-__device__ __forceinline__ int tile_of(float px, float py, float pth, float res, int W, int H) {
+__device__ __forceinline__ int tile_of(float px, float py, float pth, float res, int W, int H, int TILE_SHIFT) {
   int cx = min(max(round_cell(px, res), 0), W - 1), cy = min(max(round_cell(py, res), 0), H - 1);
   int hb = __float2int_rd(pth * (HEADING_BINS / 6.283185307179586f)) & (HEADING_BINS - 1);
   return ((cy >> TILE_SHIFT) * ((W >> TILE_SHIFT) + 1) + (cx >> TILE_SHIFT)) * HEADING_BINS + hb;
@@ -324,10 +330,10 @@ __device__ __forceinline__ int tile_of(float px, float py, float pth, float res,
 
 __global__ void __launch_bounds__(256)
 tile_hist_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th,
-                 int64_t n, float res, int W, int H, uint32_t *counters, const uint32_t *bbox, float compact_m) {
+                 int64_t n, float res, int W, int H, int shift, uint32_t *counters, const uint32_t *bbox, float compact_m) {
   if (bbox && cloud_is_compact(bbox, compact_m)) return;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(&counters[tile_of(__ldg(x + i), __ldg(y + i), __ldg(th + i), res, W, H)], 1u);
+  if (i < n) atomicAdd(&counters[tile_of(__ldg(x + i), __ldg(y + i), __ldg(th + i), res, W, H, shift)], 1u);
 }
 
 __global__ void __launch_bounds__(1024)
@@ -350,22 +356,24 @@ tile_scan_kernel(uint32_t *counters, int ntiles, const uint32_t *bbox, float com
 
 __global__ void __launch_bounds__(256)
 tile_scatter_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ th,
-                    int64_t n, float res, int W, int H, uint32_t *cursors, int32_t *perm, const uint32_t *bbox, float compact_m) {
+                    int64_t n, float res, int W, int H, int shift, uint32_t *cursors, int32_t *perm, const uint32_t *bbox,
+                    float compact_m) {
   if (bbox && cloud_is_compact(bbox, compact_m)) return;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) perm[atomicAdd(&cursors[tile_of(__ldg(x + i), __ldg(y + i), __ldg(th + i), res, W, H)], 1u)] = (int32_t)i;
+  if (i < n) perm[atomicAdd(&cursors[tile_of(__ldg(x + i), __ldg(y + i), __ldg(th + i), res, W, H, shift)], 1u)] = (int32_t)i;
 }
 
 cudaError_t launch_tile_order(const float *x, const float *y, const float *th, int64_t n, float res, int W, int H,
                               uint32_t *counters, int32_t *perm, const uint32_t *bbox, float compact_m,
-                              cudaStream_t s) {
+                              int shift, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  int ntiles = tile_count(W, H);
+  if (shift < TILE_SHIFT_MIN || shift > TILE_SHIFT_MAX) shift = TILE_SHIFT_MIN;
+  int ntiles = tile_count_at(W, H, shift);
   cudaMemsetAsync(counters, 0, sizeof(uint32_t) * (size_t)ntiles, s);
   unsigned blocks = (unsigned)((n + 255) / 256);
-  tile_hist_kernel<<<blocks, 256, 0, s>>>(x, y, th, n, res, W, H, counters, bbox, compact_m);
+  tile_hist_kernel<<<blocks, 256, 0, s>>>(x, y, th, n, res, W, H, shift, counters, bbox, compact_m);
   tile_scan_kernel<<<1, 1024, 0, s>>>(counters, ntiles, bbox, compact_m);
-  tile_scatter_kernel<<<blocks, 256, 0, s>>>(x, y, th, n, res, W, H, counters, perm, bbox, compact_m);
+  tile_scatter_kernel<<<blocks, 256, 0, s>>>(x, y, th, n, res, W, H, shift, counters, perm, bbox, compact_m);
   return cudaGetLastError();
 }
 

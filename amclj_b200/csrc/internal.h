@@ -24,6 +24,7 @@ struct DeviceMap {
   int32_t row_bytes4 = 0;    // multiple of 16
   int32_t pitch8 = 0;
   size_t bytes4 = 0, bytes8 = 0;
+  int64_t free_cells = 0;    // cells with value 0 (counted at set_map)
   uint8_t *wedge = nullptr;  // WEDGE_CLASSES planes of (H+2) x pitch8 bytes: directional distance fields
   size_t wedge_plane = 0;
   bool fits_smem = false;
@@ -198,7 +199,7 @@ struct PersistentTables {
   uint32_t *bin_start = nullptr;   // [n_slots + 2] exclusive prefix; [n_slots + 1] = n
   uint32_t *cursor = nullptr;      // [n_slots + 2] write cursors of the scatter
   int32_t *pkey = nullptr;         // [pkey_cap] slot of every particle
-  double2 *pstate_d = nullptr;     // [pkey_cap] heading sine / cosine in double, sorted order
+  double2 *pstate_d = nullptr;     // [2 * pkey_cap] per particle {heading (sin, cos), ray origin (x, y)} in double, sorted order
   int64_t pkey_cap = 0;
   bool enable = true;              // AMCLJ_PTABLE=0 turns the path off
   bool built = false;
@@ -235,7 +236,7 @@ struct PtLaunch {
   int32_t *pkey;
   int32_t *perm;
   float4 *pstate;
-  double2 *pstate_d;   // [n] (sin, cos) of the heading in double, sorted order: read only on the near-tie path
+  double2 *pstate_d;   // [2n] {(sin, cos) of the heading, ray origin} in double, sorted order: read only on the near-tie path
   double rinv_d;       // 1 / resolution in double
   long long *qacc;
   int32_t warps;   // look-up warps per CTA
@@ -337,7 +338,12 @@ struct amclj_ctx {
   amclj::RayTables rt;
   amclj::PersistentTables pt;
   uint32_t *walk_ctr = nullptr;  // device {tail counter, CTAs finished} of the walk kernel
+  int32_t tile_shift = 0;      // walking-order tile side (2^shift cells); 0: from the particle density (AMCLJ_TILE_SHIFT)
+  int32_t walk_carveout = 20;  // shared-memory carve-out (percent) asked for the walk kernel on the global fields, the rest is L1
+                               // (C5: 75.9 -> 72.1 ms against the driver's own choice); -1: driver's choice
   int32_t walk_tail_pct = 0;   // spread-out clouds: CTA-contiguous task runs, this share of the tasks as a common tail
+  int32_t walk_tail_pct_global = 20; // the same on the L2-resident byte field of a large map, whose regions differ in wall
+                               // density (C5: SM active cycles 149 M .. 184 M without a tail; 82.5 -> 75.5 ms)
   int64_t map_gen = 0;     // bumped by every set_map
   bool ring_setup = true;  // walk kernel reads its line set-up from per-ring-cell records (AMCLJ_RING_SETUP=0: computes it)
   bool rt_enable = true;   // auto policy may take the ray-table path (AMCLJ_RAYTABLE=0 turns it off)
@@ -436,8 +442,10 @@ cudaError_t launch_motion(const MotionLaunch &a, cudaStream_t s);
 cudaError_t launch_tile_order(const float *x, const float *y, const float *th, int64_t n, float res, int W,
                               int H,
                               uint32_t *counters, int32_t *perm, const uint32_t *bbox, float compact_m,
+                              int shift /* tile side 2^shift cells, 3..8 (tile_order_shift) */,
                               cudaStream_t s);
 int tile_count(int W, int H);
+int tile_order_shift(int64_t n, int64_t free_cells);
 cudaError_t launch_bbox(const float *x, const float *y, int64_t n, uint32_t *bbox, int sm_count,
                         cudaStream_t s);
 cudaError_t build_distance_fields(amclj_ctx *c, bool want8, cudaStream_t s);

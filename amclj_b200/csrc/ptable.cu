@@ -77,10 +77,8 @@ pt_hist_kernel(const __grid_constant__ PtLaunch L) {
   int key = -1 - lane; /* lanes past the end: a key nobody shares */
   if (i < a.n) {
     L.qacc[i] = 0; /* the weight accumulators of this update */
-    const ResDiv rdv = make_resdiv(a.res);
     const float4 o = pt_origin(a, i);
     int x0, y0;
-    (void)rdv;
     x0 = round_cell_start(o.x, a.res); y0 = round_cell_start(o.y, a.res);
     const bool in = (uint32_t)x0 < (uint32_t)a.W && (uint32_t)y0 < (uint32_t)a.H;
     key = in ? __ldg(L.slot_of_cell + (size_t)y0 * a.W + x0) : L.n_slots;
@@ -194,11 +192,18 @@ pt_scatter_kernel(const __grid_constant__ PtLaunch L) {
   if (key < 0) return;
   const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
   L.perm[pos] = (int32_t)i;
-  L.pstate[pos] = pt_origin(a, i);
-  /* for the near-tie end cells of the look-up (contract.h): the heading's sine and cosine in double, once per particle */
+  /* what every look-up of this particle starts from (contract.h): the offset inside its start cell (+ K) per axis,
+   * heading sine / cosine — computed once per particle instead of once per segment */
+  const float4 o = pt_origin(a, i);
+  float fKx, fKy;
+  start_cell_frac(o.x, a.res, a.cr.K, fKx);
+  start_cell_frac(o.y, a.res, a.cr.K, fKy);
+  L.pstate[pos] = make_float4(fKx, fKy, o.z, o.w);
+  /* for the near-tie end cells: the heading's sine and cosine in double, and the ray origin */
   double st_d = 0.0, ct_d = 1.0; /* S1 off: rotation by zero */
   if (a.s1) sincos_det_d((double)__ldg(a.th + i), st_d, ct_d);
-  L.pstate_d[pos] = make_double2(st_d, ct_d);
+  L.pstate_d[2 * (size_t)pos] = make_double2(st_d, ct_d);
+  L.pstate_d[2 * (size_t)pos + 1] = make_double2((double)o.x, (double)o.y);
 }
 
 // ---- the look-up -------------------------------------------------------------------------------
@@ -217,28 +222,23 @@ __device__ __forceinline__ uint32_t lds_u1(uint32_t addr) {
   return v;
 }
 
-/* exact end cells (contract.h) of those of the beams jb, jb + 1 whose float quotient lies next to a .5 boundary
- * (which & 1, which & 2); out of line and once per PAIR of beams, so that the hot loop below stays two
- * straight-line halves.  The end point lies on the map's window (the particle stands on a cell of the map), so
- * the quotient needs no clamping here. */
-static __device__ __noinline__ int4 pt_exact_pair(const SensorLaunch &a, double rinv_d, float ox, float oy,
-                                                  const double2 *psd, int jb, int which, int4 cells) {
-  const double2 hd = __ldg(psd); /* (sin, cos) of the heading; S1 off: (0, 1), which gives back (cb, sb) */
-  const double Rd = (double)a.R, res = (double)a.res, oxd = (double)ox, oyd = (double)oy;
+/* exact end cells (contract.h) of those of the beams jb, jb + 1 whose float offset lies next to a .5 boundary
+ * (which & 1, which & 2), as (offset x, ring row) like the fast half; out of line and once per PAIR of beams, so
+ * that the hot loop below stays two straight-line halves.  psd: {(sin, cos) of the heading, ray origin}. */
+static __device__ __noinline__ int4 pt_exact_pair(const SensorLaunch &a, double rinv_d, const double2 *psd, int E, int jb,
+                                                  int which, int4 cells) {
+  const double2 hd = __ldg(psd); /* S1 off: (0, 1), which gives back (cb, sb) */
+  const double2 od = __ldg(psd + 1);
+  const double Rd = (double)a.R, res = (double)a.res;
+  const int x0 = round_cell_start((float)od.x, a.res), y0 = round_cell_start((float)od.y, a.res);
 #pragma unroll
   for (int u = 0; u < 2; u++) {
     if (!(which & (1 << u))) continue;
     const double cbd = __ldg(a.beam_d + 2 * (jb + u)), sbd = __ldg(a.beam_d + 2 * (jb + u) + 1);
     const double cd = fma(hd.y, cbd, -(hd.x * sbd)), sd = fma(hd.x, cbd, hd.y * sbd);
-    const double vx = fma(Rd, cd, oxd), vy = fma(Rd, sd, oyd);
-    const double tx = fma(vx, rinv_d, 0.5), ty = fma(vy, rinv_d, 0.5);
-    double fx = floor(tx), fy = floor(ty);
-    /* the product is within 4e-13 of the quotient: only a value that close to an integer needs the real divide */
-    if (fmin(fmin(tx - fx, (fx + 1.0) - tx), fmin(ty - fy, (fy + 1.0) - ty)) < 1.0e-7) {
-      fx = floor(vx / res + 0.5);
-      fy = floor(vy / res + 0.5);
-    }
-    if (u == 0) { cells.x = (int)fx; cells.y = (int)fy; } else { cells.z = (int)fx; cells.w = (int)fy; }
+    const double vx = fma(Rd, cd, od.x), vy = fma(Rd, sd, od.y);
+    const int cx = cell_exact_d(vx, res, rinv_d), cy = cell_exact_d(vy, res, rinv_d); /* NaN -> -1e9: off the ring */
+    if (u == 0) { cells.x = cx - x0; cells.y = cy - y0 + E; } else { cells.z = cx - x0; cells.w = cy - y0 + E; }
   }
   return cells;
 }
@@ -248,10 +248,9 @@ static __device__ __noinline__ int4 pt_exact_pair(const SensorLaunch &a, double 
 // re-taken in double, out of line] -> [ring index, table entry, beam mixture of both].  Each half is
 // straight-line, so the compiler pairs the two beams' instructions as it did before the refinement.
 template <bool S7, bool DBG, bool R32>
-__device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunch &L, const ResDiv &rdv, uint32_t s_tab,
-                                            uint32_t s_mix, uint32_t s_dir, uint32_t s_rows, float ox, float oy, float st,
-                                            float ct, const double2 *psd, int xoff, int yoff, int jb0, int jb1,
-                                            float *dbg_row) {
+__device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunch &L, uint32_t s_tab, uint32_t s_mix,
+                                            uint32_t s_dir, uint32_t s_rows, float fKx, float fKy, float st, float ct,
+                                            const double2 *psd, int jb0, int jb1, float *dbg_row) {
   float acc = 0.0f, prod = 1.0f;
   int pexp = 0;
   const uint32_t last_row = (uint32_t)L.nrows - 1u, nan_entry = (uint32_t)L.n_entries - 1u;
@@ -259,25 +258,21 @@ __device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunc
   float rc = a.s1 ? ct : 1.0f, rs = a.s1 ? st : 0.0f;
   asm volatile("" : "+f"(rc), "+f"(rs)); /* kept in registers: left alone, the selection is redone for every pair of beams */
   const CellRefine cr = a.cr;
+  const int coff_row = cr.coff - L.E; /* ring rows start at offset -E */
 
-  /* first half: sensor.clj:130-135 / map.clj:36-46, the cell of the beam's end point in float arithmetic
-   * (contract.h); returns the low mantissa bits the near-tie test looks at */
-  auto cells = [&](int jb, int &x1, int &y1) -> uint32_t {
+  /* first half: sensor.clj:130-135 / map.clj:36-46, the end cell relative to the start cell — one FMA per
+   * coordinate (contract.h) — as (offset x, ring row); returns the low mantissa bits the near-tie test looks at */
+  auto cells = [&](int jb, int &ex, int &ry) -> uint32_t {
     const float2 bd = lds_f2(s_dir + (uint32_t)jb * 8u);
     const float c = fmaf(rc, bd.x, -(rs * bd.y)), s = fmaf(rs, bd.x, rc * bd.y); /* S1: angle addition */
-    const float ex_w = fmaf(a.R, c, ox), ey_w = fmaf(a.R, s, oy);
-    const float qx0 = ex_w * rdv.r, qy0 = ey_w * rdv.r;
-    const float qx = fmaf(fmaf(-qx0, rdv.res, ex_w), rdv.r, qx0);
-    const float qy = fmaf(fmaf(-qy0, rdv.res, ey_w), rdv.r, qy0);
-    const int ux = __float_as_int(qx + cr.K), uy = __float_as_int(qy + cr.K);
-    x1 = (ux >> cr.fb) - cr.coff;
-    y1 = (uy >> cr.fb) - cr.coff;
+    const int ux = __float_as_int(fmaf(cr.rc, c, fKx)), uy = __float_as_int(fmaf(cr.rc, s, fKy));
+    ex = (ux >> cr.fb) - cr.coff;
+    ry = (uy >> cr.fb) - coff_row;
     return min((uint32_t)ux & cr.mask, (uint32_t)uy & cr.mask); /* 0: next to a .5 boundary */
   };
   /* second half: ring entry of the end cell, range from the table, sensor.clj:149-162 beam mixture */
-  auto score = [&](int jb, int x1, int y1) {
-    const int ex = x1 - xoff;
-    const uint32_t ry = (uint32_t)(y1 - yoff);
+  auto score = [&](int jb, int ex, int ryi) {
+    const uint32_t ry = (uint32_t)ryi;
     const uint32_t ryc = min(ry, R32 ? last_row + 1u : last_row);
     uint32_t r_base, r_lo, r_cnt; /* the row's first entry, first |ex|, entries per arc (the negative arc follows the positive) */
     if (R32) { /* one word per row: a random 4-byte read meets ~3.5-way bank conflicts, a 16-byte one ~8 wavefronts */
@@ -305,8 +300,8 @@ __device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunc
   for (; jb + 1 < jb1; jb += 2) {
     int xa, ya, xb, yb;
     const uint32_t na = cells(jb, xa, ya), nb = cells(jb + 1, xb, yb);
-    if (min(na, nb) == 0u) { /* 0.4 % of the pairs */
-      const int4 e = pt_exact_pair(a, L.rinv_d, ox, oy, psd, jb, (na == 0u ? 1 : 0) | (nb == 0u ? 2 : 0), make_int4(xa, ya, xb, yb));
+    if (min(na, nb) == 0u) { /* 0.1 % of the pairs at fb = 14 */
+      const int4 e = pt_exact_pair(a, L.rinv_d, psd, L.E, jb, (na == 0u ? 1 : 0) | (nb == 0u ? 2 : 0), make_int4(xa, ya, xb, yb));
       xa = e.x; ya = e.y; xb = e.z; yb = e.w;
     }
     score(jb, xa, ya);
@@ -315,7 +310,7 @@ __device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunc
   if (jb < jb1) { /* a last segment with an odd number of beams */
     int xa, ya;
     if (cells(jb, xa, ya) == 0u) {
-      const int4 e = pt_exact_pair(a, L.rinv_d, ox, oy, psd, jb, 1, make_int4(xa, ya, 0, 0));
+      const int4 e = pt_exact_pair(a, L.rinv_d, psd, L.E, jb, 1, make_int4(xa, ya, 0, 0));
       xa = e.x; ya = e.y;
     }
     score(jb, xa, ya);
@@ -325,25 +320,14 @@ __device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunc
 
 /* a segment whose table look-up came back NaN (an end cell off the ring, a NaN pose): walk its rays */
 template <int MODE, bool WIDE>
-__device__ __noinline__ float pt_segment_walk(const SensorLaunch &a, float ox, float oy, float st, float ct, float th,
-                                              int jb0, int jb1, float *dbg_row) {
-  const ResDiv rdv = make_resdiv(a.res);
+__device__ __noinline__ float pt_segment_walk(const SensorLaunch &a, float ox, float oy, float th, int jb0, int jb1,
+                                              float *dbg_row) {
   const float4 *mixt = reinterpret_cast<const float4 *>(a.beam);
-  const float2 *dirt = reinterpret_cast<const float2 *>(a.beam + 4 * (size_t)a.nb);
-  int x0, y0;
-  x0 = round_cell_start(ox, a.res); y0 = round_cell_start(oy, a.res);
   float acc = 0.0f, prod = 1.0f;
   int pexp = 0;
   for (int jb = jb0; jb < jb1; jb++) {
-    const float2 bd = __ldg(dirt + jb);
-    float c = bd.x, s = bd.y;
-    if (a.s1) {
-      c = fmaf(ct, bd.x, -(st * bd.y));
-      s = fmaf(st, bd.x, ct * bd.y);
-    }
-    const float ex_w = fmaf(a.R, c, ox), ey_w = fmaf(a.R, s, oy);
     RayOut o;
-    const float rng = cast_ray_slow<MODE, WIDE, false>(a, x0, y0, ex_w, ey_w, ox, oy, th, jb, o);
+    const float rng = cast_ray_slow<MODE, WIDE, false>(a, ox, oy, th, jb, o);
     if (dbg_row) dbg_row[jb] = rng;
     const float4 mx = __ldg(mixt + jb);
     const float z = mx.x - rng;
@@ -408,7 +392,6 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
   const int64_t chunk = max((int64_t)8, min((int64_t)PT_TAIL_CHUNK, n / (Wt * 4)));
   const int nbins = L.n_slots + 1;
   const uint32_t *start = L.bin_start;
-  const ResDiv rdv = make_resdiv(a.res);
   float wmax = -INFINITY;
   int it = 0; /* tables staged so far by this warp (mbarrier phase) */
   uint32_t q_lo = (uint32_t)(n_static * g / Wt), q_hi = (uint32_t)(n_static * (g + 1) / Wt);
@@ -489,9 +472,6 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
       }
     }
     const uint32_t s_tab = s_tab0 + (uint32_t)buf * tab_bytes;
-    int2 cc = make_int2(0, 0);
-    if (c_slot < L.n_slots) cc = __ldg(L.cell_of_slot + c_slot);
-    const int xoff = cc.x, yoff = cc.y - L.E; /* end cell relative to the start cell; ring rows start at -E */
     const int ntask = c_cnt * nseg; /* (segment, particle) pairs, particle fastest: a warp shares its beams */
     for (int t = lane; t < ntask; t += 32) {
       const int sgm = t / c_cnt, j = t - sgm * c_cnt;
@@ -504,13 +484,14 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
         dbg_row = a.dbg_range + (p - a.dbg_first) * nb;
       float v;
       if (L.rows32)
-        v = a.s7 ? pt_segment<true, DBG, true>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + pos, xoff, yoff, jb0, jb1, dbg_row)
-                 : pt_segment<false, DBG, true>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + pos, xoff, yoff, jb0, jb1, dbg_row);
+        v = a.s7 ? pt_segment<true, DBG, true>(a, L, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + 2 * (size_t)pos, jb0, jb1, dbg_row)
+                 : pt_segment<false, DBG, true>(a, L, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + 2 * (size_t)pos, jb0, jb1, dbg_row);
       else
-        v = a.s7 ? pt_segment<true, DBG, false>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + pos, xoff, yoff, jb0, jb1, dbg_row)
-                 : pt_segment<false, DBG, false>(a, L, rdv, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + pos, xoff, yoff, jb0, jb1, dbg_row);
+        v = a.s7 ? pt_segment<true, DBG, false>(a, L, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + 2 * (size_t)pos, jb0, jb1, dbg_row)
+                 : pt_segment<false, DBG, false>(a, L, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + 2 * (size_t)pos, jb0, jb1, dbg_row);
       if (v != v) {
-        v = pt_segment_walk<MODE, WIDE>(a, ps.x, ps.y, ps.z, ps.w, __ldg(a.th + p), jb0, jb1, dbg_row);
+        const double2 od = __ldg(L.pstate_d + 2 * (size_t)pos + 1); /* the ray origin (float values, kept as doubles) */
+        v = pt_segment_walk<MODE, WIDE>(a, (float)od.x, (float)od.y, __ldg(a.th + p), jb0, jb1, dbg_row);
         if (a.stats) atomicAdd(a.stats + 11, 1ull); /* table_misses: expected 0 */
       }
       /* close the segment: one rounding to fixed point; segments add as integers */

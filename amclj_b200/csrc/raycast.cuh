@@ -92,15 +92,24 @@ __device__ __forceinline__ float cast_ray(const SensorLaunch &a, const uint8_t *
   return rng;
 }
 
-/* the rare paths of the look-up kernel, kept out of line so that its beam loop stays small */
+/* the rare paths of the look-up kernels, kept out of line so that their beam loops stay small: beam jb of the
+ * particle at (ox, oy) with heading th, everything recomputed with the full handling of sensor.cu (a start off
+ * the map, huge / NaN coordinates) and the refinement */
 template <int MODE, bool WIDE, bool DIAG>
-__device__ __noinline__ float cast_ray_slow(const SensorLaunch &a, int x0, int y0, float ex_w, float ey_w, float ox, float oy,
-                                            float th, int jb, RayOut &out) {
-  /* the end point again, with the full range handling of sensor.cu (huge / NaN coordinates) and the refinement */
+__device__ __noinline__ float cast_ray_slow(const SensorLaunch &a, float ox, float oy, float th, int jb, RayOut &out) {
   const ResDiv rdv = make_resdiv(a.res);
+  float st, ct;
+  sincos_det(th, st, ct);
+  const RayStart rst = make_ray_start(a, ox, oy, st, ct);
+  const float2 bd = __ldg(reinterpret_cast<const float2 *>(a.beam + 4 * (size_t)a.nb) + jb); /* (cos, sin) of the beam */
+  float c = bd.x, s = bd.y;
+  if (a.s1) {
+    c = fmaf(ct, bd.x, -(st * bd.y));
+    s = fmaf(st, bd.x, ct * bd.y);
+  }
   int x1, y1;
-  end_cell(a, rdv, ex_w, ey_w, ox, oy, th, jb, x1, y1);
-  return cast_ray<MODE, WIDE, DIAG>(a, a.df, x0, y0, x1, y1, out);
+  end_cell(a, rdv, rst, c, s, ox, oy, th, jb, x1, y1);
+  return cast_ray<MODE, WIDE, DIAG>(a, a.df, rst.x0, rst.y0, x1, y1, out);
 }
 
 __device__ __forceinline__ float2 lds_f2(uint32_t addr) {

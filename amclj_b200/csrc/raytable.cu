@@ -286,36 +286,34 @@ template <bool S7, bool TS>
 __device__ __forceinline__ float table_segment(const SensorLaunch &a, const RtLaunch &L, const ResDiv &rdv,
                                                const float *__restrict__ table, uint32_t s_mix, uint32_t s_dir,
                                                uint32_t s_rows, const float4 *mixt, const float2 *dirt, float ox, float oy,
-                                               float st, float ct, float th, int x0, int y0, int jb0, int jb1) {
+                                               float st, float ct, float th, const RayStart &rst, int jb0, int jb1) {
   float acc = 0.0f, prod = 1.0f;
   int pexp = 0;
   const uint32_t last_row = (uint32_t)L.nrows - 1u, nan_entry = (uint32_t)L.n_entries - 1u;
-  const int xoff = x0, yoff = y0 - L.E;
   /* S1 off = rotation by zero: fma(1, cb, -(0 * sb)) and fma(0, cb, 1 * sb) give back (cb, sb) */
   const float rc = a.s1 ? ct : 1.0f, rs = a.s1 ? st : 0.0f;
 #pragma unroll 2
   for (int jb = jb0; jb < jb1; jb++) {
     const float2 bd = TS ? lds_f2(s_dir + (uint32_t)jb * 8u) : __ldg(dirt + jb);
     const float c = fmaf(rc, bd.x, -(rs * bd.y)), s = fmaf(rs, bd.x, rc * bd.y); /* S1: angle addition */
-    /* sensor.clj:130-135: end point of the beam to its cell: map.clj:36-46 round(v / res) as in
-     * round_cell2_inrange; a start inside a table cell keeps the quotient far from the int32 range,
-     * so the clamps (and their NaN duty) are not needed */
-    const float ex_w = fmaf(a.R, c, ox), ey_w = fmaf(a.R, s, oy);
-    int x1, y1; /* float arithmetic, the reference's double computation next to a .5 boundary (contract.h) */
+    /* sensor.clj:130-135: the end cell relative to the start cell — one float FMA per coordinate, the reference's
+     * double computation next to a .5 boundary (contract.h) */
+    int ex, ey;
     if (a.cr.K != 0.0f) {
-      if (end_cells_fast(ex_w, ey_w, rdv, a.cr, x1, y1)) {
+      if (end_offsets_fast(c, s, rst.fKx, rst.fKy, a.cr, ex, ey)) {
         const int2 e = end_cells_exact(a, ox, oy, th, jb);
-        x1 = e.x; y1 = e.y;
+        ex = e.x - rst.x0; ey = e.y - rst.y0;
       }
-    } else { /* large maps: plain float rounding, floor(q + 0.5) as an add with round-down against 1.5 * 2^23 */
+    } else { /* very long rays: plain float rounding of the end point, floor(q + 0.5) as an add with round-down
+              * against 1.5 * 2^23 (a start inside a table cell keeps the quotient far from the int32 range) */
+      const float ex_w = fmaf(a.R, c, ox), ey_w = fmaf(a.R, s, oy);
       const float qx0 = ex_w * rdv.r, qy0 = ey_w * rdv.r;
       const float qx = fmaf(fmaf(-qx0, rdv.res, ex_w), rdv.r, qx0);
       const float qy = fmaf(fmaf(-qy0, rdv.res, ey_w), rdv.r, qy0);
-      x1 = __float_as_int(__fadd_rd(qx + 0.5f, 12582912.0f)) - 0x4B400000;
-      y1 = __float_as_int(__fadd_rd(qy + 0.5f, 12582912.0f)) - 0x4B400000;
+      ex = __float_as_int(__fadd_rd(qx + 0.5f, 12582912.0f)) - 0x4B400000 - rst.x0;
+      ey = __float_as_int(__fadd_rd(qy + 0.5f, 12582912.0f)) - 0x4B400000 - rst.y0;
     }
-    const int ex = x1 - xoff;
-    const uint32_t ry = (uint32_t)(y1 - yoff);
+    const uint32_t ry = (uint32_t)(ey + L.E);
     /* ring entry of the end cell; off the ring: the NaN entry, which poisons the segment */
     const uint32_t ryc = min(ry, last_row);
     const uint4 rw = TS ? lds_u4(s_rows + ryc * 16u) : __ldg(L.rows + ryc);
@@ -438,17 +436,18 @@ rt_lookup_kernel(const __grid_constant__ RtLaunch L) {
         ox = nx; oy = ny;
       }
     }
-    int x0, y0;
-    x0 = round_cell_start(ox, a.res); y0 = round_cell_start(oy, a.res);
+    const RayStart rst = make_ray_start(a, ox, oy, st, ct);
+    const int x0 = rst.x0, y0 = rst.y0;
     /* the table belongs to cell (cx, cy): a particle that is not there walks (the sort and this
      * kernel round the same coordinates the same way, so this fires only with S10) */
-    const bool use_table = table != nullptr && x0 == cx && y0 == cy && fast_round && abs(x0) < (1 << 21) && abs(y0) < (1 << 21);
+    const bool use_table = table != nullptr && x0 == cx && y0 == cy && fast_round && abs(x0) < (1 << 21) && abs(y0) < (1 << 21) &&
+                           (rst.fast || a.cr.K == 0.0f); /* a NaN heading takes the general path */
     const int jb0 = sgm * SEG, jb1 = min(jb0 + SEG, nb);
     float v = 0.0f;
     bool general = DIAG || !use_table;
     if (!general) {
-      v = a.s7 ? table_segment<true, TS>(a, L, rdv, table, s_mix, s_dir, s_rows, mixt, dirt, ox, oy, st, ct, __ldg(a.th + p), x0, y0, jb0, jb1)
-               : table_segment<false, TS>(a, L, rdv, table, s_mix, s_dir, s_rows, mixt, dirt, ox, oy, st, ct, __ldg(a.th + p), x0, y0, jb0, jb1);
+      v = a.s7 ? table_segment<true, TS>(a, L, rdv, table, s_mix, s_dir, s_rows, mixt, dirt, ox, oy, st, ct, __ldg(a.th + p), rst, jb0, jb1)
+               : table_segment<false, TS>(a, L, rdv, table, s_mix, s_dir, s_rows, mixt, dirt, ox, oy, st, ct, __ldg(a.th + p), rst, jb0, jb1);
       general = v != v;
     }
     if (general) { /* sparse cells, diagnostics, and the segments the fast path gave back */
@@ -462,12 +461,11 @@ rt_lookup_kernel(const __grid_constant__ RtLaunch L) {
           c = fmaf(ct, bd.x, -(st * bd.y));
           s = fmaf(st, bd.x, ct * bd.y);
         }
-        const float ex_w = fmaf(a.R, c, ox), ey_w = fmaf(a.R, s, oy);
         bool ok = false;
         uint32_t ent = 0;
         if (use_table) {
           int x1, y1;
-          end_cell(a, rdv, ex_w, ey_w, ox, oy, __ldg(a.th + p), jb, x1, y1);
+          end_cell(a, rdv, rst, c, s, ox, oy, __ldg(a.th + p), jb, x1, y1);
           const int ex = x1 - x0, ey = y1 - y0;
           const uint32_t ry = (uint32_t)(ey + L.E);
           if (ry < nrows) {
@@ -491,7 +489,7 @@ rt_lookup_kernel(const __grid_constant__ RtLaunch L) {
             rng = __ldg(table + ent);
           }
         } else {
-          rng = cast_ray_slow<MODE, WIDE, DIAG>(a, x0, y0, ex_w, ey_w, ox, oy, __ldg(a.th + p), jb, o);
+          rng = cast_ray_slow<MODE, WIDE, DIAG>(a, ox, oy, __ldg(a.th + p), jb, o);
           if (DIAG && use_table) n_miss++; /* an end cell outside the ring: never seen */
         }
         const float4 mx = TS ? lds_f4(s_mix + (uint32_t)jb * 16u) : __ldg(mixt + jb);

@@ -195,8 +195,9 @@ sensor_kernel(const SensorLaunch a) {
       float ny = oy + fmaf(a.laser_x, st, a.laser_y * ct);
       ox = nx; oy = ny;
     }
-    int x0, y0;
-    x0 = round_cell_start(ox, a.res); y0 = round_cell_start(oy, a.res); /* once per task: the reference's own double divide */
+    /* once per task: the start cell by the reference's own double divide, and the offset inside it (contract.h) */
+    const RayStart rst = make_ray_start(a, ox, oy, st, ct);
+    const int x0 = rst.x0, y0 = rst.y0;
     const bool start_in = (uint32_t)x0 < (uint32_t)a.W && (uint32_t)y0 < (uint32_t)a.H;
     /* padded field: cell (x, y) lives at (y+1)*row + (x+1); entry 0 is a ring cell (d = 0),
      * which makes an out-of-range start an immediate hit (the start cell is tested first) */
@@ -267,12 +268,11 @@ sensor_kernel(const SensorLaunch a) {
             c = fmaf(ct, cb, -(st * sb));
             s = fmaf(st, cb, ct * sb);
           }
-          /* sensor.clj:99-103 project-pose, map.clj:36-46 world->map */
-          const float ex_w = fmaf(a.R, c, ox), ey_w = fmaf(a.R, s, oy);
-          /* the cell of the end point (contract.h: float arithmetic, the reference's double computation next to a
-           * .5 boundary) — once, for the record look-up and for the computed set-up alike */
+          /* sensor.clj:99-103 project-pose, map.clj:36-46 world->map: the cell of the end point (contract.h: one
+           * float FMA per coordinate relative to the start cell, the reference's double computation next to a .5
+           * boundary) — once, for the record look-up and for the computed set-up alike */
           int x1, y1;
-          end_cell(a, rdv, ex_w, ey_w, ox, oy, th, jb, x1, y1);
+          end_cell(a, rdv, rst, c, s, ox, oy, th, jb, x1, y1);
           bool from_table = false;
           if (RS) {
             /* Everything sensor.clj:130-139 derives after the two roundings (steep?, the swaps, calc-step,
@@ -364,7 +364,7 @@ sensor_kernel(const SensorLaunch a) {
         for (int u = 0; u < (MODE == DF_WEDGE8 ? PROBES_PER_VOTE_WEDGE : PROBES_PER_VOTE); u++) {
           /* branch-free: a parked lane reads d = 0, which makes every update a no-op */
           if (DIAG && idx >= idx_limit) { n_oob++; idx = 0; } /* never taken: see tests */
-          const uint32_t d = df_probe<MODE>(df, idx, am);
+          const uint32_t d = df_probe_parked<MODE>(df, idx, am);
           if (DIAG) dg_probes += am ? 1 : 0;
           k += (int)d;
           const bool fin = d == 0 || k > kmax; /* blocked cell, or every cell to the end is free */
@@ -374,6 +374,7 @@ sensor_kernel(const SensorLaunch a) {
           err = e2 + (int)jd * ndx;
           j += (int)jd;
           idx += (uint32_t)((int)d * stepA + (int)jd * stepB);
+          if (BYTES && PARK_ON_ZERO) idx = fin ? 0u : idx; /* entry 0: d = 0 (df_probe_parked) */
           am = fin ? 0u : am;
         }
         act = __ballot_sync(FULL, am != 0);
@@ -495,6 +496,10 @@ static cudaError_t launch_t(const amclj_ctx *c, const SensorLaunch &a, cudaStrea
   size_t smem = (MODE == DF_SMEM4 ? a.df_bytes : 0) + (TS ? table_bytes(a) : 0) + (RS ? ring_bytes(a) : 0);
   if (smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  if (MODE != DF_SMEM4 && c->walk_carveout >= 0) { /* the rest of the SM's 256 KB serves the field as L1 */
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, c->walk_carveout > 100 ? 100 : c->walk_carveout);
     if (e != cudaSuccess) return e;
   }
   /* one CTA per SM (the staged field owns the SM's shared memory); warps sized to the work */

@@ -319,24 +319,35 @@ static void sincos_det_f64(double a, double *sn, double *cs) {
 
 ORACLE_API void amclj_oracle_sincos_f64(double a, double *sn, double *cs) { sincos_det_f64(a, sn, cs); }
 
-static int refine_fraction_bits(int32_t W, int32_t H, double rcells) {
-  double maxq = (double)(W > H ? W : H) + ceil(rcells) + 6.0;
-  int fb = 12;
-  while (fb > 4 && maxq >= ldexp(1.0, 22 - fb) - 2.0) fb--;
-  if (fb < 10) return 0; /* map + ray beyond ~4,000 cells per axis: plain float rounding (the contract's own limit) */
-  return fb;
+/* contract (csrc/contract.h, CellRefine): fraction bits of the relative end-cell arithmetic for a ray of R / res
+ * cells; 0 = no refinement (rays of 4,000 cells or more, odd resolutions): plain float rounding */
+static int refine_fraction_bits(float R, float res) {
+  double ar = fabs((double)R / (double)res);
+  if (!(ar < 4000.0) || !(res > 1.0e-6f && res < 1.0e6f)) return 0;
+  int fb = 14;
+  while (fb >= 8 && (ar + 3.0 >= ldexp(1.0, 22 - fb) || 3.1e-7 * (ar + 1.0) * ldexp(1.0, fb) > 0.9)) fb--;
+  return fb < 8 ? 0 : fb;
 }
 
-/* cell of one coordinate from its float quotient; *near = the double computation must decide */
-static int32_t cell_from_quotient(float q, int fb, int *near) {
+/* offset of the end cell from the start cell along one axis: u = fma(rc, c, fK); *near = the double computation
+ * must decide (u within two units of 2^-fb of a .5 boundary) */
+static int32_t offset_from_fma(float rc, float c, float fK, int fb, int *near) {
   float big = (float)ldexp(1.5, 23 - fb);
-  float K = big + 0.5f + (float)ldexp(1.0, 1 - fb);
-  float t = q + K;
+  float u = fmaf(rc, c, fK);
   uint32_t bits, bbig;
-  memcpy(&bits, &t, 4);
+  memcpy(&bits, &u, 4);
   memcpy(&bbig, &big, 4);
   if ((bits & ((1u << fb) - 4u)) == 0u) *near = 1;
   return (int32_t)((int32_t)bits >> fb) - (int32_t)(bbig >> fb);
+}
+
+/* start cell (the JVM's own double divide on the float32 input) and fK = float((v / res - cell) + K) */
+static int32_t start_cell_frac(float v, float res, float K, float *fK) {
+  double q = (double)v / (double)res;
+  double t = floor(q + 0.5);
+  t = fmin(fmax(t, -1.0e9), 1.0e9); /* NaN -> -1e9 */
+  *fK = (float)((q - t) + (double)K);
+  return (int32_t)t;
 }
 
 ORACLE_API void amclj_oracle_map_range_f32(const amclj_params *p, const int8_t *cells,
@@ -357,23 +368,23 @@ ORACLE_API void amclj_oracle_map_range_f32(const amclj_params *p, const int8_t *
     ox = nx;
     oy = ny;
   }
-  /* contract: the START cell is taken once per particle with the JVM's own double divide on the float32
-   * inputs (Math/round((double)x / (double)res), map.clj:36-46); end cells stay in float arithmetic */
-  int32_t x0 = (int32_t)round_cell_f64((double)ox, (double)res), y0 = (int32_t)round_cell_f64((double)oy, (double)res);
-  float ex = fmaf(R, c, ox), ey = fmaf(R, s, oy);
+  /* contract: the START cell is taken once per particle with the JVM's own double divide on the float32 inputs
+   * (Math/round((double)x / (double)res), map.clj:36-46); the END cell relative to it by one float FMA per axis,
+   * u = fma(R / res, c, (x / res - x0) + K), and by the reference's own double computation where u lies next to
+   * a .5 boundary.  A start off the map, a non-finite heading or a geometry without refinement keeps the plain
+   * float rounding of the absolute end point. */
+  int fb = refine_fraction_bits(R, res);
+  float K = fb ? (float)ldexp(1.5, 23 - fb) + 0.5f + (float)ldexp(1.0, 1 - fb) : 0.0f;
+  float fKx, fKy;
+  int32_t x0 = start_cell_frac(ox, res, K, &fKx), y0 = start_cell_frac(oy, res, K, &fKy);
   int32_t x1, y1;
-  int fb = (res > 1.0e-6f && res < 1.0e6f) ? refine_fraction_bits(W, H, fabs((double)R) / (double)res) : 0;
-  /* the window test: coordinates whose quotient fits the mantissa trick (NaN, inf and far-away starts do not) */
-  float vmax = fb ? (float)((double)res * (ldexp(1.0, 22 - fb) - 4.0)) : 0.0f;
-  if (fb && fabsf(ex) < vmax && fabsf(ey) < vmax) { /* NaN fails both */
+  int fast = fb && x0 >= 0 && x0 < W && y0 >= 0 && y0 < H &&
+             (!p->s1_use_heading || (fabsf(st) <= 1.001f && fabsf(ct) <= 1.001f)); /* a NaN heading fails */
+  if (fast) {
     int near = 0;
-    if (fb == 0) {
-      x1 = round_cell_f32(ex, res);
-      y1 = round_cell_f32(ey, res);
-    } else {
-      x1 = cell_from_quotient(ex / res, fb, &near);
-      y1 = cell_from_quotient(ey / res, fb, &near);
-    }
+    float rc = (float)((double)R / (double)res);
+    x1 = x0 + offset_from_fma(rc, c, fKx, fb, &near);
+    y1 = y0 + offset_from_fma(rc, s, fKy, fb, &near);
     if (near) { /* the reference's own computation from the same float32 inputs */
       double cd = cbd, sd = sbd;
       if (p->s1_use_heading) {
@@ -386,7 +397,8 @@ ORACLE_API void amclj_oracle_map_range_f32(const amclj_params *p, const int8_t *
       x1 = (int32_t)round_cell_f64(exd, (double)res);
       y1 = (int32_t)round_cell_f64(eyd, (double)res);
     }
-  } else { /* odd geometry: plain float rounding */
+  } else { /* plain float rounding of the end point */
+    float ex = fmaf(R, c, ox), ey = fmaf(R, s, oy);
     x1 = round_cell_f32(ex, res);
     y1 = round_cell_f32(ey, res);
   }
