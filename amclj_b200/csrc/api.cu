@@ -537,20 +537,30 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
     ctx->pin_tab = nullptr;
     CK(cudaMallocHost(&ctx->pin_tab, dbl_off + dbl_bytes));
     ctx->pin_tab_bytes = dbl_off + dbl_bytes;
+    ctx->beams.dirs_valid = false; /* a fresh staging buffer holds no directions */
   }
   CK(cudaEventSynchronize(ctx->ev[4])); /* the previous upload from this buffer has finished */
   /* float4 (obs, e2, p34, 0) first so that it stays 16-byte aligned for any beam count | float2 (cb, sb) */
   float *mix = reinterpret_cast<float *>(ctx->pin_tab), *dir = mix + 4 * (size_t)nb;
   double *dird = reinterpret_cast<double *>(reinterpret_cast<char *>(ctx->pin_tab) + dbl_off); /* near-tie refinement */
   float zshort = p.z_short, lam = p.lambda_short;
+  /* the beam directions depend on the scan geometry only: a laser sends the same one with every message, so the
+   * 2 x nb cos / sin calls and the upload of the double table happen when it changes (the pinned staging buffer
+   * and the device tables still hold the previous directions otherwise) */
+  BeamTable &bt = ctx->beams;
+  const bool same_dirs = bt.dirs_valid && bt.dirs_pin == ctx->pin_tab && bt.dirs_n == n && bt.dirs_step == step &&
+                         bt.dirs_nb == nb && memcmp(&bt.dirs_amin, &angle_min, 4) == 0 &&
+                         memcmp(&bt.dirs_ainc, &angle_inc, 4) == 0 && nb <= bt.cap;
   int j = 0;
   for (int i = 0; i < n; i += step, j++) {
-    /* sensor.clj:93-97 bearing: float32 message fields, double arithmetic */
-    double a = (double)angle_min + (double)i * (double)angle_inc;
-    dird[2 * j] = cos(a);
-    dird[2 * j + 1] = sin(a);
-    dir[2 * j] = (float)dird[2 * j];
-    dir[2 * j + 1] = (float)dird[2 * j + 1];
+    if (!same_dirs) {
+      /* sensor.clj:93-97 bearing: float32 message fields, double arithmetic */
+      double a = (double)angle_min + (double)i * (double)angle_inc;
+      dird[2 * j] = cos(a);
+      dird[2 * j + 1] = sin(a);
+      dir[2 * j] = (float)dird[2 * j];
+      dir[2 * j + 1] = (float)dird[2 * j + 1];
+    }
     float o = ranges ? ranges[i] : 0.0f;
     mix[4 * j] = o;
     mix[4 * j + 1] = zshort * lam * expf(-lam * o);            /* sensor.clj:154-157 */
@@ -578,8 +588,14 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
     CK(dalloc(&b.dev_d, (size_t)nb * 2));
     b.cap = nb;
   }
-  CK(cudaMemcpyAsync(b.dev, ctx->pin_tab, tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(b.dev_d, dird, dbl_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (same_dirs) { /* only the per-message part: (obs, e2, p34, 0) per beam */
+    CK(cudaMemcpyAsync(b.dev, ctx->pin_tab, sizeof(float) * (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    CK(cudaMemcpyAsync(b.dev, ctx->pin_tab, tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(b.dev_d, dird, dbl_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    b.dirs_valid = true; b.dirs_pin = ctx->pin_tab; b.dirs_n = n; b.dirs_step = step; b.dirs_nb = nb;
+    b.dirs_amin = angle_min; b.dirs_ainc = angle_inc;
+  }
   b.cr = make_cell_refine(R, ctx->map.res, ctx->exact_cells);
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   b.nb = nb;

@@ -57,10 +57,7 @@ __device__ __forceinline__ int motion_one(const MotionLaunch &a, int64_t i, floa
       ox = nx + fmaf(a.hist_laser_x, ct, -(a.hist_laser_y * st));
       oy = ny + fmaf(a.hist_laser_x, st, a.hist_laser_y * ct);
     }
-    const ResDiv rdv = make_resdiv(a.hist_res);
-    int x0, y0;
-    (void)rdv;
-    x0 = round_cell_start(ox, a.hist_res); y0 = round_cell_start(oy, a.hist_res);
+    const int x0 = round_cell_start(ox, a.hist_res), y0 = round_cell_start(oy, a.hist_res);
     const bool in = (uint32_t)x0 < (uint32_t)a.hist_W && (uint32_t)y0 < (uint32_t)a.hist_H;
     hkey = in ? __ldg(a.hist_slot_of_cell + (size_t)y0 * a.hist_W + x0) : a.hist_n_slots;
     a.hist_pkey[i] = hkey;

@@ -38,6 +38,11 @@ struct BeamTable {       // float4 mix[nb] = (obs, e2, p34, 0) then float2 dir[n
   int32_t n_scan = 0;
   float angle_min = 0, angle_inc = 0, range_max = 0;
   bool staged = false;
+  /* what the staged directions were computed from (stage_scan recomputes them only when this changes) */
+  bool dirs_valid = false;
+  const void *dirs_pin = nullptr;
+  int32_t dirs_n = 0, dirs_step = 0, dirs_nb = 0;
+  float dirs_amin = 0, dirs_ainc = 0;
 };
 
 struct DivTable {        // magic reciprocals for the Bresenham minor-axis division
@@ -210,7 +215,7 @@ struct PersistentTables {
   int32_t nbuf = 0;                // table buffers per warp requested (0: one, so that more warps fit; AMCLJ_PT_NBUF)
   int32_t nbuf_used = 1, warps_req = 0;
   int32_t tail_pct = 15;           // AMCLJ_PT_TAIL_PCT (measured: 0 -> 1.046, 15 -> 0.994, 30 -> 1.014 ms on the C4 share)
-  bool fuse_motion = false;        // AMCLJ_PT_FUSE_MOTION=1: the motion kernel takes the sort's histogram pass along
+  bool fuse_motion = true;         // the motion kernel takes the sort's histogram pass along (AMCLJ_PT_FUSE_MOTION=0: pt_hist_kernel)
   bool hist_done = false;          // ... and did so for the update in progress
   int32_t rows32 = 1;              // AMCLJ_PT_ROWS32
   unsigned long long *scan_state = nullptr;  // bin scan ticket + tile descriptors
