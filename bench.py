@@ -488,6 +488,7 @@ def run_b200(args):
                     "rays_per_launch": n_rays, "rays_per_s": n_rays / (k_ms * 1e-3),
                     "scheduler_cycles_per_ray": (k_ms * 1e-3) * issue_peak / n_rays,
                     "reference_cells_per_ray": sd.cells_visited / max(sd.rays, 1),
+                    "field_probes_per_ray": sd.probes / max(sd.rays, 1),
                     "reference_cells_per_s": (sd.cells_visited / max(sd.rays, 1)) * n_rays / (k_ms * 1e-3),
                     "hit_fraction": sd.hits / max(sd.rays, 1),
                     "hbm": hbm,
