@@ -50,7 +50,7 @@ constexpr int mode_threads(int mode) {
 constexpr int mode_ctas(int mode) { return mode == DF_WEDGE8 ? WEDGE_CTAS : (mode == DF_SMEM4 ? 1 : GLOBAL_CTAS); }
 template <int MODE, bool DIAG, bool WIDE, bool TS, bool RS>
 __global__ void __launch_bounds__(mode_threads(MODE), mode_ctas(MODE))
-sensor_kernel(const SensorLaunch a) {
+sensor_kernel(const __grid_constant__ SensorLaunch a) {
   extern __shared__ uint4 smem_dyn[];
   __shared__ uint64_t bar;
   if (a.skip_flag && *a.skip_flag == 1) return; /* a dense cloud: the ray tables took this update (raytable.cu) */
