@@ -157,6 +157,11 @@ def lib():
                                           C.c_int32, C.c_float, C.c_float, C.c_float, f64p,
                                           f64p, f64p, C.c_int64, f64p, C.POINTER(SensorStats),
                                           C.c_int32]
+    L.amclj_oracle_rays_f64.argtypes = [PP, i8p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_float,
+                                        C.c_float, C.c_float, f64p, f64p, f64p, C.c_int64,
+                                        np.ctypeslib.ndpointer(np.int32, flags="C"),
+                                        np.ctypeslib.ndpointer(np.uint8, flags="C"),
+                                        np.ctypeslib.ndpointer(np.float64, flags="C"), C.c_int32]
     L.amclj_oracle_sensor_f32.argtypes = [PP, i8p, C.c_int32, C.c_int32, C.c_float, f32p,
                                           C.c_int32, C.c_float, C.c_float, C.c_float, f32p,
                                           f32p, f32p, C.c_int64, C.c_void_p, C.c_void_p,
@@ -256,6 +261,19 @@ def sensor_f64(p, grid, ranges, angle_min, angle_inc, range_max, x, y, theta, th
                                   angle_inc, range_max, x, y, theta, len(x), raw, C.byref(st),
                                   threads)
     return raw, st
+
+
+def rays_f64(p, grid, n_scan, angle_min, angle_inc, range_max, x, y, theta, threads=0):
+    """Per-ray view of the double restatement: (steps, hit, range_m), each [len(x)][beams_used]."""
+    cells, W, H, res = _grid(grid)
+    x, y, theta = (np.ascontiguousarray(a, np.float64) for a in (x, y, theta))
+    nb = lib().amclj_oracle_beams_used(int(n_scan), p.s6_max_beams)
+    steps = np.zeros((len(x), nb), np.int32)
+    hit = np.zeros((len(x), nb), np.uint8)
+    rng = np.zeros((len(x), nb), np.float64)
+    lib().amclj_oracle_rays_f64(C.byref(p), cells, W, H, res, int(n_scan), angle_min, angle_inc, range_max,
+                                x, y, theta, len(x), steps, hit, rng, threads)
+    return steps, hit, rng
 
 
 def sensor_f32(p, grid, ranges, angle_min, angle_inc, range_max, x, y, theta, debug=False,

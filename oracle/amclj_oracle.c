@@ -465,6 +465,34 @@ ORACLE_API void amclj_oracle_sensor_f64(const amclj_params *p, const int8_t *cel
   }
 }
 
+/* Per-ray view of the double restatement (sensor.clj:130-139 as the JVM computes it from float32-valued poses):
+ * hit flag, steps and range of every used beam of every particle, [np][beams_used].  For the tests that hold the
+ * fp32 contract (and the CUDA path) to "casts the same rays as the double path" over millions of rays. */
+ORACLE_API void amclj_oracle_rays_f64(const amclj_params *p, const int8_t *cells, int32_t W, int32_t H,
+                                      float res, int32_t n, float angle_min, float angle_inc,
+                                      float range_max, const double *x, const double *y,
+                                      const double *theta, int64_t np, int32_t *steps, uint8_t *hit,
+                                      double *range_m, int32_t threads) {
+  int32_t step = amclj_oracle_beam_step(n, p->s6_max_beams);
+  int32_t nb = amclj_oracle_beams_used(n, p->s6_max_beams);
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+#endif
+  for (int64_t ip = 0; ip < np; ip++) {
+    int32_t j = 0;
+    for (int32_t i = 0; i < n; i += step, j++) {
+      double bearing = (double)angle_min + (double)i * (double)angle_inc;
+      oracle_ray ray;
+      amclj_oracle_map_range_f64(p, cells, W, H, res, x[ip], y[ip], theta[ip], bearing, (double)range_max, &ray);
+      int64_t o = ip * nb + j;
+      if (steps) steps[o] = ray.steps;
+      if (hit) hit[o] = (uint8_t)ray.hit;
+      if (range_m) range_m[o] = ray.range;
+    }
+  }
+}
+
 /* fp32 contract.  Optional per-ray outputs, [np][beams_used]. */
 ORACLE_API void amclj_oracle_sensor_f32(const amclj_params *p, const int8_t *cells, int32_t W,
                                         int32_t H, float res, const float *ranges, int32_t n,

@@ -88,6 +88,27 @@ def test_production_lookup_ranges_c2_dense_cloud(lg):
         _ranges_vs_oracle(c, lg, w.x, w.y, w.theta, w.scan, "NS", first=40_000, count=2000)
 
 
+@pytest.mark.parametrize("which", ["c2", "c3"])
+def test_production_lookup_casts_the_rays_of_the_double_path(lg, which):
+    """The ranges the production look-up kernel reads, against the DOUBLE restatement of the Clojure ray by ray
+    (oracle.rays_f64) — 40,000 particles x 360 beams = 14.4 M rays per cloud: every hit range equal up to float
+    rounding of hypot * res, every miss exact.  A ray cast to a different cell would show as a range off by about
+    a cell (0.05 m) or as a hit turned miss; csrc/contract.h's error budget says there is none."""
+    w = workloads.c2(40_000) if which == "c2" else workloads.c3(40_000)
+    s = w.scan
+    with _lib.Context(0) as c:
+        c.set_params(_lib.params("NS", df_mode=7))
+        c.set_map(lg)
+        c.set_particles(w.x, w.y, w.theta)
+        dbg = c.raycast_debug(len(s.ranges), s.angle_min, s.angle_inc, s.range_max)
+        assert c.stats().table_misses == 0
+    _, _, rng = oracle.rays_f64(oracle.params("NS"), lg, len(s.ranges), s.angle_min, s.angle_inc, s.range_max,
+                                w.x, w.y, w.theta)
+    diff = np.abs(dbg["range_m"].astype(np.float64) - rng)
+    bad = np.argwhere(diff > 2e-6)
+    assert len(bad) == 0, f"{len(bad)} of {diff.size} rays differ from the double path, first {bad[:4].tolist()}, max {diff.max()}"
+
+
 @pytest.mark.parametrize("switches", [
     dict(s1_use_heading=0), dict(s3_proper_endpoint=0), dict(s4_endpoint_termination=0),
     dict(s2_use_scan_range_max=0), dict(s10_apply_laser_offset=1),
