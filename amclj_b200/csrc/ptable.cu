@@ -225,12 +225,22 @@ __device__ __forceinline__ uint32_t lds_u1(uint32_t addr) {
 /* exact end cells (contract.h) of those of the beams jb, jb + 1 whose float offset lies next to a .5 boundary
  * (which & 1, which & 2), as (offset x, ring row) like the fast half; out of line and once per PAIR of beams, so
  * that the hot loop below stays two straight-line halves.  psd: {(sin, cos) of the heading, ray origin}. */
-static __device__ __noinline__ int4 pt_exact_pair(const SensorLaunch &a, double rinv_d, const double2 *psd, int E, int jb,
+#ifdef AMCLJ_PT_EXACT_INLINE
+#define PT_EXACT_ATTR __forceinline__
+#else
+#define PT_EXACT_ATTR __noinline__
+#endif
+static __device__ PT_EXACT_ATTR int4 pt_exact_pair(const SensorLaunch &a, const PtLaunch &L, const double2 *psd, int slot, int jb,
                                                   int which, int4 cells) {
+  const double rinv_d = L.rinv_d;
+  const int E = L.E;
   const double2 hd = __ldg(psd); /* S1 off: (0, 1), which gives back (cb, sb) */
   const double2 od = __ldg(psd + 1);
   const double Rd = (double)a.R, res = (double)a.res;
-  const int x0 = round_cell_start((float)od.x, a.res), y0 = round_cell_start((float)od.y, a.res);
+  /* the start cell: the table's own cell (the sort put the particle there by round_cell_start of the same origin);
+   * a particle on the zero table — off the map or on a blocked cell — reads 0 whatever entry it asks for */
+  const int2 c0 = slot < L.n_slots ? __ldg(L.cell_of_slot + slot) : make_int2(0, 0);
+  const int x0 = c0.x, y0 = c0.y;
 #pragma unroll
   for (int u = 0; u < 2; u++) {
     if (!(which & (1 << u))) continue;
@@ -243,35 +253,74 @@ static __device__ __noinline__ int4 pt_exact_pair(const SensorLaunch &a, double 
   return cells;
 }
 
+// ---- packed fp32 (sm_100a FFMA2 / FMUL2 / FADD2: two IEEE round-to-nearest operations per issue slot) ----------
+// The look-up kernel is bound by instruction issue, and its beams go in pairs anyway: the float arithmetic of the
+// two beams of a pair rides in one instruction each.  Every lane of an .f32x2 operation rounds exactly like the
+// scalar operation (no fusing, no flush-to-zero), so the results stay bit-identical to sensor.cu / raytable.cu.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+  return v;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void upk2i(f32x2 v, int &lo, int &hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void lds_2x64(uint32_t addr, f32x2 &a, f32x2 &b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ f32x2 lds_64(uint32_t addr) {
+  f32x2 a;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(a) : "r"(addr));
+  return a;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x)); /* the instruction of hit_gauss */
+  return e;
+}
+
 // One 30-beam segment of one particle, every range from the staged table of its start cell.  Beams go in
-// pairs: [end cells of both, float arithmetic] -> [one test: is either next to a .5 boundary? then both are
-// re-taken in double, out of line] -> [ring index, table entry, beam mixture of both].  Each half is
-// straight-line, so the compiler pairs the two beams' instructions as it did before the refinement.
+// pairs: [end cells of both, packed float arithmetic] -> [one test: is either next to a .5 boundary? then both are
+// re-taken in double, out of line] -> [ring index and table entry of each, packed beam mixture of both].  Each half is
+// straight-line.  The beam constants are staged per PAIR of beams (pt_lookup_kernel): s_dir float4 (cos a, cos b,
+// sin a, sin b), s_mixa float4 (obs a, obs b, e2 a, e2 b), s_mixb float2 (p34 a, p34 b); jb0 is even (SEG is).
 template <bool S7, bool DBG, bool R32>
-__device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunch &L, uint32_t s_tab, uint32_t s_mix,
-                                            uint32_t s_dir, uint32_t s_rows, float fKx, float fKy, float st, float ct,
-                                            const double2 *psd, int jb0, int jb1, float *dbg_row) {
+__device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunch &L, uint32_t s_tab, uint32_t s_mixa,
+                                            uint32_t s_mixb, uint32_t s_dir, uint32_t s_rows, float fKx, float fKy, float st,
+                                            float ct, const double2 *psd, int slot, int jb0, int jb1, float *dbg_row) {
   float acc = 0.0f, prod = 1.0f;
   int pexp = 0;
   const uint32_t last_row = (uint32_t)L.nrows - 1u, nan_entry = (uint32_t)L.n_entries - 1u;
   /* S1 off = rotation by zero: fma(1, cb, -(0 * sb)) and fma(0, cb, 1 * sb) give back (cb, sb) */
-  float rc = a.s1 ? ct : 1.0f, rs = a.s1 ? st : 0.0f;
-  asm volatile("" : "+f"(rc), "+f"(rs)); /* kept in registers: left alone, the selection is redone for every pair of beams */
+  const float rc = a.s1 ? ct : 1.0f, rs = a.s1 ? st : 0.0f;
+  f32x2 rc2 = pk2(rc, rc), rs2 = pk2(rs, rs), nrs2 = pk2(-rs, -rs), fKx2 = pk2(fKx, fKx), fKy2 = pk2(fKy, fKy);
+  asm volatile("" : "+l"(rc2), "+l"(rs2), "+l"(nrs2), "+l"(fKx2), "+l"(fKy2)); /* kept as pairs: not rebuilt per pair of beams */
   const CellRefine cr = a.cr;
+  const f32x2 rcell2 = pk2(cr.rc, cr.rc), nk2 = pk2(-a.k2, -a.k2);
   const int coff_row = cr.coff - L.E; /* ring rows start at offset -E */
 
-  /* first half: sensor.clj:130-135 / map.clj:36-46, the end cell relative to the start cell — one FMA per
-   * coordinate (contract.h) — as (offset x, ring row); returns the low mantissa bits the near-tie test looks at */
-  auto cells = [&](int jb, int &ex, int &ry) -> uint32_t {
-    const float2 bd = lds_f2(s_dir + (uint32_t)jb * 8u);
-    const float c = fmaf(rc, bd.x, -(rs * bd.y)), s = fmaf(rs, bd.x, rc * bd.y); /* S1: angle addition */
-    const int ux = __float_as_int(fmaf(cr.rc, c, fKx)), uy = __float_as_int(fmaf(cr.rc, s, fKy));
-    ex = (ux >> cr.fb) - cr.coff;
-    ry = (uy >> cr.fb) - coff_row;
-    return min((uint32_t)ux & cr.mask, (uint32_t)uy & cr.mask); /* 0: next to a .5 boundary */
-  };
-  /* second half: ring entry of the end cell, range from the table, sensor.clj:149-162 beam mixture */
-  auto score = [&](int jb, int ex, int ryi) {
+  /* second half, per beam: ring entry of the end cell (offset ex, ring row ryi) -> range from the table */
+  auto range_of = [&](int ex, int ryi) -> float {
     const uint32_t ry = (uint32_t)ryi;
     const uint32_t ryc = min(ry, R32 ? last_row + 1u : last_row);
     uint32_t r_base, r_lo, r_cnt; /* the row's first entry, first |ex|, entries per arc (the negative arc follows the positive) */
@@ -285,57 +334,77 @@ __device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunc
     const uint32_t tt = (uint32_t)abs(ex) - r_lo;
     const bool ok = R32 ? tt < r_cnt : (tt < r_cnt && ry <= last_row);
     const uint32_t ent = ok ? r_base + tt + (ex < 0 ? r_cnt : 0u) : nan_entry;
-    const float rng = lds_f1(s_tab + ent * 4u);
-    if (DBG && dbg_row) dbg_row[jb] = rng;
-    const float4 mx = lds_f4(s_mix + (uint32_t)jb * 16u);
-    const float z = mx.x - rng;
-    const float pz1 = hit_gauss(z, a.k2, a.z_hit);
-    const float pz2 = z < 0.0f ? mx.y : 0.0f;
-    const float sum = (pz1 + pz2) + mx.z;
-    if (S7) logprod_mul(acc, prod, pexp, sum);
-    else acc += (sum * sum) * sum;
+    return lds_f1(s_tab + ent * 4u);
   };
 
   int jb = jb0;
-#ifdef AMCLJ_PT_OUTLOOP_EXACT
-  /* variant: the hot loop holds no call — a pair with a beam next to a .5 boundary leaves it, is finished out of
-   * line and the loop is entered again.  Fewer instructions (the compiler unrolls it to four beams: 46.8 per beam
-   * against 50) but measured slower on B200: look-up kernel 1.116 against 1.046 ms on the C4 share; kept for A/B */
-  for (;;) {
-    int xa = 0, ya = 0, xb = 0, yb = 0;
-    uint32_t na = 1u, nb = 1u;
-    bool near = false;
-    for (; jb + 1 < jb1; jb += 2) {
-      na = cells(jb, xa, ya); nb = cells(jb + 1, xb, yb);
-      if (min(na, nb) == 0u) { near = true; break; }
-      score(jb, xa, ya);
-      score(jb + 1, xb, yb);
-    }
-    if (!near) break;
-    const int4 e = pt_exact_pair(a, L.rinv_d, psd, L.E, jb, (na == 0u ? 1 : 0) | (nb == 0u ? 2 : 0), make_int4(xa, ya, xb, yb));
-    score(jb, e.x, e.y);
-    score(jb + 1, e.z, e.w);
-    jb += 2;
-  }
-#else
   for (; jb + 1 < jb1; jb += 2) {
-    int xa, ya, xb, yb;
-    const uint32_t na = cells(jb, xa, ya), nb = cells(jb + 1, xb, yb);
+    const uint32_t k = (uint32_t)jb >> 1;
+    /* first half: sensor.clj:130-135 / map.clj:36-46, the end cells relative to the start cell — one FMA per
+     * coordinate (contract.h) — as (offset x, ring row) */
+    f32x2 C, S;
+    lds_2x64(s_dir + k * 16u, C, S);
+    const f32x2 cd = fma2(rc2, C, mul2(nrs2, S)); /* S1: angle addition, c = fma(rc, cb, -(rs * sb)) */
+    const f32x2 sd = fma2(rs2, C, mul2(rc2, S));  /*                     s = fma(rs, cb, rc * sb)    */
+    int uxa, uxb, uya, uyb;
+    upk2i(fma2(rcell2, cd, fKx2), uxa, uxb);
+    upk2i(fma2(rcell2, sd, fKy2), uya, uyb);
+    int xa = (uxa >> cr.fb) - cr.coff, ya = (uya >> cr.fb) - coff_row;
+    int xb = (uxb >> cr.fb) - cr.coff, yb = (uyb >> cr.fb) - coff_row;
+    const uint32_t na = min((uint32_t)uxa & cr.mask, (uint32_t)uya & cr.mask); /* 0: next to a .5 boundary */
+    const uint32_t nb = min((uint32_t)uxb & cr.mask, (uint32_t)uyb & cr.mask);
     if (min(na, nb) == 0u) { /* 0.1 % of the pairs at fb = 14 */
-      const int4 e = pt_exact_pair(a, L.rinv_d, psd, L.E, jb, (na == 0u ? 1 : 0) | (nb == 0u ? 2 : 0), make_int4(xa, ya, xb, yb));
+      const int4 e = pt_exact_pair(a, L, psd, slot, jb, (na == 0u ? 1 : 0) | (nb == 0u ? 2 : 0), make_int4(xa, ya, xb, yb));
       xa = e.x; ya = e.y; xb = e.z; yb = e.w;
     }
-    score(jb, xa, ya);
-    score(jb + 1, xb, yb);
+    /* second half: ranges from the table, sensor.clj:149-162 beam mixture of both */
+    const float rga = range_of(xa, ya), rgb = range_of(xb, yb);
+    if (DBG && dbg_row) { dbg_row[jb] = rga; dbg_row[jb + 1] = rgb; }
+    f32x2 OBS, E2;
+    lds_2x64(s_mixa + k * 16u, OBS, E2);
+    const f32x2 P34 = lds_64(s_mixb + k * 8u);
+    const f32x2 Z = sub2(OBS, pk2(rga, rgb));
+    float za, zb, ta, tb, e2a, e2b;
+    upk2(Z, za, zb);
+    upk2(mul2(mul2(Z, Z), nk2), ta, tb); /* -(z * z) * k2 */
+    upk2(E2, e2a, e2b);
+    /* z_hit * e stays scalar: ptxas (12.9) contracts a packed multiply that feeds a packed add into one FFMA2 —
+     * whatever --fmad and the .rn modifiers say — and a fused (z_hit * e + pz2) would round differently from the
+     * other sensor paths; no other packed product here feeds a sum */
+    const f32x2 PZ1 = pk2(a.z_hit * ex2_approx(ta), a.z_hit * ex2_approx(tb));
+    const f32x2 PZ2 = pk2(za < 0.0f ? e2a : 0.0f, zb < 0.0f ? e2b : 0.0f);
+    const f32x2 SUM = add2(add2(PZ1, PZ2), P34);
+    float sa, sb;
+    if (S7) {
+      upk2(SUM, sa, sb);
+      logprod_mul(acc, prod, pexp, sa);
+      logprod_mul(acc, prod, pexp, sb);
+    } else {
+      upk2(mul2(mul2(SUM, SUM), SUM), sa, sb);
+      acc += sa;
+      acc += sb;
+    }
   }
-#endif
-  if (jb < jb1) { /* a last segment with an odd number of beams */
-    int xa, ya;
-    if (cells(jb, xa, ya) == 0u) {
-      const int4 e = pt_exact_pair(a, L.rinv_d, psd, L.E, jb, 1, make_int4(xa, ya, 0, 0));
+  if (jb < jb1) { /* a last segment with an odd number of beams: the first half of its pair */
+    const uint32_t k = (uint32_t)jb >> 1;
+    const float4 bd = lds_f4(s_dir + k * 16u);
+    const float c = fmaf(rc, bd.x, -(rs * bd.z)), s = fmaf(rs, bd.x, rc * bd.z);
+    const int ux = __float_as_int(fmaf(cr.rc, c, fKx)), uy = __float_as_int(fmaf(cr.rc, s, fKy));
+    int xa = (ux >> cr.fb) - cr.coff, ya = (uy >> cr.fb) - coff_row;
+    if (min((uint32_t)ux & cr.mask, (uint32_t)uy & cr.mask) == 0u) {
+      const int4 e = pt_exact_pair(a, L, psd, slot, jb, 1, make_int4(xa, ya, 0, 0));
       xa = e.x; ya = e.y;
     }
-    score(jb, xa, ya);
+    const float rng = range_of(xa, ya);
+    if (DBG && dbg_row) dbg_row[jb] = rng;
+    const float4 ma = lds_f4(s_mixa + k * 16u);
+    const float2 mb = lds_f2(s_mixb + k * 8u);
+    const float z = ma.x - rng;
+    const float pz1 = hit_gauss(z, a.k2, a.z_hit);
+    const float pz2 = z < 0.0f ? ma.z : 0.0f;
+    const float sum = (pz1 + pz2) + mb.x;
+    if (S7) logprod_mul(acc, prod, pexp, sum);
+    else acc += (sum * sum) * sum;
   }
   return S7 ? logprod_close(acc, prod, pexp) : acc;
 }
@@ -373,16 +442,27 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
   __shared__ uint64_t bars[PT_MAX_WARPS][2];
   const int nb = a.nb, nseg = (nb + SEG - 1) / SEG;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  /* [mix float4[nb] | rows uint4[nrows] | dir float2[nb] | pad to 16 | per warp: 2 tables of stride floats] */
-  float4 *smix = reinterpret_cast<float4 *>(smem_dyn);
-  uint4 *srows = reinterpret_cast<uint4 *>(smix + nb);
-  float2 *sdir = reinterpret_cast<float2 *>(srows + L.nrows);
-  float *stab = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(sdir + nb) + 15) & ~(uintptr_t)15) +
+  /* beam constants per PAIR of beams (pt_segment's packed arithmetic):
+   * [mixa float4[np] (obs a, obs b, e2 a, e2 b) | dir float4[np] (cos a, cos b, sin a, sin b) | rows uint4[nrows] |
+   *  mixb float2[np] (p34 a, p34 b) | pad to 16 | per warp: nbuf tables of stride floats] */
+  const int np = (nb + 1) >> 1;
+  float4 *smixa = reinterpret_cast<float4 *>(smem_dyn);
+  float4 *sdir = smixa + np;
+  uint4 *srows = reinterpret_cast<uint4 *>(sdir + np);
+  float2 *smixb = reinterpret_cast<float2 *>(srows + L.nrows);
+  float *stab = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(smixb + np) + 15) & ~(uintptr_t)15) +
                 (size_t)wid * L.nbuf * L.stride;
   {
     const float4 *mixt = reinterpret_cast<const float4 *>(a.beam);
     const float2 *dirt = reinterpret_cast<const float2 *>(a.beam + 4 * (size_t)nb);
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) { smix[i] = __ldg(mixt + i); sdir[i] = __ldg(dirt + i); }
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+      const int ja = 2 * i, jc = min(2 * i + 1, nb - 1); /* an odd beam count: the last pair repeats its first half (never read) */
+      const float4 ma = __ldg(mixt + ja), mb = __ldg(mixt + jc);
+      const float2 da = __ldg(dirt + ja), db = __ldg(dirt + jc);
+      smixa[i] = make_float4(ma.x, mb.x, ma.y, mb.y);
+      smixb[i] = make_float2(ma.z, mb.z);
+      sdir[i] = make_float4(da.x, db.x, da.y, db.y);
+    }
     if (L.rows32) {
       uint32_t *srows32 = reinterpret_cast<uint32_t *>(srows);
       for (int i = threadIdx.x; i < L.nrows; i += blockDim.x) {
@@ -394,8 +474,8 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
       for (int i = threadIdx.x; i < L.nrows; i += blockDim.x) srows[i] = __ldg(L.rows + i);
     }
   }
-  uint32_t s_mix = smem_u32(smix), s_dir = smem_u32(sdir), s_rows = smem_u32(srows);
-  asm volatile("" : "+r"(s_mix), "+r"(s_dir), "+r"(s_rows));
+  uint32_t s_mixa = smem_u32(smixa), s_mixb = smem_u32(smixb), s_dir = smem_u32(sdir), s_rows = smem_u32(srows);
+  asm volatile("" : "+r"(s_mixa), "+r"(s_mixb), "+r"(s_dir), "+r"(s_rows));
   const uint32_t s_tab0 = smem_u32(stab), tab_bytes = (uint32_t)L.stride * 4u;
   const uint32_t bar0 = smem_u32(&bars[wid][0]);
   if (lane == 0) {
@@ -506,11 +586,11 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
         dbg_row = a.dbg_range + (p - a.dbg_first) * nb;
       float v;
       if (L.rows32)
-        v = a.s7 ? pt_segment<true, DBG, true>(a, L, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + 2 * (size_t)pos, jb0, jb1, dbg_row)
-                 : pt_segment<false, DBG, true>(a, L, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + 2 * (size_t)pos, jb0, jb1, dbg_row);
+        v = a.s7 ? pt_segment<true, DBG, true>(a, L, s_tab, s_mixa, s_mixb, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + 2 * (size_t)pos, c_slot, jb0, jb1, dbg_row)
+                 : pt_segment<false, DBG, true>(a, L, s_tab, s_mixa, s_mixb, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + 2 * (size_t)pos, c_slot, jb0, jb1, dbg_row);
       else
-        v = a.s7 ? pt_segment<true, DBG, false>(a, L, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + 2 * (size_t)pos, jb0, jb1, dbg_row)
-                 : pt_segment<false, DBG, false>(a, L, s_tab, s_mix, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + 2 * (size_t)pos, jb0, jb1, dbg_row);
+        v = a.s7 ? pt_segment<true, DBG, false>(a, L, s_tab, s_mixa, s_mixb, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + 2 * (size_t)pos, c_slot, jb0, jb1, dbg_row)
+                 : pt_segment<false, DBG, false>(a, L, s_tab, s_mixa, s_mixb, s_dir, s_rows, ps.x, ps.y, ps.z, ps.w, L.pstate_d + 2 * (size_t)pos, c_slot, jb0, jb1, dbg_row);
       if (v != v) {
         const double2 od = __ldg(L.pstate_d + 2 * (size_t)pos + 1); /* the ray origin (float values, kept as doubles) */
         v = pt_segment_walk<MODE, WIDE>(a, (float)od.x, (float)od.y, __ldg(a.th + p), jb0, jb1, dbg_row);
@@ -552,22 +632,44 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
   }
 }
 
-// raw[p] = the fixed-point sum of the particle's segments as a float, plus the max for the normaliser
-__global__ void __launch_bounds__(256)
+// raw[p] = the fixed-point sum of the particle's segments as a float, plus the max for the normaliser.  Four
+// particles per thread (two 128-bit loads, one 128-bit store) and ONE atomic per CTA: one atomicMax per warp on
+// the same word (39,000 of them for 1.25 M particles) was most of this kernel's 28 us.
+constexpr int PT_FIN_THREADS = 256, PT_FIN_ITEMS = 4;
+__global__ void __launch_bounds__(PT_FIN_THREADS)
 pt_finish_kernel(const long long *__restrict__ qacc, int64_t n, float *__restrict__ raw, uint32_t *rawmax_ord) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  float v = -INFINITY;
-  if (i < n) {
-    v = fixed_to_raw(__ldg(qacc + i));
-    if (raw) raw[i] = v;
-  }
+  __shared__ float warp_max[PT_FIN_THREADS / 32];
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PT_FIN_ITEMS;
+  float v[PT_FIN_ITEMS];
+  if (i0 + PT_FIN_ITEMS <= n) {
+    const longlong2 q0 = __ldg(reinterpret_cast<const longlong2 *>(qacc + i0));
+    const longlong2 q1 = __ldg(reinterpret_cast<const longlong2 *>(qacc + i0) + 1);
+    v[0] = fixed_to_raw(q0.x); v[1] = fixed_to_raw(q0.y); v[2] = fixed_to_raw(q1.x); v[3] = fixed_to_raw(q1.y);
+    if (raw) *reinterpret_cast<float4 *>(raw + i0) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
-  if ((threadIdx.x & 31) == 0 && rawmax_ord && v > -INFINITY) atomicMax(rawmax_ord, ord_of_float(v));
+    for (int k = 0; k < PT_FIN_ITEMS; k++) {
+      v[k] = -INFINITY;
+      if (i0 + k < n) {
+        v[k] = fixed_to_raw(__ldg(qacc + i0 + k));
+        if (raw) raw[i0 + k] = v[k];
+      }
+    }
+  }
+  float m = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+  if ((threadIdx.x & 31) == 0) warp_max[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0 && rawmax_ord) {
+#pragma unroll
+    for (int k = 1; k < PT_FIN_THREADS / 32; k++) m = fmaxf(m, warp_max[k]);
+    if (m > -INFINITY) atomicMax(rawmax_ord, ord_of_float(m));
+  }
 }
 
 size_t pt_lookup_smem(const PtLaunch &L, int warps) {
-  return (size_t)L.s.nb * 24 + (size_t)L.nrows * 16 + 16 + (size_t)warps * L.nbuf * L.stride * 4;
+  return (size_t)((L.s.nb + 1) / 2) * 40 + (size_t)L.nrows * 16 + 32 + (size_t)warps * L.nbuf * L.stride * 4;
 }
 int pt_max_warps() { return PT_MAX_WARPS; }
 
@@ -627,7 +729,10 @@ cudaError_t launch_pt_update(const amclj_ctx *c, const PtLaunch &L, int mode, bo
     default: e = launch_pt_lookup_m<DF_GLOBAL4>(c, L, wide, dbg, s); break;
   }
   if (e != cudaSuccess) return e;
-  if (!L.fuse_finish) pt_finish_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(L.qacc, a.n, a.raw, a.rawmax_ord);
+  if (!L.fuse_finish) {
+    const int64_t per_cta = (int64_t)PT_FIN_THREADS * PT_FIN_ITEMS;
+    pt_finish_kernel<<<(unsigned)((a.n + per_cta - 1) / per_cta), PT_FIN_THREADS, 0, s>>>(L.qacc, a.n, a.raw, a.rawmax_ord);
+  }
   return cudaGetLastError();
 }
 
