@@ -39,7 +39,7 @@ SYMBOLS = [
     "amclj_shard_motion_sensor_async", "amclj_shard_cdf_async", "amclj_shard_generate_async",
     "amclj_shard_get_stage_idx", "amclj_shard_adopt_async", "amclj_plan_systematic",
     "amclj_device_ptr", "amclj_reserve_stage", "amclj_shard_export", "amclj_shard_import",
-    "amclj_shard_attach_local", "amclj_shard_pull_async", "amclj_shard_update_async", "amclj_shard_update_host",
+    "amclj_shard_attach_local", "amclj_shard_pull_async", "amclj_shard_update_async", "amclj_shard_update_host", "amclj_shard_rendezvous_async", "amclj_host_register", "amclj_host_unregister",
     "amclj_create_multi", "amclj_destroy_multi", "amclj_multi_size", "amclj_multi_ctx", "amclj_mlast_error",
     "amclj_mset_params", "amclj_mset_map", "amclj_mset_particles", "amclj_mget_particles", "amclj_mnum_particles",
     "amclj_minit_uniform", "amclj_mstage_scan", "amclj_mfilter_update_async", "amclj_mfilter_update_host",
@@ -161,6 +161,9 @@ def lib():
         "amclj_shard_attach_local": ([vp, i32, vp], i32),
         "amclj_shard_pull_async": ([vp, f64], i32),
         "amclj_shard_update_async": ([vp, d3, d3, u64, f64], i32),
+        "amclj_shard_rendezvous_async": ([vp], i32),
+        "amclj_host_register": ([vp, vp, i64], i32),
+        "amclj_host_unregister": ([vp, vp], i32),
         "amclj_shard_update_host": ([vp, vp, vp, vp, vp, i64, d3, d3, u64, vp, i32, f32, f32, f32, f64], i32),
         "amclj_create_multi": ([vp, i32, C.POINTER(vp)], i32),
         "amclj_destroy_multi": ([vp], i32),
@@ -482,6 +485,17 @@ class Context:
     def shard_update_async(self, curr, prev, seed, u0):
         """The whole sharded update in one call: exchanges through peer-memory mailboxes, no collective library."""
         self._ck(self._L.amclj_shard_update_async(self._h, _d3(curr), _d3(prev), int(seed), float(u0)))
+
+    def host_register(self, arr):
+        """Page-lock a caller-owned numpy buffer for the *_host calls (what the JNA shim does with its Memory)."""
+        self._ck(self._L.amclj_host_register(self._h, _vp(arr), int(arr.nbytes)))
+
+    def host_unregister(self, arr):
+        self._ck(self._L.amclj_host_unregister(self._h, _vp(arr)))
+
+    def shard_rendezvous_async(self):
+        """Device-side barrier among the connected shards (one GPU each): what follows starts together."""
+        self._ck(self._L.amclj_shard_rendezvous_async(self._h))
 
     def shard_update_host(self, x, y, theta, w, curr, prev, ranges, angle_min, angle_inc, range_max, u0, seed=0):
         ranges = _f32(ranges)

@@ -2057,6 +2057,7 @@ int32_t amclj_shard_export(amclj_ctx *ctx, uint8_t *handles) {
   ctx->flip = 0;
   ctx->frozen = true;
   ctx->gen = 0;
+  ctx->sync_gen = 0;
   CK(cudaMemsetAsync(ctx->mbox, 0, sizeof(unsigned long long) * MBOX_WORDS, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   void *bufs[AMCLJ_IPC_BUFFERS] = {ctx->x, ctx->y, ctx->th, ctx->x2, ctx->y2, ctx->th2, ctx->cdf, ctx->mbox};
@@ -2096,6 +2097,7 @@ int32_t amclj_shard_attach_local(amclj_ctx *ctx, int32_t rank, amclj_ctx *peer) 
     ctx->flip = 0;
     ctx->frozen = true;
     ctx->gen = 0;
+    ctx->sync_gen = 0;
     CK(cudaMemsetAsync(ctx->mbox, 0, sizeof(unsigned long long) * MBOX_WORDS, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   } else if (peer->device != ctx->device) { /* one process, several GPUs: plain peer access */
@@ -2107,6 +2109,7 @@ int32_t amclj_shard_attach_local(amclj_ctx *ctx, int32_t rank, amclj_ctx *peer) 
     else CK(pe);
   }
   NEED(peer->flip == 0, AMCLJ_ERR_STATE, "shard_attach_local: attach before the first pull");
+  if (peer != ctx && peer->device == ctx->device) ctx->peer_shares_device = true;
   peer->frozen = true;
   local_views(peer, &ctx->peers[0][rank], &ctx->peers[1][rank]);
   ctx->peer_mbox[rank] = peer->mbox;
@@ -2193,6 +2196,45 @@ int32_t amclj_shard_update_async(amclj_ctx *ctx, const double curr[3], const dou
   rc = shard_phase_b(ctx);
   if (rc) return rc;
   return shard_phase_c(ctx, u0);
+}
+
+int32_t amclj_host_register(amclj_ctx *ctx, void *ptr, int64_t bytes) {
+  ENTER();
+  NEED(ptr && bytes > 0, AMCLJ_ERR_INVALID, "host_register: null or empty buffer");
+  cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    (void)cudaGetLastError();
+    return AMCLJ_OK;
+  }
+  CK(e);
+  return AMCLJ_OK;
+}
+
+int32_t amclj_host_unregister(amclj_ctx *ctx, void *ptr) {
+  ENTER();
+  NEED(ptr, AMCLJ_ERR_INVALID, "host_unregister: null buffer");
+  CK(cudaStreamSynchronize(ctx->stream)); /* no copy from or into it may be in flight */
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e == cudaErrorHostMemoryNotRegistered) {
+    (void)cudaGetLastError();
+    return AMCLJ_OK;
+  }
+  CK(e);
+  return AMCLJ_OK;
+}
+
+int32_t amclj_shard_rendezvous_async(amclj_ctx *ctx) {
+  ENTER();
+  NEED(ctx->world >= 1 && ctx->world <= MAX_WORLD, AMCLJ_ERR_INVALID, "shard_rendezvous: world %d", ctx->world);
+  for (int g = 0; g < ctx->world; g++)
+    NEED(ctx->peer_set[g] && ctx->peer_mbox[g], AMCLJ_ERR_STATE, "shard_rendezvous: rank %d not connected", g);
+  NEED(!ctx->peer_shares_device, AMCLJ_ERR_STATE,
+       "shard_rendezvous: a peer shares this GPU (kernels that wait on one another must not share a device)");
+  MailboxArgs m;
+  mailbox_args(ctx, m);
+  m.gen = ++ctx->sync_gen;
+  CK(launch_mailbox(m, 4, ctx->stream));
+  return AMCLJ_OK;
 }
 
 int32_t amclj_shard_update_host(amclj_ctx *ctx, float *x, float *y, float *theta, float *w, int64_t n,

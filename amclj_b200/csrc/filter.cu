@@ -1137,8 +1137,21 @@ __global__ void wait_total_kernel(const MailboxArgs a) {
   a.totals_all[g] = ld_sys_u64(a.mbox + MBOX_TOTAL + g);
 }
 
+// A barrier among the shards on the DEVICE time line: every rank stores the call's count into its slot of every
+// rank's mailbox and polls its own until all slots carry it.  What follows it in the stream starts at the same
+// instant on every GPU (to within a store over NVLink), whatever the skew between the hosts that enqueued it.
+__global__ void rendezvous_kernel(const MailboxArgs a) {
+  const int g = threadIdx.x;
+  if (g >= a.world) return;
+  st_sys_u64(a.peer_mbox[g] + MBOX_SYNC + a.rank, (unsigned long long)a.gen);
+  long long spins = 0;
+  while ((uint32_t)ld_sys_u64(a.mbox + MBOX_SYNC + g) != a.gen && ++spins < MBOX_SPIN_LIMIT) {}
+  if (spins >= MBOX_SPIN_LIMIT && a.error_flag) atomicAdd(a.error_flag, 1ull);
+}
+
 cudaError_t launch_mailbox(const MailboxArgs &a, int what, cudaStream_t s) {
   switch (what) {
+    case 4: rendezvous_kernel<<<1, 32, 0, s>>>(a); break;
     case 0: publish_max_kernel<<<1, 32, 0, s>>>(a); break;
     case 1: wait_max_kernel<<<1, 32, 0, s>>>(a); break;
     case 2: publish_total_kernel<<<1, 32, 0, s>>>(a); break;

@@ -319,6 +319,8 @@ struct amclj_ctx {
   unsigned long long *mbox = nullptr;                        /* this rank's mailbox (device memory, zeroed) */
   unsigned long long *peer_mbox[amclj::MAX_WORLD] = {};      /* every rank's mailbox as seen from here */
   uint32_t gen = 0;                                          /* sharded updates so far (the mailbox tag) */
+  uint32_t sync_gen = 0;                                     /* rendezvous calls so far (amclj_shard_rendezvous_async) */
+  bool peer_shares_device = false;                           /* a peer runs on this GPU (emulated shards) */
   cudaEvent_t ev_pub[2] = {nullptr, nullptr};                /* recorded after this rank published its max / its total */
   int flip = 0;            // swaps since export, mod 2
   bool frozen = false;     // buffers exported: no reallocation
@@ -410,7 +412,7 @@ struct PullArgs {
 };
 cudaError_t launch_pull(const PullArgs &a, cudaStream_t s);
 /* mailbox exchange of a sharded update (filter.cu): word offsets inside a rank's mailbox */
-constexpr int MBOX_MAX = 0, MBOX_TOTAL = MAX_WORLD, MBOX_TOTAL_GEN = 2 * MAX_WORLD, MBOX_WORDS = 3 * MAX_WORLD;
+constexpr int MBOX_MAX = 0, MBOX_TOTAL = MAX_WORLD, MBOX_TOTAL_GEN = 2 * MAX_WORLD, MBOX_SYNC = 3 * MAX_WORLD, MBOX_WORDS = 4 * MAX_WORLD;
 struct MailboxArgs {
   unsigned long long *mbox;                 /* this rank's mailbox (its own memory) */
   unsigned long long *peer_mbox[MAX_WORLD]; /* every rank's mailbox as seen from this GPU */
@@ -424,7 +426,7 @@ struct MailboxArgs {
 };
 /* polls before a wait gives up (a few seconds): a mis-wired exchange must not hang the GPU */
 constexpr long long MBOX_SPIN_LIMIT = 1ll << 24;
-/* what: 0 publish max, 1 wait for every max, 2 publish total, 3 wait for every total */
+/* what: 0 publish max, 1 wait for every max, 2 publish total, 3 wait for every total, 4 rendezvous (gen = its own count) */
 cudaError_t launch_mailbox(const MailboxArgs &a, int what, cudaStream_t s);
 
 struct RouletteArgs {

@@ -148,6 +148,8 @@ def config_of(w, world):
             "preset": "NS (north-star semantics: heading-correct Bresenham, all beams, log-weights, systematic)",
             "step": "scan staged (host beam table + upload) + motion + sensor + normalise + systematic resample",
             "l2": "flushed between timed steps (256 MiB memset, untimed); particle set restored before each step (untimed)",
+            "barrier": "per step: dist.barrier + synchronize on both sides; N > 1: its release aligned on the device time line "
+                       "by amclj_shard_rendezvous_async (a one-warp kernel over the peer-memory mailboxes) before the start event",
             "parallelism": f"particles sharded x{world}, map and scan replicated"}
 
 
@@ -367,6 +369,11 @@ def run_b200(args):
                 restore()
                 flush.fill_(k & 0xff)
                 barrier()
+                if filt and args.shard_mode == "mailbox":
+                    # the barrier's release made precise on the DEVICE time line: the ranks' hosts leave the NCCL
+                    # barrier tens of microseconds apart, and with one barrier per step that skew would be timed as
+                    # part of every step (a rank that starts early waits inside the update for the one that starts late)
+                    ctx.shard_rendezvous_async()
                 ev[k][0].record(stream)
                 one_step(args.warmup + k)
                 ev[k][1].record(stream)
@@ -388,7 +395,7 @@ def run_b200(args):
 
     # ---- stage and dominant-kernel times: K more steps with event records at the stage boundaries and around
     # the dominant sensor kernel (collect_stats bit 1; the headline loop above runs without them) -------------
-    sensor_ms, main_ms = [], []
+    sensor_ms, main_ms, motion_ms, resample_ms = [], [], [], []
     ctx.set_params(_lib.params("NS", collect_stats=2, df_mode=args.df_mode))
     ctx.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max)
     with torch.cuda.stream(stream):
@@ -401,15 +408,22 @@ def run_b200(args):
             st2 = ctx.stats()
             main_ms.append(st2.ms_sensor_main)
             sensor_ms.append(st2.ms_sensor)
+            motion_ms.append(st2.ms_motion)
+            resample_ms.append(st2.ms_resample)
     ctx.set_params(_lib.params("NS", df_mode=args.df_mode))
     ctx.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max)
 
     # ---- e2e: host PoseArray in, resampled PoseArray out, through the C ABI (N > 1: every rank its shard) ----
-    def e2e_leg(pinned):
+    def e2e_leg(kind):
+        """kind: "pinned" (cudaHostAlloc'ed buffers), "pageable" (plain malloc), "registered" (plain malloc'ed buffers
+        page-locked once with amclj_host_register: what the JNA shim does with its Memory objects)."""
         bufs = [torch.empty(w.n, dtype=torch.float32) for _ in range(4)]
-        if pinned:
+        if kind == "pinned":
             bufs = [b.pin_memory() for b in bufs]
         nx, ny, nt, nw = (b.numpy() for b in bufs)
+        if kind == "registered":
+            for a in (nx, ny, nt, nw):
+                ctx.host_register(a)
         e_ms = []
         for k in range(3 + min(args.steps, 10)):
             nx[:], ny[:], nt[:] = w.x, w.y, w.theta
@@ -424,6 +438,9 @@ def run_b200(args):
                                        s.range_max, w.u0, seed=500 + k)
             barrier()
             e_ms.append(1e3 * (time.perf_counter() - t0))
+        if kind == "registered":
+            for a in (nx, ny, nt, nw):
+                ctx.host_unregister(a)
         m = float(np.mean(e_ms[3:]))
         if world > 1:
             t = torch.tensor([m], device=dev, dtype=torch.float64)
@@ -433,12 +450,15 @@ def run_b200(args):
 
     e2e = None
     if not (filt and args.shard_mode != "mailbox"):
-        m_pin, m_page = e2e_leg(True), e2e_leg(False)
+        m_pin, m_page, m_reg = e2e_leg("pinned"), e2e_leg("pageable"), e2e_leg("registered")
         e2e = {"value": n_total * nb / (m_pin * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(world * (3 * 4 * w.n + 6 * 4 * nb)), "d2h_bytes_per_step": int(world * 4 * 4 * w.n),
                "ms_per_step": m_pin,
                "pageable": {"value": n_total * nb / (m_page * 1e-3), "ms_per_step": m_page,
                             "note": "the same call with plain malloc'ed host buffers (what a JNA Memory is)"},
+               "pageable_registered": {"value": n_total * nb / (m_reg * 1e-3), "ms_per_step": m_reg,
+                                       "note": "plain malloc'ed host buffers page-locked once with amclj_host_register "
+                                               "(what the JNA shim does with its Memory objects)"},
                "call": ("amclj_shard_update_host on every rank (its shard)" if filt else "amclj_filter_update_host")
                        + ": pinned host buffers, wall clock around the synchronous call, max over ranks"}
 
@@ -520,7 +540,10 @@ def run_b200(args):
                 if args.shard_mode == "mailbox" else f"torch.distributed NCCL ({args.shard_mode})"),
             "table_fill_ms_once": float(st_last.ms_table_fill), "table_bytes": int(st_last.table_bytes),
             "wall_s_timed_loop": t_wall,
-            "stage_ms": {"sensor": stage_ms, "sensor_main_kernel": k_ms, "total_lib_events": float(np.mean(total_ms_lib))},
+            "stage_ms": {"motion": float(np.mean(motion_ms)), "sensor": stage_ms, "sensor_main_kernel": k_ms,
+                         "normalise_resample_exchange": float(np.mean(resample_ms)),
+                         "total_lib_events": float(np.mean(total_ms_lib)),
+                         "note": "library events on rank 0; motion / sensor / resample from a separate pass with stage events"},
             "configs": configs,
         }
         print(json.dumps(line), flush=True)

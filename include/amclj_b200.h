@@ -235,6 +235,13 @@ int32_t amclj_stage_scan(amclj_ctx *ctx, const float *ranges, int32_t n, float a
                          float angle_increment, float range_max);
 int32_t amclj_filter_update_async(amclj_ctx *ctx, const double curr[3], const double prev[3],
                                   uint64_t seed, double u0);
+/* Page-lock a caller-owned host buffer (a JNA Memory, a direct ByteBuffer, a malloc'ed array) so that the
+ * copies of the *_host calls run at the bus's speed instead of through the driver's staging buffers (measured
+ * on B200, 1.25 M particles: 3.99 ms per update with plain pageable buffers, the pinned figure once they are
+ * registered).  Once per buffer, for as long as the host reuses it; unregister before freeing it.  No reference
+ * counterpart (amclj keeps its particles in JVM vectors); the buffers are those of INTEGRATION.md's shim. */
+int32_t amclj_host_register(amclj_ctx *ctx, void *ptr, int64_t bytes);
+int32_t amclj_host_unregister(amclj_ctx *ctx, void *ptr);
 /* The same step for a host-resident PoseArray: uploads x,y,theta, runs the fused update,
  * downloads the resampled particles and weights (in place). */
 int32_t amclj_filter_update_host(amclj_ctx *ctx, float *x, float *y, float *theta, float *w,
@@ -311,6 +318,12 @@ int32_t amclj_shard_pull_async(amclj_ctx *ctx, double u0);
  * shard_motion_sensor_async + all-reduce + shard_cdf_async + all-gather + shard_pull_async. */
 int32_t amclj_shard_update_async(amclj_ctx *ctx, const double curr[3], const double prev[3], uint64_t seed,
                                  double u0);
+/* A barrier among the connected shards on the DEVICE time line (no reference counterpart: amclj runs one JVM):
+ * enqueues a one-warp kernel that stores this call's count into every rank's mailbox and returns when every rank's
+ * count has arrived, so whatever follows it in the stream starts at the same instant on every GPU, however far
+ * apart the hosts enqueued it.  Same number of calls on every rank; every rank on its own GPU (AMCLJ_ERR_STATE
+ * when a peer shares this device: kernels that wait on one another must not share a GPU). */
+int32_t amclj_shard_rendezvous_async(amclj_ctx *ctx);
 /* The same for a host-resident shard: upload x, y, theta of this rank's n particles, stage the scan, update,
  * download the rank's resampled slots (in place).  n must equal the connected shard size. */
 int32_t amclj_shard_update_host(amclj_ctx *ctx, float *x, float *y, float *theta, float *w, int64_t n,

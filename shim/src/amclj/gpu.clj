@@ -130,6 +130,29 @@
            Pointer/NULL (long seed) (float-mem r) (int (count r))
            (float (:angleMin scan)) (float (:angleIncrement scan)) (float (:rangeMax scan)) (double u0))))
 
+(defn host-buffers
+  "Four float buffers (x, y, theta, w) of n particles for filter-update-host!, page-locked once with
+  amclj_host_register: a JNA Memory is plain malloc'ed memory, and copies from pageable memory go through the
+  driver's staging buffers at about a quarter of the bus's speed.  Keep and reuse them; release-host-buffers!
+  before they are garbage-collected."
+  [ctx n]
+  (let [bufs (vec (repeatedly 4 #(Memory. (* 4 (long n)))))]
+    (doseq [^Memory b bufs] (call! ctx "amclj_host_register" b (long (.size b))))
+    bufs))
+
+(defn release-host-buffers! [ctx bufs]
+  (doseq [^Memory b bufs] (call! ctx "amclj_host_unregister" b)))
+
+(defn filter-update-host!
+  "The same iteration for a host-resident cloud (the reference keeps its particles in the JVM): x, y, theta in
+  the buffers of host-buffers are uploaded, updated and overwritten by the resampled cloud and its weights."
+  [ctx [x y theta w] n [curr prev] to-heading scan u0 seed]
+  (let [r (:ranges scan)]
+    (call! ctx "amclj_filter_update_host" x y theta w (long n)
+           (yaw-pose curr to-heading) (yaw-pose prev to-heading) Pointer/NULL (long seed)
+           (float-mem r) (int (count r))
+           (float (:angleMin scan)) (float (:angleIncrement scan)) (float (:rangeMax scan)) (double u0))))
+
 (defn pose-estimate
   "pf.clj:67-84: unweighted mean of x, y and of the quaternion's z, w, without a download."
   [ctx]

@@ -638,3 +638,30 @@ def test_raycast_very_long_rays_use_the_shifted_reciprocal(preset):
         c.set_map(grid)
         _ray_parity(c, grid, x, y, th, scan, preset, **kw)
     c.close()
+
+
+def test_host_register_same_results(ctx, lg):
+    """amclj_host_register: a plain (pageable) host buffer page-locked by the library gives the same update as
+    an unregistered one; registering twice and unregistering an unknown buffer are not errors."""
+    w = workloads.c1(4000)
+    s = w.scan
+    ctx.set_params(_lib.params("NS"))
+    ctx.set_map(lg)
+    outs = []
+    for reg in (False, True):
+        x, y, t = w.x.copy(), w.y.copy(), w.theta.copy()
+        wt = np.zeros_like(x)
+        if reg:
+            for a in (x, y, t, wt):
+                ctx.host_register(a)
+            ctx.host_register(x)  # again: already registered
+        ctx.set_particles(x, y, t)
+        ctx.filter_update_host(x, y, t, wt, w.curr, w.prev, s.ranges, s.angle_min, s.angle_inc, s.range_max, w.u0, seed=11)
+        if reg:
+            for a in (x, y, t, wt):
+                ctx.host_unregister(a)
+            ctx.host_unregister(x)  # again: not registered any more
+        outs.append((x, y, t, wt))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    assert not np.array_equal(outs[0][0], w.x)  # the update did move the cloud
