@@ -398,6 +398,8 @@ void fill_pt_args(const amclj_ctx *ctx, PtLaunch &L) {
   L.scan_state = t.scan_state;
   L.scan_words = t.scan_words;
   L.tail_pct = t.tail_pct;
+  L.tail_div = t.tail_div;
+  L.tail_min = t.tail_min;
   L.tail_ctr = reinterpret_cast<uint32_t *>(t.scan_state) + 1;
   L.rows32 = (t.rows32 && r.n_entries < 65536 && r.E < 250) ? 1 : 0; /* base : 16 | lo : 8 | cnt : 8 (cnt <= ~sqrt(8 r) + 4) */
   L.fuse_finish = (t.fuse_finish && (ctx->beams.nb + 29) / 30 <= 15) ? 1 : 0;
@@ -1226,6 +1228,8 @@ int32_t amclj_create(int32_t device, amclj_ctx **out) {
   if (const char *e = getenv("AMCLJ_PT_WARPS")) ctx->pt.warps_req = atoi(e);
   if (const char *e = getenv("AMCLJ_PT_NBUF")) ctx->pt.nbuf = atoi(e);
   if (const char *e = getenv("AMCLJ_PT_FUSE_MOTION")) ctx->pt.fuse_motion = atoi(e) != 0;
+  if (const char *e = getenv("AMCLJ_PT_TAIL_DIV")) ctx->pt.tail_div = atoi(e) < 1 ? 1 : atoi(e);
+  if (const char *e = getenv("AMCLJ_PT_TAIL_MIN")) ctx->pt.tail_min = atoi(e) < 1 ? 1 : atoi(e);
   if (const char *e = getenv("AMCLJ_PT_TAIL_PCT")) ctx->pt.tail_pct = atoi(e) < 0 ? 0 : (atoi(e) > 100 ? 100 : atoi(e));
   if (const char *e = getenv("AMCLJ_PT_ROWS32")) ctx->pt.rows32 = atoi(e) != 0;
   if (const char *e = getenv("AMCLJ_PT_FUSE")) ctx->pt.fuse_finish = atoi(e) != 0;

@@ -214,6 +214,7 @@ struct PersistentTables {
                                    // an atomic that returns its old value stalls the warp, a plain reduction does not)
   int32_t nbuf = 0;                // table buffers per warp requested (0: one, so that more warps fit; AMCLJ_PT_NBUF)
   int32_t nbuf_used = 1, warps_req = 0;
+  int32_t tail_div = 4, tail_min = 8; // AMCLJ_PT_TAIL_DIV, AMCLJ_PT_TAIL_MIN
   int32_t tail_pct = 15;           // AMCLJ_PT_TAIL_PCT (measured: 0 -> 1.046, 15 -> 0.994, 30 -> 1.014 ms on the C4 share)
   bool fuse_motion = true;         // the motion kernel takes the sort's histogram pass along (AMCLJ_PT_FUSE_MOTION=0: pt_hist_kernel)
   bool hist_done = false;          // ... and did so for the update in progress
@@ -250,6 +251,7 @@ struct PtLaunch {
   unsigned long long *scan_state;  // bin scan: {ticket | tail counter, descriptor per tile}
   int32_t scan_words;
   int32_t tail_pct;     // share of the sorted particles handed out in chunks at the end of the look-up
+  int32_t tail_div, tail_min;  // a unit of that tail: what is left / (tail_div x warps), at least tail_min particles
   uint32_t *tail_ctr;   // next chunk of that tail (zeroed by the histogram)
   int32_t rows32;       // 1: ring rows packed into one word in shared memory (base < 8192, lo < 256, cnt < 2048)
 };

@@ -498,14 +498,21 @@ pt_lookup_kernel(const __grid_constant__ PtLaunch L) {
   int it = 0; /* tables staged so far by this warp (mbarrier phase) */
   uint32_t q_lo = (uint32_t)(n_static * g / Wt), q_hi = (uint32_t)(n_static * (g + 1) / Wt);
   for (bool own = true;; own = false) {
-  if (!own) { /* next chunk of the common tail */
-    uint32_t c = 0;
-    if (lane == 0) c = atomicAdd(L.tail_ctr, 1u);
+  if (!own) { /* next unit of the common tail: units shrink as the tail runs out (a quarter of what is left per warp,
+               * 8 .. chunk particles), so that the SMs finish within a few hundred particle-segments of one another
+               * (fixed units of 64 left them 1.79 M .. 1.98 M active cycles apart) */
+    uint32_t c = 0, want = 0;
+    if (lane == 0) {
+      const int64_t left = (n - n_static) - (int64_t)*reinterpret_cast<volatile uint32_t *>(L.tail_ctr);
+      want = (uint32_t)max((int64_t)L.tail_min, min(chunk, left / (L.tail_div * Wt)));
+      c = atomicAdd(L.tail_ctr, want);
+    }
     c = __shfl_sync(FULL, c, 0);
-    const int64_t lo64 = n_static + (int64_t)c * chunk;
+    want = __shfl_sync(FULL, want, 0);
+    const int64_t lo64 = n_static + (int64_t)c;
     if (lo64 >= n) break;
     q_lo = (uint32_t)lo64;
-    q_hi = (uint32_t)min(lo64 + chunk, n);
+    q_hi = (uint32_t)min(lo64 + (int64_t)want, n);
   }
   if (q_lo >= q_hi) continue;
   int s; /* the slot holding position q_lo: the last one with start[s] <= q_lo */
