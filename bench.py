@@ -518,7 +518,11 @@ def run_b200(args):
             wi = float(prof["warp_instructions"])
             roofline.update({"achieved": wi / (k_ms * 1e-3), "frac": wi / (k_ms * 1e-3) / issue_peak,
                              "warp_instructions_per_launch": wi, "warp_instructions_per_ray": wi / n_rays,
-                             "profile": prof.get("source")})
+                             "profile": prof.get("source"),
+                             # which pipe those instructions queue for (ncu, same capture): on B200 integer / logic /
+                             # compare / select instructions issue every second cycle on the ALU pipe (tools/pipe_rates.cu)
+                             "pipes_under_ncu": {"issue_active_pct": prof.get("issue_active_pct"),
+                                                 "alu_pipe_pct": prof.get("alu_pipe_pct"), "fma_pipe_pct": prof.get("fma_pipe_pct")}})
         cpu = None if args.quick else cpu_baseline(headline_workload(1) if args.workload == "c4share" else w)
         configs = None
         if world == 1 and not args.quick and args.workload == "c4share":

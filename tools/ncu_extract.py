@@ -25,6 +25,15 @@ METRICS = [
     "l1tex__t_sector_hit_rate.pct", "sm__cycles_active.avg", "sm__cycles_active.min", "sm__cycles_active.max",
     "sm__cycles_elapsed.max", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "smsp__warps_eligible.avg.per_cycle_active",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
 ]
 
 
@@ -69,6 +78,8 @@ def main():
                "warp_instructions": num("smsp__inst_executed.sum"), "dram_bytes_read": num("dram__bytes_read.sum"),
                "dram_bytes_write": num("dram__bytes_write.sum"), "kernel_seconds_under_ncu": num("gpu__time_duration.sum"),
                "issue_active_pct": float(row["smsp__issue_active.avg.pct_of_peak_sustained_active"][1]),
+               "alu_pipe_pct": float(row.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", ("", "nan"))[1]),
+               "fma_pipe_pct": float(row.get("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", ("", "nan"))[1]),
                "source": Path(a.out_prefix).name + "_raw_metrics.txt (ncu --set full --clock-control none, one launch)"}
         jf = ROOT / "profiles" / "dominant_kernel_metrics.json"
         data = json.loads(jf.read_text()) if jf.exists() else {"kernels": []}
