@@ -202,3 +202,35 @@ def test_multi_context_skewed_weights():
             assert np.array_equal(a, b)
         idx = ref.resample_indices()
         assert (idx >= n - len(gx)).mean() > 0.9  # the test does what it says
+
+
+def test_rendezvous_alone_and_refused_on_a_shared_device():
+    """amclj_shard_rendezvous_async: a shard that is its own world passes straight through (twice: the count
+    advances); shards that share one GPU are refused (kernels that wait on one another must not share a device)."""
+    g = maps.lgfloor()
+    w = workloads.c3(4000)
+    c = _lib.Context(0, "NS")
+    c.set_map(g)
+    c.set_shard(0, 1, 0, w.n)
+    c.set_particles(w.x, w.y, w.theta)
+    c.shard_attach_local(0, c)
+    c.shard_rendezvous_async()
+    c.shard_rendezvous_async()
+    c.synchronize()
+    c.close()
+    shards = []
+    for r in range(2):
+        lo, cnt = slots_of(r, 2, w.n)
+        d = _lib.Context(0, "NS")
+        d.set_map(g)
+        d.set_shard(r, 2, lo, w.n)
+        d.set_particles(w.x[lo:lo + cnt], w.y[lo:lo + cnt], w.theta[lo:lo + cnt])
+        shards.append(d)
+    for d in shards:
+        for r, peer in enumerate(shards):
+            d.shard_attach_local(r, peer)
+    with pytest.raises(_lib.AmcljError) as e:
+        shards[0].shard_rendezvous_async()
+    assert e.value.code == _lib.ERR_STATE
+    for d in shards:
+        d.close()

@@ -324,3 +324,28 @@ def test_fp32_contract_casts_the_rays_of_the_double_path_in_bulk(preset):
         bad = (steps != d32["steps"]) | (hit != d32["hit"])
         assert int(bad.sum()) == 0, f"{w.name}: {int(bad.sum())} of {bad.size} rays differ, first {np.argwhere(bad)[:4].tolist()}"
         assert float(np.abs(rng - d32["range_m"]).max()) < 2e-6
+
+
+def test_divide_free_quotient_of_the_exact_cells_is_the_correctly_rounded_one():
+    """csrc/sensor_common.cuh cell_exact_d replaces `v / res` (a subroutine call inside the look-up loop) by
+    Markstein's final division step on the host's correctly rounded reciprocal: q0 = RN(v * rinv),
+    r = fma(-q0, res, v) (exact), q = RN(q0 + r * rinv).  Restated here with exact rational arithmetic for the
+    fused steps and checked against the IEEE quotient for the map resolutions in use and end points all over a
+    map, including the ones engineered to land next to a cell boundary (where the device code takes this path)."""
+    from fractions import Fraction
+
+    def fma(a, b, c):
+        return float(Fraction(a) * Fraction(b) + Fraction(c))  # one rounding, to nearest even
+
+    rng = np.random.Generator(np.random.PCG64(77))
+    for res32 in (np.float32(0.05), np.float32(0.025), np.float32(0.1), np.float32(0.0123)):
+        res = float(res32)
+        rinv = 1.0 / res
+        vs = list(rng.uniform(-50.0, 500.0, 20000))
+        cells = rng.integers(-1000, 9000, 20000)
+        vs += [float(np.float32((c + 0.5) * res)) for c in cells]                      # float32 end points near a boundary
+        vs += [(c + 0.5) * res * (1.0 + e) for c, e in zip(cells[:5000], rng.uniform(-3e-16, 3e-16, 5000))]
+        for v in vs:
+            q0 = v * rinv
+            q = fma(fma(-q0, res, v), rinv, q0)
+            assert q == v / res, (res, v)
