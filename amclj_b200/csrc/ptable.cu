@@ -304,6 +304,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // re-taken in double, out of line] -> [ring index and table entry of each, packed beam mixture of both].  Each half is
 // straight-line.  The beam constants are staged per PAIR of beams (pt_lookup_kernel): s_dir float4 (cos a, cos b,
 // sin a, sin b), s_mixa float4 (obs a, obs b, e2 a, e2 b), s_mixb float2 (p34 a, p34 b); jb0 is even (SEG is).
+static_assert(SEG % 2 == 0, "pt_segment takes its beams in pairs that start on an even beam");
 template <bool S7, bool DBG, bool R32>
 __device__ __forceinline__ float pt_segment(const SensorLaunch &a, const PtLaunch &L, uint32_t s_tab, uint32_t s_mixa,
                                             uint32_t s_mixb, uint32_t s_dir, uint32_t s_rows, float fKx, float fKy, float st,
