@@ -39,7 +39,7 @@ SYMBOLS = [
     "amclj_shard_motion_sensor_async", "amclj_shard_cdf_async", "amclj_shard_generate_async",
     "amclj_shard_get_stage_idx", "amclj_shard_adopt_async", "amclj_plan_systematic",
     "amclj_device_ptr", "amclj_reserve_stage", "amclj_shard_export", "amclj_shard_import",
-    "amclj_shard_attach_local", "amclj_shard_pull_async", "amclj_shard_update_async", "amclj_shard_update_host", "amclj_shard_rendezvous_async", "amclj_host_register", "amclj_host_unregister",
+    "amclj_shard_attach_local", "amclj_shard_pull_async", "amclj_shard_update_async", "amclj_shard_update_host", "amclj_shard_rendezvous_async", "amclj_filter_update_scan_async", "amclj_shard_update_scan_async", "amclj_host_register", "amclj_host_unregister",
     "amclj_create_multi", "amclj_destroy_multi", "amclj_multi_size", "amclj_multi_ctx", "amclj_mlast_error",
     "amclj_mset_params", "amclj_mset_map", "amclj_mset_particles", "amclj_mget_particles", "amclj_mnum_particles",
     "amclj_minit_uniform", "amclj_mstage_scan", "amclj_mfilter_update_async", "amclj_mfilter_update_host",
@@ -162,6 +162,8 @@ def lib():
         "amclj_shard_pull_async": ([vp, f64], i32),
         "amclj_shard_update_async": ([vp, d3, d3, u64, f64], i32),
         "amclj_shard_rendezvous_async": ([vp], i32),
+        "amclj_filter_update_scan_async": ([vp, d3, d3, u64, f64, vp, i32, f32, f32, f32], i32),
+        "amclj_shard_update_scan_async": ([vp, d3, d3, u64, f64, vp, i32, f32, f32, f32], i32),
         "amclj_host_register": ([vp, vp, i64], i32),
         "amclj_host_unregister": ([vp, vp], i32),
         "amclj_shard_update_host": ([vp, vp, vp, vp, vp, i64, d3, d3, u64, vp, i32, f32, f32, f32, f64], i32),
@@ -485,6 +487,17 @@ class Context:
     def shard_update_async(self, curr, prev, seed, u0):
         """The whole sharded update in one call: exchanges through peer-memory mailboxes, no collective library."""
         self._ck(self._L.amclj_shard_update_async(self._h, _d3(curr), _d3(prev), int(seed), float(u0)))
+
+    def filter_update_scan_async(self, curr, prev, seed, u0, ranges, angle_min, angle_inc, range_max):
+        """stage_scan + filter_update_async in one call (motion first when the scan's geometry is staged)."""
+        ranges = _f32(ranges)
+        self._ck(self._L.amclj_filter_update_scan_async(self._h, _d3(curr), _d3(prev), int(seed), float(u0), _vp(ranges),
+                                                        len(ranges), angle_min, angle_inc, range_max))
+
+    def shard_update_scan_async(self, curr, prev, seed, u0, ranges, angle_min, angle_inc, range_max):
+        ranges = _f32(ranges)
+        self._ck(self._L.amclj_shard_update_scan_async(self._h, _d3(curr), _d3(prev), int(seed), float(u0), _vp(ranges),
+                                                       len(ranges), angle_min, angle_inc, range_max))
 
     def host_register(self, arr):
         """Page-lock a caller-owned numpy buffer for the *_host calls (what the JNA shim does with its Memory)."""

@@ -518,6 +518,26 @@ int enqueue_ptable(amclj_ctx *ctx, const SensorLaunch &base, bool dbg) {
   return AMCLJ_OK;
 }
 
+/* the per-message part of the beam table: (obs, e2, p34, 0) of one beam (sensor.clj:154-161) */
+static inline void fill_mix(const amclj_params &p, float o, float range_max, float *mix4) {
+  mix4[0] = o;
+  mix4[1] = p.z_short * p.lambda_short * expf(-p.lambda_short * o);      /* sensor.clj:154-157 */
+  float pz3 = o == range_max ? p.z_max : 0.0f;               /* sensor.clj:158-159 */
+  float pz4 = o < range_max ? p.z_rand / range_max : 0.0f;   /* sensor.clj:160-161 */
+  mix4[2] = pz3 + pz4;
+  mix4[3] = 0.0f;
+  if (p.s7_log_weights && !(o <= range_max && o >= -3.0e38f)) {
+    /* Log-weights only (the north-star aggregation; no reference counterpart): a return beyond
+     * rangeMax, an inf or a NaN — common in ROS LaserScans — has probability 0 under every term
+     * of sensor.clj:151-161, and log 0 would wipe out every particle alike.  Such a beam is left
+     * out: z = +inf makes pz1 = pz2 = 0 and the constant term 1 makes the beam's factor exactly 1.
+     * The reference's sum of cubes (S7 off) just adds 0 for it and keeps doing so here. */
+    mix4[0] = INFINITY;
+    mix4[1] = 0.0f;
+    mix4[2] = 1.0f;
+  }
+}
+
 int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min, float angle_inc,
                     float range_max) {
   NEED(n > 0 && n <= (1 << 20), AMCLJ_ERR_INVALID, "scan: n = %d out of range", n);
@@ -545,7 +565,6 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
   /* float4 (obs, e2, p34, 0) first so that it stays 16-byte aligned for any beam count | float2 (cb, sb) */
   float *mix = reinterpret_cast<float *>(ctx->pin_tab), *dir = mix + 4 * (size_t)nb;
   double *dird = reinterpret_cast<double *>(reinterpret_cast<char *>(ctx->pin_tab) + dbl_off); /* near-tie refinement */
-  float zshort = p.z_short, lam = p.lambda_short;
   /* the beam directions depend on the scan geometry only: a laser sends the same one with every message, so the
    * 2 x nb cos / sin calls and the upload of the double table happen when it changes (the pinned staging buffer
    * and the device tables still hold the previous directions otherwise) */
@@ -563,23 +582,7 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
       dir[2 * j] = (float)dird[2 * j];
       dir[2 * j + 1] = (float)dird[2 * j + 1];
     }
-    float o = ranges ? ranges[i] : 0.0f;
-    mix[4 * j] = o;
-    mix[4 * j + 1] = zshort * lam * expf(-lam * o);            /* sensor.clj:154-157 */
-    float pz3 = o == range_max ? p.z_max : 0.0f;               /* sensor.clj:158-159 */
-    float pz4 = o < range_max ? p.z_rand / range_max : 0.0f;   /* sensor.clj:160-161 */
-    mix[4 * j + 2] = pz3 + pz4;
-    mix[4 * j + 3] = 0.0f;
-    if (p.s7_log_weights && !(o <= range_max && o >= -3.0e38f)) {
-      /* Log-weights only (the north-star aggregation; no reference counterpart): a return beyond
-       * rangeMax, an inf or a NaN — common in ROS LaserScans — has probability 0 under every term
-       * of sensor.clj:151-161, and log 0 would wipe out every particle alike.  Such a beam is left
-       * out: z = +inf makes pz1 = pz2 = 0 and the constant term 1 makes the beam's factor exactly 1.
-       * The reference's sum of cubes (S7 off) just adds 0 for it and keeps doing so here. */
-      mix[4 * j] = INFINITY;
-      mix[4 * j + 1] = 0.0f;
-      mix[4 * j + 2] = 1.0f;
-    }
+    fill_mix(p, ranges ? ranges[i] : 0.0f, range_max, mix + 4 * j);
   }
   BeamTable &b = ctx->beams;
   if (nb > b.cap) {
@@ -668,6 +671,32 @@ int stage_scan_impl(amclj_ctx *ctx, const float *ranges, int n, float angle_min,
   }
   b.staged = true;
   return pt_prepare(ctx, rcells);
+}
+
+/* Is this scan's geometry (beam count, angles, range_max) the one that is staged?  set_map / set_params clear
+ * `staged`, so everything else the staging derived (directions, ring, dividers, ray tables) still holds. */
+bool scan_geometry_staged(const amclj_ctx *ctx, int n, float angle_min, float angle_inc, float range_max) {
+  const BeamTable &b = ctx->beams;
+  if (!b.staged || !b.dirs_valid || b.dirs_pin != ctx->pin_tab || n <= 0) return false;
+  const int step = beam_step(n, ctx->p.s6_max_beams), nb = beams_used(n, ctx->p.s6_max_beams);
+  return b.dirs_n == n && b.dirs_step == step && b.dirs_nb == nb && b.nb == nb && nb <= b.cap &&
+         memcmp(&b.dirs_amin, &angle_min, 4) == 0 && memcmp(&b.dirs_ainc, &angle_inc, 4) == 0 &&
+         memcmp(&b.range_max, &range_max, 4) == 0;
+}
+
+/* The per-message part of a scan whose geometry is staged already: the nb (obs, e2, p34, 0) entries, built in the
+ * pinned staging buffer and uploaded on the ctx stream.  Same values as stage_scan_impl writes. */
+int restage_ranges(amclj_ctx *ctx, const float *ranges, int n, float range_max) {
+  const amclj_params &p = ctx->p;
+  const int step = beam_step(n, p.s6_max_beams), nb = ctx->beams.nb;
+  CK(cudaEventSynchronize(ctx->ev[4])); /* the previous upload from this buffer has finished */
+  float *mix = reinterpret_cast<float *>(ctx->pin_tab);
+  int j = 0;
+  for (int i = 0; i < n; i += step, j++) fill_mix(p, ranges ? ranges[i] : 0.0f, range_max, mix + 4 * j);
+  CK(cudaMemcpyAsync(ctx->beams.dev, ctx->pin_tab, sizeof(float) * (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  ctx->beams.n_scan = n;
+  return AMCLJ_OK;
 }
 
 void fill_sensor_args(const amclj_ctx *ctx, SensorLaunch &a, int mode) {
@@ -1749,6 +1778,44 @@ int32_t amclj_filter_update_async(amclj_ctx *ctx, const double curr[3], const do
   return AMCLJ_OK;
 }
 
+/* stage_scan + filter_update_async in ONE call.  When the scan's geometry is the staged one (every message of a
+ * laser after the first), the motion kernel — which needs nothing of the scan — is enqueued FIRST and the host builds
+ * and uploads the message's beam table while it runs, instead of the GPU waiting for the host to do so. */
+int32_t amclj_filter_update_scan_async(amclj_ctx *ctx, const double curr[3], const double prev[3], uint64_t seed,
+                                       double u0, const float *ranges, int32_t n, float angle_min,
+                                       float angle_increment, float range_max) {
+  ENTER();
+  NEED(curr && prev && ranges, AMCLJ_ERR_INVALID, "filter_update_scan: null argument");
+  const bool fast = scan_geometry_staged(ctx, n, angle_min, angle_increment, range_max) && ctx->n > 0 &&
+                    ctx->p.s8_resampler == AMCLJ_RESAMPLE_SYSTEMATIC && u0 >= 0.0 && u0 < 1.0;
+  if (!fast) {
+    int rc = stage_scan_impl(ctx, ranges, n, angle_min, angle_increment, range_max);
+    if (rc) return rc;
+    return amclj_filter_update_async(ctx, curr, prev, seed, u0);
+  }
+  stamp(ctx, 0);
+  CK(reset_ctrl(ctx, true));
+  ctx->ctrl_fresh = true;
+  ctx->bbox_done = false;
+  ctx->time_main = ctx->time_main_env || (ctx->p.collect_stats & 2) != 0;
+  ctx->stages_timed = ctx->time_main;
+  int rc = enqueue_motion(ctx, curr, prev, ctx->normals_staged, seed);
+  ctx->normals_staged = false;
+  if (rc) return rc;
+  rc = restage_ranges(ctx, ranges, n, range_max);
+  if (rc) return rc;
+  if (ctx->stages_timed) stamp(ctx, 1);
+  rc = enqueue_sensor(ctx, false);
+  if (rc) return rc;
+  if (ctx->stages_timed) stamp(ctx, 2);
+  rc = enqueue_cdf(ctx, true, true);
+  if (rc) return rc;
+  rc = enqueue_systematic(ctx, u0);
+  if (rc) return rc;
+  stamp(ctx, 3);
+  return AMCLJ_OK;
+}
+
 int32_t amclj_filter_update(amclj_ctx *ctx, const double curr[3], const double prev[3],
                             const float *normals, uint64_t seed, const float *ranges, int32_t n,
                             float angle_min, float angle_increment, float range_max, double u0) {
@@ -2137,7 +2204,10 @@ static void mailbox_args(amclj_ctx *ctx, MailboxArgs &a) {
 }
 
 /* phase A: motion + sensor, publish the local max */
-static int shard_phase_a(amclj_ctx *ctx, const double curr[3], const double prev[3], uint64_t seed) {
+/* ranges != null: the per-message beam table of a scan whose geometry is staged, built and uploaded while the motion
+ * kernel runs (amclj_shard_update_scan_async) */
+static int shard_phase_a(amclj_ctx *ctx, const double curr[3], const double prev[3], uint64_t seed,
+                         const float *ranges = nullptr, int n_ranges = 0, float range_max = 0.0f) {
   NEED(curr && prev, AMCLJ_ERR_INVALID, "shard_update: null control");
   NEED(ctx->n > 0, AMCLJ_ERR_STATE, "shard_update: no particles");
   NEED(ctx->beams.staged, AMCLJ_ERR_STATE, "shard_update: no scan staged");
@@ -2154,6 +2224,10 @@ static int shard_phase_a(amclj_ctx *ctx, const double curr[3], const double prev
   int rc = enqueue_motion(ctx, curr, prev, ctx->normals_staged, seed);
   ctx->normals_staged = false;
   if (rc) return rc;
+  if (ranges) {
+    rc = restage_ranges(ctx, ranges, n_ranges, range_max);
+    if (rc) return rc;
+  }
   if (ctx->stages_timed) stamp(ctx, 1);
   rc = enqueue_sensor(ctx, false);
   if (rc) return rc;
@@ -2225,6 +2299,26 @@ int32_t amclj_host_unregister(amclj_ctx *ctx, void *ptr) {
   }
   CK(e);
   return AMCLJ_OK;
+}
+
+int32_t amclj_shard_update_scan_async(amclj_ctx *ctx, const double curr[3], const double prev[3], uint64_t seed,
+                                      double u0, const float *ranges, int32_t n, float angle_min,
+                                      float angle_increment, float range_max) {
+  ENTER();
+  NEED(ranges, AMCLJ_ERR_INVALID, "shard_update_scan: null ranges");
+  NEED(u0 >= 0.0 && u0 < 1.0, AMCLJ_ERR_INVALID, "shard_update: u0 must be in [0,1)");
+  int rc;
+  if (scan_geometry_staged(ctx, n, angle_min, angle_increment, range_max)) {
+    rc = shard_phase_a(ctx, curr, prev, seed, ranges, n, range_max);
+  } else {
+    rc = stage_scan_impl(ctx, ranges, n, angle_min, angle_increment, range_max);
+    if (rc) return rc;
+    rc = shard_phase_a(ctx, curr, prev, seed);
+  }
+  if (rc) return rc;
+  rc = shard_phase_b(ctx);
+  if (rc) return rc;
+  return shard_phase_c(ctx, u0);
 }
 
 int32_t amclj_shard_rendezvous_async(amclj_ctx *ctx) {

@@ -94,8 +94,11 @@ class CudaShard:
     def pull(self, u0):
         self.ctx.shard_pull_async(u0)
 
-    def update_mailbox(self, curr, prev, seed, u0):
-        self.ctx.shard_update_async(curr, prev, seed, u0)
+    def update_mailbox(self, curr, prev, seed, u0, scan=None):
+        if scan is not None:  # stage the scan and update in one library call
+            self.ctx.shard_update_scan_async(curr, prev, seed, u0, scan.ranges, scan.angle_min, scan.angle_inc, scan.range_max)
+        else:
+            self.ctx.shard_update_async(curr, prev, seed, u0)
 
 
 def slots_of(rank, world, n_global):
@@ -139,18 +142,20 @@ class ShardedFilter:
     def reset(self, n_local):
         self.backend.set_shard(self.rank, self.world, self.slot0, self.n_global)
 
-    def update(self, curr, prev, seed, u0):
+    def update(self, curr, prev, seed, u0, scan=None):
         if self.stream is not None:
             with torch.cuda.stream(self.stream):
-                return self._update(curr, prev, seed, u0)
-        return self._update(curr, prev, seed, u0)
+                return self._update(curr, prev, seed, u0, scan)
+        return self._update(curr, prev, seed, u0, scan)
 
-    def _update(self, curr, prev, seed, u0):
+    def _update(self, curr, prev, seed, u0, scan=None):
         b = self.backend
         if self.mode == "mailbox":
             self.connect()
-            b.update_mailbox(curr, prev, seed, u0)  # one library call: the kernels do the exchanges
+            b.update_mailbox(curr, prev, seed, u0, scan)  # one library call: the kernels do the exchanges
             return None
+        if scan is not None:
+            self.stage_scan(scan)
         b.motion_sensor(curr, prev, seed)
         mx = b.raw_max()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)

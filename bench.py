@@ -146,7 +146,7 @@ def config_of(w, world):
             "particles_per_gpu": PER_GPU, "particles_total": PER_GPU * world, "beams": len(w.scan.ranges),
             "range_max_m": w.scan.range_max,
             "preset": "NS (north-star semantics: heading-correct Bresenham, all beams, log-weights, systematic)",
-            "step": "scan staged (host beam table + upload) + motion + sensor + normalise + systematic resample",
+            "step": "scan staged (host beam table + upload) + motion + sensor + normalise + systematic resample, one library call",
             "l2": "flushed between timed steps (256 MiB memset, untimed); particle set restored before each step (untimed)",
             "barrier": "per step: dist.barrier + synchronize on both sides; N > 1: its release aligned on the device time line "
                        "by amclj_shard_rendezvous_async (a one-warp kernel over the peer-memory mailboxes) before the start event",
@@ -239,9 +239,10 @@ def time_single(ctx, w, stream, flush, steps, warmup, torch, df_mode=0, stage_in
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            if stage_in_step:
-                ctx.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max)
-            ctx.filter_update_async(w.curr, w.prev, 100 + k, w.u0)
+            if stage_in_step:  # a real filter gets a new scan every update: staging it is part of the step
+                ctx.filter_update_scan_async(w.curr, w.prev, 100 + k, w.u0, s.ranges, s.angle_min, s.angle_inc, s.range_max)
+            else:
+                ctx.filter_update_async(w.curr, w.prev, 100 + k, w.u0)
             e1.record(stream)
             torch.cuda.synchronize()
             if k >= warmup:
@@ -315,11 +316,19 @@ def run_b200(args):
         filt.connect()
 
     def one_step(k):
-        ctx.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max)  # a real filter gets a new scan every update
-        if filt:
+        # a real filter gets a new scan every update: staging it (host beam table + upload) is part of the step.  One
+        # library call does both; with the geometry of the previous scan it enqueues the motion kernel first and builds
+        # the table while that runs (amclj_filter_update_scan_async / amclj_shard_update_scan_async)
+        if filt and args.shard_mode == "mailbox":
+            filt.update(w.curr, w.prev, seed=100 + k, u0=w.u0, scan=s)
+        elif filt:
+            ctx.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max)
             filt.update(w.curr, w.prev, seed=100 + k, u0=w.u0)
-        else:
+        elif args.two_calls:
+            ctx.stage_scan(s.ranges, s.angle_min, s.angle_inc, s.range_max)
             ctx.filter_update_async(w.curr, w.prev, 100 + k, w.u0)
+        else:
+            ctx.filter_update_scan_async(w.curr, w.prev, 100 + k, w.u0, s.ranges, s.angle_min, s.angle_inc, s.range_max)
 
     def restore():
         ctx.set_particles(w.x, w.y, w.theta)
@@ -568,6 +577,7 @@ def main():
     ap.add_argument("--shard-mode", default="mailbox", choices=["mailbox", "pull", "a2a"])
     ap.add_argument("--df-mode", type=int, default=0, help="amclj_params.df_mode (0 auto)")
     ap.add_argument("--quick", action="store_true", help="skip the CPU baseline leg and the sub-records (tuning sweeps)")
+    ap.add_argument("--two-calls", action="store_true", help="N = 1: amclj_stage_scan + amclj_filter_update_async instead of the fused call (A/B)")
     ap.add_argument("--skip-c5", action="store_true", help="leave the C5 sub-record out (it builds an 8192^2 map)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

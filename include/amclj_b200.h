@@ -242,6 +242,13 @@ int32_t amclj_filter_update_async(amclj_ctx *ctx, const double curr[3], const do
  * counterpart (amclj keeps its particles in JVM vectors); the buffers are those of INTEGRATION.md's shim. */
 int32_t amclj_host_register(amclj_ctx *ctx, void *ptr, int64_t bytes);
 int32_t amclj_host_unregister(amclj_ctx *ctx, void *ptr);
+/* amclj_stage_scan + amclj_filter_update_async in one call (one mcl* iteration, pf.clj:229-233, for a device-resident
+ * cloud).  When the scan has the geometry of the staged one — every message of a laser after its first — the motion
+ * kernel, which needs nothing of the scan, is enqueued first and the message's beam table is built and uploaded
+ * while it runs; otherwise exactly the two calls.  Results are identical either way. */
+int32_t amclj_filter_update_scan_async(amclj_ctx *ctx, const double curr[3], const double prev[3], uint64_t seed,
+                                       double u0, const float *ranges, int32_t n, float angle_min,
+                                       float angle_increment, float range_max);
 /* The same step for a host-resident PoseArray: uploads x,y,theta, runs the fused update,
  * downloads the resampled particles and weights (in place). */
 int32_t amclj_filter_update_host(amclj_ctx *ctx, float *x, float *y, float *theta, float *w,
@@ -318,6 +325,10 @@ int32_t amclj_shard_pull_async(amclj_ctx *ctx, double u0);
  * shard_motion_sensor_async + all-reduce + shard_cdf_async + all-gather + shard_pull_async. */
 int32_t amclj_shard_update_async(amclj_ctx *ctx, const double curr[3], const double prev[3], uint64_t seed,
                                  double u0);
+/* amclj_stage_scan + amclj_shard_update_async in one call, as amclj_filter_update_scan_async. */
+int32_t amclj_shard_update_scan_async(amclj_ctx *ctx, const double curr[3], const double prev[3], uint64_t seed,
+                                      double u0, const float *ranges, int32_t n, float angle_min,
+                                      float angle_increment, float range_max);
 /* A barrier among the connected shards on the DEVICE time line (no reference counterpart: amclj runs one JVM):
  * enqueues a one-warp kernel that stores this call's count into every rank's mailbox and returns when every rank's
  * count has arrived, so whatever follows it in the stream starts at the same instant on every GPU, however far

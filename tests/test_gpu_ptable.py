@@ -286,3 +286,36 @@ def test_zero_probability_scan_keeps_the_particles(lg):
         # the next good update is back to normal
         c.set_params(_lib.params("NS"))
         c.filter_update(w.curr, w.prev, s.ranges, s.angle_min, s.angle_inc, s.range_max, 0.3, seed=2)
+
+
+def test_fused_scan_and_update_call_equals_the_two_calls(lg):
+    """amclj_filter_update_scan_async = amclj_stage_scan + amclj_filter_update_async, bit for bit: on its fast path
+    (the geometry of the staged scan: motion kernel first, beam table built while it runs), with other ranges in the
+    same geometry, and when the geometry changes (then it IS the two calls)."""
+    w = workloads.c3(30_000)
+    s = w.scan
+    rng = np.random.Generator(np.random.PCG64(5))
+    scans = [np.asarray(s.ranges, np.float32)]
+    scans.append(np.clip(scans[0] + rng.normal(0, 0.3, len(scans[0])).astype(np.float32), 0, s.range_max).astype(np.float32))
+    scans.append(scans[1][::2].copy())  # another beam count: a new geometry
+    outs = []
+    for fused in (False, True):
+        with _lib.Context(0, "NS") as c:
+            c.set_map(lg)
+            c.set_particles(w.x, w.y, w.theta)
+            got = []
+            for it, r in enumerate(scans + [scans[0]]):
+                inc = s.angle_inc * (2 if len(r) != len(scans[0]) else 1)
+                if fused:
+                    c.filter_update_scan_async(w.curr, w.prev, 40 + it, w.u0, r, s.angle_min, inc, s.range_max)
+                else:
+                    c.stage_scan(r, s.angle_min, inc, s.range_max)
+                    c.filter_update_async(w.curr, w.prev, 40 + it, w.u0)
+                c.synchronize()
+                got.append(c.get_particles()[:3])
+            assert c.stats().sensor_path == 3
+            outs.append(got)
+    for a, b in zip(*outs):
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v)
+    assert not np.array_equal(outs[0][0][0], outs[0][1][0])
