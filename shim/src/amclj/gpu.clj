@@ -130,6 +130,16 @@
            Pointer/NULL (long seed) (float-mem r) (int (count r))
            (float (:angleMin scan)) (float (:angleIncrement scan)) (float (:rangeMax scan)) (double u0))))
 
+(defn filter-update-async!
+  "The same iteration without waiting for it: scan staging and update in one call (the motion kernel is enqueued
+  first and the message's beam table built while it runs once the laser's geometry is staged).  Systematic
+  resampling only; (call! ctx \"amclj_synchronize\") or any download waits for it."
+  [ctx [curr prev] to-heading scan u0 seed]
+  (let [r (:ranges scan)]
+    (call! ctx "amclj_filter_update_scan_async" (yaw-pose curr to-heading) (yaw-pose prev to-heading)
+           (long seed) (double u0) (float-mem r) (int (count r))
+           (float (:angleMin scan)) (float (:angleIncrement scan)) (float (:rangeMax scan)))))
+
 (defn host-buffers
   "Four float buffers (x, y, theta, w) of n particles for filter-update-host!, page-locked once with
   amclj_host_register: a JNA Memory is plain malloc'ed memory, and copies from pageable memory go through the
